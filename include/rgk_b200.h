@@ -1,0 +1,300 @@
+/* rgk_b200.h -- C ABI of librgk_b200.so: the B200 (sm_100a) implementation of
+ * RGKrt's data-parallel hot path (kd-tree closest-hit / shadow traversal and the
+ * unidirectional path-tracing bounce loop).
+ *
+ * The reference (Enhex/RGK) has no plugin or FFI interface; its seam is the C++
+ * class boundary RenderDriver -> PathTracer -> Scene.  Every entry point below
+ * names the reference interface it replaces (paths relative to the reference
+ * tree).  Plain pointers and sizes only; the caller owns every host buffer, the
+ * library owns device memory behind the opaque context; no exception crosses
+ * this boundary -- every call returns an rgk_status and rgk_last_error() holds
+ * the text.  There is no CPU fallback: without a CUDA device every compute
+ * entry point fails with RGK_ERR_NO_DEVICE.
+ */
+#ifndef RGK_B200_H
+#define RGK_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGK_ABI_VERSION 1
+
+typedef enum rgk_status {
+    RGK_OK = 0,
+    RGK_ERR_INVALID = 1,     /* bad argument / inconsistent scene (reference: ConfigFileException, std::runtime_error) */
+    RGK_ERR_CUDA = 2,        /* CUDA runtime error (text in rgk_last_error) */
+    RGK_ERR_NOMEM = 3,
+    RGK_ERR_NO_DEVICE = 4,   /* no CUDA device: the library never falls back to the CPU */
+    RGK_ERR_NO_SCENE = 5,    /* compute call before rgk_scene_commit */
+    RGK_ERR_UNSUPPORTED = 6  /* e.g. reverse > 0 (bidirectional splats, out of scope) */
+} rgk_status;
+
+typedef struct rgk_context rgk_context;
+
+/* ---- scene description (host side, input) ------------------------------- */
+
+/* BxDF kinds, src/bxdf/bxdf.cpp:63-84 */
+enum {
+    RGK_BXDF_DIFFUSE = 0, RGK_BXDF_MIX = 1, RGK_BXDF_DIELECTRIC = 2, RGK_BXDF_MIRROR = 3,
+    RGK_BXDF_TRANSPARENT = 4, RGK_BXDF_LTC_BECKMANN = 5, RGK_BXDF_LTC_GGX = 6,
+    RGK_BXDF_LTC_BECKMANN_DIFFUSE = 7, RGK_BXDF_LTC_GGX_DIFFUSE = 8
+};
+
+/* ReadableTexture, src/texture.hpp:10-80.  kind 0 = SolidTexture(color),
+ * kind 1 = FileTexture(width x height, texels[(y*width+x)*3 + c], already
+ * gamma-decoded / flipped by the loader, src/texture.cpp:189-321). */
+typedef struct rgk_texture {
+    uint32_t kind;
+    uint32_t width, height;
+    float color[3];
+    const float* texels;
+} rgk_texture;
+
+/* Material + its BxDF, src/bxdf/bxdf.hpp:19-159.  Texture slots index
+ * rgk_scene_desc::textures; -1 = EmptyTexture (only meaningful for tex_bump,
+ * "no bump map"; an absent colour slot reads as black like EmptyTexture).
+ *   diffuse:           tex_diffuse
+ *   mirror/dielectric: tex_color (+ ior)
+ *   ltc_*:             tex_color (specular), roughness; *_diffuse adds tex_diffuse
+ *   mix:               mix_a, mix_b (material indices, must be < own index), amount */
+typedef struct rgk_material {
+    uint32_t bxdf;
+    uint32_t no_russian;
+    float emission[3];
+    float roughness;
+    float ior;
+    float amount;
+    int32_t mix_a, mix_b;
+    int32_t tex_diffuse, tex_color, tex_bump;
+    uint32_t _pad[3];
+} rgk_material; /* 64 bytes */
+
+/* One imported mesh / primitive: a run of triangles sharing one material.  A
+ * mesh whose material emits becomes one ArealLight (src/scene.cpp:149-206,
+ * 215-249), which is why the grouping is part of the input. */
+typedef struct rgk_mesh {
+    uint32_t first_triangle, n_triangles;
+    uint32_t material;
+    uint32_t _pad;
+} rgk_mesh;
+
+/* Light{FULL_SPHERE}, src/primitives.hpp:26-43, src/config.cpp:372-387 */
+typedef struct rgk_point_light {
+    float position[3];
+    float color[3];
+    float intensity;
+    float size;
+} rgk_point_light;
+
+/* src/scene.hpp:122-133,164-172: mode 0 = SimpleRadiance(color*intensity),
+ * mode 1 = lat-long envmap (texture index), rotate in degrees. */
+typedef struct rgk_sky {
+    uint32_t mode;
+    float color[3];
+    float intensity;
+    float rotate;
+    int32_t envmap;
+} rgk_sky;
+
+/* LTC lobe tables, src/LTC/ltc.hpp:6-35: 64x64 entries, index = alpha + theta*64;
+ * M as 9 floats per entry in mat33::m order (the double table cast to float as
+ * mat33::operator glm::mat3 does), amplitude one float per entry. */
+typedef struct rgk_ltc_table {
+    const float* M;
+    const float* amplitude;
+} rgk_ltc_table;
+
+typedef struct rgk_scene_desc {
+    uint32_t n_vertices;
+    const float* positions;   /* 3*n_vertices  Scene::vertices  */
+    const float* normals;     /* 3*n_vertices  Scene::normals   */
+    const float* tangents;    /* 3*n_vertices  Scene::tangents  */
+    const float* texcoords;   /* 2*n_vertices  Scene::texcoords */
+    uint32_t n_triangles;
+    const uint32_t* indices;  /* 3*n_triangles (va,vb,vc) */
+    uint32_t n_meshes;
+    const rgk_mesh* meshes;   /* cover [0,n_triangles) in order */
+    uint32_t n_materials;
+    const rgk_material* materials;
+    uint32_t n_textures;
+    const rgk_texture* textures;
+    uint32_t n_point_lights;
+    const rgk_point_light* point_lights;
+    rgk_sky sky;
+    rgk_ltc_table ltc_ggx, ltc_beckmann;
+    uint32_t thinglass; /* nonzero selects FindIntersectKdOtherThanWithThinglass (result-identical) */
+} rgk_scene_desc;
+
+/* The flattened kd-tree in the reference's own encoding, src/scene.hpp:212-253:
+ * nodes[2*i] = split_plane bits | triangles_start, nodes[2*i+1] = (other_child
+ * | triangles_num) << 2 | kind; left child = i+1; preorder (src/scene.cpp:637-657). */
+typedef struct rgk_kdtree {
+    uint32_t n_nodes;
+    const uint32_t* nodes;
+    uint32_t n_refs;
+    const uint32_t* refs;     /* Scene::compressed_triangles */
+} rgk_kdtree;
+
+typedef struct rgk_scene_info {
+    float epsilon;            /* Scene::epsilon = 1e-5 * bbox diagonal, src/scene.cpp:390 */
+    float bbox[6];            /* xBB.first, xBB.second, yBB..., zBB... (src/scene.cpp:393-395) */
+    uint32_t n_nodes, n_refs, n_triangles, n_areal_lights;
+    uint32_t max_depth;       /* deepest node of the committed tree */
+    float total_point_power, total_areal_power;
+} rgk_scene_info;
+
+/* ---- rays --------------------------------------------------------------- */
+
+/* Ray, src/ray.hpp:6-29 (near = 0, far = 10000 for directional rays). */
+typedef struct rgk_ray {
+    float origin[3];
+    float direction[3];
+    float tnear, tfar;
+} rgk_ray;
+
+#define RGK_NO_TRIANGLE 0xFFFFFFFFu
+/* Intersection, src/primitives.hpp:98-110 (triangle pointer -> index). */
+typedef struct rgk_hit {
+    uint32_t triangle;
+    float t, a, b, c;
+} rgk_hit;
+
+/* Work counters of one traversal batch (algorithmic bytes per ray =
+ * 36 + 20 + 8*inner + 8*leaf + 4*refs + 48*tests). */
+typedef struct rgk_trav_stats {
+    uint64_t rays, inner, leaf, refs, tests;
+} rgk_trav_stats;
+
+/* ---- rendering ---------------------------------------------------------- */
+
+/* Camera's public fields, src/camera.hpp:27-41. */
+typedef struct rgk_camera {
+    float origin[3], lookat[3], direction[3];
+    float cameraup[3], cameraleft[3];
+    float viewscreen[3], viewscreen_x[3], viewscreen_y[3];
+    float lens_size;
+    int32_t xsize, ysize;
+} rgk_camera;
+
+enum {
+    RGK_SAMPLER_MT19937 = 0, /* bit-exact device replica of StratifiedSampler(seed,64,ms), src/sampler.cpp:85-116 */
+    RGK_SAMPLER_TABLES = 1,  /* caller supplies per-pixel sample tables (rgk_render_set_tables) */
+    RGK_SAMPLER_FAST = 2     /* counter-based stratified+permuted sampler: same distribution, different sequence */
+};
+
+/* PathTracer ctor arguments, src/path_tracer.hpp:10-21 / src/render_driver.cpp:164-173 */
+typedef struct rgk_render_params {
+    uint32_t xres, yres;
+    uint32_t multisample;
+    uint32_t depth;           /* recursion-max */
+    float clamp;
+    float russian;
+    float bumpmap_scale;
+    uint32_t force_fresnell;  /* stored, never used (as in the reference) */
+    uint32_t reverse;         /* must be 0 */
+    uint32_t sampler_mode;
+} rgk_render_params;
+
+/* RenderTask, src/tracer.hpp:14-24 */
+typedef struct rgk_task {
+    uint32_t x1, x2, y1, y2;
+} rgk_task;
+
+typedef struct rgk_round_stats {
+    uint64_t closest_rays;    /* PathTracer raycount (src/path_tracer.cpp:126) */
+    uint64_t shadow_rays;     /* Scene::Visibility calls (not counted upstream) */
+    uint64_t samples;         /* camera samples traced */
+    uint64_t kernel_launches; /* kernels launched by the library during the call */
+    float gpu_ms;             /* device time of the call, CUDA events on the context stream */
+    float trace_ms;           /* of which closest-hit + shadow traversal kernels */
+} rgk_round_stats;
+
+/* ---- entry points ------------------------------------------------------- */
+
+uint32_t rgk_abi_version(void);
+const char* rgk_status_string(rgk_status s);
+
+/* Replaces: nothing upstream (process-wide CPU state).  device = CUDA ordinal;
+ * stream = a cudaStream_t to run on (NULL: the library creates its own). */
+rgk_status rgk_context_create(int device, void* stream, rgk_context** out);
+void rgk_context_destroy(rgk_context* ctx);
+const char* rgk_last_error(const rgk_context* ctx);
+
+/* Replaces Scene::Commit (src/scene.cpp:294-429): planes, areal lights, epsilon,
+ * bbox, SAH kd-tree build + Compress on the host, flatten to the device layout,
+ * upload.  If tree != NULL the given flattened tree is used instead of building
+ * one (parity mode: the reference's own arrays). */
+rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* desc, const rgk_kdtree* tree);
+rgk_status rgk_scene_get_info(const rgk_context* ctx, rgk_scene_info* out);
+/* Copies out the committed tree in the reference encoding (sizes from rgk_scene_info). */
+rgk_status rgk_scene_get_kdtree(const rgk_context* ctx, uint32_t* nodes, uint32_t* refs);
+
+/* Replaces Scene::FindIntersectKdOtherThan (src/scene_intersect.cpp:211-327) over a
+ * batch; ignore[i] = triangle index to skip or RGK_NO_TRIANGLE (then it is
+ * Scene::FindIntersectKd, :4-116); ignore may be NULL.  Host buffers. */
+rgk_status rgk_trace_closest(rgk_context* ctx, const rgk_ray* rays, const uint32_t* ignore,
+                             uint64_t n, rgk_hit* hits, rgk_trav_stats* stats);
+/* Replaces Scene::Visibility(a,b) (src/scene.cpp:670-673): visible[i] = 1 iff no
+ * triangle is hit on the segment a_i -> b_i shortened by 20*epsilon at both ends. */
+rgk_status rgk_trace_shadow(rgk_context* ctx, const float* a, const float* b,
+                            uint64_t n, uint8_t* visible, rgk_trav_stats* stats);
+/* Same two queries on device-resident buffers (bench / pipelines); asynchronous on
+ * the context stream.  d_stats may be NULL. */
+rgk_status rgk_trace_closest_device(rgk_context* ctx, const rgk_ray* d_rays, const uint32_t* d_ignore,
+                                    uint64_t n, rgk_hit* d_hits, rgk_trav_stats* d_stats);
+rgk_status rgk_trace_shadow_device(rgk_context* ctx, const float* d_a, const float* d_b,
+                                   uint64_t n, uint8_t* d_visible, rgk_trav_stats* d_stats);
+
+/* Replaces Camera::Camera (src/camera.cpp:7-24). */
+void rgk_camera_init(rgk_camera* cam, const float pos[3], const float lookat[3], const float up[3],
+                     float yview, float xview, int32_t xres, int32_t yres, float focus_plane, float lens_size);
+/* Replaces Camera::GetPixelRay / GetPixelRayLens (src/camera.cpp:32-46) for a batch of
+ * (x, y, subpixel offset, lens sample); lens may be NULL when lens_size == 0. Host buffers. */
+rgk_status rgk_camera_rays(rgk_context* ctx, const rgk_camera* cam, uint32_t xres, uint32_t yres,
+                           const int32_t* xy, const float* offsets, const float* lens,
+                           uint64_t n, rgk_ray* rays);
+
+/* Replaces GenerateTaskList (src/render_driver.cpp:30-46): tile_size x tile_size tiles
+ * sorted by distance of their midpoint to the image centre.  Returns the count;
+ * writes at most capacity tasks. */
+uint32_t rgk_generate_tasks(uint32_t tile_size, uint32_t xres, uint32_t yres, rgk_task* out, uint32_t capacity);
+
+/* Replaces StratifiedSampler(seed, 64, multisample) table construction
+ * (src/sampler.cpp:85-116) for a batch of seeds, on the device, for tests:
+ * out1d[seed][dim][set] (n1d dims), out2d[seed][dim][set][2] (n2d dims),
+ * set_size = rgk_sampler_set_size(multisample). */
+uint32_t rgk_sampler_set_size(uint32_t multisample);
+rgk_status rgk_sampler_tables(rgk_context* ctx, const uint32_t* seeds, uint32_t n_seeds, uint32_t multisample,
+                              uint32_t n1d, uint32_t n2d, float* out1d, float* out2d);
+
+/* Replaces RenderDriver::RenderRound (src/render_driver.cpp:144-190): every task i is
+ * rendered by a PathTracer seeded seedstart + seedcount_base + i (:160,173), pixels
+ * y-major/x-minor with the per-pixel seed bump (src/tracer.cpp:8-9,
+ * src/path_tracer.cpp:47), and (sum of samples, multisample) is added to
+ * rgb_sum[(y*xres+x)*3+c] / count[y*xres+x] (src/tracer.cpp:18,
+ * src/texture.cpp:342-348).  Host framebuffer; rgb_sum/count are read-modify-written. */
+rgk_status rgk_render_round(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* params,
+                            const rgk_task* tasks, uint32_t n_tasks, uint32_t seedstart, uint32_t seedcount_base,
+                            float* rgb_sum, uint32_t* count, rgk_round_stats* stats);
+/* Same with a device-resident framebuffer (multi-GPU reduce, bench); asynchronous. */
+rgk_status rgk_render_round_device(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* params,
+                                   const rgk_task* tasks, uint32_t n_tasks, uint32_t seedstart, uint32_t seedcount_base,
+                                   float* d_rgb_sum, uint32_t* d_count, rgk_round_stats* stats);
+/* Replaces RenderDriver::RenderFrame's Rounds loop (src/render_driver.cpp:192-253):
+ * task list, seedstart = 42, seedcount running across rounds; framebuffer zeroed
+ * first; (sum,count) returned un-normalised. */
+rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* params,
+                            uint32_t rounds, float* rgb_sum, uint32_t* count, rgk_round_stats* stats);
+/* RGK_SAMPLER_TABLES: tables for the pixels of the next rgk_render_round call, in
+ * task order then y-major/x-minor: t1d[pixel][dim][set], t2d[pixel][dim][set][2]. */
+rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t n1d, uint32_t n2d,
+                                 const float* t1d, const float* t2d, uint64_t n_pixels);
+
+/* Blocks until the context stream is idle. */
+rgk_status rgk_synchronize(rgk_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGK_B200_H */

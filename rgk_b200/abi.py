@@ -1,0 +1,172 @@
+"""ctypes mirror of include/rgk_b200.h (struct layouts + the product library loader).
+
+The product library is rgk_b200/librgk_b200.so (built by __graft_entry__.build()).
+There is no CPU fallback: load_library() raises if the CUDA extension is missing.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librgk_b200.so")
+
+RGK_NO_TRIANGLE = 0xFFFFFFFF
+(BXDF_DIFFUSE, BXDF_MIX, BXDF_DIELECTRIC, BXDF_MIRROR, BXDF_TRANSPARENT, BXDF_LTC_BECKMANN,
+ BXDF_LTC_GGX, BXDF_LTC_BECKMANN_DIFFUSE, BXDF_LTC_GGX_DIFFUSE) = range(9)
+SAMPLER_MT19937, SAMPLER_TABLES, SAMPLER_FAST = 0, 1, 2
+
+f32p = C.POINTER(C.c_float)
+u32p = C.POINTER(C.c_uint32)
+
+
+class Texture(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("color", C.c_float * 3), ("texels", f32p)]
+
+
+class Material(C.Structure):
+    _fields_ = [("bxdf", C.c_uint32), ("no_russian", C.c_uint32), ("emission", C.c_float * 3),
+                ("roughness", C.c_float), ("ior", C.c_float), ("amount", C.c_float),
+                ("mix_a", C.c_int32), ("mix_b", C.c_int32),
+                ("tex_diffuse", C.c_int32), ("tex_color", C.c_int32), ("tex_bump", C.c_int32),
+                ("_pad", C.c_uint32 * 3)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("first_triangle", C.c_uint32), ("n_triangles", C.c_uint32), ("material", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class PointLight(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("color", C.c_float * 3), ("intensity", C.c_float), ("size", C.c_float)]
+
+
+class Sky(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("color", C.c_float * 3), ("intensity", C.c_float), ("rotate", C.c_float),
+                ("envmap", C.c_int32)]
+
+
+class LtcTable(C.Structure):
+    _fields_ = [("M", f32p), ("amplitude", f32p)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint32), ("positions", f32p), ("normals", f32p), ("tangents", f32p),
+                ("texcoords", f32p),
+                ("n_triangles", C.c_uint32), ("indices", u32p),
+                ("n_meshes", C.c_uint32), ("meshes", C.POINTER(Mesh)),
+                ("n_materials", C.c_uint32), ("materials", C.POINTER(Material)),
+                ("n_textures", C.c_uint32), ("textures", C.POINTER(Texture)),
+                ("n_point_lights", C.c_uint32), ("point_lights", C.POINTER(PointLight)),
+                ("sky", Sky), ("ltc_ggx", LtcTable), ("ltc_beckmann", LtcTable), ("thinglass", C.c_uint32)]
+
+
+class KdTree(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("nodes", u32p), ("n_refs", C.c_uint32), ("refs", u32p)]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("epsilon", C.c_float), ("bbox", C.c_float * 6), ("n_nodes", C.c_uint32), ("n_refs", C.c_uint32),
+                ("n_triangles", C.c_uint32), ("n_areal_lights", C.c_uint32), ("max_depth", C.c_uint32),
+                ("total_point_power", C.c_float), ("total_areal_power", C.c_float)]
+
+
+class Ray(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("direction", C.c_float * 3), ("tnear", C.c_float), ("tfar", C.c_float)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("triangle", C.c_uint32), ("t", C.c_float), ("a", C.c_float), ("b", C.c_float), ("c", C.c_float)]
+
+
+class TravStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("inner", C.c_uint64), ("leaf", C.c_uint64), ("refs", C.c_uint64),
+                ("tests", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+    def bytes_per_ray(self, out_bytes=20):
+        """36 in + out + 8*inner + 8*leaf + 4*refs + 48*tests, averaged over the batch."""
+        n = max(1, int(self.rays))
+        return 36 + out_bytes + (8 * self.inner + 8 * self.leaf + 4 * self.refs + 48 * self.tests) / n
+
+
+class Camera(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("lookat", C.c_float * 3), ("direction", C.c_float * 3),
+                ("cameraup", C.c_float * 3), ("cameraleft", C.c_float * 3), ("viewscreen", C.c_float * 3),
+                ("viewscreen_x", C.c_float * 3), ("viewscreen_y", C.c_float * 3), ("lens_size", C.c_float),
+                ("xsize", C.c_int32), ("ysize", C.c_int32)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("xres", C.c_uint32), ("yres", C.c_uint32), ("multisample", C.c_uint32), ("depth", C.c_uint32),
+                ("clamp", C.c_float), ("russian", C.c_float), ("bumpmap_scale", C.c_float),
+                ("force_fresnell", C.c_uint32), ("reverse", C.c_uint32), ("sampler_mode", C.c_uint32)]
+
+
+class Task(C.Structure):
+    _fields_ = [("x1", C.c_uint32), ("x2", C.c_uint32), ("y1", C.c_uint32), ("y2", C.c_uint32)]
+
+
+class RoundStats(C.Structure):
+    _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("samples", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_float), ("trace_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: (int(getattr(self, k)) if "ms" not in k else float(getattr(self, k))) for k, _ in self._fields_}
+
+
+assert C.sizeof(Material) == 64 and C.sizeof(Ray) == 32 and C.sizeof(Hit) == 20
+
+# Every symbol include/rgk_b200.h declares (tests check that the library exports all of them).
+EXPORTS = [
+    "rgk_abi_version", "rgk_status_string", "rgk_context_create", "rgk_context_destroy", "rgk_last_error",
+    "rgk_scene_commit", "rgk_scene_get_info", "rgk_scene_get_kdtree", "rgk_trace_closest", "rgk_trace_shadow",
+    "rgk_trace_closest_device", "rgk_trace_shadow_device", "rgk_camera_init", "rgk_camera_rays",
+    "rgk_generate_tasks", "rgk_sampler_set_size", "rgk_sampler_tables", "rgk_render_round",
+    "rgk_render_round_device", "rgk_render_frame", "rgk_render_set_tables", "rgk_synchronize",
+]
+
+
+def load_library(path=None):
+    """dlopen the CUDA library. Fails loudly when it has not been built (no CPU fallback exists)."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "rgk_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.rgk_abi_version.restype = C.c_uint32
+    lib.rgk_status_string.restype = C.c_char_p
+    lib.rgk_status_string.argtypes = [C.c_int]
+    lib.rgk_context_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.rgk_context_destroy.argtypes = [vp]
+    lib.rgk_context_destroy.restype = None
+    lib.rgk_last_error.restype = C.c_char_p
+    lib.rgk_last_error.argtypes = [vp]
+    lib.rgk_scene_commit.argtypes = [vp, C.POINTER(SceneDesc), C.POINTER(KdTree)]
+    lib.rgk_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
+    lib.rgk_scene_get_kdtree.argtypes = [vp, vp, vp]
+    lib.rgk_trace_closest.argtypes = [vp, vp, vp, C.c_uint64, vp, C.POINTER(TravStats)]
+    lib.rgk_trace_shadow.argtypes = [vp, vp, vp, C.c_uint64, vp, C.POINTER(TravStats)]
+    lib.rgk_trace_closest_device.argtypes = [vp, vp, vp, C.c_uint64, vp, vp]
+    lib.rgk_trace_shadow_device.argtypes = [vp, vp, vp, C.c_uint64, vp, vp]
+    lib.rgk_camera_init.argtypes = [C.POINTER(Camera), f32p, f32p, f32p, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                    C.c_float, C.c_float]
+    lib.rgk_camera_init.restype = None
+    lib.rgk_camera_rays.argtypes = [vp, C.POINTER(Camera), C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]
+    lib.rgk_generate_tasks.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Task), C.c_uint32]
+    lib.rgk_generate_tasks.restype = C.c_uint32
+    lib.rgk_sampler_set_size.argtypes = [C.c_uint32]
+    lib.rgk_sampler_set_size.restype = C.c_uint32
+    lib.rgk_sampler_tables.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+    rr = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.POINTER(Task), C.c_uint32, C.c_uint32, C.c_uint32,
+          vp, vp, C.POINTER(RoundStats)]
+    lib.rgk_render_round.argtypes = rr
+    lib.rgk_render_round_device.argtypes = rr
+    lib.rgk_render_frame.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_uint32, vp, vp,
+                                     C.POINTER(RoundStats)]
+    lib.rgk_render_set_tables.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64]
+    lib.rgk_synchronize.argtypes = [vp]
+    return lib

@@ -1,0 +1,270 @@
+// host_scene.cpp -- host side of rgk_scene_commit: what Scene::Commit does on the CPU
+// (src/scene.cpp:294-429), producing the flattened arrays the kernels read.
+//
+// north_star keeps the SAH kd-tree build on the host.  The build follows the reference's
+// procedure step for step (events per node, std::sort with the (pos, BEGIN<END) comparator,
+// SAH sweep with ISECT 80 / TRAV 2 / EMPTY_BONUS 0.5, up to two axis retries, max depth
+// log2(n)+8) because closest-hit triangle IDs are only bit-exact on the *same* tree with
+// the same leaf order.  It emits the preorder node array directly
+// (left child = i+1, right child index stored in the parent), i.e. Scene::Compress's
+// output (src/scene.cpp:606-657), without building a pointer tree first.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include "rgk_internal.h"
+
+namespace {
+
+struct F3 { float x, y, z; };
+inline F3 ld3(const float* p) { return F3{p[0], p[1], p[2]}; }
+inline F3 sub(F3 a, F3 b) { return F3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline F3 cross3(F3 x, F3 y) { return F3{x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y}; }
+inline float comp(F3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+struct Event { float pos; int tri; int kind; };  // kind 0 = BEGIN, 1 = END
+
+struct Builder {
+    const std::vector<float>* ev;   // ev[axis][2*tri + {0,1}] = min / max of the triangle on that axis
+    std::vector<uint32_t>& nodes;
+    std::vector<uint32_t>& refs;
+    unsigned max_depth;
+    unsigned deepest = 0;
+
+    void emit_leaf(const std::vector<uint32_t>& tris) {
+        nodes.push_back((uint32_t)refs.size());
+        nodes.push_back(((uint32_t)tris.size() << 2) | 3u);
+        refs.insert(refs.end(), tris.begin(), tris.end());
+    }
+
+    // UncompressedKdNode::Subdivide (src/scene.cpp:431-574) fused with CompressRec (:637-657)
+    void build(std::vector<uint32_t>& tris, float bb[3][2], unsigned depth) {
+        deepest = std::max(deepest, depth);
+        const unsigned n = (unsigned)tris.size();
+        if (depth >= max_depth || n < 2) { emit_leaf(tris); return; }
+        const float size[3] = {bb[0][1] - bb[0][0], bb[1][1] - bb[1][0], bb[2][1] - bb[2][0]};
+        unsigned axis = (unsigned)(std::max_element(size, size + 3) - size);
+        std::vector<Event> events(2 * (size_t)n);
+        int best_offset = -1; float best_pos = 0.0f;
+        for (unsigned attempt = 0;; attempt++) {
+            const std::vector<float>& a = ev[axis];
+            for (unsigned i = 0; i < n; i++) {
+                const int t = (int)tris[i];
+                events[2 * i] = Event{a[2 * t], t, 0};
+                events[2 * i + 1] = Event{a[2 * t + 1], t, 1};
+            }
+            std::sort(events.begin(), events.end(), [](const Event& l, const Event& r) {
+                if (l.pos == r.pos) return l.kind < r.kind;
+                return l.pos < r.pos;
+            });
+            const float lo = bb[axis][0], hi = bb[axis][1];
+            const unsigned a2 = (axis + 1) % 3, a3 = (axis + 2) % 3;
+            const float inv_total_sa = 1.f / (2.f * (size[0] * size[1] + size[0] * size[2] + size[1] * size[2]));
+            const float nosplit_cost = 80.0f * n;
+            float best_cost = std::numeric_limits<float>::infinity();
+            best_offset = -1;
+            int n_before = 0, n_after = (int)n;
+            for (unsigned i = 0; i < 2 * n; i++) {
+                if (events[i].kind == 1) n_after--;
+                const float pos = events[i].pos;
+                if (pos > lo && pos < hi) {
+                    const float below = 2 * (size[a2] * size[a3] + (pos - lo) * size[a2] + (pos - lo) * size[a3]);
+                    const float above = 2 * (size[a2] * size[a3] + (hi - pos) * size[a2] + (hi - pos) * size[a3]);
+                    const float p_before = below * inv_total_sa, p_after = above * inv_total_sa;
+                    const float bonus = (n_before == 0 || n_after == 0) ? 0.5f : 0.f;
+                    const float cost = 2.0f + 80.0f * (1.f - bonus) * (p_before * n_before + p_after * n_after);
+                    if (cost < best_cost) { best_cost = cost; best_offset = (int)i; best_pos = pos; }
+                }
+                if (events[i].kind == 0) n_before++;
+            }
+            if (best_offset != -1 && !(best_cost > nosplit_cost)) break;
+            if (attempt >= 2) { emit_leaf(tris); return; }
+            axis = (axis + 1) % 3;
+        }
+        std::vector<uint32_t> below, above;
+        for (int i = 0; i < best_offset; i++) if (events[i].kind == 0) below.push_back((uint32_t)events[i].tri);
+        for (unsigned i = (unsigned)best_offset + 1; i < 2 * n; i++) if (events[i].kind == 1) above.push_back((uint32_t)events[i].tri);
+        std::vector<Event>().swap(events);
+        std::vector<uint32_t>().swap(tris);
+        const size_t me = nodes.size();
+        uint32_t bits; std::memcpy(&bits, &best_pos, 4);
+        nodes.push_back(bits);
+        nodes.push_back(axis);
+        float cb[3][2]; std::memcpy(cb, bb, sizeof cb);
+        cb[axis][1] = best_pos;
+        build(below, cb, depth + 1);
+        nodes[me + 1] = axis | ((uint32_t)(nodes.size() / 2) << 2);
+        std::memcpy(cb, bb, sizeof cb);
+        cb[axis][0] = best_pos;
+        build(above, cb, depth + 1);
+    }
+};
+
+unsigned measure_depth(const std::vector<uint32_t>& nodes) {
+    // iterative preorder walk (the given tree may come from the caller)
+    unsigned deepest = 0;
+    std::vector<std::pair<uint32_t, unsigned>> st;
+    if (!nodes.empty()) st.push_back({0u, 0u});
+    const size_t nn = nodes.size() / 2;
+    while (!st.empty()) {
+        auto [i, d] = st.back(); st.pop_back();
+        if (i >= nn) throw std::runtime_error("kd-tree: child index out of range");
+        deepest = std::max(deepest, d);
+        const uint32_t w1 = nodes[2 * i + 1];
+        if ((w1 & 3u) == 3u) continue;
+        st.push_back({w1 >> 2, d + 1});
+        st.push_back({i + 1, d + 1});
+        if (d > 4096) throw std::runtime_error("kd-tree: cycle");
+    }
+    return deepest;
+}
+
+} // namespace
+
+void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScene& hs) {
+    hs = HostScene();
+    const uint32_t nt = d->n_triangles, nv = d->n_vertices;
+    if (nt == 0) throw std::runtime_error("scene has no triangles");
+    if (!d->positions || !d->normals || !d->tangents || !d->texcoords || !d->indices || !d->meshes || !d->materials)
+        throw std::runtime_error("scene description has null arrays");
+    for (uint32_t i = 0; i < 3 * nt; i++)
+        if (d->indices[i] >= nv) throw std::runtime_error("triangle index out of range");
+    // triangles -> material through the mesh ranges; areal lights per emissive mesh (src/scene.cpp:149-206,215-249)
+    std::vector<uint32_t> tri_mat(nt, 0xFFFFFFFFu);
+    uint32_t cursor = 0;
+    for (uint32_t m = 0; m < d->n_meshes; m++) {
+        const rgk_mesh& me = d->meshes[m];
+        if (me.first_triangle != cursor || me.first_triangle + me.n_triangles > nt) throw std::runtime_error("mesh ranges must tile [0, n_triangles) in order");
+        if (me.material >= d->n_materials) throw std::runtime_error("mesh material index out of range");
+        cursor += me.n_triangles;
+        for (uint32_t t = 0; t < me.n_triangles; t++) tri_mat[me.first_triangle + t] = me.material;
+    }
+    if (cursor != nt) throw std::runtime_error("mesh ranges must tile [0, n_triangles) in order");
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const rgk_material& m = d->materials[i];
+        if (m.bxdf > RGK_BXDF_LTC_GGX_DIFFUSE) throw std::runtime_error("Unsupported BRDF id in config!");
+        if (m.bxdf == RGK_BXDF_MIX && (m.mix_a < 0 || m.mix_b < 0 || (uint32_t)m.mix_a >= i || (uint32_t)m.mix_b >= i))
+            throw std::runtime_error("mix material refers to a material that was not (yet) defined");
+        const int32_t tx[3] = {m.tex_diffuse, m.tex_color, m.tex_bump};
+        for (int32_t t : tx) if (t >= (int32_t)d->n_textures) throw std::runtime_error("texture index out of range");
+        if (m.bxdf >= RGK_BXDF_LTC_BECKMANN && !(m.roughness >= 0.0f && m.roughness <= 1.0f))
+            throw std::runtime_error("LTC roughness must be in [0,1]");   // assert in src/LTC/ltc.cpp:60
+    }
+
+    // planes: Triangle::CalculatePlane (src/primitives.cpp:24-36), GLM cross / normalize formulas
+    hs.planes.resize(4 * (size_t)nt);
+    hs.tri_shade.resize(4 * (size_t)nt);
+    for (uint32_t i = 0; i < nt; i++) {
+        const uint32_t va = d->indices[3 * i], vb = d->indices[3 * i + 1], vc = d->indices[3 * i + 2];
+        const F3 v0 = ld3(d->positions + 3 * va), v1 = ld3(d->positions + 3 * vb), v2 = ld3(d->positions + 3 * vc);
+        const F3 d0 = sub(v1, v0), d1 = sub(v2, v0);
+        const F3 c = cross3(d1, d0);
+        const float inv = 1.0f / std::sqrt(dot3(c, c));
+        const F3 n = F3{c.x * inv, c.y * inv, c.z * inv};
+        float* p = &hs.planes[4 * (size_t)i];
+        p[0] = n.x; p[1] = n.y; p[2] = n.z; p[3] = -dot3(n, v0);
+        uint32_t* s = &hs.tri_shade[4 * (size_t)i];
+        s[0] = va; s[1] = vb; s[2] = vc; s[3] = tri_mat[i];
+    }
+
+    // areal lights: areas, descending sort, power (src/scene.cpp:323-340)
+    float total_areal = 0.0f;
+    for (uint32_t m = 0; m < d->n_meshes; m++) {
+        const rgk_mesh& me = d->meshes[m];
+        const float* e = d->materials[me.material].emission;
+        if (!(e[0] > 0 || e[1] > 0 || e[2] > 0) || me.n_triangles == 0) continue;
+        std::vector<std::pair<float, unsigned>> ta;
+        float total_area = 0.0f;
+        for (uint32_t t = 0; t < me.n_triangles; t++) {
+            const uint32_t ti = me.first_triangle + t;
+            const F3 a = ld3(d->positions + 3 * d->indices[3 * ti]), b = ld3(d->positions + 3 * d->indices[3 * ti + 1]),
+                     c = ld3(d->positions + 3 * d->indices[3 * ti + 2]);
+            const F3 x = cross3(sub(a, b), sub(c, b));
+            const float area = 0.5f * std::sqrt(dot3(x, x));   // Triangle::GetArea, src/primitives.cpp:38-45
+            ta.push_back({area, ti});
+            total_area += area;
+        }
+        std::sort(ta.rbegin(), ta.rend());
+        DevArealLight al{};
+        al.total_area = total_area;
+        al.emission[0] = e[0]; al.emission[1] = e[1]; al.emission[2] = e[2];
+        al.power = total_area * (e[0] + e[1] + e[2]);
+        al.first = (uint32_t)hs.areal_tris.size(); al.count = (uint32_t)ta.size();
+        for (auto& p : ta) hs.areal_tris.push_back(DevArealTri{p.first, p.second});
+        hs.areal_lights.push_back(al);
+        total_areal += al.power;
+    }
+    float total_point = 0.0f;
+    for (uint32_t i = 0; i < d->n_point_lights; i++) total_point += d->point_lights[i].intensity * 4.0f * 3.14159265358979323846264338327950288f;
+
+    // per-axis triangle extents, scene bbox, epsilon (src/scene.cpp:364-395)
+    std::vector<float> ev[3];
+    float mn[3], mx[3];
+    for (int ax = 0; ax < 3; ax++) {
+        ev[ax].resize(2 * (size_t)nt);
+        for (uint32_t i = 0; i < nt; i++) {
+            const float a = d->positions[3 * d->indices[3 * i] + ax], b = d->positions[3 * d->indices[3 * i + 1] + ax],
+                        c = d->positions[3 * d->indices[3 * i + 2] + ax];
+            const auto mm = std::minmax({a, b, c});
+            ev[ax][2 * i] = mm.first; ev[ax][2 * i + 1] = mm.second;
+        }
+        const auto mm = std::minmax_element(ev[ax].begin(), ev[ax].end());
+        mn[ax] = *mm.first; mx[ax] = *mm.second;
+    }
+    const float xs = mx[0] - mn[0], ys = mx[1] - mn[1], zs = mx[2] - mn[2];
+    const float diameter = std::sqrt(xs * xs + ys * ys + zs * zs);
+    const float eps = 0.00001f * diameter;
+    float bb[3][2];
+    for (int ax = 0; ax < 3; ax++) { bb[ax][0] = mn[ax] - eps; bb[ax][1] = mx[ax] + eps; }
+
+    // kd-tree
+    unsigned deepest;
+    if (tree) {
+        if (!tree->nodes || tree->n_nodes == 0 || (tree->n_refs && !tree->refs)) throw std::runtime_error("given kd-tree is empty");
+        hs.nodes.assign(tree->nodes, tree->nodes + 2 * (size_t)tree->n_nodes);
+        hs.refs.assign(tree->refs, tree->refs + tree->n_refs);
+        for (size_t i = 0; i < hs.nodes.size() / 2; i++) {
+            const uint32_t w0 = hs.nodes[2 * i], w1 = hs.nodes[2 * i + 1];
+            if ((w1 & 3u) == 3u && (uint64_t)w0 + (w1 >> 2) > hs.refs.size()) throw std::runtime_error("kd-tree: leaf range out of bounds");
+        }
+        for (uint32_t r : hs.refs) if (r >= nt) throw std::runtime_error("kd-tree: triangle reference out of range");
+        deepest = measure_depth(hs.nodes);
+    } else {
+        Builder b{ev, hs.nodes, hs.refs, (unsigned)(int)(std::log2(nt) + 8)};
+        std::vector<uint32_t> all(nt);
+        for (uint32_t i = 0; i < nt; i++) all[i] = i;
+        b.build(all, bb, 0);
+        deepest = b.deepest;
+    }
+    if (deepest + 2 > RGK_STACK_CAP) throw std::runtime_error("kd-tree deeper than the traversal stack capacity");
+
+    // intersection records: the ray-independent part of Triangle::TestIntersection (src/primitives.cpp:83,104-133,141,149)
+    hs.tri_isect.resize(12 * (size_t)nt);
+    for (uint32_t i = 0; i < nt; i++) {
+        const float* p = &hs.planes[4 * (size_t)i];
+        const float px = std::fabs(p[0]), py = std::fabs(p[1]), pz = std::fabs(p[2]);
+        int i1, i2; uint32_t code;
+        if (px > py && px > pz) { i1 = 1; i2 = 2; code = 0; }
+        else if (py > pz) { i1 = 0; i2 = 2; code = 1; }
+        else { i1 = 0; i2 = 1; code = 2; }
+        const uint32_t* s = &hs.tri_shade[4 * (size_t)i];
+        const F3 v0 = ld3(d->positions + 3 * s[0]), v1 = ld3(d->positions + 3 * s[1]), v2 = ld3(d->positions + 3 * s[2]);
+        const float q1x = comp(v1, i1) - comp(v0, i1), q1y = comp(v1, i2) - comp(v0, i2);
+        const float q2x = comp(v2, i1) - comp(v0, i1), q2y = comp(v2, i2) - comp(v0, i2);
+        const float denom = q2y * q1x - q2x * q1y;
+        if (q1x > -eps && q1x < eps) code |= 4u;
+        float* r = &hs.tri_isect[12 * (size_t)i];
+        r[0] = p[0]; r[1] = p[1]; r[2] = p[2]; r[3] = p[3];
+        r[4] = comp(v0, i1); r[5] = comp(v0, i2); r[6] = q1x; r[7] = q1y;
+        r[8] = q2x; r[9] = q2y; r[10] = denom; std::memcpy(&r[11], &code, 4);
+    }
+
+    rgk_scene_info& in = hs.info;
+    in.epsilon = eps;
+    for (int ax = 0; ax < 3; ax++) { in.bbox[2 * ax] = bb[ax][0]; in.bbox[2 * ax + 1] = bb[ax][1]; }
+    in.n_nodes = (uint32_t)(hs.nodes.size() / 2); in.n_refs = (uint32_t)hs.refs.size(); in.n_triangles = nt;
+    in.n_areal_lights = (uint32_t)hs.areal_lights.size(); in.max_depth = deepest;
+    in.total_point_power = total_point; in.total_areal_power = total_areal;
+}

@@ -1,0 +1,665 @@
+// render.cu -- the unidirectional bounce loop as a wavefront of kernels
+// (replaces PathTracer::RenderPixel / TracePath / GeneratePath, src/path_tracer.cpp:42-512,
+// Tracer::Render, src/tracer.cpp:6-37, and the per-task body of RenderDriver::RenderRound,
+// src/render_driver.cpp:158-184).
+//
+// One call renders a list of tasks (tiles).  Tiles are processed in chunks sized to HBM; a
+// chunk holds every multisample of its pixels: path slot = sample * npix + pixel, so that
+// adjacent threads are adjacent pixels of one tile row (coherent primary rays, coalesced
+// state and sampler-table access).  Per chunk:
+//   pixel_setup -> sampler tables (device mt19937 replica) -> raygen (+ light pick)
+//   repeat per bounce: closest-hit traversal -> shade (vertex set-up, NEE set-up, BxDF
+//   sample, termination, warp-aggregated compaction into the next queue) -> shadow traversal
+//   fused with the NEE resolve (visibility * direct + emission, clamp, accumulate)
+//   finish: per pixel, samples summed in order and added to the framebuffer.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include "trace_device.cuh"
+#include "shade_device.cuh"
+
+// ------------------------------------------------------------------ buffers
+struct PathBuffers {
+    size_t cap_paths = 0, cap_pixels = 0, cap_t1 = 0, cap_t2 = 0, cap_tiles = 0;
+    float4 *ray_o = nullptr, *ray_d = nullptr, *hit = nullptr, *cum = nullptr, *tot = nullptr;
+    float4 *light_pos = nullptr, *light_col = nullptr, *light_nrm = nullptr;
+    float4 *sh_pos = nullptr, *sh_direct = nullptr, *sh_emis = nullptr, *sh_contrib = nullptr;
+    uint32_t *last_tri = nullptr, *cur1 = nullptr, *queue_a = nullptr, *queue_b = nullptr, *queue_s = nullptr;
+    uint32_t *pix_xy = nullptr, *pix_seed = nullptr;
+    uint32_t *mt_state = nullptr;
+    float *t1 = nullptr; float2 *t2 = nullptr;
+    uint4 *tiles = nullptr; uint2 *tiles2 = nullptr;
+    unsigned long long *counters = nullptr;   // device
+    unsigned long long *h_counters = nullptr; // pinned
+};
+
+enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_CLOSEST_RAYS = 4, C_SHADOW_RAYS = 5, C_COUNT = 8 };
+
+struct RenderConst {
+    rgk_camera cam;
+    uint32_t xres, yres, ms, depth;
+    float clamp, russian, bump_scale;
+    uint32_t set_size, n1d, n2d, base2, sampler_mode, lens;
+    uint32_t npix;          // pixels in the chunk
+};
+
+namespace {
+
+template <class T> bool alloc_dev(T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)) == cudaSuccess;
+}
+
+// ------------------------------------------------------------------ sampler: device replica of StratifiedSampler
+// (src/sampler.cpp:5-36,85-116) over libstdc++'s mt19937 / generate_canonical / uniform_int_distribution (Lemire)
+// / std::shuffle (pairwise) -- SURVEY Appendix C.  One thread per pixel; the 624-word generator state lives in
+// global memory, interleaved across threads (state[k * stride + thread]) so every access is coalesced.
+struct MT {
+    uint32_t* st; size_t stride; int idx;
+    __device__ void seed(uint32_t s) {
+        uint32_t prev = s; st[0] = s;
+        for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; st[(size_t)i * stride] = prev; }
+        idx = 624;
+    }
+    __device__ void regen() {
+        uint32_t first = st[0], cur = first;
+        for (int k = 0; k < 624; k++) {
+            const uint32_t nxt = (k == 623) ? st[0] : st[(size_t)(k + 1) * stride];
+            const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+            const int k397 = (k + 397 < 624) ? k + 397 : k + 397 - 624;
+            const uint32_t v = st[(size_t)k397 * stride] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            st[(size_t)k * stride] = v;
+            cur = nxt;
+        }
+        (void)first;
+        idx = 0;
+    }
+    __device__ uint32_t next() {
+        if (idx >= 624) regen();
+        uint32_t y = st[(size_t)(idx++) * stride];
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        return y;
+    }
+    // generate_canonical<float,24>: one 32-bit draw / 2^32, result clamped below 1
+    __device__ float canonical() {
+        float r = __uint2float_rn(next()) / 4294967296.0f;
+        if (r >= 1.0f) r = 0.99999994f;   // nextafterf(1, 0)
+        return r;
+    }
+    __device__ float uniform_real(float a, float b) { return canonical() * (b - a) + a; }
+    __device__ uint32_t lemire(uint32_t range) {
+        unsigned long long product = (unsigned long long)next() * (unsigned long long)range;
+        uint32_t low = (uint32_t)product;
+        if (low < range) {
+            const uint32_t threshold = (0u - range) % range;
+            while (low < threshold) { product = (unsigned long long)next() * (unsigned long long)range; low = (uint32_t)product; }
+        }
+        return (uint32_t)(product >> 32);
+    }
+};
+
+template <class T>
+__device__ __forceinline__ void dev_swap(T* base, size_t stride, uint32_t i, uint32_t j) {
+    const T a = base[(size_t)i * stride], b = base[(size_t)j * stride];
+    base[(size_t)i * stride] = b; base[(size_t)j * stride] = a;
+}
+// std::shuffle, pairwise variant; `store` false only advances the generator
+template <class T>
+__device__ void dev_shuffle(T* base, size_t stride, uint32_t n, MT& g, bool store) {
+    uint32_t i = 1;
+    if ((n % 2) == 0) { const uint32_t d = g.lemire(2); if (store) dev_swap(base, stride, i, d); i++; }
+    while (i != n) {
+        const uint32_t swap_range = i + 1;
+        const uint32_t x = g.lemire(swap_range * (swap_range + 1));
+        const uint32_t p1 = x / (swap_range + 1), p2 = x % (swap_range + 1);
+        if (store) { dev_swap(base, stride, i, p1); dev_swap(base, stride, i + 1, p2); }
+        i += 2;
+    }
+}
+
+// Tables: t1[(dim * ss + set) * npix + pixel], t2 likewise (float2).  One scratch dim is appended to each
+// table (index n1d / n2d) so that dims nobody reads still have a place to live while the stream advances.
+__global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
+                             float* __restrict__ t1, float2* __restrict__ t2, uint32_t* __restrict__ state) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    MT g; g.st = state + p; g.stride = npix;
+    g.seed(seeds[p]);
+    const float len1 = 1.0f / (float)ss, len2 = 1.0f / (float)sq;
+    const uint32_t last_dim = max(n1d, n2d);   // dims >= last_dim are never read: stop there (the stream is not reused)
+    for (uint32_t dim = 0; dim < last_dim; dim++) {
+        const bool keep1 = dim < n1d, keep2 = dim < n2d;
+        float* a = t1 + ((size_t)(keep1 ? dim : n1d) * ss) * npix + p;
+        for (uint32_t k = 0; k < ss; k++) {
+            const float begin = (float)k / (float)ss;
+            const float v = begin + g.uniform_real(0.0f, len1);
+            if (keep1) a[(size_t)k * npix] = v;
+        }
+        dev_shuffle(a, (size_t)npix, ss, g, keep1);
+        float2* b = t2 + ((size_t)(keep2 ? dim : n2d) * ss) * npix + p;
+        for (uint32_t sy = 0; sy < sq; sy++)
+            for (uint32_t sx = 0; sx < sq; sx++) {
+                const float bx = (float)sx / (float)sq, by = (float)sy / (float)sq;
+                const float x = bx + g.uniform_real(0.0f, len2);
+                const float y = by + g.uniform_real(0.0f, len2);
+                if (keep2) b[(size_t)(sy * sq + sx) * npix] = make_float2(x, y);
+            }
+        dev_shuffle(b, (size_t)npix, ss, g, keep2);
+    }
+}
+
+// Counter-based sampler with the same structure (jittered strata visited in a per-(pixel,dim) random order),
+// no tables, no sequential generator: RGK_SAMPLER_FAST.  Same distribution, different sequence.
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x;
+}
+__device__ __forceinline__ uint32_t permute(uint32_t i, uint32_t l, uint32_t p) {   // Kensler's bijection on [0,l)
+    uint32_t w = l - 1; w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        i ^= p; i *= 0xe170893du; i ^= p >> 16; i ^= (i & w) >> 4; i ^= p >> 8; i *= 0x0929eb3fu; i ^= p >> 23;
+        i ^= (i & w) >> 1; i *= 1 | p >> 27; i *= 0x6935fa69u; i ^= (i & w) >> 11; i *= 0x74dcb303u; i ^= (i & w) >> 2;
+        i *= 0x9e501cc3u; i ^= (i & w) >> 2; i *= 0xc860a3dfu; i &= w; i ^= i >> 5;
+    } while (i >= l);
+    return (i + p) % l;
+}
+__device__ __forceinline__ float u01(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
+
+struct SamplerView {
+    const float* t1; const float2* t2; uint32_t npix, ss, sq, mode;
+    __device__ __forceinline__ float get1d(uint32_t pixel, uint32_t seed, uint32_t set, uint32_t dim) const {
+        if (mode != RGK_SAMPLER_FAST) return __ldg(t1 + ((size_t)dim * ss + set) * npix + pixel);
+        const uint32_t key = hash32(seed ^ hash32(dim * 2u + 1u));
+        const uint32_t k = permute(set, ss, key);
+        return ((float)k + u01(hash32(key ^ (set * 0x9e3779b9u + 0x85ebca6bu)))) / (float)ss;
+    }
+    __device__ __forceinline__ V2 get2d(uint32_t pixel, uint32_t seed, uint32_t set, uint32_t dim) const {
+        if (mode != RGK_SAMPLER_FAST) { const float2 v = __ldg(t2 + ((size_t)dim * ss + set) * npix + pixel); return V2{v.x, v.y}; }
+        const uint32_t key = hash32(seed ^ hash32(dim * 2u + 2u));
+        const uint32_t k = permute(set, ss, key);
+        const uint32_t sx = k % sq, sy = k / sq;
+        const uint32_t h = hash32(key ^ (set * 0x9e3779b9u + 0xc2b2ae35u));
+        return V2{((float)sx + u01(h)) / (float)sq, ((float)sy + u01(hash32(h))) / (float)sq};
+    }
+};
+
+// ------------------------------------------------------------------ kernels
+// tiles[i] = (x1, x2, y1, y2); tiles2[i] = (first pixel of the tile inside the chunk, tile seed)
+__global__ void k_pixel_setup(const uint4* __restrict__ tiles, const uint2* __restrict__ tiles2,
+                              uint32_t* __restrict__ pix_xy, uint32_t* __restrict__ pix_seed) {
+    const uint4 t = tiles[blockIdx.x];
+    const uint2 u = tiles2[blockIdx.x];
+    const uint32_t w = t.y - t.x, n = w * (t.w - t.z);
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const uint32_t x = t.x + k % w, y = t.z + k / w;
+        pix_xy[u.x + k] = x | (y << 16);
+        // PathTracer::RenderPixel: samplerSeed += 0x42424242 before every pixel, y-major / x-minor (src/tracer.cpp:8-9)
+        pix_seed[u.x + k] = u.y + (k + 1u) * 0x42424242u;
+    }
+}
+
+// Camera::GetPixelRay / GetPixelRayLens (src/camera.cpp:26-46) + Ray(from, dir) (src/ray.hpp:9-13)
+__device__ __forceinline__ void camera_ray(const rgk_camera& c, int x, int y, uint32_t xres, uint32_t yres, V2 off, V2 lens, V3& o, V3& d) {
+    const float fx = ((float)x + off.x) / (float)xres, fy = ((float)y + off.y) / (float)yres;
+    const V3 p = v3(c.viewscreen) + fx * v3(c.viewscreen_x) + fy * v3(c.viewscreen_y);
+    o = v3(c.origin);
+    if (c.lens_size != 0.0f) {
+        const V2 dsk = disc_uniform(lens);
+        const V2 lo = V2{dsk.x * c.lens_size, dsk.y * c.lens_size};
+        o = o + lo.x * v3(c.cameraleft) + lo.y * v3(c.cameraup);
+    }
+    d = normalize(p - o);
+}
+
+__global__ void k_camera_rays(rgk_camera cam, uint32_t xres, uint32_t yres, const int32_t* __restrict__ xy, const float* __restrict__ off,
+                              const float* __restrict__ lens, uint64_t n, rgk_ray* __restrict__ rays) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 o, d;
+    camera_ray(cam, xy[2 * i], xy[2 * i + 1], xres, yres, V2{off[2 * i], off[2 * i + 1]}, lens ? V2{lens[2 * i], lens[2 * i + 1]} : V2{0, 0}, o, d);
+    rgk_ray r; r.origin[0] = o.x; r.origin[1] = o.y; r.origin[2] = o.z; r.direction[0] = d.x; r.direction[1] = d.y; r.direction[2] = d.z;
+    r.tnear = 0.0f; r.tfar = 10000.0f;
+    rays[i] = r;
+}
+
+// RenderPixel's per-sample prologue (src/path_tracer.cpp:53-61) and TracePath's light pick (:315-322,337-346)
+__global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers B) {
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t npaths = (size_t)R.npix * R.ms;
+    if (slot >= npaths) return;
+    const uint32_t pixel = (uint32_t)(slot % R.npix), set = (uint32_t)(slot / R.npix);
+    const uint32_t xy = B.pix_xy[pixel], seed = B.pix_seed[pixel];
+    uint32_t d2 = 0;
+    const V2 coords = smp.get2d(pixel, seed, set, d2++);
+    V2 lens = V2{0, 0};
+    if (R.lens) lens = smp.get2d(pixel, seed, set, d2++);
+    V3 o, d;
+    camera_ray(R.cam, (int)(xy & 0xffffu), (int)(xy >> 16), R.xres, R.yres, coords, lens, o, d);
+    const V2 areal = smp.get2d(pixel, seed, set, d2++);
+    d2++;                                                       // lightdir_sample: drawn, unused when reverse == 0
+    const V2 choice = smp.get2d(pixel, seed, set, d2++);
+    const float ls = smp.get1d(pixel, seed, set, 0);
+    LightRec L = random_light(S, choice, ls, areal);
+    if (L.valid && L.type == 0) { const V3 dir = sphere_uniform(areal); L.pos = L.pos + L.size * dir; }
+    B.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+    B.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+    B.cum[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));      // .w = n (bounces done)
+    B.tot[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    B.last_tri[slot] = RGK_NO_TRIANGLE;
+    B.cur1[slot] = 1u;
+    B.light_pos[slot] = make_float4(L.pos.x, L.pos.y, L.pos.z, __uint_as_float((L.valid ? 1u : 0u) | ((uint32_t)L.type << 1)));
+    B.light_col[slot] = make_float4(L.color.r, L.color.g, L.color.b, L.intensity);
+    B.light_nrm[slot] = make_float4(L.normal.x, L.normal.y, L.normal.z, 0.0f);
+}
+
+constexpr int TRACE_THREADS = 128;
+
+// closest-hit over the live queue (queue == nullptr: identity), persistent warps
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work) {
+    const unsigned lane = threadIdx.x & 31;
+    TravCount cnt;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(work, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const uint32_t i = (uint32_t)base + lane;
+        if (i < count) {
+            const uint32_t slot = queue ? __ldg(queue + i) : i;
+            const float4 o = B.ray_o[slot], d = B.ray_d[slot];
+            HitRec h;
+            kd_traverse<false, false>(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot], h, cnt);
+            B.hit[slot] = make_float4(h.t, h.alpha, h.beta, __uint_as_float(h.tri));
+        }
+    }
+}
+
+// shadow traversal fused with the NEE resolve (src/path_tracer.cpp:431-460,485-496)
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work) {
+    const unsigned lane = threadIdx.x & 31;
+    TravCount cnt;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(work, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const uint32_t i = (uint32_t)base + lane;
+        if (i < count) {
+            const uint32_t slot = __ldg(queue + i);
+            const float4 a = B.light_pos[slot], b = B.sh_pos[slot];
+            const float ex = b.x - a.x, ey = b.y - a.y, ez = b.z - a.z;
+            const float d2 = ex * ex + ey * ey + ez * ez;
+            const float inv = 1.0f / sqrtf(d2), len = sqrtf(d2);
+            const float e20 = S.epsilon * 20.0f;
+            HitRec h;
+            const bool blocked = kd_traverse<true, false>(S, a.x, a.y, a.z, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20,
+                                                          RGK_NO_TRIANGLE, h, cnt);
+            const float4 dr = B.sh_direct[slot], em = B.sh_emis[slot], cb = B.sh_contrib[slot];
+            float hr = blocked ? 0.0f : dr.x, hg = blocked ? 0.0f : dr.y, hb = blocked ? 0.0f : dr.z;
+            hr += em.x; hg += em.y; hb += em.z;
+            if (hr > clampv) hr = clampv;
+            if (hg > clampv) hg = clampv;
+            if (hb > clampv) hb = clampv;
+            float4 t = B.tot[slot];
+            t.x += hr * cb.x; t.y += hg * cb.y; t.z += hb * cb.z;
+            B.tot[slot] = t;
+        }
+    }
+}
+
+__device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* counter, bool want, uint32_t slot) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);   // every lane of the warp reaches this point
+    if (!want) return;
+    const unsigned lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    queue[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+}
+
+// One vertex of GeneratePath (src/path_tracer.cpp:122-302) plus the NEE set-up of TracePath (:405-496)
+__global__ void __launch_bounds__(128)
+k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count,
+        uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, unsigned long long* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool cont = false, shadow = false;
+    uint32_t slot = 0;
+    if (i < count) {
+        slot = queue ? __ldg(queue + i) : i;
+        const float4 hit = B.hit[slot];
+        const uint32_t tri = __float_as_uint(hit.w);
+        const float4 ro4 = B.ray_o[slot], rd4 = B.ray_d[slot];
+        const V3 ro = v3(ro4), rd = v3(rd4);
+        float4 cum4 = B.cum[slot];
+        uint32_t n = __float_as_uint(cum4.w) + 1u;
+        const RGB contribution = rgb(cum4.x, cum4.y, cum4.z);
+        const V3 Vr = -rd;
+        if (tri == RGK_NO_TRIANGLE) {
+            const RGB sky = sky_radiance(S, Vr);
+            float4 t = B.tot[slot];
+            t.x += sky.r * contribution.r; t.y += sky.g * contribution.g; t.z += sky.b * contribution.b;
+            B.tot[slot] = t;
+        } else {
+            const uint4 tv = __ldg(S.tri_shade + tri);
+            const float ia = 1.0f - hit.y - hit.z, ib = hit.y, ic = hit.z;   // Intersection a,b,c (src/scene_intersect.cpp:280-283)
+            const V3 pos = ro + hit.x * rd;
+            const V3 nA = v3(__ldg(S.normals + tv.x)), nB = v3(__ldg(S.normals + tv.y)), nC = v3(__ldg(S.normals + tv.z));
+            V3 faceN = ia * nA + ib * nB + ic * nC;
+            bool ok = true;
+            if (isnan(faceN.x)) { faceN = nA; if (isnan(faceN.x)) { faceN = nB; if (isnan(faceN.x)) { faceN = nC; if (isnan(faceN.x)) ok = false; } } }
+            if (ok && length(faceN) <= 0.0f) ok = false;
+            if (ok) {
+                faceN = normalize(faceN);
+                const DevMaterial mat = S.materials[tv.w];
+                const float2 ta = __ldg(S.texcoords + tv.x), tb = __ldg(S.texcoords + tv.y), tc = __ldg(S.texcoords + tv.z);
+                const V2 uv = V2{ia * ta.x + ib * tb.x + ic * tc.x, ia * ta.y + ib * tb.y + ic * tc.y};
+                V3 lightN = faceN;
+                if (mat.tex_bump >= 0) {
+                    float right, bottom; tex_slopes(S, mat.tex_bump, uv, right, bottom);
+                    V3 tangent = ia * v3(__ldg(S.tangents + tv.x)) + ib * v3(__ldg(S.tangents + tv.y)) + ic * v3(__ldg(S.tangents + tv.z));
+                    if (!(tangent.x * tangent.x + tangent.y * tangent.y + tangent.z * tangent.z < 0.001f)) {
+                        tangent = normalize(tangent);
+                        const V3 bitangent = normalize(cross(faceN, tangent));
+                        const V3 tangent2 = cross(bitangent, faceN);
+                        lightN = normalize(faceN + (tangent2 * right + bitangent * bottom) * R.bump_scale);
+                        if (isnan(lightN.x)) lightN = faceN;
+                    }
+                }
+                const Frame fr = system_transform_z(lightN);
+                const V3 VrL = qrot(fr.g2l, Vr);
+                // ---- next-event estimation set-up (the visibility test runs in k_shadow)
+                const float4 lp4 = B.light_pos[slot];
+                const uint32_t lflags = __float_as_uint(lp4.w);
+                RGB emis = rgb(0.0f, 0.0f, 0.0f);
+                if (dot(faceN, Vr) > 0) emis = rgb(mat.emission[0], mat.emission[1], mat.emission[2]);
+                if (lflags & 1u) {
+                    const V3 lpos = v3(lp4);
+                    const float4 lc = B.light_col[slot];
+                    const V3 Vi = normalize(lpos - pos);
+                    const RGB f = bxdf_value(S, tv.w, qrot(fr.g2l, Vi), VrL, uv);
+                    const V3 dlt = lpos - pos;
+                    const float G = fabsf(dot(lightN, Vi)) / dot(dlt, dlt);
+                    float df = 1.0f;
+                    if (lflags & 2u) df = gmax(0.0f, dot(-Vi, v3(B.light_nrm[slot])));
+                    const float k = lc.w * df;
+                    const RGB inc = rgb(lc.x * k, lc.y * k, lc.z * k);
+                    B.sh_pos[slot] = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                    B.sh_direct[slot] = make_float4(inc.r * (G * f.r), inc.g * (G * f.g), inc.b * (G * f.b), 0.0f);
+                    B.sh_emis[slot] = make_float4(emis.r, emis.g, emis.b, 0.0f);
+                    B.sh_contrib[slot] = make_float4(contribution.r, contribution.g, contribution.b, 0.0f);
+                    shadow = true;
+                } else {
+                    RGB here = emis;
+                    if (here.r > R.clamp) here.r = R.clamp;
+                    if (here.g > R.clamp) here.g = R.clamp;
+                    if (here.b > R.clamp) here.b = R.clamp;
+                    float4 t = B.tot[slot];
+                    t.x += here.r * contribution.r; t.y += here.g * contribution.g; t.z += here.b * contribution.b;
+                    B.tot[slot] = t;
+                }
+                // ---- continuation
+                const uint32_t pixel = slot % R.npix, set = slot / R.npix;
+                const uint32_t seed = B.pix_seed[pixel];
+                const V2 sample = smp.get2d(pixel, seed, set, R.base2 + (n - 1u));
+                V3 dir; RGB tcf; bool may_leak;
+                bxdf_sample(S, tv.w, VrL, uv, sample, dir, tcf, may_leak);
+                const bool inside = dir.z < 0;
+                dir = qrot(fr.l2g, dir);
+                if (!(dot(dir, faceN) * dot(Vr, faceN) > 0) && !may_leak) n += 10000u;
+                const float rcoef = (!mat.no_russian && R.russian > 0.0f && n > 1u) ? 1.0f / R.russian : 1.0f;
+                RGB cum = rgb(rcoef * contribution.r, rcoef * contribution.g, rcoef * contribution.b);
+                cum = rgb(tcf.r * cum.r, tcf.g * cum.g, tcf.b * cum.b);
+                cont = true;
+                if (gmax(gmax(cum.r, cum.g), cum.b) < 0.001f) cont = false;
+                if (cont && !mat.no_russian && R.russian >= 0.0f) {
+                    const uint32_t c1 = B.cur1[slot];
+                    B.cur1[slot] = c1 + 1u;
+                    if (smp.get1d(pixel, seed, set, c1) > R.russian) cont = false;
+                }
+                if (cont && n > R.depth) cont = false;
+                if (cont && !(n < R.depth)) cont = false;          // while (n < depth)
+                if (cont) {
+                    const V3 no = pos + faceN * S.epsilon * 10.0f * (inside ? -1.0f : 1.0f);
+                    const V3 nd = normalize(normalize(dir));
+                    B.ray_o[slot] = make_float4(no.x, no.y, no.z, 0.0f);
+                    B.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+                    B.cum[slot] = make_float4(cum.r, cum.g, cum.b, __uint_as_float(n));
+                    B.last_tri[slot] = tri;
+                }
+            }
+        }
+    }
+    push_queue(next_queue, counters + C_NEXT, cont, slot);
+    push_queue(shadow_queue, counters + C_SHADOW, shadow, slot);
+}
+
+// TracePath's epilogue (clamp, NaN/negative guard, src/path_tracer.cpp:501-507), RenderPixel's in-order sum
+// over the samples (:64) and EXRTexture::AddPixel (src/texture.cpp:342-348)
+__global__ void k_finish(RenderConst R, PathBuffers B, float* __restrict__ fb, uint32_t* __restrict__ fb_count) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= R.npix) return;
+    float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+    for (uint32_t s = 0; s < R.ms; s++) {
+        const float4 t = B.tot[(size_t)s * R.npix + p];
+        float r = t.x, g = t.y, b = t.z;
+        if (r > R.clamp) r = R.clamp;
+        if (g > R.clamp) g = R.clamp;
+        if (b > R.clamp) b = R.clamp;
+        if (isnan(r) || r < 0.0f) r = 0.0f;
+        if (isnan(g) || g < 0.0f) g = 0.0f;
+        if (isnan(b) || b < 0.0f) b = 0.0f;
+        sr += r; sg += g; sb += b;
+    }
+    const uint32_t xy = B.pix_xy[p];
+    const size_t px = (size_t)(xy >> 16) * R.xres + (xy & 0xffffu);
+    fb[3 * px] += sr; fb[3 * px + 1] += sg; fb[3 * px + 2] += sb;
+    fb_count[px] += R.ms;
+}
+
+int machine_blocks(rgk_context* ctx, const void* kernel, int threads) {
+    int sms = 148, per = 4;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, threads, 0);
+    return sms * std::max(per, 1);
+}
+
+size_t env_size(const char* name, size_t def) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return def;
+    const double d = std::atof(v);
+    return d > 0 ? (size_t)d : def;
+}
+
+rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t t1_floats, size_t t2_float2s, size_t tiles, bool need_mt) {
+    if (!ctx->paths) ctx->paths = new PathBuffers();
+    PathBuffers& B = *ctx->paths;
+    bool ok = true;
+    if (paths > B.cap_paths) {
+        RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ok = ok && alloc_dev(&B.ray_o, paths) && alloc_dev(&B.ray_d, paths) && alloc_dev(&B.hit, paths) && alloc_dev(&B.cum, paths) &&
+             alloc_dev(&B.tot, paths) && alloc_dev(&B.light_pos, paths) && alloc_dev(&B.light_col, paths) && alloc_dev(&B.light_nrm, paths) &&
+             alloc_dev(&B.sh_pos, paths) && alloc_dev(&B.sh_direct, paths) && alloc_dev(&B.sh_emis, paths) && alloc_dev(&B.sh_contrib, paths) &&
+             alloc_dev(&B.last_tri, paths) && alloc_dev(&B.cur1, paths) && alloc_dev(&B.queue_a, paths) && alloc_dev(&B.queue_b, paths) &&
+             alloc_dev(&B.queue_s, paths);
+        B.cap_paths = ok ? paths : 0;
+    }
+    if (ok && pixels > B.cap_pixels) {
+        RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ok = alloc_dev(&B.pix_xy, pixels) && alloc_dev(&B.pix_seed, pixels);
+        if (ok && B.mt_state) { cudaFree(B.mt_state); B.mt_state = nullptr; }
+        B.cap_pixels = ok ? pixels : 0;
+    }
+    if (ok && need_mt && !B.mt_state) ok = alloc_dev(&B.mt_state, B.cap_pixels * 624);
+    if (ok && t1_floats > B.cap_t1) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t1, t1_floats); B.cap_t1 = ok ? t1_floats : 0; }
+    if (ok && t2_float2s > B.cap_t2) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t2, t2_float2s); B.cap_t2 = ok ? t2_float2s : 0; }
+    if (ok && tiles > B.cap_tiles) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.tiles, tiles) && alloc_dev(&B.tiles2, tiles); B.cap_tiles = ok ? tiles : 0; }
+    if (ok && !B.counters) {
+        ok = alloc_dev(&B.counters, (size_t)C_COUNT);
+        ok = ok && cudaMallocHost((void**)&B.h_counters, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
+    }
+    if (!ok) { cudaGetLastError(); return rgk_fail(ctx, RGK_ERR_NOMEM, "path-state allocation failed (lower RGK_CHUNK_PATHS)"); }
+    return RGK_OK;
+}
+
+} // namespace
+
+void free_path_buffers(rgk_context* ctx) {
+    if (!ctx->paths) return;
+    PathBuffers& B = *ctx->paths;
+    void* ptrs[] = {B.ray_o, B.ray_d, B.hit, B.cum, B.tot, B.light_pos, B.light_col, B.light_nrm, B.sh_pos, B.sh_direct, B.sh_emis,
+                    B.sh_contrib, B.last_tri, B.cur1, B.queue_a, B.queue_b, B.queue_s, B.pix_xy, B.pix_seed, B.mt_state, B.t1, B.t2,
+                    B.tiles, B.tiles2, B.counters};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (B.h_counters) cudaFreeHost(B.h_counters);
+    delete ctx->paths;
+    ctx->paths = nullptr;
+}
+
+// round_up_to_square, src/sampler.cpp:77-83
+uint32_t host_sampler_set_size(uint32_t x) {
+    const float s = (float)std::sqrt((double)x);
+    float i; const float frac = std::modf(s, &i);
+    if (frac < 0.0001f) return (uint32_t)(i * i);
+    return (uint32_t)((i + 1) * (i + 1));
+}
+
+rgk_status launch_camera_rays(rgk_context* ctx, const rgk_camera* cam, uint32_t xres, uint32_t yres, const int32_t* d_xy,
+                              const float* d_off, const float* d_lens, uint64_t n, rgk_ray* d_rays) {
+    k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(*cam, xres, yres, d_xy, d_off, d_lens, n, d_rays);
+    ctx->launches++;
+    RGK_CUDA(ctx, cudaGetLastError());
+    return RGK_OK;
+}
+
+rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint32_t n_seeds, uint32_t ms, uint32_t n1d, uint32_t n2d,
+                                 float* d_out1, float* d_out2) {
+    const uint32_t ss = host_sampler_set_size(ms);
+    if ((uint64_t)ss * ss > 0xFFFFFFFFull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "multisample too large for the pairwise shuffle");
+    const uint32_t sq = (uint32_t)(std::sqrt((double)ss) + 0.5f);
+    // tables need one scratch dim each; the caller's buffers have exactly n1d / n2d dims, so run into private buffers
+    float* t1 = nullptr; float2* t2 = nullptr; uint32_t* st = nullptr;
+    const size_t e1 = (size_t)(n1d + 1) * ss * n_seeds, e2 = (size_t)(n2d + 1) * ss * n_seeds;
+    if (cudaMalloc((void**)&t1, e1 * 4) != cudaSuccess || cudaMalloc((void**)&t2, e2 * 8) != cudaSuccess ||
+        cudaMalloc((void**)&st, (size_t)n_seeds * 624 * 4) != cudaSuccess) {
+        cudaGetLastError(); if (t1) cudaFree(t1); if (t2) cudaFree(t2); if (st) cudaFree(st);
+        return rgk_fail(ctx, RGK_ERR_NOMEM, "sampler table allocation failed");
+    }
+    k_sampler_mt<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && n1d) e = cudaMemcpyAsync(d_out1, t1, (size_t)n1d * ss * n_seeds * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess && n2d) e = cudaMemcpyAsync(d_out2, t2, (size_t)n2d * ss * n_seeds * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(t1); cudaFree(t2); cudaFree(st);
+    if (e != cudaSuccess) return rgk_fail(ctx, RGK_ERR_CUDA, cudaGetErrorString(e));
+    return RGK_OK;
+}
+
+rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* P, const rgk_task* tasks,
+                             uint32_t n_tasks, uint32_t seedstart, uint32_t seedcount_base, float* d_rgb, uint32_t* d_count,
+                             rgk_round_stats* stats) {
+    const uint64_t launches0 = ctx->launches;
+    const uint32_t ms = P->multisample;
+    const uint32_t ss = host_sampler_set_size(ms);
+    const uint32_t sq = (uint32_t)(std::sqrt((double)ss) + 0.5f);
+    const uint32_t lens = cam->lens_size != 0.0f ? 1u : 0u;
+    const uint32_t base2 = 4u + lens;                  // 2-D dims: jitter, [lens], areal, lightdir, choice, then one per bounce
+    const uint32_t n2d = base2 + P->depth, n1d = 1u + P->depth;
+    if (P->sampler_mode == RGK_SAMPLER_TABLES) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "RGK_SAMPLER_TABLES is not implemented yet");
+    if (P->sampler_mode == RGK_SAMPLER_MT19937 && (n2d > 64 || n1d > 64))
+        return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "recursion-max above 59 leaves the 64 tabulated sampler dimensions (live-generator fallback, src/sampler.cpp:26-36, is not replicated)");
+    if ((uint64_t)ss * ss > 0xFFFFFFFFull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "multisample too large");
+    const bool mt = P->sampler_mode == RGK_SAMPLER_MT19937;
+
+    // chunking: whole tiles, every multisample of a pixel in the same chunk
+    const size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)8 << 20);
+    const size_t per_pixel_table = mt ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
+    const size_t max_table_bytes = env_size("RGK_TABLE_BYTES", (size_t)24 << 30);
+    std::vector<uint4> h_tiles; std::vector<uint2> h_tiles2;
+    rgk_round_stats total{};
+    cudaEvent_t ev0 = ctx->ev[0], ev1 = ctx->ev[1], evt0 = ctx->ev[2], evt1 = ctx->ev[3];
+    RGK_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    float trace_ms = 0.0f;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dummy;
+    uint32_t ti = 0;
+    while (ti < n_tasks) {
+        h_tiles.clear(); h_tiles2.clear();
+        size_t npix = 0;
+        while (ti < n_tasks) {
+            const rgk_task& t = tasks[ti];
+            const size_t px = (size_t)(t.x2 - t.x1) * (t.y2 - t.y1);
+            if (npix && ((npix + px) * ms > max_paths || (per_pixel_table && (npix + px) * per_pixel_table > max_table_bytes))) break;
+            if (px) {
+                h_tiles.push_back(make_uint4(t.x1, t.x2, t.y1, t.y2));
+                h_tiles2.push_back(make_uint2((uint32_t)npix, seedstart + seedcount_base + ti));
+            }
+            npix += px; ti++;
+        }
+        if (npix == 0) continue;
+        const size_t npaths = npix * ms;
+        if (npaths > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "a single chunk exceeds 2^32 paths");
+        rgk_status s = ensure_buffers(ctx, npaths, npix, mt ? (size_t)(n1d + 1) * ss * npix : 0, mt ? (size_t)(n2d + 1) * ss * npix : 0,
+                                      h_tiles.size(), mt);
+        if (s != RGK_OK) return s;
+        PathBuffers& B = *ctx->paths;
+        RGK_CUDA(ctx, cudaMemcpyAsync(B.tiles, h_tiles.data(), h_tiles.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+        RGK_CUDA(ctx, cudaMemcpyAsync(B.tiles2, h_tiles2.data(), h_tiles2.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed);
+        ctx->launches++;
+        RenderConst R{};
+        R.cam = *cam; R.xres = P->xres; R.yres = P->yres; R.ms = ms; R.depth = P->depth; R.clamp = P->clamp; R.russian = P->russian;
+        R.bump_scale = P->bumpmap_scale; R.set_size = ss; R.n1d = n1d; R.n2d = n2d; R.base2 = base2; R.sampler_mode = P->sampler_mode;
+        R.lens = lens; R.npix = (uint32_t)npix;
+        SamplerView smp{B.t1, B.t2, (uint32_t)npix, ss, sq, P->sampler_mode};
+        if (mt) {
+            k_sampler_mt<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
+            ctx->launches++;
+        }
+        k_raygen<<<(unsigned)((npaths + 127) / 128), 128, 0, ctx->stream>>>(ctx->dev, R, smp, B);
+        ctx->launches++;
+        RGK_CUDA(ctx, cudaGetLastError());
+
+        const int tgrid = machine_blocks(ctx, (const void*)k_closest, TRACE_THREADS);
+        uint32_t count = (uint32_t)npaths;
+        const uint32_t* queue = nullptr;
+        uint32_t* qnext = B.queue_a;
+        for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {
+            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+            const int g1 = (int)std::min<uint64_t>(tgrid, ((uint64_t)count + TRACE_THREADS - 1) / TRACE_THREADS);
+            RGK_CUDA(ctx, cudaEventRecord(evt0, ctx->stream));
+            k_closest<<<g1, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, queue, count, B.counters + C_WORK_A);
+            RGK_CUDA(ctx, cudaEventRecord(evt1, ctx->stream));
+            k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
+            ctx->launches += 2;
+            RGK_CUDA(ctx, cudaMemcpyAsync(B.h_counters, B.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms_c = 0.0f; cudaEventElapsedTime(&ms_c, evt0, evt1); trace_ms += ms_c;
+            const uint32_t next_count = (uint32_t)B.h_counters[C_NEXT], shadow_count = (uint32_t)B.h_counters[C_SHADOW];
+            total.closest_rays += count; total.shadow_rays += shadow_count;
+            if (shadow_count) {
+                const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
+                RGK_CUDA(ctx, cudaEventRecord(evt0, ctx->stream));
+                k_shadow<<<g2, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B);
+                RGK_CUDA(ctx, cudaEventRecord(evt1, ctx->stream));
+                ctx->launches++;
+                RGK_CUDA(ctx, cudaEventSynchronize(evt1));
+                cudaEventElapsedTime(&ms_c, evt0, evt1); trace_ms += ms_c;
+            }
+            queue = qnext; qnext = (qnext == B.queue_a) ? B.queue_b : B.queue_a;
+            count = next_count;
+        }
+        k_finish<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(R, B, d_rgb, d_count);
+        ctx->launches++;
+        RGK_CUDA(ctx, cudaGetLastError());
+        total.samples += npaths;
+    }
+    RGK_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+    RGK_CUDA(ctx, cudaEventSynchronize(ev1));
+    float ms_total = 0.0f; cudaEventElapsedTime(&ms_total, ev0, ev1);
+    total.gpu_ms = ms_total; total.trace_ms = trace_ms; total.kernel_launches = ctx->launches - launches0;
+    if (stats) *stats = total;
+    return RGK_OK;
+}

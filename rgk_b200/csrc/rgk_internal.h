@@ -1,0 +1,129 @@
+// rgk_internal.h -- shared between the host layer (scene commit, driver) and the CUDA
+// kernels of librgk_b200.so.  Not part of the public ABI (include/rgk_b200.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "rgk_b200.h"
+
+// ------------------------------------------------------------------ device scene layout (HBM)
+// All arrays are 16-byte aligned (cudaMalloc) and read through the read-only path.
+//
+//  nodes     uint2 / node     the reference's CompressedKdNode words (src/scene.hpp:212-253):
+//                             .x = split_plane bits | first ref, .y = (other child | n refs) << 2 | kind
+//  refs      u32 / reference  Scene::compressed_triangles
+//  tri_isect 3 x float4 / triangle (48 B), the ray-independent part of
+//            Triangle::TestIntersection (src/primitives.cpp:83,104-133,149), precomputed with
+//            the reference's float op order:
+//              [0] plane n.x n.y n.z d
+//              [1] v0[i1] v0[i2] q1.x q1.y          (q1 = v1 - v0 projected on the dominant plane)
+//              [2] q2.x q2.y denom flags             (denom = q2.y*q1.x - q2.x*q1.y;
+//                                                     flags bits 0-1 = axis code, bit 2 = |q1.x| < eps)
+//  tri_shade uint4 / triangle  va vb vc material   (touched by shading only)
+//  positions/normals/tangents float4 / vertex, texcoords float2 / vertex
+struct DevTexture {          // 32 B
+    uint32_t kind, width, height, _pad;
+    float color[3];
+    uint32_t offset;         // first texel in the float4 texel pool
+};
+struct DevMaterial {         // 64 B (same fields as rgk_material)
+    uint32_t bxdf, no_russian;
+    float emission[3];
+    float roughness, ior, amount;
+    int32_t mix_a, mix_b, tex_diffuse, tex_color, tex_bump;
+    uint32_t _pad[3];
+};
+struct DevPointLight { float pos[3]; float color[3]; float intensity; float size; };
+struct DevArealLight { float power, total_area; float emission[3]; uint32_t first, count; uint32_t _pad; };
+struct DevArealTri { float area; uint32_t tri; };
+
+struct DevScene {
+    const uint2* nodes;
+    const uint32_t* refs;
+    const float4* tri_isect;
+    const uint4* tri_shade;
+    const float4* positions;
+    const float4* normals;
+    const float4* tangents;
+    const float2* texcoords;
+    const DevMaterial* materials;
+    const DevTexture* textures;
+    const float4* texels;
+    const DevPointLight* point_lights;
+    const DevArealLight* areal_lights;
+    const DevArealTri* areal_tris;
+    const float4* ltc_M[2];      // 3 x float4 per entry (9 floats + pad), [0] GGX [1] Beckmann
+    const float* ltc_amp[2];
+    uint32_t n_nodes, n_refs, n_triangles, n_vertices, n_materials, n_textures;
+    uint32_t n_point_lights, n_areal_lights;
+    float total_point_power, total_areal_power;
+    float epsilon;
+    float bb[6];
+    uint32_t sky_mode; float sky_color[3]; float sky_intensity, sky_rotate; int32_t sky_envmap;
+    uint32_t has_ltc;
+};
+
+#define RGK_STACK_CAP 64  // traversal stack entries per ray (tree depth <= log2(n)+8, src/scene.cpp:409)
+
+// ------------------------------------------------------------------ host scene (product host layer)
+struct HostScene {
+    std::vector<uint32_t> nodes, refs;          // reference encoding
+    std::vector<float> planes;                  // 4 / triangle
+    std::vector<float> tri_isect;               // 12 / triangle
+    std::vector<uint32_t> tri_shade;            // 4 / triangle
+    std::vector<DevArealLight> areal_lights;
+    std::vector<DevArealTri> areal_tris;
+    rgk_scene_info info{};
+};
+// Scene::Commit (src/scene.cpp:294-429) on the host. Throws std::runtime_error on bad input.
+void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScene& out);
+
+// ------------------------------------------------------------------ context
+struct PathBuffers;   // render.cu
+struct rgk_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string last_error;
+    bool has_scene = false;
+    HostScene host;
+    DevScene dev{};
+    std::vector<void*> scene_allocs;
+    // scratch for host-buffer entry points
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_size[4] = {0, 0, 0, 0};
+    rgk_trav_stats* d_stats = nullptr;
+    PathBuffers* paths = nullptr;
+    uint64_t launches = 0;
+    // caller-supplied sampler tables (RGK_SAMPLER_TABLES)
+    float* d_user_t1 = nullptr; float* d_user_t2 = nullptr; uint32_t user_n1d = 0, user_n2d = 0; uint64_t user_npix = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+rgk_status rgk_fail(rgk_context* ctx, rgk_status s, const std::string& msg);
+#define RGK_CUDA(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return rgk_fail(ctx, e_ == cudaErrorMemoryAllocation ? RGK_ERR_NOMEM : RGK_ERR_CUDA,   \
+                            std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+    } while (0)
+
+void* rgk_scratch(rgk_context* ctx, int slot, size_t bytes);  // grows a reusable device buffer (nullptr on failure)
+
+// trace.cu
+rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const uint32_t* d_ignore, uint64_t n,
+                                rgk_hit* d_hits, rgk_trav_stats* d_stats);
+rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* d_b, uint64_t n,
+                               uint8_t* d_visible, rgk_trav_stats* d_stats);
+// render.cu
+rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* p, const rgk_task* tasks,
+                             uint32_t n_tasks, uint32_t seedstart, uint32_t seedcount_base, float* d_rgb, uint32_t* d_count,
+                             rgk_round_stats* stats);
+rgk_status launch_camera_rays(rgk_context* ctx, const rgk_camera* cam, uint32_t xres, uint32_t yres, const int32_t* d_xy,
+                              const float* d_off, const float* d_lens, uint64_t n, rgk_ray* d_rays);
+rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint32_t n_seeds, uint32_t multisample,
+                                 uint32_t n1d, uint32_t n2d, float* d_out1, float* d_out2);
+void free_path_buffers(rgk_context* ctx);
+uint32_t host_sampler_set_size(uint32_t multisample);

@@ -1,0 +1,134 @@
+// trace.cu -- batch entry points for closest-hit and shadow traversal
+// (rgk_trace_closest / rgk_trace_shadow and their *_device variants).
+//
+// Persistent-thread kernels: the grid is sized to the machine (SMs x resident CTAs) and
+// every warp pulls work in 32-ray packets from a global counter, so long rays do not hold a
+// whole CTA's slot hostage.  Compiled with -fmad=false (see trace_device.cuh).
+#include "trace_device.cuh"
+
+namespace {
+
+constexpr int TRACE_THREADS = 128;
+
+template <bool COUNT>
+__device__ __forceinline__ void flush_counts(const TravCount& c, uint64_t nrays, rgk_trav_stats* stats) {
+    if (!COUNT) return;
+    // warp-aggregate, one atomic per counter per warp
+    unsigned long long v[5] = {nrays, c.inner, c.leaf, c.refs, c.tests};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long*)&stats->rays, v[0]);
+        atomicAdd((unsigned long long*)&stats->inner, v[1]);
+        atomicAdd((unsigned long long*)&stats->leaf, v[2]);
+        atomicAdd((unsigned long long*)&stats->refs, v[3]);
+        atomicAdd((unsigned long long*)&stats->tests, v[4]);
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, uint64_t n,
+                rgk_hit* __restrict__ hits, rgk_trav_stats* stats, unsigned long long* next) {
+    TravCount cnt{0, 0, 0, 0};
+    uint64_t mine = 0;
+    const unsigned lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(next, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint64_t i = base + lane;
+        if (i < n) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(rays + i));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+            const uint32_t ign = ignore ? __ldg(ignore + i) : RGK_NO_TRIANGLE;
+            HitRec h;
+            kd_traverse<false, COUNT>(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, ign, h, cnt);
+            rgk_hit out;
+            out.triangle = h.tri; out.t = h.t;
+            if (h.tri != RGK_NO_TRIANGLE) { out.a = 1.0f - h.alpha - h.beta; out.b = h.alpha; out.c = h.beta; }
+            else { out.a = 0.0f; out.b = 0.0f; out.c = 0.0f; }
+            hits[i] = out;
+            mine++;
+        }
+    }
+    flush_counts<COUNT>(cnt, mine, stats);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, uint64_t n,
+               uint8_t* __restrict__ visible, rgk_trav_stats* stats, unsigned long long* next) {
+    TravCount cnt{0, 0, 0, 0};
+    uint64_t mine = 0;
+    const unsigned lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(next, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint64_t i = base + lane;
+        if (i < n) {
+            // Ray(from, to, eps) (src/ray.hpp:15-22) + Scene::Visibility (src/scene.cpp:670-673)
+            const float ax = pa[3 * i], ay = pa[3 * i + 1], az = pa[3 * i + 2];
+            const float ex = pb[3 * i] - ax, ey = pb[3 * i + 1] - ay, ez = pb[3 * i + 2] - az;
+            const float d2 = ex * ex + ey * ey + ez * ez;
+            const float inv = 1.0f / sqrtf(d2);
+            const float len = sqrtf(d2);
+            const float e20 = S.epsilon * 20.0f;
+            HitRec h;
+            const bool blocked = kd_traverse<true, COUNT>(S, ax, ay, az, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20,
+                                                          RGK_NO_TRIANGLE, h, cnt);
+            visible[i] = blocked ? 0 : 1;
+            mine++;
+        }
+    }
+    flush_counts<COUNT>(cnt, mine, stats);
+}
+
+int trace_grid(rgk_context* ctx) {
+    static int blocks = 0;
+    if (!blocks) {
+        int sms = 148, per = 8;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_trace_closest<false>, TRACE_THREADS, 0);
+        blocks = sms * (per > 0 ? per : 1);
+    }
+    return blocks;
+}
+
+} // namespace
+
+rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const uint32_t* d_ignore, uint64_t n,
+                                rgk_hit* d_hits, rgk_trav_stats* d_stats) {
+    if (n == 0) return RGK_OK;
+    unsigned long long* next = (unsigned long long*)rgk_scratch(ctx, 3, 256);
+    if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
+    RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
+    const uint64_t warps = (n + 31) / 32;
+    const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32));
+    if (d_stats) k_trace_closest<true><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
+    else k_trace_closest<false><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
+    ctx->launches++;
+    RGK_CUDA(ctx, cudaGetLastError());
+    return RGK_OK;
+}
+
+rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* d_b, uint64_t n,
+                               uint8_t* d_visible, rgk_trav_stats* d_stats) {
+    if (n == 0) return RGK_OK;
+    unsigned long long* next = (unsigned long long*)rgk_scratch(ctx, 3, 256);
+    if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
+    RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
+    const uint64_t warps = (n + 31) / 32;
+    const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32));
+    if (d_stats) k_trace_shadow<true><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
+    else k_trace_shadow<false><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
+    ctx->launches++;
+    RGK_CUDA(ctx, cudaGetLastError());
+    return RGK_OK;
+}

@@ -1,0 +1,157 @@
+"""Thin ctypes wrapper over librgk_b200.so for tests, bench.py and tools.
+
+Everything here goes through the C ABI (include/rgk_b200.h); numpy arrays are host buffers,
+integer addresses (e.g. torch tensor .data_ptr()) are device buffers.  There is no CPU path:
+creating a Context without a CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+RAY_DT = np.dtype([("origin", np.float32, 3), ("direction", np.float32, 3), ("tnear", np.float32), ("tfar", np.float32)])
+HIT_DT = np.dtype([("triangle", np.uint32), ("t", np.float32), ("a", np.float32), ("b", np.float32), ("c", np.float32)])
+
+
+class RgkError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"rgk status {status}: {text}")
+        self.status = status
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    def __init__(self, device=0, stream=None, lib=None):
+        self.lib = lib or abi.load_library()
+        h = C.c_void_p()
+        st = self.lib.rgk_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if st != 0:
+            raise RgkError(st, self.lib.rgk_last_error(None).decode())
+        self.h = h
+        self._desc = None
+
+    def close(self):
+        if self.h:
+            self.lib.rgk_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != 0:
+            raise RgkError(st, self.lib.rgk_last_error(self.h).decode())
+
+    # ---- scene
+    def commit(self, desc, tree=None):
+        self._desc = desc
+        self._check(self.lib.rgk_scene_commit(self.h, C.byref(desc), C.byref(tree) if tree is not None else None))
+
+    def scene_info(self):
+        info = abi.SceneInfo()
+        self._check(self.lib.rgk_scene_get_info(self.h, C.byref(info)))
+        return info
+
+    def scene_kdtree(self):
+        info = self.scene_info()
+        nodes = np.zeros(2 * info.n_nodes, np.uint32)
+        refs = np.zeros(max(1, info.n_refs), np.uint32)
+        self._check(self.lib.rgk_scene_get_kdtree(self.h, _p(nodes), _p(refs)))
+        return nodes, refs[:info.n_refs]
+
+    # ---- traversal (host buffers)
+    def trace_closest(self, rays, ignore=None, want_stats=False):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DT)
+        hits = np.zeros(len(rays), dtype=HIT_DT)
+        st = abi.TravStats()
+        if ignore is not None:
+            ignore = np.ascontiguousarray(ignore, np.uint32)
+        self._check(self.lib.rgk_trace_closest(self.h, _p(rays), _p(ignore), C.c_uint64(len(rays)), _p(hits),
+                                               C.byref(st) if want_stats else None))
+        return (hits, st) if want_stats else hits
+
+    def trace_shadow(self, a, b, want_stats=False):
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        vis = np.zeros(len(a), np.uint8)
+        st = abi.TravStats()
+        self._check(self.lib.rgk_trace_shadow(self.h, _p(a), _p(b), C.c_uint64(len(a)), _p(vis),
+                                              C.byref(st) if want_stats else None))
+        return (vis, st) if want_stats else vis
+
+    # ---- traversal (device buffers: integer addresses)
+    def trace_closest_device(self, d_rays, d_ignore, n, d_hits, d_stats=None):
+        self._check(self.lib.rgk_trace_closest_device(self.h, _p(d_rays), _p(d_ignore), C.c_uint64(n), _p(d_hits), _p(d_stats)))
+
+    def trace_shadow_device(self, d_a, d_b, n, d_visible, d_stats=None):
+        self._check(self.lib.rgk_trace_shadow_device(self.h, _p(d_a), _p(d_b), C.c_uint64(n), _p(d_visible), _p(d_stats)))
+
+    # ---- camera / tasks / sampler
+    def camera(self, pos, lookat, up, yview, xview, xres, yres, focus_plane=1.0, lens_size=0.0):
+        cam = abi.Camera()
+        f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+        self.lib.rgk_camera_init(C.byref(cam), f3(pos), f3(lookat), f3(up), yview, xview, xres, yres, focus_plane, lens_size)
+        return cam
+
+    def camera_rays(self, cam, xres, yres, xy, offsets, lens=None):
+        xy = np.ascontiguousarray(xy, np.int32)
+        offsets = np.ascontiguousarray(offsets, np.float32)
+        if lens is not None:
+            lens = np.ascontiguousarray(lens, np.float32)
+        rays = np.zeros(len(xy), dtype=RAY_DT)
+        self._check(self.lib.rgk_camera_rays(self.h, C.byref(cam), xres, yres, _p(xy), _p(offsets), _p(lens),
+                                             C.c_uint64(len(xy)), _p(rays)))
+        return rays
+
+    def generate_tasks(self, tile, xres, yres):
+        n = self.lib.rgk_generate_tasks(tile, xres, yres, None, 0)
+        out = (abi.Task * n)()
+        self.lib.rgk_generate_tasks(tile, xres, yres, out, n)
+        return out
+
+    def sampler_set_size(self, ms):
+        return int(self.lib.rgk_sampler_set_size(ms))
+
+    def sampler_tables(self, seeds, ms, n1d, n2d):
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        ss = self.sampler_set_size(ms)
+        t1 = np.zeros((len(seeds), n1d, ss), np.float32)
+        t2 = np.zeros((len(seeds), n2d, ss, 2), np.float32)
+        self._check(self.lib.rgk_sampler_tables(self.h, _p(seeds), len(seeds), ms, n1d, n2d, _p(t1), _p(t2)))
+        return t1, t2
+
+    # ---- rendering
+    def render_round(self, cam, params, tasks, seedstart=42, seedcount_base=0, fb=None):
+        if fb is None:
+            fb = (np.zeros((params.yres, params.xres, 3), np.float32), np.zeros((params.yres, params.xres), np.uint32))
+        st = abi.RoundStats()
+        self._check(self.lib.rgk_render_round(self.h, C.byref(cam), C.byref(params), tasks, len(tasks), seedstart,
+                                              seedcount_base, _p(fb[0]), _p(fb[1]), C.byref(st)))
+        return fb[0], fb[1], st
+
+    def render_round_device(self, cam, params, tasks, d_rgb, d_count, seedstart=42, seedcount_base=0):
+        st = abi.RoundStats()
+        self._check(self.lib.rgk_render_round_device(self.h, C.byref(cam), C.byref(params), tasks, len(tasks), seedstart,
+                                                     seedcount_base, _p(d_rgb), _p(d_count), C.byref(st)))
+        return st
+
+    def render_frame(self, cam, params, rounds=1):
+        fb = np.zeros((params.yres, params.xres, 3), np.float32)
+        cnt = np.zeros((params.yres, params.xres), np.uint32)
+        st = abi.RoundStats()
+        self._check(self.lib.rgk_render_frame(self.h, C.byref(cam), C.byref(params), rounds, _p(fb), _p(cnt), C.byref(st)))
+        return fb, cnt, st
+
+    def synchronize(self):
+        self._check(self.lib.rgk_synchronize(self.h))

@@ -208,6 +208,11 @@ typedef struct rgk_round_stats {
     uint64_t kernel_launches; /* kernels launched by the library during the call */
     float gpu_ms;             /* device time of the call, CUDA events on the context stream */
     float trace_ms;           /* of which closest-hit + shadow traversal kernels */
+    float closest_ms;         /* closest-hit traversal kernels only */
+    float shadow_ms;          /* shadow traversal (+ NEE resolve) kernels only */
+    float sampler_ms;         /* sampler table generation */
+    float shade_ms;           /* raygen + shade + finish */
+    uint32_t closest_launches, shadow_launches;
 } rgk_round_stats;
 
 /* ---- entry points ------------------------------------------------------- */
@@ -290,6 +295,12 @@ rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_r
  * task order then y-major/x-minor: t1d[pixel][dim][set], t2d[pixel][dim][set][2]. */
 rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t n1d, uint32_t n2d,
                                  const float* t1d, const float* t2d, uint64_t n_pixels);
+
+/* Traversal work counters of the rendering calls: when enabled, the closest-hit and shadow
+ * kernels of rgk_render_round* count visited nodes / references / triangle tests (slower; off by default,
+ * never on in a timed run) and rgk_render_get_trav_stats returns the totals of the last rendering call. */
+rgk_status rgk_render_set_counting(rgk_context* ctx, int enabled);
+rgk_status rgk_render_get_trav_stats(const rgk_context* ctx, rgk_trav_stats* closest, rgk_trav_stats* shadow);
 
 /* Blocks until the context stream is idle. */
 rgk_status rgk_synchronize(rgk_context* ctx);

@@ -110,7 +110,9 @@ class Task(C.Structure):
 
 class RoundStats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("samples", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_float), ("trace_ms", C.c_float)]
+                ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_float), ("trace_ms", C.c_float),
+                ("closest_ms", C.c_float), ("shadow_ms", C.c_float), ("sampler_ms", C.c_float), ("shade_ms", C.c_float),
+                ("closest_launches", C.c_uint32), ("shadow_launches", C.c_uint32)]
 
     def as_dict(self):
         return {k: (int(getattr(self, k)) if "ms" not in k else float(getattr(self, k))) for k, _ in self._fields_}
@@ -125,6 +127,7 @@ EXPORTS = [
     "rgk_trace_closest_device", "rgk_trace_shadow_device", "rgk_camera_init", "rgk_camera_rays",
     "rgk_generate_tasks", "rgk_sampler_set_size", "rgk_sampler_tables", "rgk_render_round",
     "rgk_render_round_device", "rgk_render_frame", "rgk_render_set_tables", "rgk_synchronize",
+    "rgk_render_set_counting", "rgk_render_get_trav_stats",
 ]
 
 
@@ -169,4 +172,6 @@ def load_library(path=None):
                                      C.POINTER(RoundStats)]
     lib.rgk_render_set_tables.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64]
     lib.rgk_synchronize.argtypes = [vp]
+    lib.rgk_render_set_counting.argtypes = [vp, C.c_int]
+    lib.rgk_render_get_trav_stats.argtypes = [vp, C.POINTER(TravStats), C.POINTER(TravStats)]
     return lib

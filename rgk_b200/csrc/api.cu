@@ -461,11 +461,24 @@ rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_r
         seedcount += nt;
         total.closest_rays += rs.closest_rays; total.shadow_rays += rs.shadow_rays; total.samples += rs.samples;
         total.kernel_launches += rs.kernel_launches; total.gpu_ms += rs.gpu_ms; total.trace_ms += rs.trace_ms;
+        total.closest_ms += rs.closest_ms; total.shadow_ms += rs.shadow_ms; total.sampler_ms += rs.sampler_ms; total.shade_ms += rs.shade_ms;
+        total.closest_launches += rs.closest_launches; total.shadow_launches += rs.shadow_launches;
     }
     RGK_CUDA(ctx, cudaMemcpyAsync(rgb_sum, d_rgb, npx * 12, cudaMemcpyDeviceToHost, ctx->stream));
     RGK_CUDA(ctx, cudaMemcpyAsync(count, d_cnt, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
     RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (stats) *stats = total;
+    return RGK_OK;
+}
+
+rgk_status rgk_render_set_counting(rgk_context* ctx, int enabled) {
+    if (!ctx) return RGK_ERR_INVALID;
+    ctx->counting = enabled != 0;
+    return RGK_OK;
+}
+rgk_status rgk_render_get_trav_stats(const rgk_context* ctx, rgk_trav_stats* closest, rgk_trav_stats* shadow) {
+    if (!ctx || !closest || !shadow) return RGK_ERR_INVALID;
+    *closest = ctx->last_closest; *shadow = ctx->last_shadow;
     return RGK_OK;
 }
 

@@ -32,6 +32,7 @@ struct PathBuffers {
     uint4 *tiles = nullptr; uint2 *tiles2 = nullptr;
     unsigned long long *counters = nullptr;   // device
     unsigned long long *h_counters = nullptr; // pinned
+    struct EventPool* events = nullptr;       // host only
 };
 
 enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_CLOSEST_RAYS = 4, C_SHADOW_RAYS = 5, C_COUNT = 8 };
@@ -254,48 +255,59 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
 
 constexpr int TRACE_THREADS = 128;
 
-// closest-hit over the live queue (queue == nullptr: identity), persistent warps
-__global__ void __launch_bounds__(TRACE_THREADS)
-k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work) {
-    const unsigned lane = threadIdx.x & 31;
-    TravCount cnt;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(work, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        const uint32_t i = (uint32_t)base + lane;
-        if (i < count) {
-            const uint32_t slot = queue ? __ldg(queue + i) : i;
-            const float4 o = B.ray_o[slot], d = B.ray_d[slot];
-            HitRec h;
-            kd_traverse<false, false>(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot], h, cnt);
-            B.hit[slot] = make_float4(h.t, h.alpha, h.beta, __uint_as_float(h.tri));
-        }
+template <bool COUNT>
+__device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays, rgk_trav_stats* stats) {
+    if (!COUNT) return;
+    unsigned long long v[5] = {nrays, c.inner, c.leaf, c.refs, c.tests};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long*)&stats->rays, v[0]); atomicAdd((unsigned long long*)&stats->inner, v[1]);
+        atomicAdd((unsigned long long*)&stats->leaf, v[2]); atomicAdd((unsigned long long*)&stats->refs, v[3]);
+        atomicAdd((unsigned long long*)&stats->tests, v[4]);
     }
 }
 
-// shadow traversal fused with the NEE resolve (src/path_tracer.cpp:431-460,485-496)
+// closest-hit over the live queue (queue == nullptr: identity), persistent warps
+template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS)
-k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work) {
-    const unsigned lane = threadIdx.x & 31;
-    TravCount cnt;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(work, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        const uint32_t i = (uint32_t)base + lane;
-        if (i < count) {
+k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, rgk_trav_stats* stats) {
+    TravCount cnt{0, 0, 0, 0};
+    uint32_t mine = 0;
+    trace_persistent<false, COUNT>(S, count, work, cnt, mine,
+        [&](uint32_t i, Traverser<false, COUNT>& T) {
+            const uint32_t slot = queue ? __ldg(queue + i) : i;
+            const float4 o = B.ray_o[slot], d = B.ray_d[slot];
+            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot]);
+        },
+        [&](uint32_t i, bool found, const HitRec& h) {
+            const uint32_t slot = queue ? __ldg(queue + i) : i;
+            B.hit[slot] = make_float4(h.t, h.alpha, h.beta, __uint_as_float(found ? h.tri : RGK_NO_TRIANGLE));
+        });
+    flush_counts<COUNT>(cnt, mine, stats);
+}
+
+// shadow traversal fused with the NEE resolve (src/path_tracer.cpp:431-460,485-496)
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, rgk_trav_stats* stats) {
+    TravCount cnt{0, 0, 0, 0};
+    uint32_t mine = 0;
+    trace_persistent<true, COUNT>(S, count, work, cnt, mine,
+        [&](uint32_t i, Traverser<true, COUNT>& T) {
             const uint32_t slot = __ldg(queue + i);
             const float4 a = B.light_pos[slot], b = B.sh_pos[slot];
             const float ex = b.x - a.x, ey = b.y - a.y, ez = b.z - a.z;
             const float d2 = ex * ex + ey * ey + ez * ez;
             const float inv = 1.0f / sqrtf(d2), len = sqrtf(d2);
             const float e20 = S.epsilon * 20.0f;
-            HitRec h;
-            const bool blocked = kd_traverse<true, false>(S, a.x, a.y, a.z, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20,
-                                                          RGK_NO_TRIANGLE, h, cnt);
+            return T.init(S, a.x, a.y, a.z, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20, RGK_NO_TRIANGLE);
+        },
+        [&](uint32_t i, bool blocked, const HitRec&) {
+            const uint32_t slot = __ldg(queue + i);
             const float4 dr = B.sh_direct[slot], em = B.sh_emis[slot], cb = B.sh_contrib[slot];
             float hr = blocked ? 0.0f : dr.x, hg = blocked ? 0.0f : dr.y, hb = blocked ? 0.0f : dr.z;
             hr += em.x; hg += em.y; hb += em.z;
@@ -305,8 +317,8 @@ k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t
             float4 t = B.tot[slot];
             t.x += hr * cb.x; t.y += hg * cb.y; t.z += hb * cb.z;
             B.tot[slot] = t;
-        }
-    }
+        });
+    flush_counts<COUNT>(cnt, mine, stats);
 }
 
 __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* counter, bool want, uint32_t slot) {
@@ -506,6 +518,7 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
 
 } // namespace
 
+void free_event_pool(struct EventPool* p);
 void free_path_buffers(rgk_context* ctx) {
     if (!ctx->paths) return;
     PathBuffers& B = *ctx->paths;
@@ -514,6 +527,7 @@ void free_path_buffers(rgk_context* ctx) {
                     B.tiles, B.tiles2, B.counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (B.h_counters) cudaFreeHost(B.h_counters);
+    free_event_pool(B.events);
     delete ctx->paths;
     ctx->paths = nullptr;
 }
@@ -558,6 +572,21 @@ rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint
     return RGK_OK;
 }
 
+enum { T_CLOSEST = 0, T_SHADOW = 1, T_SAMPLER = 2, T_SHADE = 3, T_KINDS = 4 };
+struct EventPool {
+    std::vector<cudaEvent_t> ev; std::vector<int> tag; size_t used = 0;
+    cudaEvent_t get() { if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); } return ev[used++]; }
+    void begin(cudaStream_t s, int kind) { tag.push_back(kind); cudaEventRecord(get(), s); }
+    void end(cudaStream_t s) { cudaEventRecord(get(), s); }
+    void collect(float* ms) { for (size_t i = 0; i < tag.size(); i++) { float t = 0; cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]); ms[tag[i]] += t; } used = 0; tag.clear(); }
+};
+
+void free_event_pool(EventPool* p) {
+    if (!p) return;
+    for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+    delete p;
+}
+
 rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* P, const rgk_task* tasks,
                              uint32_t n_tasks, uint32_t seedstart, uint32_t seedcount_base, float* d_rgb, uint32_t* d_count,
                              rgk_round_stats* stats) {
@@ -573,17 +602,22 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "recursion-max above 59 leaves the 64 tabulated sampler dimensions (live-generator fallback, src/sampler.cpp:26-36, is not replicated)");
     if ((uint64_t)ss * ss > 0xFFFFFFFFull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "multisample too large");
     const bool mt = P->sampler_mode == RGK_SAMPLER_MT19937;
+    const bool counting = ctx->counting;
+    rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
+    if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
 
     // chunking: whole tiles, every multisample of a pixel in the same chunk
-    const size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)8 << 20);
+    const size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)16 << 20);
     const size_t per_pixel_table = mt ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
     const size_t max_table_bytes = env_size("RGK_TABLE_BYTES", (size_t)24 << 30);
     std::vector<uint4> h_tiles; std::vector<uint2> h_tiles2;
     rgk_round_stats total{};
-    cudaEvent_t ev0 = ctx->ev[0], ev1 = ctx->ev[1], evt0 = ctx->ev[2], evt1 = ctx->ev[3];
+    cudaEvent_t ev0 = ctx->ev[0], ev1 = ctx->ev[1];
     RGK_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
-    float trace_ms = 0.0f;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dummy;
+    if (!ctx->paths) ctx->paths = new PathBuffers();
+    if (!ctx->paths->events) ctx->paths->events = new EventPool();
+    EventPool& pool = *ctx->paths->events;
+    float kind_ms[T_KINDS] = {0, 0, 0, 0};
     uint32_t ti = 0;
     while (ti < n_tasks) {
         h_tiles.clear(); h_tiles2.clear();
@@ -607,51 +641,58 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         PathBuffers& B = *ctx->paths;
         RGK_CUDA(ctx, cudaMemcpyAsync(B.tiles, h_tiles.data(), h_tiles.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
         RGK_CUDA(ctx, cudaMemcpyAsync(B.tiles2, h_tiles2.data(), h_tiles2.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-        k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed);
-        ctx->launches++;
         RenderConst R{};
         R.cam = *cam; R.xres = P->xres; R.yres = P->yres; R.ms = ms; R.depth = P->depth; R.clamp = P->clamp; R.russian = P->russian;
         R.bump_scale = P->bumpmap_scale; R.set_size = ss; R.n1d = n1d; R.n2d = n2d; R.base2 = base2; R.sampler_mode = P->sampler_mode;
         R.lens = lens; R.npix = (uint32_t)npix;
         SamplerView smp{B.t1, B.t2, (uint32_t)npix, ss, sq, P->sampler_mode};
+        pool.begin(ctx->stream, T_SAMPLER);
+        k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed);
+        ctx->launches++;
         if (mt) {
             k_sampler_mt<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
             ctx->launches++;
         }
+        pool.end(ctx->stream);
+        pool.begin(ctx->stream, T_SHADE);
         k_raygen<<<(unsigned)((npaths + 127) / 128), 128, 0, ctx->stream>>>(ctx->dev, R, smp, B);
+        pool.end(ctx->stream);
         ctx->launches++;
         RGK_CUDA(ctx, cudaGetLastError());
 
-        const int tgrid = machine_blocks(ctx, (const void*)k_closest, TRACE_THREADS);
+        const int tgrid = machine_blocks(ctx, counting ? (const void*)k_closest<true> : (const void*)k_closest<false>, TRACE_THREADS);
         uint32_t count = (uint32_t)npaths;
         const uint32_t* queue = nullptr;
         uint32_t* qnext = B.queue_a;
         for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {
             RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
             const int g1 = (int)std::min<uint64_t>(tgrid, ((uint64_t)count + TRACE_THREADS - 1) / TRACE_THREADS);
-            RGK_CUDA(ctx, cudaEventRecord(evt0, ctx->stream));
-            k_closest<<<g1, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, queue, count, B.counters + C_WORK_A);
-            RGK_CUDA(ctx, cudaEventRecord(evt1, ctx->stream));
+            pool.begin(ctx->stream, T_CLOSEST);
+            if (counting) k_closest<true><<<g1, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, queue, count, B.counters + C_WORK_A, d_st);
+            else k_closest<false><<<g1, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, queue, count, B.counters + C_WORK_A, nullptr);
+            pool.end(ctx->stream);
+            pool.begin(ctx->stream, T_SHADE);
             k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
-            ctx->launches += 2;
+            pool.end(ctx->stream);
+            ctx->launches += 2; total.closest_launches++;
             RGK_CUDA(ctx, cudaMemcpyAsync(B.h_counters, B.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
             RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            float ms_c = 0.0f; cudaEventElapsedTime(&ms_c, evt0, evt1); trace_ms += ms_c;
             const uint32_t next_count = (uint32_t)B.h_counters[C_NEXT], shadow_count = (uint32_t)B.h_counters[C_SHADOW];
             total.closest_rays += count; total.shadow_rays += shadow_count;
             if (shadow_count) {
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
-                RGK_CUDA(ctx, cudaEventRecord(evt0, ctx->stream));
-                k_shadow<<<g2, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B);
-                RGK_CUDA(ctx, cudaEventRecord(evt1, ctx->stream));
-                ctx->launches++;
-                RGK_CUDA(ctx, cudaEventSynchronize(evt1));
-                cudaEventElapsedTime(&ms_c, evt0, evt1); trace_ms += ms_c;
+                pool.begin(ctx->stream, T_SHADOW);
+                if (counting) k_shadow<true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1);
+                else k_shadow<false><<<g2, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
+                pool.end(ctx->stream);
+                ctx->launches++; total.shadow_launches++;
             }
             queue = qnext; qnext = (qnext == B.queue_a) ? B.queue_b : B.queue_a;
             count = next_count;
         }
+        pool.begin(ctx->stream, T_SHADE);
         k_finish<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(R, B, d_rgb, d_count);
+        pool.end(ctx->stream);
         ctx->launches++;
         RGK_CUDA(ctx, cudaGetLastError());
         total.samples += npaths;
@@ -659,7 +700,14 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     RGK_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
     RGK_CUDA(ctx, cudaEventSynchronize(ev1));
     float ms_total = 0.0f; cudaEventElapsedTime(&ms_total, ev0, ev1);
-    total.gpu_ms = ms_total; total.trace_ms = trace_ms; total.kernel_launches = ctx->launches - launches0;
+    pool.collect(kind_ms);
+    total.gpu_ms = ms_total; total.closest_ms = kind_ms[T_CLOSEST]; total.shadow_ms = kind_ms[T_SHADOW];
+    total.sampler_ms = kind_ms[T_SAMPLER]; total.shade_ms = kind_ms[T_SHADE];
+    total.trace_ms = total.closest_ms + total.shadow_ms; total.kernel_launches = ctx->launches - launches0;
+    if (counting) {
+        RGK_CUDA(ctx, cudaMemcpy(&ctx->last_closest, d_st, sizeof(rgk_trav_stats), cudaMemcpyDeviceToHost));
+        RGK_CUDA(ctx, cudaMemcpy(&ctx->last_shadow, d_st + 1, sizeof(rgk_trav_stats), cudaMemcpyDeviceToHost));
+    }
     if (stats) *stats = total;
     return RGK_OK;
 }

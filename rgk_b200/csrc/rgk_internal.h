@@ -99,6 +99,8 @@ struct rgk_context {
     // caller-supplied sampler tables (RGK_SAMPLER_TABLES)
     float* d_user_t1 = nullptr; float* d_user_t2 = nullptr; uint32_t user_n1d = 0, user_n2d = 0; uint64_t user_npix = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool counting = false;
+    rgk_trav_stats last_closest{}, last_shadow{};
 };
 
 rgk_status rgk_fail(rgk_context* ctx, rgk_status s, const std::string& msg);

@@ -11,7 +11,7 @@ namespace {
 constexpr int TRACE_THREADS = 128;
 
 template <bool COUNT>
-__device__ __forceinline__ void flush_counts(const TravCount& c, uint64_t nrays, rgk_trav_stats* stats) {
+__device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays, rgk_trav_stats* stats) {
     if (!COUNT) return;
     // warp-aggregate, one atomic per counter per warp
     unsigned long long v[5] = {nrays, c.inner, c.leaf, c.refs, c.tests};
@@ -34,28 +34,20 @@ __global__ void __launch_bounds__(TRACE_THREADS)
 k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, uint64_t n,
                 rgk_hit* __restrict__ hits, rgk_trav_stats* stats, unsigned long long* next) {
     TravCount cnt{0, 0, 0, 0};
-    uint64_t mine = 0;
-    const unsigned lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(next, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint64_t i = base + lane;
-        if (i < n) {
+    uint32_t mine = 0;
+    trace_persistent<false, COUNT>(S, (uint32_t)n, next, cnt, mine,
+        [&](uint32_t i, Traverser<false, COUNT>& T) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(rays + i));
             const float4 b = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
-            const uint32_t ign = ignore ? __ldg(ignore + i) : RGK_NO_TRIANGLE;
-            HitRec h;
-            kd_traverse<false, COUNT>(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, ign, h, cnt);
+            return T.init(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, ignore ? __ldg(ignore + i) : RGK_NO_TRIANGLE);
+        },
+        [&](uint32_t i, bool found, const HitRec& h) {
             rgk_hit out;
-            out.triangle = h.tri; out.t = h.t;
-            if (h.tri != RGK_NO_TRIANGLE) { out.a = 1.0f - h.alpha - h.beta; out.b = h.alpha; out.c = h.beta; }
+            out.triangle = found ? h.tri : RGK_NO_TRIANGLE; out.t = found ? h.t : __int_as_float(0x7f800000);
+            if (found) { out.a = 1.0f - h.alpha - h.beta; out.b = h.alpha; out.c = h.beta; }
             else { out.a = 0.0f; out.b = 0.0f; out.c = 0.0f; }
             hits[i] = out;
-            mine++;
-        }
-    }
+        });
     flush_counts<COUNT>(cnt, mine, stats);
 }
 
@@ -64,29 +56,18 @@ __global__ void __launch_bounds__(TRACE_THREADS)
 k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, uint64_t n,
                uint8_t* __restrict__ visible, rgk_trav_stats* stats, unsigned long long* next) {
     TravCount cnt{0, 0, 0, 0};
-    uint64_t mine = 0;
-    const unsigned lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(next, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint64_t i = base + lane;
-        if (i < n) {
+    uint32_t mine = 0;
+    trace_persistent<true, COUNT>(S, (uint32_t)n, next, cnt, mine,
+        [&](uint32_t i, Traverser<true, COUNT>& T) {
             // Ray(from, to, eps) (src/ray.hpp:15-22) + Scene::Visibility (src/scene.cpp:670-673)
-            const float ax = pa[3 * i], ay = pa[3 * i + 1], az = pa[3 * i + 2];
-            const float ex = pb[3 * i] - ax, ey = pb[3 * i + 1] - ay, ez = pb[3 * i + 2] - az;
+            const float ax = pa[3 * (size_t)i], ay = pa[3 * (size_t)i + 1], az = pa[3 * (size_t)i + 2];
+            const float ex = pb[3 * (size_t)i] - ax, ey = pb[3 * (size_t)i + 1] - ay, ez = pb[3 * (size_t)i + 2] - az;
             const float d2 = ex * ex + ey * ey + ez * ez;
-            const float inv = 1.0f / sqrtf(d2);
-            const float len = sqrtf(d2);
+            const float inv = 1.0f / sqrtf(d2), len = sqrtf(d2);
             const float e20 = S.epsilon * 20.0f;
-            HitRec h;
-            const bool blocked = kd_traverse<true, COUNT>(S, ax, ay, az, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20,
-                                                          RGK_NO_TRIANGLE, h, cnt);
-            visible[i] = blocked ? 0 : 1;
-            mine++;
-        }
-    }
+            return T.init(S, ax, ay, az, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20, RGK_NO_TRIANGLE);
+        },
+        [&](uint32_t i, bool found, const HitRec&) { visible[i] = found ? 0 : 1; });
     flush_counts<COUNT>(cnt, mine, stats);
 }
 
@@ -106,6 +87,7 @@ int trace_grid(rgk_context* ctx) {
 rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const uint32_t* d_ignore, uint64_t n,
                                 rgk_hit* d_hits, rgk_trav_stats* d_stats) {
     if (n == 0) return RGK_OK;
+    if (n > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "more than 2^32 rays in one batch");
     unsigned long long* next = (unsigned long long*)rgk_scratch(ctx, 3, 256);
     if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
     RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
@@ -121,6 +103,7 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
 rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* d_b, uint64_t n,
                                uint8_t* d_visible, rgk_trav_stats* d_stats) {
     if (n == 0) return RGK_OK;
+    if (n > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "more than 2^32 rays in one batch");
     unsigned long long* next = (unsigned long long*)rgk_scratch(ctx, 3, 256);
     if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
     RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));

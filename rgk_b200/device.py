@@ -153,5 +153,13 @@ class Context:
         self._check(self.lib.rgk_render_frame(self.h, C.byref(cam), C.byref(params), rounds, _p(fb), _p(cnt), C.byref(st)))
         return fb, cnt, st
 
+    def set_counting(self, enabled):
+        self._check(self.lib.rgk_render_set_counting(self.h, int(bool(enabled))))
+
+    def render_trav_stats(self):
+        a, b = abi.TravStats(), abi.TravStats()
+        self._check(self.lib.rgk_render_get_trav_stats(self.h, C.byref(a), C.byref(b)))
+        return a, b
+
     def synchronize(self):
         self._check(self.lib.rgk_synchronize(self.h))

@@ -119,6 +119,7 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
                                 rgk_hit* d_hits, rgk_trav_stats* d_stats);
 rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* d_b, uint64_t n,
                                uint8_t* d_visible, rgk_trav_stats* d_stats);
+int rgk_traversal_variant();
 // render.cu
 rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* p, const rgk_task* tasks,
                              uint32_t n_tasks, uint32_t seedstart, uint32_t seedcount_base, float* d_rgb, uint32_t* d_count,

@@ -4,6 +4,7 @@
 // Persistent-thread kernels: the grid is sized to the machine (SMs x resident CTAs) and
 // every warp pulls work in 32-ray packets from a global counter, so long rays do not hold a
 // whole CTA's slot hostage.  Compiled with -fmad=false (see trace_device.cuh).
+#include <cstdlib>
 #include "trace_device.cuh"
 
 namespace {
@@ -29,13 +30,13 @@ __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays,
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, int VARIANT>
 __global__ void __launch_bounds__(TRACE_THREADS)
 k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, uint64_t n,
                 rgk_hit* __restrict__ hits, rgk_trav_stats* stats, unsigned long long* next) {
     TravCount cnt{0, 0, 0, 0};
     uint32_t mine = 0;
-    trace_persistent<false, COUNT>(S, (uint32_t)n, next, cnt, mine,
+    trace_rays<VARIANT, false, COUNT>(S, (uint32_t)n, next, cnt, mine,
         [&](uint32_t i, Traverser<false, COUNT>& T) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(rays + i));
             const float4 b = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
@@ -51,13 +52,13 @@ k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __
     flush_counts<COUNT>(cnt, mine, stats);
 }
 
-template <bool COUNT>
+template <bool COUNT, int VARIANT>
 __global__ void __launch_bounds__(TRACE_THREADS)
 k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, uint64_t n,
                uint8_t* __restrict__ visible, rgk_trav_stats* stats, unsigned long long* next) {
     TravCount cnt{0, 0, 0, 0};
     uint32_t mine = 0;
-    trace_persistent<true, COUNT>(S, (uint32_t)n, next, cnt, mine,
+    trace_rays<VARIANT, true, COUNT>(S, (uint32_t)n, next, cnt, mine,
         [&](uint32_t i, Traverser<true, COUNT>& T) {
             // Ray(from, to, eps) (src/ray.hpp:15-22) + Scene::Visibility (src/scene.cpp:670-673)
             const float ax = pa[3 * (size_t)i], ay = pa[3 * (size_t)i + 1], az = pa[3 * (size_t)i + 2];
@@ -71,12 +72,22 @@ k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict
     flush_counts<COUNT>(cnt, mine, stats);
 }
 
+} // namespace
+
+// RGK_TRAVERSAL=2|3 selects the traversal control structure (A/B knob for profiling; results are identical)
+int rgk_traversal_variant() {
+    static int v = 0;
+    if (!v) { const char* e = std::getenv("RGK_TRAVERSAL"); v = (e && e[0] == '3') ? 3 : 2; }
+    return v;
+}
+
+namespace {
 int trace_grid(rgk_context* ctx) {
     static int blocks = 0;
     if (!blocks) {
         int sms = 148, per = 8;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_trace_closest<false>, TRACE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_trace_closest<false, 2>, TRACE_THREADS, 0);
         blocks = sms * (per > 0 ? per : 1);
     }
     return blocks;
@@ -93,8 +104,10 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
     RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
     const uint64_t warps = (n + 31) / 32;
     const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32));
-    if (d_stats) k_trace_closest<true><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
-    else k_trace_closest<false><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
+    const int variant = rgk_traversal_variant();
+    if (d_stats) k_trace_closest<true, 2><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
+    else if (variant == 3) k_trace_closest<false, 3><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
+    else k_trace_closest<false, 2><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     ctx->launches++;
     RGK_CUDA(ctx, cudaGetLastError());
     return RGK_OK;
@@ -109,8 +122,10 @@ rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* 
     RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
     const uint64_t warps = (n + 31) / 32;
     const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32));
-    if (d_stats) k_trace_shadow<true><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
-    else k_trace_shadow<false><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
+    const int variant = rgk_traversal_variant();
+    if (d_stats) k_trace_shadow<true, 2><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
+    else if (variant == 3) k_trace_shadow<false, 3><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
+    else k_trace_shadow<false, 2><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     ctx->launches++;
     RGK_CUDA(ctx, cudaGetLastError());
     return RGK_OK;

@@ -100,11 +100,26 @@ struct Traverser {
             if (COUNT) cnt.tests++;
             const float4* rec = S.tri_isect + 3 * (size_t)ti;
             const float4 r0 = __ldg(rec);
-            const double dt = (double)(dx * r0.x + dy * r0.y + dz * r0.z);
-            if (dt != dt) continue;                                      // std::isnan(dot)
-            if (dt < (double)eps && dt > (double)(-eps)) continue;      // parallel to the plane
-            const double dot2 = (double)(ox * r0.x + oy * r0.y + oz * r0.z);
-            const float t = (float)(-((double)r0.w + dot2) / dt);
+            const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;         // glm::dot(direction, planeN), fp32
+            if (dtf != dtf) continue;                                    // std::isnan(dot)
+            if (dtf < eps && dtf > -eps) continue;                       // parallel to the plane (exact in fp32: both are floats)
+            const float dot2f = ox * r0.x + oy * r0.y + oz * r0.z;
+            {
+                // Conservative fp32 pre-rejection of "t outside [lo, min(hi, best)]" that avoids the fp64 divide for most
+                // triangles.  n32 = -(w + dot2) has relative error <= 2^-24, the exact t (rounded as the reference
+                // rounds it) differs from n/dt by <= 2^-23 relative, the products lo*dt, hi*dt by 2^-24: a relative
+                // margin of 2^-20 (+ an absolute floor against underflow) can never reject a triangle the exact
+                // test below would accept.  Anything not rejected here goes through the exact evaluation.
+                const float n32 = -(r0.w + dot2f);
+                const float hi2 = ANY ? hi : fminf(hi, res.t);
+                const float a = lo * dtf, b = hi2 * dtf;
+                const float ma = fabsf(a) * 9.5367431640625e-7f + 1e-30f, mb = fabsf(b) * 9.5367431640625e-7f + 1e-30f;
+                const bool pos = dtf > 0.0f;
+                const bool out_lo = pos ? (n32 < a - ma) : (n32 > a + ma);
+                const bool out_hi = pos ? (n32 > b + mb) : (n32 < b - mb);
+                if ((out_lo || out_hi) && fabsf(a) < 1e30f && fabsf(b) < 1e30f && fabsf(n32) < 1e30f) continue;
+            }
+            const float t = (float)(-((double)r0.w + (double)dot2f) / (double)dtf);
             if (t < lo || t > hi) continue;                              // outside this node's interval (:272)
             if (!(t < res.t)) continue;                                  // not closer than the best so far (:275)
             const float4 r1 = __ldg(rec + 1);
@@ -121,7 +136,19 @@ struct Traverser {
                 if (beta < 0.0f || beta > 1.0f) continue;
                 alpha = (q0y - beta * r2.y) / r1.w;
             } else {
-                beta = (q0y * r1.z - q0x * r1.w) / r2.z;
+                const float num = q0y * r1.z - q0x * r1.w, den = r2.z;
+                // RN(num/den) < 0 or > 1 decided without dividing when num, den are ordinary numbers: the rounded
+                // quotient is > 1 exactly when |num| > |den| with equal signs (the next float above |den| already
+                // gives a quotient > 1 + 2^-24), and < 0 exactly when the signs differ and the quotient does not
+                // round to -0 (|num| > |den| * 2^-100 with |den| in (1e-6, 1e6) keeps every intermediate a normal
+                // number).  Everything else divides.
+                const float an = fabsf(num), ad = fabsf(den);
+                if (ad > 1e-6f && ad < 1e6f && an < 1e30f) {
+                    const bool same = (num < 0.0f) == (den < 0.0f);
+                    if (same && an > ad) continue;                       // beta > 1
+                    if (!same && an > ad * 7.8886090522101181e-31f) continue;   // beta < 0
+                }
+                beta = num / den;
                 if (beta < 0.0f || beta > 1.0f) continue;
                 alpha = (q0x - beta * r2.x) / r1.z;
             }
@@ -180,4 +207,160 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, uint32_t cou
             else if (!T.pop(K)) { commit(item, false, T.res); active = false; }
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Warp-voted traversal (RGK_TRAVERSAL == 3).  Every lane is a small state machine over the same ray state:
+//   INNER  -- at an inner node (or about to read its node word)
+//   LEAF   -- scanning the references of a leaf with the cheap fp32 pre-rejection
+//   EXACT  -- one reference survived the pre-rejection and needs Triangle::TestIntersection proper (fp64 divide,
+//             barycentric divides)
+//   IDLE   -- ray finished, waiting for a refill
+// Each iteration the warp votes and executes only the block most lanes are waiting for (a few steps of it), so a
+// lane never idles behind another lane's long leaf or rare exact test: waiting groups only ever gain lanes while the
+// total stays 32, hence every group is served eventually.  Which lane evaluates what, in which order along ITS OWN
+// ray, is unchanged -- results are identical to the sequential traversal.
+enum { TM_IDLE = 0, TM_INNER = 1, TM_LEAF = 2, TM_EXACT = 3 };
+#define RGK_STEPS_INNER 3
+#define RGK_STEPS_LEAF 3
+
+template <bool ANY, bool COUNT, class Fetch, class Commit>
+__device__ __forceinline__ void trace_voted(const DevScene& S, uint32_t count, unsigned long long* work,
+                                            TravCount& cnt, uint32_t& done, Fetch fetch, Commit commit) {
+    Traverser<ANY, COUNT> T;
+    TravStack K;
+    const unsigned lane = threadIdx.x & 31;
+    const float eps = S.epsilon;
+    int mode = TM_IDLE;
+    bool exhausted = false, hit = false;
+    uint32_t item = 0, p = 0, pend = 0, cand = 0;
+    for (;;) {
+        const unsigned m_idle = __ballot_sync(0xffffffffu, mode == TM_IDLE);
+        if (m_idle != 0u && !exhausted && (__popc(m_idle) >= RGK_REFILL_THRESHOLD || m_idle == 0xffffffffu)) {
+            const int leader = __ffs(m_idle) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(work, (unsigned long long)__popc(m_idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + __popc(m_idle) >= count) exhausted = true;
+            if (mode == TM_IDLE) {
+                const unsigned long long mine = base + __popc(m_idle & ((1u << lane) - 1u));
+                if (mine < count) {
+                    item = (uint32_t)mine;
+                    done++;
+                    if (fetch(item, T)) mode = TM_INNER;
+                    else commit(item, false, T.res);
+                }
+            }
+        }
+        const int n_inner = __popc(__ballot_sync(0xffffffffu, mode == TM_INNER));
+        const int n_leaf = __popc(__ballot_sync(0xffffffffu, mode == TM_LEAF));
+        const int n_exact = __popc(__ballot_sync(0xffffffffu, mode == TM_EXACT));
+        if ((n_inner | n_leaf | n_exact) == 0) { if (exhausted) break; else continue; }
+        if (n_exact >= n_inner && n_exact >= n_leaf) {
+            if (mode == TM_EXACT) {
+                // Triangle::TestIntersection proper, on the reference's operation order (src/primitives.cpp:85-164)
+                const float4* rec = S.tri_isect + 3 * (size_t)cand;
+                const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+                const float dtf = T.dx * r0.x + T.dy * r0.y + T.dz * r0.z;
+                const float dot2f = T.ox * r0.x + T.oy * r0.y + T.oz * r0.z;
+                const float t = (float)(-((double)r0.w + (double)dot2f) / (double)dtf);
+                bool ok = !(t < T.tmin - eps || t > T.tmax + eps) && (t < T.res.t);
+                float alpha = 0.0f, beta = 0.0f;
+                if (ok) {
+                    const uint32_t flags = __float_as_uint(r2.w);
+                    const uint32_t code = flags & 3u;
+                    const float o1 = (code == 0u) ? T.oy : T.ox, d1 = (code == 0u) ? T.dy : T.dx;
+                    const float o2 = (code == 2u) ? T.oy : T.oz, d2 = (code == 2u) ? T.dy : T.dz;
+                    const float q0x = (o1 + d1 * t) - r1.x;
+                    const float q0y = (o2 + d2 * t) - r1.y;
+                    if (flags & 4u) {
+                        beta = q0x / r2.x;
+                        ok = !(beta < 0.0f || beta > 1.0f);
+                        alpha = (q0y - beta * r2.y) / r1.w;
+                    } else {
+                        beta = (q0y * r1.z - q0x * r1.w) / r2.z;
+                        ok = !(beta < 0.0f || beta > 1.0f);
+                        alpha = (q0x - beta * r2.x) / r1.z;
+                    }
+                    if (ok) ok = !(alpha < 0.0f || (alpha + beta) > 1.0f);
+                }
+                mode = TM_LEAF;
+                if (ok) {
+                    T.res.tri = cand; T.res.t = t; T.res.alpha = alpha; T.res.beta = beta;
+                    hit = true;
+                    if (ANY) { commit(item, true, T.res); mode = TM_IDLE; }
+                }
+            }
+        } else if (n_leaf >= n_inner) {
+            if (mode == TM_LEAF) {
+                const float lo = T.tmin - eps, hi = T.tmax + eps;
+#pragma unroll 1
+                for (int s = 0; s < RGK_STEPS_LEAF && mode == TM_LEAF; s++) {
+                    if (p == pend) {                       // leaf finished (src/scene_intersect.cpp:290-292)
+                        if (hit) { commit(item, true, T.res); mode = TM_IDLE; }
+                        else if (T.pop(K)) mode = TM_INNER;
+                        else { commit(item, false, T.res); mode = TM_IDLE; }
+                        break;
+                    }
+                    const uint32_t ti = __ldg(S.refs + p);
+                    ++p;
+                    if (COUNT) cnt.refs++;
+                    if (ti == T.ignore) continue;
+                    if (COUNT) cnt.tests++;
+                    const float4 r0 = __ldg(S.tri_isect + 3 * (size_t)ti);
+                    const float dtf = T.dx * r0.x + T.dy * r0.y + T.dz * r0.z;
+                    const float dot2f = T.ox * r0.x + T.oy * r0.y + T.oz * r0.z;
+                    // conservative fp32 pre-rejection (see Traverser::leaf): never rejects what the exact test accepts
+                    const float n32 = -(r0.w + dot2f);
+                    const float hi2 = ANY ? hi : fminf(hi, T.res.t);
+                    const float a = lo * dtf, b = hi2 * dtf;
+                    const float ma = fabsf(a) * 9.5367431640625e-7f + 1e-30f, mb = fabsf(b) * 9.5367431640625e-7f + 1e-30f;
+                    const bool pos = dtf > 0.0f;
+                    const bool out_lo = pos ? (n32 < a - ma) : (n32 > a + ma);
+                    const bool out_hi = pos ? (n32 > b + mb) : (n32 < b - mb);
+                    const bool sane = fabsf(a) < 1e30f && fabsf(b) < 1e30f && fabsf(n32) < 1e30f;
+                    const bool reject = (dtf != dtf) || (dtf < eps && dtf > -eps) || ((out_lo || out_hi) && sane);
+                    if (!reject) { cand = ti; mode = TM_EXACT; }
+                }
+            }
+        } else {
+            if (mode == TM_INNER) {
+#pragma unroll 1
+                for (int s = 0; s < RGK_STEPS_INNER; s++) {
+                    const uint2 w = __ldg(S.nodes + T.node);
+                    if ((w.y & 3u) == 3u) {
+                        if (COUNT) cnt.leaf++;
+                        p = w.x; pend = w.x + (w.y >> 2); hit = false; mode = TM_LEAF;
+                        break;
+                    }
+                    if (COUNT) cnt.inner++;
+                    const uint32_t axis = w.y & 3u;
+                    const float split = __uint_as_float(w.x);
+                    const float oa = axis == 0u ? T.ox : (axis == 1u ? T.oy : T.oz);
+                    const float da = axis == 0u ? T.dx : (axis == 1u ? T.dy : T.dz);
+                    const float ia = axis == 0u ? T.ix : (axis == 1u ? T.iy : T.iz);
+                    const float tplane = (split - oa) * ia;
+                    const bool below_first = (oa < split) || (oa == split && da <= 0.0f);
+                    const uint32_t other = w.y >> 2;
+                    const uint32_t first = below_first ? T.node + 1u : other;
+                    const uint32_t second = below_first ? other : T.node + 1u;
+                    if (tplane > T.tmax || tplane <= 0.0f) T.node = first;
+                    else if (tplane < T.tmin) T.node = second;
+                    else {
+                        K.node[T.sp] = second; K.tmin[T.sp] = tplane; K.tmax[T.sp] = T.tmax; ++T.sp;
+                        T.node = first; T.tmax = tplane;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// VARIANT 2: descend-to-leaf / process-leaf phases with idle-lane refill; VARIANT 3: warp-voted state machine.
+template <int VARIANT, bool ANY, bool COUNT, class Fetch, class Commit>
+__device__ __forceinline__ void trace_rays(const DevScene& S, uint32_t count, unsigned long long* work,
+                                           TravCount& cnt, uint32_t& done, Fetch fetch, Commit commit) {
+    if (VARIANT == 3) trace_voted<ANY, COUNT>(S, count, work, cnt, done, fetch, commit);
+    else trace_persistent<ANY, COUNT>(S, count, work, cnt, done, fetch, commit);
 }

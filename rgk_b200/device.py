@@ -32,7 +32,11 @@ class Context:
     def __init__(self, device=0, stream=None, lib=None):
         self.lib = lib or abi.load_library()
         h = C.c_void_p()
-        st = self.lib.rgk_context_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        # stream: None -> the library creates its own stream; an integer cudaStream_t handle -> run on that stream
+        # (torch's default stream has handle 0, which CUDA spells cudaStreamLegacy = 0x1)
+        if stream is not None and int(stream) == 0:
+            stream = 1
+        st = self.lib.rgk_context_create(int(device), C.c_void_p(stream) if stream is not None else None, C.byref(h))
         if st != 0:
             raise RgkError(st, self.lib.rgk_last_error(None).decode())
         self.h = h

@@ -1,0 +1,88 @@
+"""Host-side logic that needs no GPU: the JSON scene config reader, the scene pack, the product's host kd-tree
+builder (through a scene commit is GPU-only, so the builder is checked via the oracle's identical tree in the
+GPU tests; here: config / packing / sharding arithmetic)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from rgk_b200 import abi, scene, scenes
+
+
+def test_json_config_with_comments_and_defaults(tmp_path):
+    cfgd = scenes.cornell_box(width=32, height=16, multisample=2)
+    text = json.dumps(cfgd, indent=1).replace('"rounds": 1,', '"rounds": 1, // one round\n /* block\n comment */')
+    path = tmp_path / "c.json"
+    path.write_text(text)
+    pack, cfg = scene.load_json_config(str(path))
+    assert (cfg.xres, cfg.yres, cfg.multisample, cfg.recursion_level) == (32, 16, 2, 40)
+    assert cfg.russian == pytest.approx(0.74) and cfg.clamp == 20.0 and cfg.bumpmap_scale == 1.0 and cfg.reverse == 0
+    assert pack.n_triangles == 36 and len(pack.materials) == 4 and len(pack.meshes) == 9
+    # defaults of ConfigJSON (src/config.cpp:295-301)
+    d = dict(cfgd); [d.pop(k) for k in ("russian", "clamp", "recursion-max", "multisample")]
+    _, cfg2 = scene.load_config(d)
+    assert cfg2.russian == pytest.approx(0.74) and cfg2.clamp == 10000000.0 and cfg2.recursion_level == 40 and cfg2.multisample == 1
+
+
+def test_config_errors_mirror_reference_exceptions():
+    d = scenes.cornell_box()
+    bad = dict(d); bad.pop("camera")
+    with pytest.raises(scene.ConfigFileException):
+        scene.load_config(bad)
+    bad = dict(d); bad["render-time"] = 3
+    with pytest.raises(scene.ConfigFileException):
+        scene.load_config(bad)
+    bad = json.loads(json.dumps(d)); bad["scene"][0]["material"] = "nope"
+    with pytest.raises(ValueError, match="was not defined"):
+        scene.load_config(bad)
+    bad = json.loads(json.dumps(d)); bad["materials"][0]["brdf"] = "cooktorr"
+    with pytest.raises(scene.ConfigFileException, match="Unsupported BRDF"):
+        scene.load_config(bad)
+
+
+def test_color255_and_broadcast_vectors():
+    d = scenes.cornell_box()
+    d["materials"][0] = {"name": "LeftWall", "diffuse255": [255, 0, 127.5], "brdf": "diffuse"}
+    d["sky"] = {"color": 0.25, "intensity": 2.0}
+    d["lights"] = [{"position": [0, 1, 0], "intensity": 3.0, "color255": 255}]
+    pack, _ = scene.load_config(d)
+    tex = pack.textures[pack.materials[0]["tex_diffuse"]]
+    assert tex[0] == "solid" and tex[1] == pytest.approx((1.0, 0.0, 0.5))
+    assert pack.sky["color"] == (0.25, 0.25, 0.25) and pack.sky["intensity"] == 2.0
+    assert pack.point_lights[0][1] == (1.0, 1.0, 1.0)
+
+
+def test_scene_desc_layout(cornell):
+    pack, cfg, desc = cornell
+    assert desc.n_triangles == 36 and desc.n_vertices == 108 and desc.n_meshes == 9
+    m = [desc.meshes[i] for i in range(desc.n_meshes)]
+    assert [x.first_triangle for x in m] == [0, 2, 4, 6, 8, 10, 22, 34, 35] and sum(x.n_triangles for x in m) == 36
+    pos = np.ctypeslib.as_array(desc.positions, (108 * 3,))
+    assert not np.any(np.signbit(pos) & (pos == 0))          # -0.0 canonicalised like the reference's transform does
+    assert desc.materials[3].emission[0] == 17.0
+    ltc = scene.load_ltc_tables()
+    assert ltc["ggx_M"].shape == (4096, 9) and ltc["beckmann_amp"].shape == (4096,)
+
+
+def test_primitives_match_reference_tables():
+    """planeY / trigY / cube as in src/primitives.cpp:168-228 (spot checks of the generated tables)."""
+    P, N, UV, T = scene.primitive_data("plane")
+    assert P.tolist() == [[1, 0, 1], [1, 0, -1], [-1, 0, 1], [-1, 0, -1], [-1, 0, 1], [1, 0, -1]]
+    assert UV.tolist() == [[1, 1], [1, 0], [0, 1], [0, 0], [0, 1], [1, 0]] and N[0].tolist() == [0, 1, 0] and T[0].tolist() == [0, 0, 1]
+    P, N, UV, T = scene.primitive_data("cube")
+    assert len(P) == 36
+    assert P[18].tolist() == [-1, -1, 1] and N[18].tolist() == [0, -1, 0] and UV[18].tolist() == [1, 1] and T[18].tolist() == [1, 0, 0]
+    assert P[25].tolist() == [-1, 1, 1] and N[25].tolist() == [0, 0, 1] and UV[25].tolist() == [1, 0] and T[25].tolist() == [0, 1, 0]
+    assert P[35].tolist() == [-1, 1, -1] and N[35].tolist() == [0, 0, -1]
+    assert len(scene.primitive_data("tri")[0]) == 3
+
+
+def test_camera_args_fov_and_focal():
+    _, cfg = scenes.load_builtin("cornell-box", width=200, height=100)
+    ca = cfg.camera_args()
+    assert ca["xview"] == pytest.approx(2 * np.tan(np.float32(19.5 * 0.0174533) / 2), rel=1e-6)
+    assert ca["yview"] == pytest.approx(ca["xview"] * 100 / 200, rel=1e-6)
+    cfg.camera = {"position": [0, 0, 5], "lookat": [0, 0, 0], "focal": 1.6}
+    ca = cfg.camera_args()
+    assert ca["yview"] == pytest.approx(1.6) and ca["xview"] == pytest.approx(1.6 * 2)

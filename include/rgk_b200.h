@@ -302,6 +302,18 @@ rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t n1d, uint32_t n2d,
 rgk_status rgk_render_set_counting(rgk_context* ctx, int enabled);
 rgk_status rgk_render_get_trav_stats(const rgk_context* ctx, rgk_trav_stats* closest, rgk_trav_stats* shadow);
 
+/* Parity probe (no reference counterpart): evaluates ONE device shading function on n caller-supplied inputs so
+ * tests can compare it with the CPU path function by function.  Host buffers; float rows per item:
+ *   RGK_PROBE_BXDF_SAMPLE  index = material  in Vi[3] uv[2] sample[2]          out dir[3] weight[3] may_leak   (BxDF::sample)
+ *   RGK_PROBE_BXDF_VALUE   index = material  in Vi[3] Vr[3] uv[2]               out rgb                          (BxDF::value)
+ *   RGK_PROBE_TEXTURE      index = texture   in uv[2]                           out rgb slope_right slope_bottom (src/texture.cpp:35-102)
+ *   RGK_PROBE_RANDOM_LIGHT                   in choice[2] light tri_sample[2]   out type pos[3] colour[3] intensity size normal[3]
+ *   RGK_PROBE_SKY                            in dir[3]                          out rgb                          (Scene::GetSkyboxRay)
+ *   RGK_PROBE_FRAME                          in normal[3] v[3]                  out toLocal(v)[3] toGlobal(toLocal(v))[3] (SystemTransform) */
+enum { RGK_PROBE_BXDF_SAMPLE = 0, RGK_PROBE_BXDF_VALUE = 1, RGK_PROBE_TEXTURE = 2, RGK_PROBE_RANDOM_LIGHT = 3, RGK_PROBE_SKY = 4,
+       RGK_PROBE_FRAME = 5 };
+rgk_status rgk_probe(rgk_context* ctx, uint32_t kind, uint32_t index, const float* in, uint64_t n, float* out);
+
 /* Blocks until the context stream is idle. */
 rgk_status rgk_synchronize(rgk_context* ctx);
 

@@ -13,6 +13,8 @@ RGK_NO_TRIANGLE = 0xFFFFFFFF
 (BXDF_DIFFUSE, BXDF_MIX, BXDF_DIELECTRIC, BXDF_MIRROR, BXDF_TRANSPARENT, BXDF_LTC_BECKMANN,
  BXDF_LTC_GGX, BXDF_LTC_BECKMANN_DIFFUSE, BXDF_LTC_GGX_DIFFUSE) = range(9)
 SAMPLER_MT19937, SAMPLER_TABLES, SAMPLER_FAST = 0, 1, 2
+PROBE_BXDF_SAMPLE, PROBE_BXDF_VALUE, PROBE_TEXTURE, PROBE_RANDOM_LIGHT, PROBE_SKY, PROBE_FRAME = range(6)
+PROBE_WIDTHS = {0: (7, 7), 1: (8, 3), 2: (2, 5), 3: (5, 12), 4: (3, 3), 5: (6, 6)}
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -127,7 +129,7 @@ EXPORTS = [
     "rgk_trace_closest_device", "rgk_trace_shadow_device", "rgk_camera_init", "rgk_camera_rays",
     "rgk_generate_tasks", "rgk_sampler_set_size", "rgk_sampler_tables", "rgk_render_round",
     "rgk_render_round_device", "rgk_render_frame", "rgk_render_set_tables", "rgk_synchronize",
-    "rgk_render_set_counting", "rgk_render_get_trav_stats",
+    "rgk_render_set_counting", "rgk_render_get_trav_stats", "rgk_probe",
 ]
 
 
@@ -172,6 +174,7 @@ def load_library(path=None):
                                      C.POINTER(RoundStats)]
     lib.rgk_render_set_tables.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64]
     lib.rgk_synchronize.argtypes = [vp]
+    lib.rgk_probe.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
     lib.rgk_render_set_counting.argtypes = [vp, C.c_int]
     lib.rgk_render_get_trav_stats.argtypes = [vp, C.POINTER(TravStats), C.POINTER(TravStats)]
     return lib

@@ -215,7 +215,7 @@ __device__ __forceinline__ void fresnel_dielectric(float eta, float cosTheta, fl
     R = 0.5f * (Rs * Rs + Rp * Rp); cosT = ct;
 }
 // value of a non-mix material
-__device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv) {
+static __device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv) {
     switch (m.bxdf) {
     case RGK_BXDF_DIFFUSE: {
         if (Vi.z <= 0 || Vr.z <= 0) return rgb(0, 0, 0);

@@ -157,6 +157,14 @@ class Context:
         self._check(self.lib.rgk_render_frame(self.h, C.byref(cam), C.byref(params), rounds, _p(fb), _p(cnt), C.byref(st)))
         return fb, cnt, st
 
+    def probe(self, kind, index, rows):
+        rows = np.ascontiguousarray(rows, np.float32)
+        win, wout = abi.PROBE_WIDTHS[kind]
+        assert rows.ndim == 2 and rows.shape[1] == win
+        out = np.zeros((len(rows), wout), np.float32)
+        self._check(self.lib.rgk_probe(self.h, kind, index, _p(rows), C.c_uint64(len(rows)), _p(out)))
+        return out
+
     def set_counting(self, enabled):
         self._check(self.lib.rgk_render_set_counting(self.h, int(bool(enabled))))
 

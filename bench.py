@@ -197,33 +197,18 @@ def main():
     p = cfg.params(mode)
     all_tasks = ctx.generate_tasks(32, p.xres, p.yres)
     ntasks = len(all_tasks)
+    from rgk_b200 import multigpu
+    tasks = all_tasks
     if args.shard == "tiles" and world > 1:
-        mine = [all_tasks[i] for i in range(rank, ntasks, world)]
-        tasks = (abi.Task * len(mine))(*mine)
-        seed_offsets = None   # tile i keeps seed 42 + round*ntasks + i: done by passing per-call bases below
-    else:
-        tasks = all_tasks
+        ctx.set_shard(rank, world)      # this rank renders tiles rank, rank+world, ... of every list, seeds unchanged
     fb = torch.zeros((p.yres, p.xres, 3), dtype=torch.float32, device="cuda")
     cnt = torch.zeros((p.yres, p.xres), dtype=torch.int32, device="cuda")
 
     def step(i):
         """One round per GPU (weak) or this rank's tiles of one round (strong), then the per-round reduce."""
-        if args.shard == "tiles" and world > 1:
-            # tile-sharded: every rank renders its tiles of round i; tile seeds must stay 42 + i*ntasks + tile index,
-            # so tiles are submitted one call per contiguous seed run (here: one call per tile list entry group)
-            st_tot = abi.RoundStats()
-            for k, gi in enumerate(range(rank, ntasks, world)):
-                one = (abi.Task * 1)(all_tasks[gi])
-                st = ctx.render_round_device(cam, p, one, fb.data_ptr(), cnt.data_ptr(), 42, i * ntasks + gi)
-                for f, _ in abi.RoundStats._fields_:
-                    setattr(st_tot, f, getattr(st_tot, f) + getattr(st, f))
-            st = st_tot
-        else:
-            rnd = i * world + rank
-            st = ctx.render_round_device(cam, p, tasks, fb.data_ptr(), cnt.data_ptr(), 42, rnd * ntasks)
-        if world > 1:
-            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
-            dist.reduce(cnt, dst=0, op=dist.ReduceOp.SUM)
+        rnd = i if (args.shard == "tiles" and world > 1) else multigpu.round_for_rank(i, rank, world)
+        st = ctx.render_round_device(cam, p, tasks, fb.data_ptr(), cnt.data_ptr(), 42, multigpu.seedcount_base(rnd, ntasks))
+        multigpu.reduce_framebuffer(fb, cnt)
         return st
 
     def barrier():
@@ -264,8 +249,8 @@ def main():
     h_cnt = torch.zeros((p.yres, p.xres), dtype=torch.int32).pin_memory()
     np_fb, np_cnt = h_fb.numpy(), h_cnt.numpy().view(np.uint32)
     def e2e_step(i):
-        rnd = i * world + rank
-        _, _, st = ctx.render_round(cam, p, all_tasks if args.shard == "rounds" or world == 1 else tasks, 42, rnd * ntasks, fb=(np_fb, np_cnt))
+        rnd = i if (args.shard == "tiles" and world > 1) else multigpu.round_for_rank(i, rank, world)
+        _, _, st = ctx.render_round(cam, p, all_tasks, 42, multigpu.seedcount_base(rnd, ntasks), fb=(np_fb, np_cnt))
         return st
     e2e_step(0)
     barrier()
@@ -289,6 +274,7 @@ def main():
     roofline, extra = None, {}
     if rank == 0:
         ctx.set_counting(True)
+        ctx.set_shard(0, 1)
         ctx.render_round_device(cam, p, all_tasks, fb.data_ptr(), cnt.data_ptr(), 42, 100 * ntasks)
         tc, ts = ctx.render_trav_stats()
         ctx.set_counting(False)

@@ -296,6 +296,11 @@ rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_r
 rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t n1d, uint32_t n2d,
                                  const float* t1d, const float* t2d, uint64_t n_pixels);
 
+/* Tile sharding across GPUs: of every task list given to rgk_render_round*, this context renders only
+ * tasks first, first+stride, first+2*stride, ...; each keeps the seed of its position in the full list, so the union
+ * over `stride` contexts equals the unsharded round pixel for pixel.  Default (0, 1) = everything. */
+rgk_status rgk_render_set_shard(rgk_context* ctx, uint32_t first, uint32_t stride);
+
 /* Traversal work counters of the rendering calls: when enabled, the closest-hit and shadow
  * kernels of rgk_render_round* count visited nodes / references / triangle tests (slower; off by default,
  * never on in a timed run) and rgk_render_get_trav_stats returns the totals of the last rendering call. */

@@ -129,7 +129,7 @@ EXPORTS = [
     "rgk_trace_closest_device", "rgk_trace_shadow_device", "rgk_camera_init", "rgk_camera_rays",
     "rgk_generate_tasks", "rgk_sampler_set_size", "rgk_sampler_tables", "rgk_render_round",
     "rgk_render_round_device", "rgk_render_frame", "rgk_render_set_tables", "rgk_synchronize",
-    "rgk_render_set_counting", "rgk_render_get_trav_stats", "rgk_probe",
+    "rgk_render_set_counting", "rgk_render_get_trav_stats", "rgk_probe", "rgk_render_set_shard",
 ]
 
 
@@ -176,5 +176,6 @@ def load_library(path=None):
     lib.rgk_synchronize.argtypes = [vp]
     lib.rgk_probe.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
     lib.rgk_render_set_counting.argtypes = [vp, C.c_int]
+    lib.rgk_render_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.rgk_render_get_trav_stats.argtypes = [vp, C.POINTER(TravStats), C.POINTER(TravStats)]
     return lib

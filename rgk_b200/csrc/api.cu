@@ -471,6 +471,11 @@ rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_r
     return RGK_OK;
 }
 
+rgk_status rgk_render_set_shard(rgk_context* ctx, uint32_t first, uint32_t stride) {
+    if (!ctx || stride == 0 || first >= stride) return RGK_ERR_INVALID;
+    ctx->shard_first = first; ctx->shard_stride = stride;
+    return RGK_OK;
+}
 rgk_status rgk_render_set_counting(rgk_context* ctx, int enabled) {
     if (!ctx) return RGK_ERR_INVALID;
     ctx->counting = enabled != 0;

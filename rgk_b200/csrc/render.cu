@@ -619,7 +619,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     if (!ctx->paths->events) ctx->paths->events = new EventPool();
     EventPool& pool = *ctx->paths->events;
     float kind_ms[T_KINDS] = {0, 0, 0, 0};
-    uint32_t ti = 0;
+    const uint32_t stride = ctx->shard_stride ? ctx->shard_stride : 1u;
+    uint32_t ti = ctx->shard_first;
     while (ti < n_tasks) {
         h_tiles.clear(); h_tiles2.clear();
         size_t npix = 0;
@@ -631,7 +632,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 h_tiles.push_back(make_uint4(t.x1, t.x2, t.y1, t.y2));
                 h_tiles2.push_back(make_uint2((uint32_t)npix, seedstart + seedcount_base + ti));
             }
-            npix += px; ti++;
+            npix += px; ti += stride;
         }
         if (npix == 0) continue;
         const size_t npaths = npix * ms;

@@ -165,6 +165,9 @@ class Context:
         self._check(self.lib.rgk_probe(self.h, kind, index, _p(rows), C.c_uint64(len(rows)), _p(out)))
         return out
 
+    def set_shard(self, first, stride):
+        self._check(self.lib.rgk_render_set_shard(self.h, first, stride))
+
     def set_counting(self, enabled):
         self._check(self.lib.rgk_render_set_counting(self.h, int(bool(enabled))))
 

@@ -191,11 +191,15 @@ __global__ void k_pixel_setup(const uint4* __restrict__ tiles, const uint2* __re
     const uint4 t = tiles[blockIdx.x];
     const uint2 u = tiles2[blockIdx.x];
     const uint32_t w = t.y - t.x, n = w * (t.w - t.z);
+    const bool full = (w == 32u) && (t.w - t.z == 32u);
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-        const uint32_t x = t.x + k % w, y = t.z + k / w;
-        pix_xy[u.x + k] = x | (y << 16);
+        const uint32_t lx = k % w, ly = k / w;
+        // position of the pixel inside the chunk: full 32x32 tiles are laid out as 8x4-pixel blocks so that one warp
+        // of primary rays covers a compact footprint; the pixel's seed still follows the reference's y-major order
+        const uint32_t pos = full ? ((((ly >> 2) << 2) + (lx >> 3)) << 5) + ((ly & 3u) << 3) + (lx & 7u) : k;
+        pix_xy[u.x + pos] = (t.x + lx) | ((t.z + ly) << 16);
         // PathTracer::RenderPixel: samplerSeed += 0x42424242 before every pixel, y-major / x-minor (src/tracer.cpp:8-9)
-        pix_seed[u.x + k] = u.y + (k + 1u) * 0x42424242u;
+        pix_seed[u.x + pos] = u.y + (k + 1u) * 0x42424242u;
     }
 }
 
@@ -604,6 +608,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const bool mt = P->sampler_mode == RGK_SAMPLER_MT19937;
     const bool counting = ctx->counting;
     const int variant = rgk_traversal_variant();
+    const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 8);
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
 
@@ -669,10 +674,14 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {
             RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
             const int g1 = (int)std::min<uint64_t>(tgrid, ((uint64_t)count + TRACE_THREADS - 1) / TRACE_THREADS);
+            // camera rays (and the shadow rays of their hit points) are coherent: keep warps in lockstep (refill only
+            // when the whole warp is done); later bounces are incoherent: refill as soon as a quarter of the warp idles
+            DevScene dev = ctx->dev;
+            dev.refill_threshold = bounce == 0 ? refill_coherent : refill_incoherent;
             pool.begin(ctx->stream, T_CLOSEST);
-            if (counting) k_closest<true, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, queue, count, B.counters + C_WORK_A, d_st);
-            else if (variant == 3) k_closest<false, 3><<<g1, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, queue, count, B.counters + C_WORK_A, nullptr);
-            else k_closest<false, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, queue, count, B.counters + C_WORK_A, nullptr);
+            if (counting) k_closest<true, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
+            else if (variant == 3) k_closest<false, 3><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
+            else k_closest<false, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             pool.end(ctx->stream);
             pool.begin(ctx->stream, T_SHADE);
             k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
@@ -685,9 +694,9 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             if (shadow_count) {
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
-                if (counting) k_shadow<true, 2><<<g2, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1);
-                else if (variant == 3) k_shadow<false, 3><<<g2, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
-                else k_shadow<false, 2><<<g2, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
+                if (counting) k_shadow<true, 2><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1);
+                else if (variant == 3) k_shadow<false, 3><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
+                else k_shadow<false, 2><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
                 pool.end(ctx->stream);
                 ctx->launches++; total.shadow_launches++;
             }

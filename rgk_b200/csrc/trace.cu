@@ -9,7 +9,8 @@
 
 namespace {
 
-constexpr int TRACE_THREADS = 128;
+constexpr int TRACE_THREADS_MAX = 256;
+static int trace_threads() { static int t = 0; if (!t) { const char* e = std::getenv("RGK_TRACE_THREADS"); t = e ? std::atoi(e) : 128; if (t != 64 && t != 128 && t != 256) t = 128; } return t; }
 
 template <bool COUNT>
 __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays, rgk_trav_stats* stats) {
@@ -31,7 +32,7 @@ __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays,
 }
 
 template <bool COUNT, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS)
+__global__ void __launch_bounds__(TRACE_THREADS_MAX)
 k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, uint64_t n,
                 rgk_hit* __restrict__ hits, rgk_trav_stats* stats, unsigned long long* next) {
     TravCount cnt{0, 0, 0, 0};
@@ -53,7 +54,7 @@ k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __
 }
 
 template <bool COUNT, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS)
+__global__ void __launch_bounds__(TRACE_THREADS_MAX)
 k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, uint64_t n,
                uint8_t* __restrict__ visible, rgk_trav_stats* stats, unsigned long long* next) {
     TravCount cnt{0, 0, 0, 0};
@@ -87,7 +88,7 @@ int trace_grid(rgk_context* ctx) {
     if (!blocks) {
         int sms = 148, per = 8;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_trace_closest<false, 2>, TRACE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_trace_closest<false, 2>, trace_threads(), 0);
         blocks = sms * (per > 0 ? per : 1);
     }
     return blocks;
@@ -103,11 +104,11 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
     if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
     RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
     const uint64_t warps = (n + 31) / 32;
-    const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32));
+    const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + trace_threads() / 32 - 1) / (trace_threads() / 32));
     const int variant = rgk_traversal_variant();
-    if (d_stats) k_trace_closest<true, 2><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
-    else if (variant == 3) k_trace_closest<false, 3><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
-    else k_trace_closest<false, 2><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
+    if (d_stats) k_trace_closest<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
+    else if (variant == 3) k_trace_closest<false, 3><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
+    else k_trace_closest<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     ctx->launches++;
     RGK_CUDA(ctx, cudaGetLastError());
     return RGK_OK;
@@ -121,11 +122,11 @@ rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* 
     if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
     RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
     const uint64_t warps = (n + 31) / 32;
-    const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32));
+    const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + trace_threads() / 32 - 1) / (trace_threads() / 32));
     const int variant = rgk_traversal_variant();
-    if (d_stats) k_trace_shadow<true, 2><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
-    else if (variant == 3) k_trace_shadow<false, 3><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
-    else k_trace_shadow<false, 2><<<grid, TRACE_THREADS, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
+    if (d_stats) k_trace_shadow<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
+    else if (variant == 3) k_trace_shadow<false, 3><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
+    else k_trace_shadow<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     ctx->launches++;
     RGK_CUDA(ctx, cudaGetLastError());
     return RGK_OK;

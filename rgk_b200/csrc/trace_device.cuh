@@ -14,10 +14,10 @@
 struct TravCount { uint32_t inner, leaf, refs, tests; };
 // Per-ray traversal stack (local memory, lane-interleaved by the hardware); kept outside the Traverser so that the
 // scalar ray / interval state stays in registers.
-struct TravStack { uint32_t node[RGK_STACK_CAP]; float tmin[RGK_STACK_CAP], tmax[RGK_STACK_CAP]; };
+struct TravStack { uint32_t node[RGK_STACK_CAP]; float2 range[RGK_STACK_CAP]; };   // range = (tmin, tmax)
+#define RGK_CAND_CAP 4            // deferred exact tests per leaf before a flush
 struct HitRec { uint32_t tri; float t, alpha, beta; };  // alpha/beta as returned by TestIntersection
 
-#define RGK_REFILL_THRESHOLD 8   // refill when at least this many lanes of the warp are idle
 
 template <bool ANY, bool COUNT>
 struct Traverser {
@@ -65,17 +65,21 @@ struct Traverser {
             const uint32_t axis = w.y & 3u;
             const float split = __uint_as_float(w.x);
             const float oa = axis == 0u ? ox : (axis == 1u ? oy : oz);
-            const float da = axis == 0u ? dx : (axis == 1u ? dy : dz);
             const float ia = axis == 0u ? ix : (axis == 1u ? iy : iz);
-            const float tplane = (split - oa) * ia;
-            const bool below_first = (oa < split) || (oa == split && da <= 0.0f);
-            const uint32_t other = w.y >> 2;
-            const uint32_t first = below_first ? node + 1u : other;
-            const uint32_t second = below_first ? other : node + 1u;
+            const float diff = split - oa;                 // its sign is the exact sign of (split - oa)
+            const float tplane = diff * ia;
+            bool below_first = diff > 0.0f;                // oa < split
+            if (diff == 0.0f) {                            // oa == split: decided by the direction (rare)
+                const float da = axis == 0u ? dx : (axis == 1u ? dy : dz);
+                below_first = da <= 0.0f;
+            }
+            const uint32_t other = w.y >> 2, near = node + 1u;
+            const uint32_t first = below_first ? near : other;
+            const uint32_t second = below_first ? other : near;
             if (tplane > tmax || tplane <= 0.0f) node = first;
             else if (tplane < tmin) node = second;
             else {
-                K.node[sp] = second; K.tmin[sp] = tplane; K.tmax[sp] = tmax; ++sp;
+                K.node[sp] = second; K.range[sp] = make_float2(tplane, tmax); ++sp;
                 node = first; tmax = tplane;
             }
             w = __ldg(S.nodes + node);
@@ -83,79 +87,93 @@ struct Traverser {
         return w;
     }
 
+    // Triangle::TestIntersection proper for one reference that survived the pre-rejection, on the reference's
+    // operation order (src/primitives.cpp:85-164), followed by the leaf's accept rule (src/scene_intersect.cpp:272-283).
+    __device__ __forceinline__ bool exact_test(const DevScene& S, uint32_t ti, float lo, float hi) {
+        const float4* rec = S.tri_isect + 3 * (size_t)ti;
+        const float4 r0 = __ldg(rec);
+        const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;             // glm::dot(direction, planeN), fp32
+        if (dtf != dtf) return false;                                    // std::isnan(dot)
+        const float dot2f = ox * r0.x + oy * r0.y + oz * r0.z;
+        const float t = (float)(-((double)r0.w + (double)dot2f) / (double)dtf);
+        if (t < lo || t > hi) return false;                              // outside this node's interval (:272)
+        if (!(t < res.t)) return false;                                  // not closer than the best so far (:275)
+        const float4 r1 = __ldg(rec + 1);
+        const float4 r2 = __ldg(rec + 2);
+        const uint32_t flags = __float_as_uint(r2.w);
+        const uint32_t code = flags & 3u;
+        const float o1 = (code == 0u) ? oy : ox, d1 = (code == 0u) ? dy : dx;
+        const float o2 = (code == 2u) ? oy : oz, d2 = (code == 2u) ? dy : dz;
+        const float q0x = (o1 + d1 * t) - r1.x;
+        const float q0y = (o2 + d2 * t) - r1.y;
+        float alpha, beta;
+        if (flags & 4u) {                                                // |q1.x| < eps: uncommon case
+            beta = q0x / r2.x;
+            if (beta < 0.0f || beta > 1.0f) return false;
+            alpha = (q0y - beta * r2.y) / r1.w;
+        } else {
+            const float num = q0y * r1.z - q0x * r1.w, den = r2.z;
+            // RN(num/den) < 0 or > 1 decided without dividing when num, den are ordinary numbers: the rounded quotient
+            // is > 1 exactly when |num| > |den| with equal signs (the next float above |den| already gives a quotient
+            // > 1 + 2^-24), and < 0 exactly when the signs differ and the quotient does not round to -0 (|num| > |den| *
+            // 2^-100 with |den| in (1e-6, 1e6) keeps every intermediate a normal number).  Everything else divides.
+            const float an = fabsf(num), ad = fabsf(den);
+            if (ad > 1e-6f && ad < 1e6f && an < 1e30f) {
+                const bool same = (num < 0.0f) == (den < 0.0f);
+                if (same && an > ad) return false;                       // beta > 1
+                if (!same && an > ad * 7.8886090522101181e-31f) return false;   // beta < 0
+            }
+            beta = num / den;
+            if (beta < 0.0f || beta > 1.0f) return false;
+            alpha = (q0x - beta * r2.x) / r1.z;
+        }
+        if (alpha < 0.0f || (alpha + beta) > 1.0f) return false;
+        res.tri = ti; res.t = t; res.alpha = alpha; res.beta = beta;
+        return true;
+    }
+
     // One leaf (src/scene_intersect.cpp:255-292). true: traversal is over (closest: this leaf produced the hit;
     // ANY: some triangle was accepted).  The acceptance conditions of one triangle -- plane not parallel, t inside
-    // [tmin-eps, tmax+eps], t < best so far, barycentrics inside -- are a pure conjunction, so they are evaluated
-    // cheapest-first; the values they are evaluated ON are computed exactly as Triangle::TestIntersection does.
+    // [tmin-eps, tmax+eps], t < best so far, barycentrics inside -- are a pure conjunction, so the scan applies a cheap
+    // CONSERVATIVE rejection first and defers the survivors: they are evaluated exactly, in leaf order, after the scan
+    // (lanes of the warp then run the rare fp64 path together instead of one at a time).
+    //
+    // Pre-rejection: t32 = -(w + dot2) * rcp.approx(dot).  The sum is one fp32 rounding of the exact sum (2^-24), the
+    // approximate reciprocal and the product add < 2^-22, and the reference's own t is the exact quotient rounded
+    // (2^-24): |t32 - t| < 2^-21 |t|.  A margin of 2^-19 |t32| (+1e-30 against flush-to-zero) therefore never rejects
+    // a triangle the exact test accepts; overflow gives +-inf (correctly outside), NaN compares false (kept).
     __device__ __forceinline__ bool leaf(const DevScene& S, uint2 w, TravCount& cnt) {
         if (COUNT) cnt.leaf++;
         const float eps = S.epsilon;
         const float lo = tmin - eps, hi = tmax + eps;
+        const uint32_t n = w.y >> 2;
+        const uint32_t* __restrict__ rp = S.refs + w.x;
+        uint32_t cand[RGK_CAND_CAP];
+        int nc = 0;
         bool hit = false;
-        const uint32_t n = w.y >> 2, start = w.x;
         for (uint32_t p = 0; p < n; p++) {
-            const uint32_t ti = __ldg(S.refs + start + p);
-            if (COUNT) cnt.refs++;
-            if (ti == ignore) continue;
-            if (COUNT) cnt.tests++;
-            const float4* rec = S.tri_isect + 3 * (size_t)ti;
-            const float4 r0 = __ldg(rec);
-            const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;         // glm::dot(direction, planeN), fp32
-            if (dtf != dtf) continue;                                    // std::isnan(dot)
-            if (dtf < eps && dtf > -eps) continue;                       // parallel to the plane (exact in fp32: both are floats)
+            const uint32_t ti = __ldg(rp + p);
+            const float4 r0 = __ldg(S.tri_isect + 3 * (size_t)ti);
+            if (COUNT) { cnt.refs++; if (ti != ignore) cnt.tests++; }
+            const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;
             const float dot2f = ox * r0.x + oy * r0.y + oz * r0.z;
-            {
-                // Conservative fp32 pre-rejection of "t outside [lo, min(hi, best)]" that avoids the fp64 divide for most
-                // triangles.  n32 = -(w + dot2) has relative error <= 2^-24, the exact t (rounded as the reference
-                // rounds it) differs from n/dt by <= 2^-23 relative, the products lo*dt, hi*dt by 2^-24: a relative
-                // margin of 2^-20 (+ an absolute floor against underflow) can never reject a triangle the exact
-                // test below would accept.  Anything not rejected here goes through the exact evaluation.
-                const float n32 = -(r0.w + dot2f);
-                const float hi2 = ANY ? hi : fminf(hi, res.t);
-                const float a = lo * dtf, b = hi2 * dtf;
-                const float ma = fabsf(a) * 9.5367431640625e-7f + 1e-30f, mb = fabsf(b) * 9.5367431640625e-7f + 1e-30f;
-                const bool pos = dtf > 0.0f;
-                const bool out_lo = pos ? (n32 < a - ma) : (n32 > a + ma);
-                const bool out_hi = pos ? (n32 > b + mb) : (n32 < b - mb);
-                if ((out_lo || out_hi) && fabsf(a) < 1e30f && fabsf(b) < 1e30f && fabsf(n32) < 1e30f) continue;
-            }
-            const float t = (float)(-((double)r0.w + (double)dot2f) / (double)dtf);
-            if (t < lo || t > hi) continue;                              // outside this node's interval (:272)
-            if (!(t < res.t)) continue;                                  // not closer than the best so far (:275)
-            const float4 r1 = __ldg(rec + 1);
-            const float4 r2 = __ldg(rec + 2);
-            const uint32_t flags = __float_as_uint(r2.w);
-            const uint32_t code = flags & 3u;
-            const float o1 = (code == 0u) ? oy : ox, d1 = (code == 0u) ? dy : dx;
-            const float o2 = (code == 2u) ? oy : oz, d2 = (code == 2u) ? dy : dz;
-            const float q0x = (o1 + d1 * t) - r1.x;
-            const float q0y = (o2 + d2 * t) - r1.y;
-            float alpha, beta;
-            if (flags & 4u) {                                            // |q1.x| < eps: uncommon case
-                beta = q0x / r2.x;
-                if (beta < 0.0f || beta > 1.0f) continue;
-                alpha = (q0y - beta * r2.y) / r1.w;
-            } else {
-                const float num = q0y * r1.z - q0x * r1.w, den = r2.z;
-                // RN(num/den) < 0 or > 1 decided without dividing when num, den are ordinary numbers: the rounded
-                // quotient is > 1 exactly when |num| > |den| with equal signs (the next float above |den| already
-                // gives a quotient > 1 + 2^-24), and < 0 exactly when the signs differ and the quotient does not
-                // round to -0 (|num| > |den| * 2^-100 with |den| in (1e-6, 1e6) keeps every intermediate a normal
-                // number).  Everything else divides.
-                const float an = fabsf(num), ad = fabsf(den);
-                if (ad > 1e-6f && ad < 1e6f && an < 1e30f) {
-                    const bool same = (num < 0.0f) == (den < 0.0f);
-                    if (same && an > ad) continue;                       // beta > 1
-                    if (!same && an > ad * 7.8886090522101181e-31f) continue;   // beta < 0
+            float rcp;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(dtf));
+            const float t32 = -(r0.w + dot2f) * rcp;
+            const float m = __fmaf_rn(fabsf(t32), 1.9073486328125e-6f, 1e-30f);
+            const bool reject = (ti == ignore) || (fabsf(dtf) < eps) || (t32 + m < lo) || (t32 - m > hi);
+            if (!reject) {
+                cand[nc++] = ti;
+                if (nc == RGK_CAND_CAP) {          // list full: evaluate what we have, in order
+                    for (int k = 0; k < RGK_CAND_CAP; k++) {
+                        if (exact_test(S, cand[k], lo, hi)) { if (ANY) return true; hit = true; }
+                    }
+                    nc = 0;
                 }
-                beta = num / den;
-                if (beta < 0.0f || beta > 1.0f) continue;
-                alpha = (q0x - beta * r2.x) / r1.z;
             }
-            if (alpha < 0.0f || (alpha + beta) > 1.0f) continue;
-            res.tri = ti; res.t = t; res.alpha = alpha; res.beta = beta;
-            if (ANY) return true;
-            hit = true;
+        }
+        for (int k = 0; k < nc; k++) {
+            if (exact_test(S, cand[k], lo, hi)) { if (ANY) return true; hit = true; }
         }
         return hit;
     }
@@ -164,7 +182,7 @@ struct Traverser {
     __device__ __forceinline__ bool pop(const TravStack& K) {
         if (sp == 0) return false;
         --sp;
-        node = K.node[sp]; tmin = K.tmin[sp]; tmax = K.tmax[sp];
+        node = K.node[sp]; const float2 r = K.range[sp]; tmin = r.x; tmax = r.y;
         return !(tfar < tmin);
     }
 };
@@ -184,7 +202,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, uint32_t cou
     for (;;) {
         __syncwarp();
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle != 0u && !exhausted && (__popc(idle) >= RGK_REFILL_THRESHOLD || idle == 0xffffffffu)) {
+        if (idle != 0u && !exhausted && (__popc(idle) >= (int)S.refill_threshold || idle == 0xffffffffu)) {
             const int leader = __ffs(idle) - 1;
             unsigned long long base = 0;
             if ((int)lane == leader) base = atomicAdd(work, (unsigned long long)__popc(idle));
@@ -237,7 +255,7 @@ __device__ __forceinline__ void trace_voted(const DevScene& S, uint32_t count, u
     uint32_t item = 0, p = 0, pend = 0, cand = 0;
     for (;;) {
         const unsigned m_idle = __ballot_sync(0xffffffffu, mode == TM_IDLE);
-        if (m_idle != 0u && !exhausted && (__popc(m_idle) >= RGK_REFILL_THRESHOLD || m_idle == 0xffffffffu)) {
+        if (m_idle != 0u && !exhausted && (__popc(m_idle) >= (int)S.refill_threshold || m_idle == 0xffffffffu)) {
             const int leader = __ffs(m_idle) - 1;
             unsigned long long base = 0;
             if ((int)lane == leader) base = atomicAdd(work, (unsigned long long)__popc(m_idle));
@@ -348,7 +366,7 @@ __device__ __forceinline__ void trace_voted(const DevScene& S, uint32_t count, u
                     if (tplane > T.tmax || tplane <= 0.0f) T.node = first;
                     else if (tplane < T.tmin) T.node = second;
                     else {
-                        K.node[T.sp] = second; K.tmin[T.sp] = tplane; K.tmax[T.sp] = T.tmax; ++T.sp;
+                        K.node[T.sp] = second; K.range[T.sp] = make_float2(tplane, T.tmax); ++T.sp;
                         T.node = first; T.tmax = tplane;
                     }
                 }

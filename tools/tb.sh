@@ -1,7 +1,7 @@
-for srt in 0 8 32; do RGK_TRAVERSAL=2 python tools/trace_bench.py --sort $srt 2>&1 | python -c "
+for v in ${VARIANTS:-2}; do RGK_TRAVERSAL=$v python tools/trace_bench.py --check 100000 $TB_ARGS 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
     except: print(l.strip()[:300]); continue
-    print('sort=$srt', d['variant'], d['batch'], d['rays'], round(d['ms'],2), 'ms', round(d['Mrays_s']), 'Mrays/s', round(d['bytes_per_ray']), 'B/ray', round(d['GB_s']), 'GB/s', d.get('bit_exact_vs_oracle'))
+    print(d['variant'], d['batch'], d['rays'], round(d['ms'],2), 'ms', round(d['Mrays_s']), 'Mrays/s', round(d['bytes_per_ray']), 'B/ray', round(d['GB_s']), 'GB/s', d.get('bit_exact_vs_oracle'))
 "; done

@@ -57,30 +57,38 @@ template <class T> bool alloc_dev(T** p, size_t n) {
 // / std::shuffle (pairwise) -- SURVEY Appendix C.  One thread per pixel; the 624-word generator state lives in
 // global memory, interleaved across threads (state[k * stride + thread]) so every access is coalesced.
 struct MT {
-    uint32_t* st; size_t stride; int idx;
+    uint32_t* st; size_t stride; int k0, cur;
+    uint32_t buf[8];
     __device__ void seed(uint32_t s) {
         uint32_t prev = s; st[0] = s;
         for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; st[(size_t)i * stride] = prev; }
-        idx = 624;
+        k0 = 0; cur = 8;
     }
-    __device__ void regen() {
-        uint32_t first = st[0], cur = first;
-        for (int k = 0; k < 624; k++) {
-            const uint32_t nxt = (k == 623) ? st[0] : st[(size_t)(k + 1) * stride];
-            const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
-            const int k397 = (k + 397 < 624) ? k + 397 : k + 397 - 624;
-            const uint32_t v = st[(size_t)k397 * stride] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            st[(size_t)k * stride] = v;
-            cur = nxt;
+    // The twist is done incrementally, eight words at a time, right before their tempered values are handed out (the
+    // standard implementation twists all 624 words when the block is exhausted; word k only depends on old k, old k+1
+    // -- new word 0 for k = 623 -- and word k+397 mod 624, old for k < 227 and already renewed for k >= 227, so doing
+    // it in ascending batches yields identical words).  A batch first loads its 17 inputs, then stores its 8 outputs:
+    // one memory round trip per eight draws instead of one per draw.
+    __device__ void fill() {
+        uint32_t own[9], far[8];
+#pragma unroll
+        for (int j = 0; j < 9; j++) { const int k = k0 + j; own[j] = st[(size_t)(k == 624 ? 0 : k) * stride]; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const int k = k0 + j + 397; far[j] = st[(size_t)(k < 624 ? k : k - 624) * stride]; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t y0 = (own[j] & 0x80000000u) | (own[j + 1] & 0x7fffffffu);
+            uint32_t y = far[j] ^ (y0 >> 1) ^ ((y0 & 1u) ? 0x9908b0dfu : 0u);
+            st[(size_t)(k0 + j) * stride] = y;
+            y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+            buf[j] = y;
         }
-        (void)first;
-        idx = 0;
+        k0 = (k0 + 8 == 624) ? 0 : k0 + 8;
+        cur = 0;
     }
     __device__ uint32_t next() {
-        if (idx >= 624) regen();
-        uint32_t y = st[(size_t)(idx++) * stride];
-        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-        return y;
+        if (cur == 8) fill();
+        return buf[cur++];
     }
     // generate_canonical<float,24>: one 32-bit draw / 2^32, result clamped below 1
     __device__ float canonical() {
@@ -119,35 +127,66 @@ __device__ void dev_shuffle(T* base, size_t stride, uint32_t n, MT& g, bool stor
     }
 }
 
-// Tables: t1[(dim * ss + set) * npix + pixel], t2 likewise (float2).  One scratch dim is appended to each
-// table (index n1d / n2d) so that dims nobody reads still have a place to live while the stream advances.
+// Tables: t1[(dim * ss + set) * npix + pixel], t2 likewise (float2).
+// SMEM = true: the two tables of the dimension being built live in shared memory, lane-interleaved
+// (entry k of thread t at [k * blockDim + t]: every swap of the shuffle is bank-conflict free whatever its random
+// position), and are copied out coalesced once shuffled.  SMEM = false (set sizes too large for shared memory):
+// built in place in the global table, one scratch dimension appended for dims nobody reads.
+template <bool SMEM>
 __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
                              float* __restrict__ t1, float2* __restrict__ t2, uint32_t* __restrict__ state) {
+    extern __shared__ float sm[];
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npix) return;
     MT g; g.st = state + p; g.stride = npix;
     g.seed(seeds[p]);
     const float len1 = 1.0f / (float)ss, len2 = 1.0f / (float)sq;
     const uint32_t last_dim = max(n1d, n2d);   // dims >= last_dim are never read: stop there (the stream is not reused)
+    const size_t bd = blockDim.x;
+    float* s1 = sm + threadIdx.x;                                  // ss floats
+    float2* s2 = reinterpret_cast<float2*>(sm + (size_t)ss * bd) + threadIdx.x;   // ss float2 (8-byte lanes: 2-way, still cheap)
     for (uint32_t dim = 0; dim < last_dim; dim++) {
         const bool keep1 = dim < n1d, keep2 = dim < n2d;
-        float* a = t1 + ((size_t)(keep1 ? dim : n1d) * ss) * npix + p;
+        float* out1 = t1 + ((size_t)(keep1 ? dim : n1d) * ss) * npix + p;
+        float* a = SMEM ? s1 : out1;
+        const size_t as = SMEM ? bd : (size_t)npix;
         for (uint32_t k = 0; k < ss; k++) {
             const float begin = (float)k / (float)ss;
             const float v = begin + g.uniform_real(0.0f, len1);
-            if (keep1) a[(size_t)k * npix] = v;
+            if (keep1) a[(size_t)k * as] = v;
         }
-        dev_shuffle(a, (size_t)npix, ss, g, keep1);
-        float2* b = t2 + ((size_t)(keep2 ? dim : n2d) * ss) * npix + p;
+        dev_shuffle(a, as, ss, g, keep1);
+        if (SMEM && keep1) for (uint32_t k = 0; k < ss; k++) out1[(size_t)k * npix] = s1[(size_t)k * bd];
+        float2* out2 = t2 + ((size_t)(keep2 ? dim : n2d) * ss) * npix + p;
+        float2* b = SMEM ? s2 : out2;
         for (uint32_t sy = 0; sy < sq; sy++)
             for (uint32_t sx = 0; sx < sq; sx++) {
                 const float bx = (float)sx / (float)sq, by = (float)sy / (float)sq;
                 const float x = bx + g.uniform_real(0.0f, len2);
                 const float y = by + g.uniform_real(0.0f, len2);
-                if (keep2) b[(size_t)(sy * sq + sx) * npix] = make_float2(x, y);
+                if (keep2) b[(size_t)(sy * sq + sx) * as] = make_float2(x, y);
             }
-        dev_shuffle(b, (size_t)npix, ss, g, keep2);
+        dev_shuffle(b, as, ss, g, keep2);
+        if (SMEM && keep2) for (uint32_t k = 0; k < ss; k++) out2[(size_t)k * npix] = s2[(size_t)k * bd];
     }
+}
+
+// launches the table generation with the best block size the set size allows
+static void launch_sampler_mt(cudaStream_t stream, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
+                              float* t1, float2* t2, uint32_t* state) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_sampler_mt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    static int use_smem = -1;
+    if (use_smem < 0) { const char* e = std::getenv("RGK_SAMPLER_SMEM"); use_smem = (e && e[0] == '0') ? 0 : 1; }
+    for (int bd : {128, 64}) {
+        if (!use_smem) break;
+        const size_t bytes = (size_t)bd * ss * 12;
+        if (bytes <= 100 * 1024 || (bd == 64 && bytes <= 200 * 1024)) {
+            k_sampler_mt<true><<<(npix + bd - 1) / bd, bd, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
+            return;
+        }
+    }
+    k_sampler_mt<false><<<(npix + 127) / 128, 128, 0, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
 }
 
 // Counter-based sampler with the same structure (jittered strata visited in a per-(pixel,dim) random order),
@@ -565,7 +604,7 @@ rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint
         cudaGetLastError(); if (t1) cudaFree(t1); if (t2) cudaFree(t2); if (st) cudaFree(st);
         return rgk_fail(ctx, RGK_ERR_NOMEM, "sampler table allocation failed");
     }
-    k_sampler_mt<<<(n_seeds + 127) / 128, 128, 0, ctx->stream>>>(d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
+    launch_sampler_mt(ctx->stream, d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && n1d) e = cudaMemcpyAsync(d_out1, t1, (size_t)n1d * ss * n_seeds * 4, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -657,7 +696,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed);
         ctx->launches++;
         if (mt) {
-            k_sampler_mt<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
+            launch_sampler_mt(ctx->stream, B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
             ctx->launches++;
         }
         pool.end(ctx->stream);

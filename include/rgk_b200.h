@@ -291,9 +291,11 @@ rgk_status rgk_render_round_device(rgk_context* ctx, const rgk_camera* cam, cons
  * first; (sum,count) returned un-normalised. */
 rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* params,
                             uint32_t rounds, float* rgb_sum, uint32_t* count, rgk_round_stats* stats);
-/* RGK_SAMPLER_TABLES: tables for the pixels of the next rgk_render_round call, in
- * task order then y-major/x-minor: t1d[pixel][dim][set], t2d[pixel][dim][set][2]. */
-rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t n1d, uint32_t n2d,
+/* RGK_SAMPLER_TABLES: the caller supplies the sample tables (what OfflineSampler holds per pixel, src/sampler.hpp:
+ * 62-72) for the pixels of the following rgk_render_round* calls, in task order then y-major/x-minor:
+ * t1d[pixel][dim][set], t2d[pixel][dim][set][2], set = 0 .. rgk_sampler_set_size(multisample)-1.  Needs at least
+ * 1 + depth 1-D dims and 4 (+1 with a lens) + depth 2-D dims.  Copied to the device at once. */
+rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t multisample, uint32_t n1d, uint32_t n2d,
                                  const float* t1d, const float* t2d, uint64_t n_pixels);
 
 /* Tile sharding across GPUs: of every task list given to rgk_render_round*, this context renders only

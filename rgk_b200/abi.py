@@ -172,7 +172,7 @@ def load_library(path=None):
     lib.rgk_render_round_device.argtypes = rr
     lib.rgk_render_frame.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_uint32, vp, vp,
                                      C.POINTER(RoundStats)]
-    lib.rgk_render_set_tables.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64]
+    lib.rgk_render_set_tables.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64]
     lib.rgk_synchronize.argtypes = [vp]
     lib.rgk_probe.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
     lib.rgk_render_set_counting.argtypes = [vp, C.c_int]

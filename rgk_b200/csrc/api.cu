@@ -489,10 +489,21 @@ rgk_status rgk_render_get_trav_stats(const rgk_context* ctx, rgk_trav_stats* clo
     return RGK_OK;
 }
 
-rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t n1d, uint32_t n2d, const float* t1d, const float* t2d, uint64_t n_pixels) {
-    if (!ctx || n1d > 64 || n2d > 64) return RGK_ERR_INVALID;
-    (void)t1d; (void)t2d; (void)n_pixels;
-    return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "RGK_SAMPLER_TABLES is not implemented yet; use RGK_SAMPLER_MT19937 (bit-exact device sampler)");
+rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t multisample, uint32_t n1d, uint32_t n2d, const float* t1d, const float* t2d,
+                                 uint64_t n_pixels) {
+    if (!ctx || multisample == 0 || n1d == 0 || n2d == 0 || n1d > 64 || n2d > 64 || !t1d || !t2d || n_pixels == 0) return RGK_ERR_INVALID;
+    RGK_CUDA(ctx, cudaSetDevice(ctx->device));
+    RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t ss = host_sampler_set_size(multisample);
+    if (ctx->d_user_t1) { cudaFree(ctx->d_user_t1); ctx->d_user_t1 = nullptr; }
+    if (ctx->d_user_t2) { cudaFree(ctx->d_user_t2); ctx->d_user_t2 = nullptr; }
+    const size_t b1 = (size_t)n_pixels * n1d * ss * 4, b2 = (size_t)n_pixels * n2d * ss * 8;
+    RGK_CUDA(ctx, cudaMalloc((void**)&ctx->d_user_t1, b1));
+    RGK_CUDA(ctx, cudaMalloc((void**)&ctx->d_user_t2, b2));
+    RGK_CUDA(ctx, cudaMemcpy(ctx->d_user_t1, t1d, b1, cudaMemcpyHostToDevice));
+    RGK_CUDA(ctx, cudaMemcpy(ctx->d_user_t2, t2d, b2, cudaMemcpyHostToDevice));
+    ctx->user_n1d = n1d; ctx->user_n2d = n2d; ctx->user_ss = ss; ctx->user_npix = n_pixels;
+    return RGK_OK;
 }
 
 } // extern "C"

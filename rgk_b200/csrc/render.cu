@@ -26,7 +26,7 @@ struct PathBuffers {
     float4 *light_pos = nullptr, *light_col = nullptr, *light_nrm = nullptr;
     float4 *sh_pos = nullptr, *sh_direct = nullptr, *sh_emis = nullptr, *sh_contrib = nullptr;
     uint32_t *last_tri = nullptr, *cur1 = nullptr, *queue_a = nullptr, *queue_b = nullptr, *queue_s = nullptr;
-    uint32_t *pix_xy = nullptr, *pix_seed = nullptr;
+    uint32_t *pix_xy = nullptr, *pix_seed = nullptr, *pix_src = nullptr;   // pix_src: index of the pixel in call order (task order, y-major)
     uint32_t *mt_state = nullptr;
     float *t1 = nullptr; float2 *t2 = nullptr;
     uint4 *tiles = nullptr; uint2 *tiles2 = nullptr;
@@ -171,6 +171,22 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
     }
 }
 
+// RGK_SAMPLER_TABLES: caller tables [pixel in call order][dim][set] -> chunk layout [dim][set][pixel position]
+__global__ void k_tables_from_user(const float* __restrict__ u1, const float* __restrict__ u2, uint32_t un1, uint32_t un2,
+                                   const uint32_t* __restrict__ pix_src, uint32_t npix, uint32_t ss, uint32_t n1d, uint32_t n2d,
+                                   float* __restrict__ t1, float2* __restrict__ t2) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const size_t src = pix_src[p];
+    for (uint32_t d = 0; d < n1d && d < un1; d++)
+        for (uint32_t k = 0; k < ss; k++) t1[((size_t)d * ss + k) * npix + p] = u1[(src * un1 + d) * ss + k];
+    for (uint32_t d = 0; d < n2d && d < un2; d++)
+        for (uint32_t k = 0; k < ss; k++) {
+            const float* q = u2 + ((src * un2 + d) * ss + k) * 2;
+            t2[((size_t)d * ss + k) * npix + p] = make_float2(q[0], q[1]);
+        }
+}
+
 // launches the table generation with the best block size the set size allows
 static void launch_sampler_mt(cudaStream_t stream, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
                               float* t1, float2* t2, uint32_t* state) {
@@ -226,7 +242,8 @@ struct SamplerView {
 // ------------------------------------------------------------------ kernels
 // tiles[i] = (x1, x2, y1, y2); tiles2[i] = (first pixel of the tile inside the chunk, tile seed)
 __global__ void k_pixel_setup(const uint4* __restrict__ tiles, const uint2* __restrict__ tiles2,
-                              uint32_t* __restrict__ pix_xy, uint32_t* __restrict__ pix_seed) {
+                              uint32_t* __restrict__ pix_xy, uint32_t* __restrict__ pix_seed, uint32_t* __restrict__ pix_src,
+                              uint32_t first_call_pixel) {
     const uint4 t = tiles[blockIdx.x];
     const uint2 u = tiles2[blockIdx.x];
     const uint32_t w = t.y - t.x, n = w * (t.w - t.z);
@@ -239,6 +256,7 @@ __global__ void k_pixel_setup(const uint4* __restrict__ tiles, const uint2* __re
         pix_xy[u.x + pos] = (t.x + lx) | ((t.z + ly) << 16);
         // PathTracer::RenderPixel: samplerSeed += 0x42424242 before every pixel, y-major / x-minor (src/tracer.cpp:8-9)
         pix_seed[u.x + pos] = u.y + (k + 1u) * 0x42424242u;
+        pix_src[u.x + pos] = first_call_pixel + u.x + k;
     }
 }
 
@@ -543,7 +561,7 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
     }
     if (ok && pixels > B.cap_pixels) {
         RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ok = alloc_dev(&B.pix_xy, pixels) && alloc_dev(&B.pix_seed, pixels);
+        ok = alloc_dev(&B.pix_xy, pixels) && alloc_dev(&B.pix_seed, pixels) && alloc_dev(&B.pix_src, pixels);
         if (ok && B.mt_state) { cudaFree(B.mt_state); B.mt_state = nullptr; }
         B.cap_pixels = ok ? pixels : 0;
     }
@@ -566,7 +584,7 @@ void free_path_buffers(rgk_context* ctx) {
     if (!ctx->paths) return;
     PathBuffers& B = *ctx->paths;
     void* ptrs[] = {B.ray_o, B.ray_d, B.hit, B.cum, B.tot, B.light_pos, B.light_col, B.light_nrm, B.sh_pos, B.sh_direct, B.sh_emis,
-                    B.sh_contrib, B.last_tri, B.cur1, B.queue_a, B.queue_b, B.queue_s, B.pix_xy, B.pix_seed, B.mt_state, B.t1, B.t2,
+                    B.sh_contrib, B.last_tri, B.cur1, B.queue_a, B.queue_b, B.queue_s, B.pix_xy, B.pix_seed, B.pix_src, B.mt_state, B.t1, B.t2,
                     B.tiles, B.tiles2, B.counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (B.h_counters) cudaFreeHost(B.h_counters);
@@ -640,11 +658,20 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const uint32_t lens = cam->lens_size != 0.0f ? 1u : 0u;
     const uint32_t base2 = 4u + lens;                  // 2-D dims: jitter, [lens], areal, lightdir, choice, then one per bounce
     const uint32_t n2d = base2 + P->depth, n1d = 1u + P->depth;
-    if (P->sampler_mode == RGK_SAMPLER_TABLES) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "RGK_SAMPLER_TABLES is not implemented yet");
+    const bool user_tables = P->sampler_mode == RGK_SAMPLER_TABLES;
+    if (user_tables) {
+        uint64_t need = 0;
+        for (uint32_t i = ctx->shard_first; i < n_tasks; i += (ctx->shard_stride ? ctx->shard_stride : 1u)) need += (uint64_t)(tasks[i].x2 - tasks[i].x1) * (tasks[i].y2 - tasks[i].y1);
+        if (!ctx->d_user_t1 || !ctx->d_user_t2 || ctx->user_npix < need || ctx->user_n1d < n1d || ctx->user_n2d < n2d || ctx->user_ss != ss)
+            return rgk_fail(ctx, RGK_ERR_INVALID, "RGK_SAMPLER_TABLES: rgk_render_set_tables must supply tables for every pixel of the call, "
+                                                  "at least 1+depth 1-D and 4(+1 with a lens)+depth 2-D dims, set size rgk_sampler_set_size(multisample)");
+    }
     if (P->sampler_mode == RGK_SAMPLER_MT19937 && (n2d > 64 || n1d > 64))
         return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "recursion-max above 59 leaves the 64 tabulated sampler dimensions (live-generator fallback, src/sampler.cpp:26-36, is not replicated)");
     if ((uint64_t)ss * ss > 0xFFFFFFFFull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "multisample too large");
     const bool mt = P->sampler_mode == RGK_SAMPLER_MT19937;
+    const bool tables = mt || user_tables;
+    size_t call_pixels = 0;
     const bool counting = ctx->counting;
     const int variant = rgk_traversal_variant();
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 8);
@@ -653,7 +680,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
 
     // chunking: whole tiles, every multisample of a pixel in the same chunk
     const size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)16 << 20);
-    const size_t per_pixel_table = mt ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
+    const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
     const size_t max_table_bytes = env_size("RGK_TABLE_BYTES", (size_t)24 << 30);
     std::vector<uint4> h_tiles; std::vector<uint2> h_tiles2;
     rgk_round_stats total{};
@@ -681,7 +708,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         if (npix == 0) continue;
         const size_t npaths = npix * ms;
         if (npaths > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "a single chunk exceeds 2^32 paths");
-        rgk_status s = ensure_buffers(ctx, npaths, npix, mt ? (size_t)(n1d + 1) * ss * npix : 0, mt ? (size_t)(n2d + 1) * ss * npix : 0,
+        rgk_status s = ensure_buffers(ctx, npaths, npix, tables ? (size_t)(n1d + 1) * ss * npix : 0, tables ? (size_t)(n2d + 1) * ss * npix : 0,
                                       h_tiles.size(), mt);
         if (s != RGK_OK) return s;
         PathBuffers& B = *ctx->paths;
@@ -693,12 +720,17 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         R.lens = lens; R.npix = (uint32_t)npix;
         SamplerView smp{B.t1, B.t2, (uint32_t)npix, ss, sq, P->sampler_mode};
         pool.begin(ctx->stream, T_SAMPLER);
-        k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed);
+        k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed, B.pix_src, (uint32_t)call_pixels);
         ctx->launches++;
         if (mt) {
             launch_sampler_mt(ctx->stream, B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
             ctx->launches++;
+        } else if (user_tables) {
+            k_tables_from_user<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_user_t1, ctx->d_user_t2, ctx->user_n1d, ctx->user_n2d,
+                                                                                       B.pix_src, (uint32_t)npix, ss, n1d, n2d, B.t1, B.t2);
+            ctx->launches++;
         }
+        call_pixels += npix;
         pool.end(ctx->stream);
         pool.begin(ctx->stream, T_SHADE);
         k_raygen<<<(unsigned)((npaths + 127) / 128), 128, 0, ctx->stream>>>(ctx->dev, R, smp, B);

@@ -98,7 +98,7 @@ struct rgk_context {
     PathBuffers* paths = nullptr;
     uint64_t launches = 0;
     // caller-supplied sampler tables (RGK_SAMPLER_TABLES)
-    float* d_user_t1 = nullptr; float* d_user_t2 = nullptr; uint32_t user_n1d = 0, user_n2d = 0; uint64_t user_npix = 0;
+    float* d_user_t1 = nullptr; float* d_user_t2 = nullptr; uint32_t user_n1d = 0, user_n2d = 0, user_ss = 0; uint64_t user_npix = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool counting = false;
     uint32_t shard_first = 0, shard_stride = 1;   // rgk_render_set_shard

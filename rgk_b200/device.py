@@ -165,6 +165,12 @@ class Context:
         self._check(self.lib.rgk_probe(self.h, kind, index, _p(rows), C.c_uint64(len(rows)), _p(out)))
         return out
 
+    def set_tables(self, multisample, t1, t2):
+        """t1[pixel][dim][set], t2[pixel][dim][set][2] for the pixels of the next render calls (RGK_SAMPLER_TABLES)."""
+        t1 = np.ascontiguousarray(t1, np.float32)
+        t2 = np.ascontiguousarray(t2, np.float32)
+        self._check(self.lib.rgk_render_set_tables(self.h, multisample, t1.shape[1], t2.shape[1], _p(t1), _p(t2), C.c_uint64(t1.shape[0])))
+
     def set_shard(self, first, stride):
         self._check(self.lib.rgk_render_set_shard(self.h, first, stride))
 

@@ -94,3 +94,68 @@ def test_error_paths(gpu_ctx):
     with pytest.raises(RgkError) as e:
         gpu_ctx.render_round(cam, p, gpu_ctx.generate_tasks(32, 32, 32))
     assert e.value.status == 6
+
+
+def _pixel_seeds(tasks, seedstart=42, seedcount_base=0):
+    """Seeds of the pixels of a call in task order, y-major/x-minor (src/render_driver.cpp:160,173, src/path_tracer.cpp:47)."""
+    out = []
+    for i, t in enumerate(tasks):
+        n = (t.x2 - t.x1) * (t.y2 - t.y1)
+        base = (seedstart + seedcount_base + i) & 0xFFFFFFFF
+        out.append((base + (np.arange(1, n + 1, dtype=np.uint64) * 0x42424242)) & 0xFFFFFFFF)
+    return np.concatenate(out).astype(np.uint32)
+
+
+def test_caller_supplied_tables_equal_device_sampler(gpu_ctx, oracle):
+    """RGK_SAMPLER_TABLES fed with the oracle's StratifiedSampler tables gives the image of RGK_SAMPLER_MT19937 bit for
+    bit (lens camera -> one more 2-D dim; multisample 9 -> odd set size; 40x24 -> ragged tiles)."""
+    pack, cfg = scenes.material_zoo(width=40, height=24, multisample=9, recursion_max=3, lens=0.04)
+    desc = pack.desc()
+    gpu_ctx.commit(desc)
+    cam = gpu_ctx.camera(**cfg.camera_args())
+    tasks = gpu_ctx.generate_tasks(32, 40, 24)
+    f_mt, c_mt, _ = gpu_ctx.render_round(cam, cfg.params(abi.SAMPLER_MT19937), tasks, seedcount_base=7)
+    n1d, n2d = 1 + 3, 5 + 3
+    t1, t2 = oracle.sampler_tables(_pixel_seeds(tasks, 42, 7), 9, n1d, n2d)
+    gpu_ctx.set_tables(9, t1, t2)
+    f_tb, c_tb, _ = gpu_ctx.render_round(cam, cfg.params(abi.SAMPLER_TABLES), tasks, seedcount_base=7)
+    assert np.array_equal(f_mt.view(np.uint32), f_tb.view(np.uint32)) and np.array_equal(c_mt, c_tb)
+    ho = oracle.scene_create(desc)
+    fo, _, _ = oracle.render_round(ho, cam, cfg.params(), tasks, seedcount_base=7)
+    assert abs(float(f_mt.mean()) - float(fo.mean())) <= 2e-3 * float(fo.mean())
+
+
+def test_tile_sharding_is_independent_of_n(gpu_ctx):
+    """rgk_render_set_shard: the union of N tile-sharded renders equals the unsharded round pixel for pixel."""
+    pack, cfg = scenes.load_builtin("cornell-box", width=96, height=80, multisample=4, recursion_max=5)
+    gpu_ctx.commit(pack.desc())
+    cam = gpu_ctx.camera(**cfg.camera_args())
+    p = cfg.params()
+    tasks = gpu_ctx.generate_tasks(32, 96, 80)
+    full, cfull, _ = gpu_ctx.render_round(cam, p, tasks, seedcount_base=3)
+    try:
+        for n in (2, 3):
+            fb = (np.zeros_like(full), np.zeros_like(cfull))
+            for r in range(n):
+                gpu_ctx.set_shard(r, n)
+                gpu_ctx.render_round(cam, p, tasks, seedcount_base=3, fb=fb)
+            assert np.array_equal(fb[0].view(np.uint32), full.view(np.uint32)) and np.array_equal(fb[1], cfull)
+    finally:
+        gpu_ctx.set_shard(0, 1)
+
+
+def test_chunking_does_not_change_the_image(gpu_ctx, monkeypatch):
+    """Tiny chunks (RGK_CHUNK_PATHS) split the tile list into many passes; the result must be identical."""
+    pack, cfg = scenes.load_builtin("cornell-box", width=96, height=64, multisample=4, recursion_max=4)
+    gpu_ctx.commit(pack.desc())
+    cam = gpu_ctx.camera(**cfg.camera_args())
+    p = cfg.params()
+    tasks = gpu_ctx.generate_tasks(32, 96, 64)
+    a, ca, sa = gpu_ctx.render_round(cam, p, tasks)
+    monkeypatch.setenv("RGK_CHUNK_PATHS", "5000")
+    b, cb, sb = gpu_ctx.render_round(cam, p, tasks)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ca, cb)
+    assert int(sb.kernel_launches) > int(sa.kernel_launches)
+    empty = (abi.Task * 0)()
+    z, cz, sz = gpu_ctx.render_round(cam, p, empty)
+    assert not z.any() and int(sz.samples) == 0

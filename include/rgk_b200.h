@@ -213,6 +213,8 @@ typedef struct rgk_round_stats {
     float sampler_ms;         /* sampler table generation */
     float shade_ms;           /* raygen + shade + finish */
     uint32_t closest_launches, shadow_launches;
+    uint64_t shadow_rays_skipped; /* Visibility calls of the reference not traced because their direct term is exactly 0
+                                     (the result cannot depend on them); shadow_rays counts traced rays only */
 } rgk_round_stats;
 
 /* ---- entry points ------------------------------------------------------- */

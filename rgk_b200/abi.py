@@ -114,7 +114,7 @@ class RoundStats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("samples", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("gpu_ms", C.c_float), ("trace_ms", C.c_float),
                 ("closest_ms", C.c_float), ("shadow_ms", C.c_float), ("sampler_ms", C.c_float), ("shade_ms", C.c_float),
-                ("closest_launches", C.c_uint32), ("shadow_launches", C.c_uint32)]
+                ("closest_launches", C.c_uint32), ("shadow_launches", C.c_uint32), ("shadow_rays_skipped", C.c_uint64)]
 
     def as_dict(self):
         return {k: (int(getattr(self, k)) if "ms" not in k else float(getattr(self, k))) for k, _ in self._fields_}

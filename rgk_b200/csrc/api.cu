@@ -465,6 +465,7 @@ rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_r
         total.kernel_launches += rs.kernel_launches; total.gpu_ms += rs.gpu_ms; total.trace_ms += rs.trace_ms;
         total.closest_ms += rs.closest_ms; total.shadow_ms += rs.shadow_ms; total.sampler_ms += rs.sampler_ms; total.shade_ms += rs.shade_ms;
         total.closest_launches += rs.closest_launches; total.shadow_launches += rs.shadow_launches;
+        total.shadow_rays_skipped += rs.shadow_rays_skipped;
     }
     RGK_CUDA(ctx, cudaMemcpyAsync(rgb_sum, d_rgb, npx * 12, cudaMemcpyDeviceToHost, ctx->stream));
     RGK_CUDA(ctx, cudaMemcpyAsync(count, d_cnt, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));

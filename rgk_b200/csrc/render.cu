@@ -35,13 +35,13 @@ struct PathBuffers {
     struct EventPool* events = nullptr;       // host only
 };
 
-enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_CLOSEST_RAYS = 4, C_SHADOW_RAYS = 5, C_COUNT = 8 };
+enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_SHADOW_SKIPPED = 4, C_COUNT = 8 };
 
 struct RenderConst {
     rgk_camera cam;
     uint32_t xres, yres, ms, depth;
     float clamp, russian, bump_scale;
-    uint32_t set_size, n1d, n2d, base2, sampler_mode, lens;
+    uint32_t set_size, n1d, n2d, base2, sampler_mode, lens, skip_null_shadow;
     uint32_t npix;          // pixels in the chunk
 };
 
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(128)
 k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count,
         uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, unsigned long long* counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool cont = false, shadow = false;
+    bool cont = false, shadow = false, null_shadow = false;
     uint32_t slot = 0;
     if (i < count) {
         slot = queue ? __ldg(queue + i) : i;
@@ -459,12 +459,19 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                     if (lflags & 2u) df = gmax(0.0f, dot(-Vi, v3(B.light_nrm[slot])));
                     const float k = lc.w * df;
                     const RGB inc = rgb(lc.x * k, lc.y * k, lc.z * k);
-                    B.sh_pos[slot] = make_float4(pos.x, pos.y, pos.z, 0.0f);
-                    B.sh_direct[slot] = make_float4(inc.r * (G * f.r), inc.g * (G * f.g), inc.b * (G * f.b), 0.0f);
-                    B.sh_emis[slot] = make_float4(emis.r, emis.g, emis.b, 0.0f);
-                    B.sh_contrib[slot] = make_float4(contribution.r, contribution.g, contribution.b, 0.0f);
-                    shadow = true;
-                } else {
+                    const RGB direct = rgb(inc.r * (G * f.r), inc.g * (G * f.g), inc.b * (G * f.b));
+                    // A direct term that is exactly zero (light behind the surface: BxDF::value returns Spectrum(0) for
+                    // Vi.z <= 0; hemisphere light facing away) contributes 0 whether or not the light is visible, so the
+                    // Visibility query cannot change the pixel: it is not traced (R.skip_null_shadow, on by default).
+                    if (!(R.skip_null_shadow && direct.r == 0.0f && direct.g == 0.0f && direct.b == 0.0f)) {
+                        B.sh_pos[slot] = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                        B.sh_direct[slot] = make_float4(direct.r, direct.g, direct.b, 0.0f);
+                        B.sh_emis[slot] = make_float4(emis.r, emis.g, emis.b, 0.0f);
+                        B.sh_contrib[slot] = make_float4(contribution.r, contribution.g, contribution.b, 0.0f);
+                        shadow = true;
+                    } else null_shadow = true;
+                }
+                if (!shadow) {
                     RGB here = emis;
                     if (here.r > R.clamp) here.r = R.clamp;
                     if (here.g > R.clamp) here.g = R.clamp;
@@ -507,6 +514,10 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
     }
     push_queue(next_queue, counters + C_NEXT, cont, slot);
     push_queue(shadow_queue, counters + C_SHADOW, shadow, slot);
+    {   // Visibility queries of the reference that were provably irrelevant and therefore not traced
+        const unsigned m = __ballot_sync(0xffffffffu, null_shadow);
+        if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + C_SHADOW_SKIPPED, (unsigned long long)__popc(m));
+    }
 }
 
 // TracePath's epilogue (clamp, NaN/negative guard, src/path_tracer.cpp:501-507), RenderPixel's in-order sum
@@ -537,6 +548,12 @@ int machine_blocks(rgk_context* ctx, const void* kernel, int threads) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, threads, 0);
     return sms * std::max(per, 1);
+}
+
+bool env_flag(const char* name, bool def) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return def;
+    return v[0] != '0';
 }
 
 size_t env_size(const char* name, size_t def) {
@@ -673,6 +690,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const bool tables = mt || user_tables;
     size_t call_pixels = 0;
     const bool counting = ctx->counting;
+    const uint32_t skip_null = env_flag("RGK_SKIP_NULL_SHADOW", true) ? 1u : 0u;
     const int variant = rgk_traversal_variant();
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 8);
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
@@ -717,7 +735,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         RenderConst R{};
         R.cam = *cam; R.xres = P->xres; R.yres = P->yres; R.ms = ms; R.depth = P->depth; R.clamp = P->clamp; R.russian = P->russian;
         R.bump_scale = P->bumpmap_scale; R.set_size = ss; R.n1d = n1d; R.n2d = n2d; R.base2 = base2; R.sampler_mode = P->sampler_mode;
-        R.lens = lens; R.npix = (uint32_t)npix;
+        R.lens = lens; R.npix = (uint32_t)npix; R.skip_null_shadow = skip_null;
         SamplerView smp{B.t1, B.t2, (uint32_t)npix, ss, sq, P->sampler_mode};
         pool.begin(ctx->stream, T_SAMPLER);
         k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed, B.pix_src, (uint32_t)call_pixels);
@@ -743,7 +761,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         const uint32_t* queue = nullptr;
         uint32_t* qnext = B.queue_a;
         for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {
-            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
             const int g1 = (int)std::min<uint64_t>(tgrid, ((uint64_t)count + TRACE_THREADS - 1) / TRACE_THREADS);
             // camera rays (and the shadow rays of their hit points) are coherent: keep warps in lockstep (refill only
             // when the whole warp is done); later bounces are incoherent: refill as soon as a quarter of the warp idles
@@ -758,10 +776,10 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
             pool.end(ctx->stream);
             ctx->launches += 2; total.closest_launches++;
-            RGK_CUDA(ctx, cudaMemcpyAsync(B.h_counters, B.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            RGK_CUDA(ctx, cudaMemcpyAsync(B.h_counters, B.counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
             RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             const uint32_t next_count = (uint32_t)B.h_counters[C_NEXT], shadow_count = (uint32_t)B.h_counters[C_SHADOW];
-            total.closest_rays += count; total.shadow_rays += shadow_count;
+            total.closest_rays += count; total.shadow_rays += shadow_count; total.shadow_rays_skipped += B.h_counters[C_SHADOW_SKIPPED];
             if (shadow_count) {
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);

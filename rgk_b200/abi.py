@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librgk_b200.so")
+LIB_PATH = os.environ.get("RGK_B200_LIB") or os.path.join(_HERE, "librgk_b200.so")   # RGK_B200_LIB: A/B builds of the same library
 
 RGK_NO_TRIANGLE = 0xFFFFFFFF
 (BXDF_DIFFUSE, BXDF_MIX, BXDF_DIELECTRIC, BXDF_MIRROR, BXDF_TRANSPARENT, BXDF_LTC_BECKMANN,

@@ -333,12 +333,12 @@ __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays,
 }
 
 // closest-hit over the live queue (queue == nullptr: identity), persistent warps
-template <bool COUNT, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS)
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, rgk_trav_stats* stats) {
     TravCount cnt{0, 0, 0, 0};
     uint32_t mine = 0;
-    trace_rays<VARIANT, false, COUNT>(S, count, work, cnt, mine,
+    trace_rays<2, false, COUNT>(S, count, work, cnt, mine,
         [&](uint32_t i, Traverser<false, COUNT>& T) {
             const uint32_t slot = queue ? __ldg(queue + i) : i;
             const float4 o = B.ray_o[slot], d = B.ray_d[slot];
@@ -352,12 +352,12 @@ k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_
 }
 
 // shadow traversal fused with the NEE resolve (src/path_tracer.cpp:431-460,485-496)
-template <bool COUNT, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS)
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, rgk_trav_stats* stats) {
     TravCount cnt{0, 0, 0, 0};
     uint32_t mine = 0;
-    trace_rays<VARIANT, true, COUNT>(S, count, work, cnt, mine,
+    trace_rays<2, true, COUNT>(S, count, work, cnt, mine,
         [&](uint32_t i, Traverser<true, COUNT>& T) {
             const uint32_t slot = __ldg(queue + i);
             const float4 a = B.light_pos[slot], b = B.sh_pos[slot];
@@ -691,7 +691,6 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     size_t call_pixels = 0;
     const bool counting = ctx->counting;
     const uint32_t skip_null = env_flag("RGK_SKIP_NULL_SHADOW", true) ? 1u : 0u;
-    const int variant = rgk_traversal_variant();
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 8);
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
@@ -756,7 +755,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         ctx->launches++;
         RGK_CUDA(ctx, cudaGetLastError());
 
-        const int tgrid = machine_blocks(ctx, counting ? (const void*)k_closest<true, 2> : (const void*)k_closest<false, 2>, TRACE_THREADS);
+        const int tgrid = machine_blocks(ctx, counting ? (const void*)k_closest<true, 9> : (const void*)k_closest<false, 12>, TRACE_THREADS);
         uint32_t count = (uint32_t)npaths;
         const uint32_t* queue = nullptr;
         uint32_t* qnext = B.queue_a;
@@ -768,9 +767,11 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             DevScene dev = ctx->dev;
             dev.refill_threshold = bounce == 0 ? refill_coherent : refill_incoherent;
             pool.begin(ctx->stream, T_CLOSEST);
-            if (counting) k_closest<true, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
-            else if (variant == 3) k_closest<false, 3><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
-            else k_closest<false, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
+            // two register budgets of the same kernel: 56 registers (9 CTAs/SM) for the issue-bound coherent camera rays,
+            // 40 registers (12 CTAs/SM) for later bounces, which are latency-bound and gain from the extra warps
+            if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
+            else if (bounce == 0) k_closest<false, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
+            else k_closest<false, 12><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             pool.end(ctx->stream);
             pool.begin(ctx->stream, T_SHADE);
             k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
@@ -783,9 +784,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             if (shadow_count) {
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
-                if (counting) k_shadow<true, 2><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1);
-                else if (variant == 3) k_shadow<false, 3><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
-                else k_shadow<false, 2><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
+                if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1);
+                else k_shadow<false, 12><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
                 pool.end(ctx->stream);
                 ctx->launches++; total.shadow_launches++;
             }

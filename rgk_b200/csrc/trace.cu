@@ -9,7 +9,13 @@
 
 namespace {
 
-constexpr int TRACE_THREADS_MAX = 256;
+#ifndef RGK_MIN_BLOCKS
+#define RGK_MIN_BLOCKS 1
+#endif
+#ifndef RGK_TRACE_THREADS_MAX
+#define RGK_TRACE_THREADS_MAX 256
+#endif
+constexpr int TRACE_THREADS_MAX = RGK_TRACE_THREADS_MAX;
 static int trace_threads() { static int t = 0; if (!t) { const char* e = std::getenv("RGK_TRACE_THREADS"); t = e ? std::atoi(e) : 128; if (t != 64 && t != 128 && t != 256) t = 128; } return t; }
 
 template <bool COUNT>
@@ -32,7 +38,7 @@ __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays,
 }
 
 template <bool COUNT, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS_MAX)
+__global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
 k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, uint64_t n,
                 rgk_hit* __restrict__ hits, rgk_trav_stats* stats, unsigned long long* next) {
     TravCount cnt{0, 0, 0, 0};
@@ -54,7 +60,7 @@ k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __
 }
 
 template <bool COUNT, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS_MAX)
+__global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
 k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, uint64_t n,
                uint8_t* __restrict__ visible, rgk_trav_stats* stats, unsigned long long* next) {
     TravCount cnt{0, 0, 0, 0};
@@ -78,7 +84,7 @@ k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict
 // RGK_TRAVERSAL=2|3 selects the traversal control structure (A/B knob for profiling; results are identical)
 int rgk_traversal_variant() {
     static int v = 0;
-    if (!v) { const char* e = std::getenv("RGK_TRAVERSAL"); v = (e && e[0] == '3') ? 3 : 2; }
+    if (!v) { const char* e = std::getenv("RGK_TRAVERSAL"); v = (e && e[0] >= '3' && e[0] <= '5') ? (e[0] - '0') : 2; }
     return v;
 }
 
@@ -107,6 +113,8 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
     const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + trace_threads() / 32 - 1) / (trace_threads() / 32));
     const int variant = rgk_traversal_variant();
     if (d_stats) k_trace_closest<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
+    else if (variant == 5) k_trace_closest<false, 5><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
+    else if (variant == 4) k_trace_closest<false, 4><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     else if (variant == 3) k_trace_closest<false, 3><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     else k_trace_closest<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     ctx->launches++;
@@ -125,6 +133,8 @@ rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* 
     const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + trace_threads() / 32 - 1) / (trace_threads() / 32));
     const int variant = rgk_traversal_variant();
     if (d_stats) k_trace_shadow<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
+    else if (variant == 5) k_trace_shadow<false, 5><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
+    else if (variant == 4) k_trace_shadow<false, 4><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     else if (variant == 3) k_trace_shadow<false, 3><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     else k_trace_shadow<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     ctx->launches++;

@@ -58,10 +58,18 @@ struct Traverser {
 
     // Inner-node steps until `node` is a leaf (src/scene_intersect.cpp:294-321). Pushing one child and popping it
     // straight away, as the reference does, is the same as stepping into it: the re-checked tfar < tmin is unchanged.
+    // PREFETCH: the words of BOTH children are requested as soon as the node word is known and the chosen one is
+    // selected afterwards, which takes the node-load latency out of the per-level dependency chain (the decision
+    // arithmetic overlaps with the loads).  Pays one extra load per level; used for incoherent batches, which are
+    // latency-bound rather than issue-bound.
+    template <bool PREFETCH>
     __device__ __forceinline__ uint2 descend(const DevScene& S, TravStack& K, TravCount& cnt) {
         uint2 w = __ldg(S.nodes + node);
         while ((w.y & 3u) != 3u) {
             if (COUNT) cnt.inner++;
+            const uint32_t other = w.y >> 2, near = node + 1u;
+            uint2 wn, wo;
+            if (PREFETCH) { wn = __ldg(S.nodes + near); wo = __ldg(S.nodes + other); }
             const uint32_t axis = w.y & 3u;
             const float split = __uint_as_float(w.x);
             const float oa = axis == 0u ? ox : (axis == 1u ? oy : oz);
@@ -73,16 +81,18 @@ struct Traverser {
                 const float da = axis == 0u ? dx : (axis == 1u ? dy : dz);
                 below_first = da <= 0.0f;
             }
-            const uint32_t other = w.y >> 2, near = node + 1u;
             const uint32_t first = below_first ? near : other;
             const uint32_t second = below_first ? other : near;
-            if (tplane > tmax || tplane <= 0.0f) node = first;
-            else if (tplane < tmin) node = second;
+            bool take_first = true;
+            if (tplane > tmax || tplane <= 0.0f) {}
+            else if (tplane < tmin) take_first = false;
             else {
                 K.node[sp] = second; K.range[sp] = make_float2(tplane, tmax); ++sp;
-                node = first; tmax = tplane;
+                tmax = tplane;
             }
-            w = __ldg(S.nodes + node);
+            node = take_first ? first : second;
+            if (PREFETCH) w = (node == near) ? wn : wo;
+            else w = __ldg(S.nodes + node);
         }
         return w;
     }
@@ -191,7 +201,7 @@ struct Traverser {
 // `commit(i, found, res)` stores the result.  Every lane owns one ray at a time; lanes whose ray is finished
 // stay idle until at least RGK_REFILL_THRESHOLD lanes of the warp are idle (or all are), then the warp grabs
 // that many new items from the global counter with one atomic (warp-ballot work redistribution).
-template <bool ANY, bool COUNT, class Fetch, class Commit>
+template <bool ANY, bool COUNT, bool PREFETCH, class Fetch, class Commit>
 __device__ __forceinline__ void trace_persistent(const DevScene& S, uint32_t count, unsigned long long* work,
                                                  TravCount& cnt, uint32_t& done, Fetch fetch, Commit commit) {
     Traverser<ANY, COUNT> T;
@@ -220,7 +230,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& S, uint32_t cou
         }
         if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; else continue; }
         if (active) {
-            const uint2 w = T.descend(S, K, cnt);
+            const uint2 w = T.template descend<PREFETCH>(S, K, cnt);
             if (T.leaf(S, w, cnt)) { commit(item, true, T.res); active = false; }
             else if (!T.pop(K)) { commit(item, false, T.res); active = false; }
         }
@@ -375,10 +385,115 @@ __device__ __forceinline__ void trace_voted(const DevScene& S, uint32_t count, u
     }
 }
 
-// VARIANT 2: descend-to-leaf / process-leaf phases with idle-lane refill; VARIANT 3: warp-voted state machine.
+// ------------------------------------------------------------------------------------------------------------
+// Bounded-phase traversal (VARIANT 4).  Same per-lane state machine as the voted variant, but every iteration of
+// the warp runs all three blocks with a small step budget each: up to S.steps_inner inner-node steps for lanes that
+// are descending, up to S.steps_leaf references of the pre-rejection scan for lanes inside a leaf, then the exact
+// tests of lanes whose leaf is finished (or whose candidate list is full).  A lane never waits longer than one
+// block budget for a slower neighbour (in the phase structure of variant 2 it waits for the slowest lane of the
+// whole phase: mean/max of 5 inner steps and 7 references over 32 lanes is what leaves 5 of 32 lanes busy on
+// incoherent rays).  Per-ray evaluation order is unchanged; results are identical.
+template <bool ANY, bool COUNT, class Fetch, class Commit>
+__device__ __forceinline__ void trace_bounded(const DevScene& S, uint32_t count, unsigned long long* work,
+                                              TravCount& cnt, uint32_t& done, Fetch fetch, Commit commit) {
+    Traverser<ANY, COUNT> T;
+    TravStack K;
+    const unsigned lane = threadIdx.x & 31;
+    const float eps = S.epsilon;
+    const int budget_inner = (int)S.steps_inner, budget_leaf = (int)S.steps_leaf;
+    int mode = TM_IDLE;
+    bool exhausted = false, hit = false;
+    uint32_t item = 0, p = 0, pend = 0;
+    uint32_t cand[RGK_CAND_CAP];
+    int nc = 0;
+    float lo = 0.0f, hi = 0.0f;
+    for (;;) {
+        const unsigned m_idle = __ballot_sync(0xffffffffu, mode == TM_IDLE);
+        if (m_idle != 0u && !exhausted && (__popc(m_idle) >= (int)S.refill_threshold || m_idle == 0xffffffffu)) {
+            const int leader = __ffs(m_idle) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(work, (unsigned long long)__popc(m_idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + __popc(m_idle) >= count) exhausted = true;
+            if (mode == TM_IDLE) {
+                const unsigned long long mine = base + __popc(m_idle & ((1u << lane) - 1u));
+                if (mine < count) {
+                    item = (uint32_t)mine;
+                    done++;
+                    if (fetch(item, T)) mode = TM_INNER;
+                    else commit(item, false, T.res);
+                }
+            }
+        } else if (m_idle == 0xffffffffu) break;          // everything idle and nothing left to fetch
+        // ---- block A: inner-node steps
+        if (mode == TM_INNER) {
+#pragma unroll 1
+            for (int s = 0; s < budget_inner; s++) {
+                const uint2 w = __ldg(S.nodes + T.node);
+                if ((w.y & 3u) == 3u) {
+                    if (COUNT) cnt.leaf++;
+                    p = w.x; pend = w.x + (w.y >> 2); hit = false; nc = 0; mode = TM_LEAF;
+                    lo = T.tmin - eps; hi = T.tmax + eps;
+                    break;
+                }
+                if (COUNT) cnt.inner++;
+                const uint32_t axis = w.y & 3u;
+                const float split = __uint_as_float(w.x);
+                const float oa = axis == 0u ? T.ox : (axis == 1u ? T.oy : T.oz);
+                const float ia = axis == 0u ? T.ix : (axis == 1u ? T.iy : T.iz);
+                const float diff = split - oa;
+                const float tplane = diff * ia;
+                bool below_first = diff > 0.0f;
+                if (diff == 0.0f) { const float da = axis == 0u ? T.dx : (axis == 1u ? T.dy : T.dz); below_first = da <= 0.0f; }
+                const uint32_t other = w.y >> 2, near = T.node + 1u;
+                const uint32_t first = below_first ? near : other, second = below_first ? other : near;
+                if (tplane > T.tmax || tplane <= 0.0f) T.node = first;
+                else if (tplane < T.tmin) T.node = second;
+                else { K.node[T.sp] = second; K.range[T.sp] = make_float2(tplane, T.tmax); ++T.sp; T.node = first; T.tmax = tplane; }
+            }
+        }
+        // ---- block B: pre-rejection scan of the leaf's references
+        bool run_exact = false;
+        if (mode == TM_LEAF) {
+#pragma unroll 1
+            for (int s = 0; s < budget_leaf && p < pend && nc < RGK_CAND_CAP; s++) {
+                const uint32_t ti = __ldg(S.refs + p);
+                ++p;
+                const float4 r0 = __ldg(S.tri_isect + 3 * (size_t)ti);
+                if (COUNT) { cnt.refs++; if (ti != T.ignore) cnt.tests++; }
+                const float dtf = T.dx * r0.x + T.dy * r0.y + T.dz * r0.z;
+                const float dot2f = T.ox * r0.x + T.oy * r0.y + T.oz * r0.z;
+                float rcp;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(dtf));
+                const float t32 = -(r0.w + dot2f) * rcp;
+                const float m = __fmaf_rn(fabsf(t32), 1.9073486328125e-6f, 1e-30f);
+                const bool reject = (ti == T.ignore) || (fabsf(dtf) < eps) || (t32 + m < lo) || (t32 - m > hi);
+                if (!reject) cand[nc++] = ti;
+            }
+            run_exact = (nc > 0) && (p == pend || nc == RGK_CAND_CAP);
+        }
+        // ---- block C: exact tests (leaf order), then leaf completion
+        if (run_exact) {
+            for (int k = 0; k < nc; k++)
+                if (T.exact_test(S, cand[k], lo, hi)) { hit = true; if (ANY) break; }
+            nc = 0;
+            if (ANY && hit) { commit(item, true, T.res); mode = TM_IDLE; }
+        }
+        if (mode == TM_LEAF && p == pend && nc == 0) {           // src/scene_intersect.cpp:290-292
+            if (hit) { commit(item, true, T.res); mode = TM_IDLE; }
+            else if (T.pop(K)) mode = TM_INNER;
+            else { commit(item, false, T.res); mode = TM_IDLE; }
+        }
+    }
+}
+
+// VARIANT 2: descend-to-leaf / process-leaf phases with idle-lane refill; VARIANT 3: warp-voted state machine;
+// VARIANT 4: bounded-phase state machine; VARIANT 5: variant 2 with child prefetch in the descent.
 template <int VARIANT, bool ANY, bool COUNT, class Fetch, class Commit>
 __device__ __forceinline__ void trace_rays(const DevScene& S, uint32_t count, unsigned long long* work,
                                            TravCount& cnt, uint32_t& done, Fetch fetch, Commit commit) {
-    if (VARIANT == 3) trace_voted<ANY, COUNT>(S, count, work, cnt, done, fetch, commit);
-    else trace_persistent<ANY, COUNT>(S, count, work, cnt, done, fetch, commit);
+    if (VARIANT == 4) trace_bounded<ANY, COUNT>(S, count, work, cnt, done, fetch, commit);
+    else if (VARIANT == 3) trace_voted<ANY, COUNT>(S, count, work, cnt, done, fetch, commit);
+    else if (VARIANT == 5) trace_persistent<ANY, COUNT, true>(S, count, work, cnt, done, fetch, commit);
+    else trace_persistent<ANY, COUNT, false>(S, count, work, cnt, done, fetch, commit);
 }

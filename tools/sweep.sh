@@ -1,10 +1,15 @@
-for th in 64 128 256; do for rf in 4 8 16 32; do
-echo "threads=$th refill=$rf"; RGK_TRACE_THREADS=$th RGK_REFILL=$rf python tools/trace_bench.py --reps 3 2>&1 | python -c "
+run() { echo "== $*"; env "$@" python tools/trace_bench.py --reps 3 --check 60000 2>&1 | python -c "
 import sys,json
 out=[]
 for l in sys.stdin:
     try: d=json.loads(l)
-    except: continue
-    out.append('%s %d' % (d['batch'], round(d['Mrays_s'])))
+    except: print(l.strip()[:200]); continue
+    out.append('%s %d%s' % (d['batch'], round(d['Mrays_s']), '' if d.get('bit_exact_vs_oracle', True) else ' MISMATCH'))
 print('   ', ' | '.join(out))
-"; done; done
+"; }
+L12=$PWD/rgk_b200/librgk_b200_mb12.so
+run RGK_TRAVERSAL=2 RGK_REFILL=8
+run RGK_TRAVERSAL=5 RGK_REFILL=8
+run RGK_TRAVERSAL=2 RGK_REFILL=8 RGK_B200_LIB=$L12
+run RGK_TRAVERSAL=5 RGK_REFILL=8 RGK_B200_LIB=$L12
+run RGK_TRAVERSAL=5 RGK_REFILL=32

@@ -292,8 +292,15 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = cl_rays * b_closest / (cl_ms / 1e3) / 1e9 if cl_ms > 0 else 0.0
+        traffic = None     # DRAM bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            traffic = tj["dram_bytes_per_ray"] * cl_rays / cl_launches
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_closest (kd-tree closest-hit traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write per ray x rays per launch)",
+                    "algorithmic_bytes_per_launch": cl_rays * b_closest / cl_launches, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "bytes_per_ray": b_closest, "avg_launch_ms": cl_ms / cl_launches, "launches_per_step": cl_launches / max(1, args.steps),
                     "Grays_per_s_in_kernel": cl_rays / (cl_ms / 1e3) / 1e9 if cl_ms > 0 else 0.0,
                     "shadow_kernel": {"bytes_per_ray": b_shadow, "achieved": sh_rays * b_shadow / (sh_ms / 1e3) / 1e9 if sh_ms > 0 else 0.0,

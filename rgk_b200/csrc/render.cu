@@ -394,7 +394,10 @@ __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* 
 }
 
 // One vertex of GeneratePath (src/path_tracer.cpp:122-302) plus the NEE set-up of TracePath (:405-496)
-__global__ void __launch_bounds__(128)
+#ifndef RGK_SHADE_MINB
+#define RGK_SHADE_MINB 1
+#endif
+__global__ void __launch_bounds__(128, RGK_SHADE_MINB)
 k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count,
         uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, unsigned long long* counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

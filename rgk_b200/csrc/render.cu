@@ -315,6 +315,9 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
 }
 
 constexpr int TRACE_THREADS = 128;
+#ifndef RGK_RENDER_VARIANT
+#define RGK_RENDER_VARIANT 6   // phase-synchronised traversal (trace_device.cuh)
+#endif
 
 template <bool COUNT>
 __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays, rgk_trav_stats* stats) {
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, rgk_trav_stats* stats) {
     TravCount cnt{0, 0, 0, 0};
     uint32_t mine = 0;
-    trace_rays<2, false, COUNT>(S, count, work, cnt, mine,
+    trace_rays<RGK_RENDER_VARIANT, false, COUNT>(S, count, work, cnt, mine,
         [&](uint32_t i, Traverser<false, COUNT>& T) {
             const uint32_t slot = queue ? __ldg(queue + i) : i;
             const float4 o = B.ray_o[slot], d = B.ray_d[slot];
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, rgk_trav_stats* stats) {
     TravCount cnt{0, 0, 0, 0};
     uint32_t mine = 0;
-    trace_rays<2, true, COUNT>(S, count, work, cnt, mine,
+    trace_rays<RGK_RENDER_VARIANT, true, COUNT>(S, count, work, cnt, mine,
         [&](uint32_t i, Traverser<true, COUNT>& T) {
             const uint32_t slot = __ldg(queue + i);
             const float4 a = B.light_pos[slot], b = B.sh_pos[slot];

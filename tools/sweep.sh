@@ -7,9 +7,8 @@ for l in sys.stdin:
     out.append('%s %d%s' % (d['batch'], round(d['Mrays_s']), '' if d.get('bit_exact_vs_oracle', True) else ' MISMATCH'))
 print('   ', ' | '.join(out))
 "; }
-L12=$PWD/rgk_b200/librgk_b200_mb12.so
 run RGK_TRAVERSAL=2 RGK_REFILL=8
-run RGK_TRAVERSAL=5 RGK_REFILL=8
-run RGK_TRAVERSAL=2 RGK_REFILL=8 RGK_B200_LIB=$L12
-run RGK_TRAVERSAL=5 RGK_REFILL=8 RGK_B200_LIB=$L12
-run RGK_TRAVERSAL=5 RGK_REFILL=32
+run RGK_TRAVERSAL=6 RGK_REFILL=8
+run RGK_TRAVERSAL=6 RGK_REFILL=4
+run RGK_TRAVERSAL=6 RGK_REFILL=16
+run RGK_TRAVERSAL=6 RGK_REFILL=32

@@ -142,6 +142,14 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
         for (size_t i = 0; i < nodes.size(); i++) nodes[i] = make_uint2(hs.nodes[2 * i], hs.nodes[2 * i + 1]);
         UP(nodes, &D.nodes);
         UP(hs.refs, &D.refs);
+        {
+            std::vector<float4> rp(hs.refs.size());
+            for (size_t j = 0; j < rp.size(); j++) {
+                const float* q = &hs.planes[4 * (size_t)hs.refs[j]];
+                rp[j] = make_float4(q[0], q[1], q[2], q[3]);
+            }
+            UP(rp, &D.ref_planes);
+        }
         std::vector<float4> rec(hs.tri_isect.size() / 4);
         std::memcpy(rec.data(), hs.tri_isect.data(), hs.tri_isect.size() * 4);
         UP(rec, &D.tri_isect);

@@ -315,6 +315,9 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
 }
 
 constexpr int TRACE_THREADS = 128;
+#ifndef RGK_INCOH_MINB
+#define RGK_INCOH_MINB 12   // CTAs/SM the incoherent-bounce instantiations are compiled for (register budget)
+#endif
 #ifndef RGK_RENDER_VARIANT
 #define RGK_RENDER_VARIANT 6   // phase-synchronised traversal (trace_device.cuh)
 #endif
@@ -761,7 +764,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         ctx->launches++;
         RGK_CUDA(ctx, cudaGetLastError());
 
-        const int tgrid = machine_blocks(ctx, counting ? (const void*)k_closest<true, 9> : (const void*)k_closest<false, 12>, TRACE_THREADS);
+        const int tgrid = machine_blocks(ctx, counting ? (const void*)k_closest<true, 9> : (const void*)k_closest<false, RGK_INCOH_MINB>, TRACE_THREADS);
         uint32_t count = (uint32_t)npaths;
         const uint32_t* queue = nullptr;
         uint32_t* qnext = B.queue_a;
@@ -777,7 +780,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             // 40 registers (12 CTAs/SM) for later bounces, which are latency-bound and gain from the extra warps
             if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
             else if (bounce == 0) k_closest<false, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
-            else k_closest<false, 12><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
+            else k_closest<false, RGK_INCOH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             pool.end(ctx->stream);
             pool.begin(ctx->stream, T_SHADE);
             k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
@@ -791,7 +794,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
                 if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1);
-                else k_shadow<false, 12><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
+                else k_shadow<false, RGK_INCOH_MINB><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
                 pool.end(ctx->stream);
                 ctx->launches++; total.shadow_launches++;
             }

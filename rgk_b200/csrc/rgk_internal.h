@@ -41,6 +41,8 @@ struct DevArealTri { float area; uint32_t tri; };
 struct DevScene {
     const uint2* nodes;
     const uint32_t* refs;
+    const float4* ref_planes;    // [n_refs] plane record (n.xyz, d) of triangle refs[j]: the leaf scan reads reference and plane
+                                 // side by side instead of chasing refs[j] -> tri_isect[3*refs[j]] (one dependent load less)
     const float4* tri_isect;
     const uint4* tri_shade;
     const float4* positions;

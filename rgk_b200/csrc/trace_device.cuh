@@ -15,7 +15,10 @@ struct TravCount { uint32_t inner, leaf, refs, tests; };
 // Per-ray traversal stack (local memory, lane-interleaved by the hardware); kept outside the Traverser so that the
 // scalar ray / interval state stays in registers.
 struct TravStack { uint32_t node[RGK_STACK_CAP]; float2 range[RGK_STACK_CAP]; };   // range = (tmin, tmax)
-#define RGK_CAND_CAP 4            // deferred exact tests per leaf before a flush
+#ifndef RGK_CAND_CAP
+#define RGK_CAND_CAP 4
+#endif
+// RGK_CAND_CAP:           // deferred exact tests per leaf before a flush
 struct HitRec { uint32_t tri; float t, alpha, beta; };  // alpha/beta as returned by TestIntersection
 
 
@@ -161,9 +164,10 @@ struct Traverser {
         uint32_t cand[RGK_CAND_CAP];
         int nc = 0;
         bool hit = false;
+        const float4* __restrict__ pp = S.ref_planes + w.x;   // plane of reference j, stored next to the reference
         for (uint32_t p = 0; p < n; p++) {
             const uint32_t ti = __ldg(rp + p);
-            const float4 r0 = __ldg(S.tri_isect + 3 * (size_t)ti);
+            const float4 r0 = __ldg(pp + p);
             if (COUNT) { cnt.refs++; if (ti != ignore) cnt.tests++; }
             const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;
             const float dot2f = ox * r0.x + oy * r0.y + oz * r0.z;
@@ -290,8 +294,8 @@ __device__ __forceinline__ void trace_phased(const DevScene& S, uint32_t count, 
         if (active) {
             while (p < pend && nc < RGK_CAND_CAP) {
                 const uint32_t ti = __ldg(S.refs + p);
+                const float4 r0 = __ldg(S.ref_planes + p);
                 ++p;
-                const float4 r0 = __ldg(S.tri_isect + 3 * (size_t)ti);
                 if (COUNT) { cnt.refs++; if (ti != T.ignore) cnt.tests++; }
                 const float dtf = T.dx * r0.x + T.dy * r0.y + T.dz * r0.z;
                 const float dot2f = T.ox * r0.x + T.oy * r0.y + T.oz * r0.z;
@@ -412,11 +416,11 @@ __device__ __forceinline__ void trace_voted(const DevScene& S, uint32_t count, u
                         break;
                     }
                     const uint32_t ti = __ldg(S.refs + p);
+                    const float4 r0 = __ldg(S.ref_planes + p);
                     ++p;
                     if (COUNT) cnt.refs++;
                     if (ti == T.ignore) continue;
                     if (COUNT) cnt.tests++;
-                    const float4 r0 = __ldg(S.tri_isect + 3 * (size_t)ti);
                     const float dtf = T.dx * r0.x + T.dy * r0.y + T.dz * r0.z;
                     const float dot2f = T.ox * r0.x + T.oy * r0.y + T.oz * r0.z;
                     // conservative fp32 pre-rejection (see Traverser::leaf): never rejects what the exact test accepts
@@ -538,8 +542,8 @@ __device__ __forceinline__ void trace_bounded(const DevScene& S, uint32_t count,
 #pragma unroll 1
             for (int s = 0; s < budget_leaf && p < pend && nc < RGK_CAND_CAP; s++) {
                 const uint32_t ti = __ldg(S.refs + p);
+                const float4 r0 = __ldg(S.ref_planes + p);
                 ++p;
-                const float4 r0 = __ldg(S.tri_isect + 3 * (size_t)ti);
                 if (COUNT) { cnt.refs++; if (ti != T.ignore) cnt.tests++; }
                 const float dtf = T.dx * r0.x + T.dy * r0.y + T.dz * r0.z;
                 const float dot2f = T.ox * r0.x + T.oy * r0.y + T.oz * r0.z;

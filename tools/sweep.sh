@@ -7,8 +7,5 @@ for l in sys.stdin:
     out.append('%s %d%s' % (d['batch'], round(d['Mrays_s']), '' if d.get('bit_exact_vs_oracle', True) else ' MISMATCH'))
 print('   ', ' | '.join(out))
 "; }
-run RGK_TRAVERSAL=2 RGK_REFILL=8
-run RGK_TRAVERSAL=6 RGK_REFILL=8
-run RGK_TRAVERSAL=6 RGK_REFILL=4
-run RGK_TRAVERSAL=6 RGK_REFILL=16
-run RGK_TRAVERSAL=6 RGK_REFILL=32
+run RGK_REFILL=8
+run RGK_REFILL=32

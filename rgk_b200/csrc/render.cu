@@ -401,7 +401,7 @@ __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* 
 
 // One vertex of GeneratePath (src/path_tracer.cpp:122-302) plus the NEE set-up of TracePath (:405-496)
 #ifndef RGK_SHADE_MINB
-#define RGK_SHADE_MINB 1
+#define RGK_SHADE_MINB 5   // <= 102 registers: 5 CTAs of 128 threads per SM
 #endif
 __global__ void __launch_bounds__(128, RGK_SHADE_MINB)
 k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count,

@@ -509,6 +509,7 @@ __device__ __forceinline__ void trace_bounded(const DevScene& S, uint32_t count,
                 }
             }
         } else if (m_idle == 0xffffffffu) break;          // everything idle and nothing left to fetch
+        __syncwarp();
         // ---- block A: inner-node steps
         if (mode == TM_INNER) {
 #pragma unroll 1
@@ -536,6 +537,7 @@ __device__ __forceinline__ void trace_bounded(const DevScene& S, uint32_t count,
                 else { K.node[T.sp] = second; K.range[T.sp] = make_float2(tplane, T.tmax); ++T.sp; T.node = first; T.tmax = tplane; }
             }
         }
+        __syncwarp();
         // ---- block B: pre-rejection scan of the leaf's references
         bool run_exact = false;
         if (mode == TM_LEAF) {
@@ -556,6 +558,7 @@ __device__ __forceinline__ void trace_bounded(const DevScene& S, uint32_t count,
             }
             run_exact = (nc > 0) && (p == pend || nc == RGK_CAND_CAP);
         }
+        __syncwarp();
         // ---- block C: exact tests (leaf order), then leaf completion
         if (run_exact) {
             for (int k = 0; k < nc; k++)

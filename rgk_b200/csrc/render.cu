@@ -194,11 +194,13 @@ static void launch_sampler_mt(cudaStream_t stream, const uint32_t* seeds, uint32
     if (!attr) { cudaFuncSetAttribute(k_sampler_mt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     static int use_smem = -1;
     if (use_smem < 0) { const char* e = std::getenv("RGK_SAMPLER_SMEM"); use_smem = (e && e[0] == '0') ? 0 : 1; }
-    for (int bd : {128, 64}) {
-        if (!use_smem) break;
-        const size_t bytes = (size_t)bd * ss * 12;
-        if (bytes <= 100 * 1024 || (bd == 64 && bytes <= 200 * 1024)) {
-            k_sampler_mt<true><<<(npix + bd - 1) / bd, bd, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
+    // shared-memory tables only while two 128-thread CTAs still fit an SM (set size <= 66); beyond that the CTA count
+    // per SM drops to one or two warps and the latency of the generator-state loads is no longer hidden (measured:
+    // 2.4 s vs 1.2 s per 1080p x 256 spp x depth-40 round), so larger sets are shuffled in place in global memory
+    if (use_smem) {
+        const size_t bytes = (size_t)128 * ss * 12;
+        if (bytes <= 100 * 1024) {
+            k_sampler_mt<true><<<(npix + 127) / 128, 128, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
             return;
         }
     }

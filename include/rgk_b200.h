@@ -237,6 +237,19 @@ rgk_status rgk_scene_get_info(const rgk_context* ctx, rgk_scene_info* out);
 /* Copies out the committed tree in the reference encoding (sizes from rgk_scene_info). */
 rgk_status rgk_scene_get_kdtree(const rgk_context* ctx, uint32_t* nodes, uint32_t* refs);
 
+/* Host-only half of rgk_scene_commit (no device needed): Triangle::CalculatePlane (src/primitives.cpp:24-36), areal
+ * lights, epsilon, bbox (src/scene.cpp:294-429) and the SAH kd-tree build + Compress (src/scene.cpp:431-657), the
+ * build forked over host threads (RGK_BUILD_THREADS, default = all cores; arrays are byte-identical to the
+ * sequential reference procedure).  get_records copies the 4-float plane and the 12-float intersection record of
+ * every triangle (either pointer may be NULL).  Errors: RGK_ERR_INVALID + rgk_host_last_error() (thread-local). */
+typedef struct rgk_host_scene rgk_host_scene;
+rgk_status rgk_host_scene_create(const rgk_scene_desc* desc, const rgk_kdtree* tree, rgk_host_scene** out);
+void rgk_host_scene_destroy(rgk_host_scene* hs);
+const char* rgk_host_last_error(void);
+rgk_status rgk_host_scene_get_info(const rgk_host_scene* hs, rgk_scene_info* out);
+rgk_status rgk_host_scene_get_kdtree(const rgk_host_scene* hs, uint32_t* nodes, uint32_t* refs);
+rgk_status rgk_host_scene_get_records(const rgk_host_scene* hs, float* planes, float* records);
+
 /* Replaces Scene::FindIntersectKdOtherThan (src/scene_intersect.cpp:211-327) over a
  * batch; ignore[i] = triangle index to skip or RGK_NO_TRIANGLE (then it is
  * Scene::FindIntersectKd, :4-116); ignore may be NULL.  Host buffers. */

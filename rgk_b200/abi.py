@@ -130,6 +130,8 @@ EXPORTS = [
     "rgk_generate_tasks", "rgk_sampler_set_size", "rgk_sampler_tables", "rgk_render_round",
     "rgk_render_round_device", "rgk_render_frame", "rgk_render_set_tables", "rgk_synchronize",
     "rgk_render_set_counting", "rgk_render_get_trav_stats", "rgk_probe", "rgk_render_set_shard",
+    "rgk_host_scene_create", "rgk_host_scene_destroy", "rgk_host_last_error", "rgk_host_scene_get_info",
+    "rgk_host_scene_get_kdtree", "rgk_host_scene_get_records",
 ]
 
 
@@ -175,6 +177,13 @@ def load_library(path=None):
     lib.rgk_render_set_tables.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64]
     lib.rgk_synchronize.argtypes = [vp]
     lib.rgk_probe.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
+    lib.rgk_host_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(KdTree), C.POINTER(vp)]
+    lib.rgk_host_scene_destroy.argtypes = [vp]
+    lib.rgk_host_scene_destroy.restype = None
+    lib.rgk_host_last_error.restype = C.c_char_p
+    lib.rgk_host_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
+    lib.rgk_host_scene_get_kdtree.argtypes = [vp, vp, vp]
+    lib.rgk_host_scene_get_records.argtypes = [vp, vp, vp]
     lib.rgk_render_set_counting.argtypes = [vp, C.c_int]
     lib.rgk_render_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.rgk_render_get_trav_stats.argtypes = [vp, C.POINTER(TravStats), C.POINTER(TravStats)]

@@ -250,6 +250,45 @@ rgk_status rgk_scene_get_kdtree(const rgk_context* ctx, uint32_t* nodes, uint32_
     return RGK_OK;
 }
 
+// ---- host-only scene commit (no device needed): what rgk_scene_commit computes before uploading ------------------
+struct rgk_host_scene { HostScene hs; std::string error; };
+thread_local std::string g_host_error;
+
+rgk_status rgk_host_scene_create(const rgk_scene_desc* d, const rgk_kdtree* tree, rgk_host_scene** out) {
+    if (!d || !out) return RGK_ERR_INVALID;
+    *out = nullptr;
+    rgk_host_scene* h = new rgk_host_scene();
+    try {
+        host_scene_commit(d, tree, h->hs);
+    } catch (const std::exception& e) {
+        g_host_error = e.what();
+        delete h;
+        return RGK_ERR_INVALID;
+    }
+    *out = h;
+    return RGK_OK;
+}
+void rgk_host_scene_destroy(rgk_host_scene* h) { delete h; }
+const char* rgk_host_last_error(void) { return g_host_error.c_str(); }
+rgk_status rgk_host_scene_get_info(const rgk_host_scene* h, rgk_scene_info* out) {
+    if (!h || !out) return RGK_ERR_INVALID;
+    *out = h->hs.info;
+    return RGK_OK;
+}
+rgk_status rgk_host_scene_get_kdtree(const rgk_host_scene* h, uint32_t* nodes, uint32_t* refs) {
+    if (!h || !nodes || !refs) return RGK_ERR_INVALID;
+    std::memcpy(nodes, h->hs.nodes.data(), 4 * h->hs.nodes.size());
+    std::memcpy(refs, h->hs.refs.data(), 4 * h->hs.refs.size());
+    return RGK_OK;
+}
+// triangle intersection records (12 floats / triangle) and planes (4 floats / triangle)
+rgk_status rgk_host_scene_get_records(const rgk_host_scene* h, float* planes, float* records) {
+    if (!h) return RGK_ERR_INVALID;
+    if (planes) std::memcpy(planes, h->hs.planes.data(), 4 * h->hs.planes.size());
+    if (records) std::memcpy(records, h->hs.tri_isect.data(), 4 * h->hs.tri_isect.size());
+    return RGK_OK;
+}
+
 // ---- traversal -----------------------------------------------------------
 rgk_status rgk_trace_closest_device(rgk_context* ctx, const rgk_ray* d_rays, const uint32_t* d_ignore, uint64_t n,
                                     rgk_hit* d_hits, rgk_trav_stats* d_stats) {

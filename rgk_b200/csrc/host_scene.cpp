@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <cstdlib>
 #include <stdexcept>
+#include <thread>
 #include "rgk_internal.h"
 
 namespace {
@@ -32,6 +34,12 @@ struct Builder {
     std::vector<uint32_t>& refs;
     unsigned max_depth;
     unsigned deepest = 0;
+    // Host parallelism: the two children of a node are independent, so above `fork_depth` the right
+    // child is built by another thread into its own arrays and stitched in afterwards (child indices and leaf
+    // reference offsets shifted).  Every node is still split by the reference's procedure on the same triangle order,
+    // so the arrays are byte-identical to the sequential build (tests compare them with the oracle's).
+    unsigned fork_depth = 0;
+    size_t fork_min_tris = 20000;
 
     void emit_leaf(const std::vector<uint32_t>& tris) {
         nodes.push_back((uint32_t)refs.size());
@@ -94,6 +102,28 @@ struct Builder {
         nodes.push_back(axis);
         float cb[3][2]; std::memcpy(cb, bb, sizeof cb);
         cb[axis][1] = best_pos;
+        if (depth < fork_depth && above.size() >= fork_min_tris && below.size() >= fork_min_tris) {
+            std::vector<uint32_t> rn, rr;
+            Builder right{ev, rn, rr, max_depth};
+            right.fork_depth = fork_depth; right.fork_min_tris = fork_min_tris;
+            float rb[3][2]; std::memcpy(rb, bb, sizeof rb);
+            rb[axis][0] = best_pos;
+            std::thread worker([&] { right.build(above, rb, depth + 1); });
+            build(below, cb, depth + 1);
+            worker.join();
+            const uint32_t node_off = (uint32_t)(nodes.size() / 2), ref_off = (uint32_t)refs.size();
+            nodes[me + 1] = axis | (node_off << 2);
+            nodes.reserve(nodes.size() + rn.size());
+            for (size_t i = 0; i < rn.size(); i += 2) {
+                uint32_t w0 = rn[i], w1 = rn[i + 1];
+                if ((w1 & 3u) == 3u) w0 += ref_off;              // leaf: first reference
+                else w1 += node_off << 2;                         // inner: index of the far child
+                nodes.push_back(w0); nodes.push_back(w1);
+            }
+            refs.insert(refs.end(), rr.begin(), rr.end());
+            deepest = std::max(deepest, right.deepest);
+            return;
+        }
         build(below, cb, depth + 1);
         nodes[me + 1] = axis | ((uint32_t)(nodes.size() / 2) << 2);
         std::memcpy(cb, bb, sizeof cb);
@@ -233,6 +263,13 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
         deepest = measure_depth(hs.nodes);
     } else {
         Builder b{ev, hs.nodes, hs.refs, (unsigned)(int)(std::log2(nt) + 8)};
+        {   // up to 2^fork_depth threads; RGK_BUILD_THREADS=1 forces the sequential build
+            unsigned threads = std::thread::hardware_concurrency();
+            if (const char* e = std::getenv("RGK_BUILD_THREADS")) threads = (unsigned)std::max(1, std::atoi(e));
+            unsigned fd = 0;
+            while ((1u << fd) < threads && fd < 6) fd++;
+            b.fork_depth = fd;
+        }
         std::vector<uint32_t> all(nt);
         for (uint32_t i = 0; i < nt; i++) all[i] = i;
         b.build(all, bb, 0);

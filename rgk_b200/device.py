@@ -184,3 +184,46 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.rgk_synchronize(self.h))
+
+
+class HostScene:
+    """Host-only scene commit (rgk_host_scene_*): planes, areal lights, epsilon, bbox, kd-tree build + flatten -- what
+    rgk_scene_commit computes on the CPU before uploading.  Needs no GPU."""
+
+    def __init__(self, desc, tree=None, lib=None):
+        self.lib = lib or abi.load_library()
+        h = C.c_void_p()
+        st = self.lib.rgk_host_scene_create(C.byref(desc), C.byref(tree) if tree is not None else None, C.byref(h))
+        if st != 0:
+            raise RgkError(st, self.lib.rgk_host_last_error().decode())
+        self.h = h
+
+    def info(self):
+        info = abi.SceneInfo()
+        self.lib.rgk_host_scene_get_info(self.h, C.byref(info))
+        return info
+
+    def kdtree(self):
+        info = self.info()
+        nodes = np.zeros(2 * info.n_nodes, np.uint32)
+        refs = np.zeros(max(1, info.n_refs), np.uint32)
+        self.lib.rgk_host_scene_get_kdtree(self.h, _p(nodes), _p(refs))
+        return nodes, refs[:info.n_refs]
+
+    def records(self):
+        info = self.info()
+        planes = np.zeros((info.n_triangles, 4), np.float32)
+        rec = np.zeros((info.n_triangles, 12), np.float32)
+        self.lib.rgk_host_scene_get_records(self.h, _p(planes), _p(rec))
+        return planes, rec
+
+    def close(self):
+        if self.h:
+            self.lib.rgk_host_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,6 +1,6 @@
-"""Host-side logic that needs no GPU: the JSON scene config reader, the scene pack, the product's host kd-tree
-builder (through a scene commit is GPU-only, so the builder is checked via the oracle's identical tree in the
-GPU tests; here: config / packing / sharding arithmetic)."""
+"""Host-side logic that needs no GPU: the JSON scene config reader, the scene pack, sharding arithmetic, and the
+product's host half of Scene::Commit (rgk_host_scene_*: planes, lights, kd-tree build incl. the forked build) against
+the oracle's arrays."""
 import json
 import os
 
@@ -86,3 +86,62 @@ def test_camera_args_fov_and_focal():
     cfg.camera = {"position": [0, 0, 5], "lookat": [0, 0, 0], "focal": 1.6}
     ca = cfg.camera_args()
     assert ca["yview"] == pytest.approx(1.6) and ca["xview"] == pytest.approx(1.6 * 2)
+
+
+def _host_tree(desc, threads):
+    from rgk_b200 import device
+    old = os.environ.get("RGK_BUILD_THREADS")
+    os.environ["RGK_BUILD_THREADS"] = str(threads)
+    try:
+        hs = device.HostScene(desc)
+    finally:
+        if old is None:
+            os.environ.pop("RGK_BUILD_THREADS")
+        else:
+            os.environ["RGK_BUILD_THREADS"] = old
+    info, (nodes, refs), (planes, rec) = hs.info(), hs.kdtree(), hs.records()
+    hs.close()
+    return info, nodes, refs, planes, rec
+
+
+def test_host_scene_commit_matches_oracle_cornell(cornell, oracle):
+    """rgk_host_scene_*: the product's host half of Scene::Commit (planes, epsilon, bbox, kd-tree) against the
+    oracle's restatement of src/scene.cpp:294-657 -- byte-identical arrays."""
+    pack, cfg, desc = cornell
+    info, nodes, refs, planes, rec = _host_tree(desc, 1)
+    ho = oracle.scene_create(desc)
+    oi = oracle.scene_info(ho)
+    on, orf = oracle.scene_kdtree(ho)
+    assert nodes.tobytes() == on.tobytes() and refs.tobytes() == orf.tobytes()
+    assert planes.tobytes() == oracle.scene_planes(ho).tobytes()
+    assert info.epsilon == oi.epsilon and list(info.bbox) == list(oi.bbox) and info.max_depth == oi.max_depth
+    assert info.n_areal_lights == oi.n_areal_lights == 2       # the lamp is two `tri` primitives = two ArealLights
+    assert np.array_equal(rec[:, :4], planes)                  # record word 0 = the plane
+    oracle.scene_destroy(ho)
+
+
+def test_forked_kdtree_build_is_byte_identical_to_sequential():
+    """the host-parallel kd-tree build (right subtrees built by other threads and stitched in) must
+    give the arrays of the sequential reference procedure, whatever the thread count."""
+    from rgk_b200 import standin
+    pack, cfg = standin.sponza(width=64, height=64, multisample=1, target_tris=66000)
+    desc = pack.desc()
+    i1, n1, r1, p1, t1 = _host_tree(desc, 1)
+    for threads in (2, 5, 16):
+        i2, n2, r2, p2, t2 = _host_tree(desc, threads)
+        assert n1.tobytes() == n2.tobytes() and r1.tobytes() == r2.tobytes(), threads
+        assert i1.max_depth == i2.max_depth and p1.tobytes() == p2.tobytes() and t1.tobytes() == t2.tobytes()
+
+
+def test_host_scene_rejects_bad_input():
+    """Load-time errors of the reference (ConfigFileException / std::runtime_error) become RGK_ERR_INVALID + text."""
+    from rgk_b200 import device
+    pack, cfg = scenes.load_builtin("cornell-box")
+    bad = pack.desc()
+    bad.n_meshes = 8
+    with pytest.raises(device.RgkError, match="mesh ranges"):
+        device.HostScene(bad)
+    bad = pack.desc()
+    bad.materials[0].bxdf = 99
+    with pytest.raises(device.RgkError, match="Unsupported BRDF"):
+        device.HostScene(bad)

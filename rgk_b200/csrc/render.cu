@@ -26,6 +26,7 @@ struct PathBuffers {
     float4 *light_pos = nullptr, *light_col = nullptr, *light_nrm = nullptr;
     float4 *sh_pos = nullptr, *sh_direct = nullptr, *sh_emis = nullptr, *sh_contrib = nullptr;
     uint32_t *last_tri = nullptr, *cur1 = nullptr, *queue_a = nullptr, *queue_b = nullptr, *queue_s = nullptr;
+    uint8_t *key_next = nullptr, *key_shadow = nullptr;   // per-slot direction bin of the continuation / shadow ray, 0xFF = none (binned queues)
     uint32_t *pix_xy = nullptr, *pix_seed = nullptr, *pix_src = nullptr;   // pix_src: index of the pixel in call order (task order, y-major)
     uint32_t *mt_state = nullptr;
     float *t1 = nullptr; float2 *t2 = nullptr;
@@ -42,6 +43,7 @@ struct RenderConst {
     uint32_t xres, yres, ms, depth;
     float clamp, russian, bump_scale;
     uint32_t set_size, n1d, n2d, base2, sampler_mode, lens, skip_null_shadow;
+    uint32_t binning;       // 1: k_shade writes direction-bin keys and k_bin builds the queues (coherence reordering)
     uint32_t npix;          // pixels in the chunk
 };
 
@@ -390,6 +392,65 @@ k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t
     flush_counts<COUNT>(cnt, mine, stats);
 }
 
+// Direction bin for the coherence reordering: octahedral map of the direction onto a 16x16 grid, cells numbered along
+// a Morton curve so that consecutive bins are neighbouring directions.  255 is reserved for "no ray" (merged into 254).
+__device__ __forceinline__ uint8_t dir_bin(float x, float y, float z) {
+    const float inv = 1.0f / (fabsf(x) + fabsf(y) + fabsf(z));
+    float u = x * inv, v = y * inv;
+    if (z < 0.0f) {
+        const float fu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), fv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+        u = fu; v = fv;
+    }
+    uint32_t iu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 16.0f, 0.0f), 15.0f);
+    uint32_t iv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 16.0f, 0.0f), 15.0f);
+    iu = (iu | (iu << 2)) & 0x33u; iu = (iu | (iu << 1)) & 0x55u;
+    iv = (iv | (iv << 2)) & 0x33u; iv = (iv | (iv << 1)) & 0x55u;
+    const uint32_t m = iu | (iv << 1);
+    return (uint8_t)(m > 254u ? 254u : m);
+}
+
+// Queue construction by counting sort (replaces the atomic compaction of k_shade when R.binning): one CTA owns a group of
+// PG consecutive pixel positions x SG consecutive samples (path slot = sample * npix + pixel, so the group's rays leave
+// one small patch of the image), counts its live keys per direction bin in shared memory, reserves a contiguous range
+// of the output queue with one atomic and writes its slots there bin by bin.
+constexpr int BIN_THREADS = 256;
+__global__ void __launch_bounds__(BIN_THREADS)
+k_bin(const uint8_t* __restrict__ keys, uint32_t npix, uint32_t ms, uint32_t PG, uint32_t SG, uint32_t n_pgroups,
+      uint32_t* __restrict__ out, unsigned long long* counter) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t warp_tot[BIN_THREADS / 32];
+    __shared__ unsigned long long base_s;
+    const uint32_t p0 = (blockIdx.x % n_pgroups) * PG, s0 = (blockIdx.x / n_pgroups) * SG;
+    const uint32_t np = min(PG, npix - p0), ns = min(SG, ms - s0), n = np * ns;
+    hist[threadIdx.x] = 0u;
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < n; k += BIN_THREADS) {
+        const uint32_t key = keys[(size_t)(s0 + k / np) * npix + p0 + k % np];
+        if (key != 0xFFu) atomicAdd(&hist[key], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the 256 bins (one per thread)
+    const uint32_t mine = hist[threadIdx.x];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < BIN_THREADS / 32; w++) { const uint32_t t = warp_tot[w]; if (w < (int)(threadIdx.x >> 5)) before += t; total += t; }
+    if (total == 0u) return;
+    if (threadIdx.x == 0) base_s = atomicAdd(counter, (unsigned long long)total);
+    hist[threadIdx.x] = before + incl - mine;
+    __syncthreads();
+    const unsigned long long base = base_s;
+    for (uint32_t k = threadIdx.x; k < n; k += BIN_THREADS) {
+        const uint32_t slot = (s0 + k / np) * npix + p0 + k % np;
+        const uint32_t key = keys[slot];
+        if (key != 0xFFu) out[base + atomicAdd(&hist[key], 1u)] = slot;
+    }
+}
+
 __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* counter, bool want, uint32_t slot) {
     const unsigned mask = __ballot_sync(0xffffffffu, want);   // every lane of the warp reaches this point
     if (!want) return;
@@ -523,8 +584,18 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
             }
         }
     }
-    push_queue(next_queue, counters + C_NEXT, cont, slot);
-    push_queue(shadow_queue, counters + C_SHADOW, shadow, slot);
+    if (R.binning) {
+        // queues are built by k_bin from these keys: rays of one pixel block are reordered by direction so that the lanes
+        // of a traversal warp follow similar paths through the tree (the order of the queue never changes a result)
+        if (cont && R.binning == 1u) { const float4 d = B.ray_d[slot]; B.key_next[slot] = dir_bin(d.x, d.y, d.z); }
+        if (shadow) {
+            const float4 a = B.light_pos[slot], b = B.sh_pos[slot];
+            B.key_shadow[slot] = dir_bin(b.x - a.x, b.y - a.y, b.z - a.z);
+        }
+    } else {
+        push_queue(next_queue, counters + C_NEXT, cont, slot);
+        push_queue(shadow_queue, counters + C_SHADOW, shadow, slot);
+    }
     {   // Visibility queries of the reference that were provably irrelevant and therefore not traced
         const unsigned m = __ballot_sync(0xffffffffu, null_shadow);
         if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + C_SHADOW_SKIPPED, (unsigned long long)__popc(m));
@@ -584,7 +655,7 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
              alloc_dev(&B.tot, paths) && alloc_dev(&B.light_pos, paths) && alloc_dev(&B.light_col, paths) && alloc_dev(&B.light_nrm, paths) &&
              alloc_dev(&B.sh_pos, paths) && alloc_dev(&B.sh_direct, paths) && alloc_dev(&B.sh_emis, paths) && alloc_dev(&B.sh_contrib, paths) &&
              alloc_dev(&B.last_tri, paths) && alloc_dev(&B.cur1, paths) && alloc_dev(&B.queue_a, paths) && alloc_dev(&B.queue_b, paths) &&
-             alloc_dev(&B.queue_s, paths);
+             alloc_dev(&B.queue_s, paths) && alloc_dev(&B.key_next, paths) && alloc_dev(&B.key_shadow, paths);
         B.cap_paths = ok ? paths : 0;
     }
     if (ok && pixels > B.cap_pixels) {
@@ -612,7 +683,7 @@ void free_path_buffers(rgk_context* ctx) {
     if (!ctx->paths) return;
     PathBuffers& B = *ctx->paths;
     void* ptrs[] = {B.ray_o, B.ray_d, B.hit, B.cum, B.tot, B.light_pos, B.light_col, B.light_nrm, B.sh_pos, B.sh_direct, B.sh_emis,
-                    B.sh_contrib, B.last_tri, B.cur1, B.queue_a, B.queue_b, B.queue_s, B.pix_xy, B.pix_seed, B.pix_src, B.mt_state, B.t1, B.t2,
+                    B.sh_contrib, B.last_tri, B.cur1, B.queue_a, B.queue_b, B.queue_s, B.key_next, B.key_shadow, B.pix_xy, B.pix_seed, B.pix_src, B.mt_state, B.t1, B.t2,
                     B.tiles, B.tiles2, B.counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (B.h_counters) cudaFreeHost(B.h_counters);
@@ -702,6 +773,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     size_t call_pixels = 0;
     const bool counting = ctx->counting;
     const uint32_t skip_null = env_flag("RGK_SKIP_NULL_SHADOW", true) ? 1u : 0u;
+    const bool binning = env_flag("RGK_BIN", true) && P->depth > 1;
+    const size_t bin_items = env_size("RGK_BIN_ITEMS", 4096);   // path slots per reordering group
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 8);
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
@@ -745,7 +818,11 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         RenderConst R{};
         R.cam = *cam; R.xres = P->xres; R.yres = P->yres; R.ms = ms; R.depth = P->depth; R.clamp = P->clamp; R.russian = P->russian;
         R.bump_scale = P->bumpmap_scale; R.set_size = ss; R.n1d = n1d; R.n2d = n2d; R.base2 = base2; R.sampler_mode = P->sampler_mode;
-        R.lens = lens; R.npix = (uint32_t)npix; R.skip_null_shadow = skip_null;
+        R.lens = lens; R.npix = (uint32_t)npix; R.skip_null_shadow = skip_null; R.binning = binning ? 1u : 0u;
+        // reordering groups: SG samples x PG pixel positions (a multiple of the 32-pixel blocks of k_pixel_setup)
+        const uint32_t SG = (uint32_t)std::min<size_t>(ms, 128);
+        const uint32_t PG = (uint32_t)std::max<size_t>(32, (bin_items / SG) / 32 * 32);
+        const uint32_t n_pgroups = (uint32_t)((npix + PG - 1) / PG), n_sgroups = (ms + SG - 1) / SG;
         SamplerView smp{B.t1, B.t2, (uint32_t)npix, ss, sq, P->sampler_mode};
         pool.begin(ctx->stream, T_SAMPLER);
         k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed, B.pix_src, (uint32_t)call_pixels);
@@ -785,7 +862,18 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             else k_closest<false, RGK_INCOH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             pool.end(ctx->stream);
             pool.begin(ctx->stream, T_SHADE);
+            const bool last_bounce = bounce + 1 >= P->depth;       // no continuation rays: k_shade ends every path (n == depth)
+            if (binning) {
+                if (!last_bounce) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
+                RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
+            }
             k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
+            if (binning) {
+                if (!last_bounce)
+                    k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, B.counters + C_NEXT);
+                k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_shadow, (uint32_t)npix, ms, PG, SG, n_pgroups, B.queue_s, B.counters + C_SHADOW);
+                ctx->launches += 2;
+            }
             pool.end(ctx->stream);
             ctx->launches += 2; total.closest_launches++;
             RGK_CUDA(ctx, cudaMemcpyAsync(B.h_counters, B.counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));

@@ -81,10 +81,10 @@ k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict
 
 } // namespace
 
-// RGK_TRAVERSAL=2..6 selects the traversal control structure of the batch entry points (A/B knob; results are identical)
+// RGK_TRAVERSAL=2|6 selects the traversal control structure of the batch entry points (A/B knob; results are identical)
 int rgk_traversal_variant() {
     static int v = 0;
-    if (!v) { const char* e = std::getenv("RGK_TRAVERSAL"); v = (e && e[0] >= '2' && e[0] <= '6') ? (e[0] - '0') : 6; }
+    if (!v) { const char* e = std::getenv("RGK_TRAVERSAL"); v = (e && (e[0] == '2' || e[0] == '6')) ? (e[0] - '0') : 6; }
     return v;
 }
 
@@ -114,9 +114,6 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
     const int variant = rgk_traversal_variant();
     if (d_stats) k_trace_closest<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
     else if (variant == 6) k_trace_closest<false, 6><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
-    else if (variant == 5) k_trace_closest<false, 5><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
-    else if (variant == 4) k_trace_closest<false, 4><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
-    else if (variant == 3) k_trace_closest<false, 3><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     else if (variant == 2) k_trace_closest<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     ctx->launches++;
     RGK_CUDA(ctx, cudaGetLastError());
@@ -135,9 +132,6 @@ rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* 
     const int variant = rgk_traversal_variant();
     if (d_stats) k_trace_shadow<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
     else if (variant == 6) k_trace_shadow<false, 6><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
-    else if (variant == 5) k_trace_shadow<false, 5><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
-    else if (variant == 4) k_trace_shadow<false, 4><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
-    else if (variant == 3) k_trace_shadow<false, 3><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     else if (variant == 2) k_trace_shadow<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     ctx->launches++;
     RGK_CUDA(ctx, cudaGetLastError());

@@ -164,6 +164,10 @@ typedef struct rgk_hit {
  * 36 + 20 + 8*inner + 8*leaf + 4*refs + 48*tests). */
 typedef struct rgk_trav_stats {
     uint64_t rays, inner, leaf, refs, tests;
+    /* device-side only (0 from a CPU checker): of the `tests`, how many reached the exact fp64 TestIntersection
+     * arithmetic, how many were settled before it by the conservative 2-D bounds pre-filter, and how many of those
+     * the exact test would have accepted (must be 0: the pre-filter may only reject what the reference rejects). */
+    uint64_t exact, prefiltered, prefilter_wrong;
 } rgk_trav_stats;
 
 /* ---- rendering ---------------------------------------------------------- */

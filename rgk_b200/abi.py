@@ -82,10 +82,14 @@ class Hit(C.Structure):
 
 class TravStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("inner", C.c_uint64), ("leaf", C.c_uint64), ("refs", C.c_uint64),
-                ("tests", C.c_uint64)]
+                ("tests", C.c_uint64), ("exact", C.c_uint64), ("prefiltered", C.c_uint64), ("prefilter_wrong", C.c_uint64)]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+        """The algorithmic counters (identical on the CPU checkers and the device)."""
+        return {k: int(getattr(self, k)) for k in ("rays", "inner", "leaf", "refs", "tests")}
+
+    def device_dict(self):
+        return {k: int(getattr(self, k)) for k in ("exact", "prefiltered", "prefilter_wrong")}
 
     def bytes_per_ray(self, out_bytes=20):
         """36 in + out + 8*inner + 8*leaf + 4*refs + 48*tests, averaged over the batch."""

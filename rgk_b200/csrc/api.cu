@@ -149,6 +149,11 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
                 rp[j] = make_float4(q[0], q[1], q[2], q[3]);
             }
             UP(rp, &D.ref_planes);
+            for (size_t j = 0; j < rp.size(); j++) {
+                const float* q = &hs.tri_bounds[4 * (size_t)hs.refs[j]];
+                rp[j] = make_float4(q[0], q[1], q[2], q[3]);
+            }
+            UP(rp, &D.ref_bounds);
         }
         std::vector<float4> rec(hs.tri_isect.size() / 4);
         std::memcpy(rec.data(), hs.tri_isect.data(), hs.tri_isect.size() * 4);

@@ -153,6 +153,51 @@ unsigned measure_depth(const std::vector<uint32_t>& nodes) {
 
 } // namespace
 
+// Conservative bounds of the region in which Triangle::TestIntersection can accept a hit point, in the triangle's
+// 2-D projection (the dominant-axis projection the test itself uses, src/primitives.cpp:104-133): the box of the three
+// projected vertices widened by W, an upper bound of how far outside the true triangle the test's own fp32 rounding can
+// still accept.  The test accepts iff 0 <= beta <= 1, alpha >= 0, alpha + beta <= 1 with
+//   beta = (q0y q1x - q0x q1y) / den,  alpha = (q0x - beta q2x) / q1x        (|q1x| >= eps)
+//   beta = q0x / q2x,                  alpha = (q0y - beta q2y) / q1y        (|q1x| <  eps)
+// For a point within a few triangle sizes L the rounding of the numerators is <= 4u L^2 (u = 2^-24) and of den
+// <= 4u L^2, so beta is off by db <= 16u L^2 / |den| and alpha by da <= db |q2x / q1x| + 12u L / |q1x|.  An accepted
+// point is (alpha_fl q1 + beta_fl q2), which lies in the vertex box, minus (da q1 + db q2), whose size is at most
+// 23u L^3 / |den| (1 + L / |q1x|) + 17u L^2 / |q1x| (|q1x| standing for whatever alpha is divided by).  W takes 128u for
+// every term (5x slack) and the filter is disabled (infinite box) when den is within 2^-16 L^2 of cancelling.  The
+// device adds the ray-dependent part (error of its fp32 t and of o + d t) at run time.  The axis code rides in the two
+// low mantissa bits of the first bound, which is first moved 8 ulps outwards.
+static void tri_prefilter_bounds(const float* r, uint32_t code, float* out) {
+    const double v0x = r[4], v0y = r[5], q1x = r[6], q1y = r[7], q2x = r[8], q2y = r[9], den = r[10];
+    const double L = std::max(std::max(std::fabs(q1x), std::fabs(q1y)), std::max(std::fabs(q2x), std::fabs(q2y)));
+    const double K = std::ldexp(1.0, -17);
+    const double inf = std::numeric_limits<double>::infinity();
+    double W = inf;
+    const bool flagged = (code & 4u) != 0;
+    const double den_eff = flagged ? std::min(std::fabs(den), std::fabs(q2x * q1y)) : std::fabs(den);
+    const double div_a = flagged ? std::min(std::fabs(q1y), std::fabs(q2x)) : std::fabs(q1x);
+    if (L > 0 && den_eff > std::ldexp(L * L, -16) && div_a > 0 && std::isfinite(L))
+        W = K * (L * L * L / den_eff * (1.0 + L / div_a) + L * L / div_a + L);
+    float b[4];
+    if (!(W < inf)) {
+        b[0] = -std::numeric_limits<float>::max(); b[1] = std::numeric_limits<float>::max(); b[2] = b[0]; b[3] = b[1];
+    } else {
+        const double lo1 = v0x + std::min(0.0, std::min(q1x, q2x)) - W, hi1 = v0x + std::max(0.0, std::max(q1x, q2x)) + W;
+        const double lo2 = v0y + std::min(0.0, std::min(q1y, q2y)) - W, hi2 = v0y + std::max(0.0, std::max(q1y, q2y)) + W;
+        const float ninf = -std::numeric_limits<float>::infinity(), pinf = std::numeric_limits<float>::infinity();
+        b[0] = std::nextafterf((float)lo1, ninf); b[1] = std::nextafterf((float)hi1, pinf);
+        b[2] = std::nextafterf((float)lo2, ninf); b[3] = std::nextafterf((float)hi2, pinf);
+        if (!(std::fabs(b[0]) > 1e-30f)) b[0] = -1e-30f;       // keep the bit surgery below away from zero / denormals
+        for (int k = 0; k < 8; k++) b[0] = std::nextafterf(b[0], ninf);
+        if (!std::isfinite(b[0]) || !std::isfinite(b[1]) || !std::isfinite(b[2]) || !std::isfinite(b[3])) {
+            b[0] = -std::numeric_limits<float>::max(); b[1] = std::numeric_limits<float>::max(); b[2] = b[0]; b[3] = b[1];
+        }
+    }
+    uint32_t bits; std::memcpy(&bits, &b[0], 4);
+    bits = (bits & ~3u) | (code & 3u);                          // moves the value by < 4 ulps; 8 were reserved
+    std::memcpy(&b[0], &bits, 4);
+    out[0] = b[0]; out[1] = b[1]; out[2] = b[2]; out[3] = b[3];
+}
+
 void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScene& hs) {
     hs = HostScene();
     const uint32_t nt = d->n_triangles, nv = d->n_vertices;
@@ -279,6 +324,7 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
 
     // intersection records: the ray-independent part of Triangle::TestIntersection (src/primitives.cpp:83,104-133,141,149)
     hs.tri_isect.resize(12 * (size_t)nt);
+    hs.tri_bounds.resize(4 * (size_t)nt);
     for (uint32_t i = 0; i < nt; i++) {
         const float* p = &hs.planes[4 * (size_t)i];
         const float px = std::fabs(p[0]), py = std::fabs(p[1]), pz = std::fabs(p[2]);
@@ -296,6 +342,7 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
         r[0] = p[0]; r[1] = p[1]; r[2] = p[2]; r[3] = p[3];
         r[4] = comp(v0, i1); r[5] = comp(v0, i2); r[6] = q1x; r[7] = q1y;
         r[8] = q2x; r[9] = q2y; r[10] = denom; std::memcpy(&r[11], &code, 4);
+        tri_prefilter_bounds(r, code, &hs.tri_bounds[4 * (size_t)i]);
     }
 
     rgk_scene_info& in = hs.info;

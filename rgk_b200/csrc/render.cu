@@ -329,16 +329,17 @@ constexpr int TRACE_THREADS = 128;
 template <bool COUNT>
 __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays, rgk_trav_stats* stats) {
     if (!COUNT) return;
-    unsigned long long v[5] = {nrays, c.inner, c.leaf, c.refs, c.tests};
+    unsigned long long v[8] = {nrays, c.inner, c.leaf, c.refs, c.tests, c.exact, c.prefiltered, c.wrong};
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 8; k++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd((unsigned long long*)&stats->rays, v[0]); atomicAdd((unsigned long long*)&stats->inner, v[1]);
         atomicAdd((unsigned long long*)&stats->leaf, v[2]); atomicAdd((unsigned long long*)&stats->refs, v[3]);
-        atomicAdd((unsigned long long*)&stats->tests, v[4]);
+        atomicAdd((unsigned long long*)&stats->tests, v[4]); atomicAdd((unsigned long long*)&stats->exact, v[5]);
+        atomicAdd((unsigned long long*)&stats->prefiltered, v[6]); atomicAdd((unsigned long long*)&stats->prefilter_wrong, v[7]);
     }
 }
 
@@ -346,7 +347,7 @@ __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays,
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, rgk_trav_stats* stats) {
-    TravCount cnt{0, 0, 0, 0};
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
     uint32_t mine = 0;
     trace_rays<RGK_RENDER_VARIANT, false, COUNT>(S, count, work, cnt, mine,
         [&](uint32_t i, Traverser<false, COUNT>& T) {
@@ -365,7 +366,7 @@ k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, rgk_trav_stats* stats) {
-    TravCount cnt{0, 0, 0, 0};
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
     uint32_t mine = 0;
     trace_rays<RGK_RENDER_VARIANT, true, COUNT>(S, count, work, cnt, mine,
         [&](uint32_t i, Traverser<true, COUNT>& T) {
@@ -513,6 +514,7 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                         if (isnan(lightN.x)) lightN = faceN;
                     }
                 }
+                const TexPre pre = tex_prefetch(S, mat, uv);
                 const Frame fr = system_transform_z(lightN);
                 const V3 VrL = qrot(fr.g2l, Vr);
                 // ---- next-event estimation set-up (the visibility test runs in k_shadow)
@@ -524,7 +526,7 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                     const V3 lpos = v3(lp4);
                     const float4 lc = B.light_col[slot];
                     const V3 Vi = normalize(lpos - pos);
-                    const RGB f = bxdf_value(S, tv.w, qrot(fr.g2l, Vi), VrL, uv);
+                    const RGB f = bxdf_value(S, tv.w, mat, qrot(fr.g2l, Vi), VrL, uv, pre);
                     const V3 dlt = lpos - pos;
                     const float G = fabsf(dot(lightN, Vi)) / dot(dlt, dlt);
                     float df = 1.0f;
@@ -557,7 +559,7 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                 const uint32_t seed = B.pix_seed[pixel];
                 const V2 sample = smp.get2d(pixel, seed, set, R.base2 + (n - 1u));
                 V3 dir; RGB tcf; bool may_leak;
-                bxdf_sample(S, tv.w, VrL, uv, sample, dir, tcf, may_leak);
+                bxdf_sample(S, mat, VrL, uv, sample, dir, tcf, may_leak, pre);
                 const bool inside = dir.z < 0;
                 dir = qrot(fr.l2g, dir);
                 if (!(dot(dir, faceN) * dot(Vr, faceN) > 0) && !may_leak) n += 10000u;

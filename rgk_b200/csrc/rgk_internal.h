@@ -43,6 +43,8 @@ struct DevScene {
     const uint32_t* refs;
     const float4* ref_planes;    // [n_refs] plane record (n.xyz, d) of triangle refs[j]: the leaf scan reads reference and plane
                                  // side by side instead of chasing refs[j] -> tri_isect[3*refs[j]] (one dependent load less)
+    const float4* ref_bounds;    // [n_refs] conservative 2-D bounds of triangle refs[j] in its projection plane
+                                 // (lo1 | axis code in the two low mantissa bits, hi1, lo2, hi2): pre-filter of the exact test
     const float4* tri_isect;
     const uint4* tri_shade;
     const float4* positions;
@@ -75,6 +77,7 @@ struct HostScene {
     std::vector<uint32_t> nodes, refs;          // reference encoding
     std::vector<float> planes;                  // 4 / triangle
     std::vector<float> tri_isect;               // 12 / triangle
+    std::vector<float> tri_bounds;              // 4 / triangle (see DevScene::ref_bounds)
     std::vector<uint32_t> tri_shade;            // 4 / triangle
     std::vector<DevArealLight> areal_lights;
     std::vector<DevArealTri> areal_tris;

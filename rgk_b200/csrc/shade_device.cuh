@@ -214,20 +214,41 @@ __device__ __forceinline__ void fresnel_dielectric(float eta, float cosTheta, fl
     const float Rp = (eta * ct - cosTheta) / (eta * ct + cosTheta);
     R = 0.5f * (Rs * Rs + Rp * Rp); cosT = ct;
 }
+// The two colour textures of a vertex's material, fetched once per vertex: BxDF::value (NEE) and BxDF::sample
+// (continuation) of the reference each call GetPixelInterpolated with the same texture and uv, which returns the same
+// value; `have` is false for the children of a mix material (their textures differ from the top-level one's).
+struct TexPre { bool have; RGB diffuse, color; };
+__device__ __forceinline__ RGB tex_diffuse_of(const DevScene& S, const DevMaterial& m, V2 uv, const TexPre& pre) {
+    return pre.have ? pre.diffuse : tex_fetch(S, m.tex_diffuse, uv);
+}
+__device__ __forceinline__ RGB tex_color_of(const DevScene& S, const DevMaterial& m, V2 uv, const TexPre& pre) {
+    return pre.have ? pre.color : tex_fetch(S, m.tex_color, uv);
+}
+// which of the two a material kind reads at all (the others never call the texture)
+__device__ __forceinline__ TexPre tex_prefetch(const DevScene& S, const DevMaterial& m, V2 uv) {
+    TexPre pre; pre.have = m.bxdf != RGK_BXDF_MIX; pre.diffuse = rgb(0, 0, 0); pre.color = rgb(0, 0, 0);
+    if (!pre.have) return pre;
+    const bool uses_diffuse = m.bxdf == RGK_BXDF_DIFFUSE || m.bxdf == RGK_BXDF_LTC_BECKMANN_DIFFUSE || m.bxdf == RGK_BXDF_LTC_GGX_DIFFUSE;
+    const bool uses_color = m.bxdf != RGK_BXDF_DIFFUSE && m.bxdf != RGK_BXDF_TRANSPARENT;
+    if (uses_diffuse) pre.diffuse = tex_fetch(S, m.tex_diffuse, uv);
+    if (uses_color) pre.color = tex_fetch(S, m.tex_color, uv);
+    return pre;
+}
+
 // value of a non-mix material
-static __device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv) {
+static __device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv, TexPre pre) {
     switch (m.bxdf) {
     case RGK_BXDF_DIFFUSE: {
         if (Vi.z <= 0 || Vr.z <= 0) return rgb(0, 0, 0);
-        const RGB c = tex_fetch(S, m.tex_diffuse, uv); return rgb(c.r / RGK_PI_F, c.g / RGK_PI_F, c.b / RGK_PI_F); }
+        const RGB c = tex_diffuse_of(S, m, uv, pre); return rgb(c.r / RGK_PI_F, c.g / RGK_PI_F, c.b / RGK_PI_F); }
     case RGK_BXDF_MIRROR: {
         const V3 refl = v3(-Vi.x, -Vi.y, Vi.z);
-        if (fabsf(dot(refl, Vr) - 1) < 0.0001f) return tex_fetch(S, m.tex_color, uv);
+        if (fabsf(dot(refl, Vr) - 1) < 0.0001f) return tex_color_of(S, m, uv, pre);
         return rgb(0, 0, 0); }
     case RGK_BXDF_DIELECTRIC: {
         const float eta = (Vi.z < 0) ? m.ior : (float)(1.0 / (double)m.ior);
         float R, cosT; fresnel_dielectric(eta, Vi.z, R, cosT);
-        const RGB c = tex_fetch(S, m.tex_color, uv);
+        const RGB c = tex_color_of(S, m, uv, pre);
         if (Vi.z * Vr.z > 0) {
             const V3 refl = v3(-Vi.x, -Vi.y, Vi.z);
             if (fabsf(dot(Vr, refl) - 1) < 0.001f) return rgb(c.r * R, c.g * R, c.b * R);
@@ -243,12 +264,12 @@ static __device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevM
         return rgb(0, 0, 0); }
     case RGK_BXDF_LTC_BECKMANN: case RGK_BXDF_LTC_GGX: {
         if (Vi.z <= 0 || Vr.z <= 0) return rgb(0, 0, 0);
-        const RGB c = tex_fetch(S, m.tex_color, uv);
+        const RGB c = tex_color_of(S, m, uv, pre);
         const float p = ltc_pdf(S, m.bxdf == RGK_BXDF_LTC_GGX ? 0 : 1, Vi, Vr, m.roughness);
         return rgb(p * c.r, p * c.g, p * c.b); }
     case RGK_BXDF_LTC_BECKMANN_DIFFUSE: case RGK_BXDF_LTC_GGX_DIFFUSE: {
         if (Vi.z <= 0 || Vr.z <= 0) return rgb(0, 0, 0);
-        const RGB diff = tex_fetch(S, m.tex_diffuse, uv), spec = tex_fetch(S, m.tex_color, uv);
+        const RGB diff = tex_diffuse_of(S, m, uv, pre), spec = tex_color_of(S, m, uv, pre);
         const float p = ltc_pdf(S, m.bxdf == RGK_BXDF_LTC_GGX_DIFFUSE ? 0 : 1, Vi, Vr, m.roughness);
         return rgb(p * spec.r + diff.r / RGK_PI_F, p * spec.g + diff.g / RGK_PI_F, p * spec.b + diff.b / RGK_PI_F); }
     }
@@ -256,16 +277,16 @@ static __device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevM
 }
 // BxDFMix::value (src/bxdf/bxdf.cpp:235-239) is a binary tree of lerps; evaluated without recursion by an
 // explicit post-order walk (mix children always precede the mix material, so depth is bounded; cap 8).
-__device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, V3 Vi, V3 Vr, V2 uv) {
-    const DevMaterial m = S.materials[mi];
-    if (m.bxdf != RGK_BXDF_MIX) return bxdf_value_leaf(S, m, Vi, Vr, uv);
+__device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv, const TexPre& pre) {
+    if (m.bxdf != RGK_BXDF_MIX) return bxdf_value_leaf(S, m, Vi, Vr, uv, pre);
+    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0);
     // stack of (material, state): state 0 = visit a, 1 = visit b, 2 = combine
     uint32_t st_m[8]; int st_s[8]; RGB val[9]; int sp = 0, vp = 0;
     st_m[0] = mi; st_s[0] = 0; sp = 1;
     while (sp > 0) {
         const uint32_t cur = st_m[sp - 1];
         const DevMaterial cm = S.materials[cur];
-        if (cm.bxdf != RGK_BXDF_MIX) { val[vp++] = bxdf_value_leaf(S, cm, Vi, Vr, uv); --sp; continue; }
+        if (cm.bxdf != RGK_BXDF_MIX) { val[vp++] = bxdf_value_leaf(S, cm, Vi, Vr, uv, none); --sp; continue; }
         const int s = st_s[sp - 1];
         if (s == 0) { st_s[sp - 1] = 1; if (sp < 8) { st_m[sp] = (uint32_t)cm.mix_a; st_s[sp] = 0; ++sp; } else val[vp++] = rgb(0, 0, 0); }
         else if (s == 1) { st_s[sp - 1] = 2; if (sp < 8) { st_m[sp] = (uint32_t)cm.mix_b; st_s[sp] = 0; ++sp; } else val[vp++] = rgb(0, 0, 0); }
@@ -278,22 +299,28 @@ __device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, V3 Vi,
     }
     return val[0];
 }
+__device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, V3 Vi, V3 Vr, V2 uv) {
+    const DevMaterial m = S.materials[mi];
+    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0);
+    return bxdf_value(S, mi, m, Vi, Vr, uv, none);
+}
 // BxDF::sample: returns local direction, weight and may_leak
-__device__ __forceinline__ void bxdf_sample(const DevScene& S, uint32_t mi, V3 Vi, V2 uv, V2 sample, V3& dir, RGB& w, bool& may_leak) {
-    DevMaterial m = S.materials[mi];
-    for (int guard = 0; m.bxdf == RGK_BXDF_MIX && guard < 16; guard++)          // BxDFMix::sample, src/bxdf/bxdf.cpp:241-249
+__device__ __forceinline__ void bxdf_sample(const DevScene& S, DevMaterial m, V3 Vi, V2 uv, V2 sample, V3& dir, RGB& w, bool& may_leak, TexPre pre) {
+    for (int guard = 0; m.bxdf == RGK_BXDF_MIX && guard < 16; guard++) {        // BxDFMix::sample, src/bxdf/bxdf.cpp:241-249
         m = S.materials[decide_and_rescale(sample.x, m.amount) ? m.mix_a : m.mix_b];
+        pre.have = false;
+    }
     may_leak = false;
     switch (m.bxdf) {
     case RGK_BXDF_DIFFUSE:
         if (Vi.z <= 0) { dir = v3(0, 1, 0); w = rgb(0, 0, 0); return; }
-        dir = hemi_cos_z(sample); w = tex_fetch(S, m.tex_diffuse, uv); return;
+        dir = hemi_cos_z(sample); w = tex_diffuse_of(S, m, uv, pre); return;
     case RGK_BXDF_MIRROR:
-        dir = v3(-Vi.x, -Vi.y, Vi.z); w = tex_fetch(S, m.tex_color, uv); return;
+        dir = v3(-Vi.x, -Vi.y, Vi.z); w = tex_color_of(S, m, uv, pre); return;
     case RGK_BXDF_DIELECTRIC: {
         const float eta = (Vi.z < 0) ? m.ior : (float)(1.0 / (double)m.ior);
         float R, cosT; fresnel_dielectric(eta, fabsf(Vi.z), R, cosT);
-        const RGB c = tex_fetch(S, m.tex_color, uv);
+        const RGB c = tex_color_of(S, m, uv, pre);
         if (decide_and_rescale(sample.x, R)) { dir = v3(-Vi.x, -Vi.y, Vi.z); w = c; return; }
         cosT = fabsf(cosT);
         dir = v3(-Vi.x * eta, -Vi.y * eta, (Vi.z > 0) ? -cosT : cosT); w = c; may_leak = true; return; }
@@ -304,9 +331,9 @@ __device__ __forceinline__ void bxdf_sample(const DevScene& S, uint32_t mi, V3 V
         v = ltc_random(S, m.bxdf == RGK_BXDF_LTC_GGX ? 0 : 1, Vi, m.roughness, v);
         dir = v;
         if (v.z <= 0) { w = rgb(0, 0, 0); return; }
-        w = tex_fetch(S, m.tex_color, uv); return; }
+        w = tex_color_of(S, m, uv, pre); return; }
     case RGK_BXDF_LTC_BECKMANN_DIFFUSE: case RGK_BXDF_LTC_GGX_DIFFUSE: {
-        const RGB diff = tex_fetch(S, m.tex_diffuse, uv), spec = tex_fetch(S, m.tex_color, uv);
+        const RGB diff = tex_diffuse_of(S, m, uv, pre), spec = tex_color_of(S, m, uv, pre);
         const float dp = diff.r + diff.g + diff.b, sp = spec.r + spec.g + spec.b;
         const float prob = dp / (dp + sp + 0.0001f);
         if (decide_and_rescale(sample.x, prob)) {
@@ -320,6 +347,11 @@ __device__ __forceinline__ void bxdf_sample(const DevScene& S, uint32_t mi, V3 V
         w = spec; return; }
     }
     dir = v3(0, 1, 0); w = rgb(0, 0, 0);
+}
+
+__device__ __forceinline__ void bxdf_sample(const DevScene& S, uint32_t mi, V3 Vi, V2 uv, V2 sample, V3& dir, RGB& w, bool& may_leak) {
+    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0);
+    bxdf_sample(S, S.materials[mi], Vi, uv, sample, dir, w, may_leak, none);
 }
 
 // ---- lights (src/scene.cpp:686-745, src/primitives.cpp:61-73) and sky (src/scene.cpp:748-763)

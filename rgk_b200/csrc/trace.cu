@@ -22,9 +22,9 @@ template <bool COUNT>
 __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays, rgk_trav_stats* stats) {
     if (!COUNT) return;
     // warp-aggregate, one atomic per counter per warp
-    unsigned long long v[5] = {nrays, c.inner, c.leaf, c.refs, c.tests};
+    unsigned long long v[8] = {nrays, c.inner, c.leaf, c.refs, c.tests, c.exact, c.prefiltered, c.wrong};
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 8; k++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     }
@@ -33,7 +33,8 @@ __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays,
         atomicAdd((unsigned long long*)&stats->inner, v[1]);
         atomicAdd((unsigned long long*)&stats->leaf, v[2]);
         atomicAdd((unsigned long long*)&stats->refs, v[3]);
-        atomicAdd((unsigned long long*)&stats->tests, v[4]);
+        atomicAdd((unsigned long long*)&stats->tests, v[4]); atomicAdd((unsigned long long*)&stats->exact, v[5]);
+        atomicAdd((unsigned long long*)&stats->prefiltered, v[6]); atomicAdd((unsigned long long*)&stats->prefilter_wrong, v[7]);
     }
 }
 
@@ -41,7 +42,7 @@ template <bool COUNT, int VARIANT>
 __global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
 k_trace_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, uint64_t n,
                 rgk_hit* __restrict__ hits, rgk_trav_stats* stats, unsigned long long* next) {
-    TravCount cnt{0, 0, 0, 0};
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
     uint32_t mine = 0;
     trace_rays<VARIANT, false, COUNT>(S, (uint32_t)n, next, cnt, mine,
         [&](uint32_t i, Traverser<false, COUNT>& T) {
@@ -63,7 +64,7 @@ template <bool COUNT, int VARIANT>
 __global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
 k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, uint64_t n,
                uint8_t* __restrict__ visible, rgk_trav_stats* stats, unsigned long long* next) {
-    TravCount cnt{0, 0, 0, 0};
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
     uint32_t mine = 0;
     trace_rays<VARIANT, true, COUNT>(S, (uint32_t)n, next, cnt, mine,
         [&](uint32_t i, Traverser<true, COUNT>& T) {

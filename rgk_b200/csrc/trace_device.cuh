@@ -11,7 +11,7 @@
 #pragma once
 #include "rgk_internal.h"
 
-struct TravCount { uint32_t inner, leaf, refs, tests; };
+struct TravCount { uint32_t inner, leaf, refs, tests, exact, prefiltered, wrong; };
 // Per-ray traversal stack (local memory, lane-interleaved by the hardware); kept outside the Traverser so that the
 // scalar ray / interval state stays in registers.  An entry is (far child, bits of its tmin): the reference's
 // NodeToDo{node, tmin, tmax} (src/scene_intersect.cpp:242) without tmax, because a pushed child's interval is
@@ -112,14 +112,45 @@ struct Traverser {
         lo_c = (lo - fabsf(lo) * 3.814697265625e-6f) - 1e-30f;
         hi_c = (hi + fabsf(hi) * 3.814697265625e-6f) + 1e-30f;
     }
-    // one reference of the leaf scan: true = survives the pre-rejection (needs the exact test)
-    __device__ __forceinline__ bool prescreen(const float4 r0, float eps, float lo_c, float hi_c) const {
+    // one reference of the leaf scan: true = survives the pre-rejection (needs the exact test); t32 = its approximate t
+    __device__ __forceinline__ bool prescreen(const float4 r0, float eps, float lo_c, float hi_c, float& t32) const {
         const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;
         const float dot2f = ox * r0.x + oy * r0.y + oz * r0.z;
         float rcp;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(dtf));
-        const float t32 = -(r0.w + dot2f) * rcp;
+        t32 = -(r0.w + dot2f) * rcp;
         return !((fabsf(dtf) < eps) || (t32 < lo_c) || (t32 > hi_c));
+    }
+
+    // Second conservative filter, applied to the survivors of the scan before the exact arithmetic: the approximate hit
+    // point o + d t32, projected like TestIntersection projects it, against the triangle's widened 2-D bounds
+    // (DevScene::ref_bounds, built by tri_prefilter_bounds in host_scene.cpp, which bounds the test's own rounding).
+    // The run-time margin covers the difference between this point and the one the exact test computes:
+    // |t32 - t| < 2^-21 |t| moves it by < 2^-21 |t| (|d| = 1), and the two evaluations of o + d t round differently by
+    // < 2^-22 (|o| + |t|); 2^-17 (|t32| + |ox| + |oy| + |oz|) is 16x that.  NaNs compare false (candidate kept).
+    // Most survivors of the scan cross the plane inside the leaf but far from the triangle: this settles them with one
+    // 16-byte load instead of the fp64 divide and two more record loads.
+    __device__ __forceinline__ bool outside_bounds(const DevScene& S, uint32_t p, float t32) const {
+        const float4 b = __ldg(S.ref_bounds + p);
+        const uint32_t code = __float_as_uint(b.x) & 3u;
+        const float o1 = (code == 0u) ? oy : ox, d1 = (code == 0u) ? dy : dx;
+        const float o2 = (code == 2u) ? oy : oz, d2 = (code == 2u) ? dy : dz;
+        const float m = (((fabsf(t32) + fabsf(ox)) + fabsf(oy)) + fabsf(oz)) * 7.62939453125e-6f;
+        const float p1 = __fmaf_rn(d1, t32, o1), p2 = __fmaf_rn(d2, t32, o2);
+        return (p1 + m < b.x) || (p1 - m > b.y) || (p2 + m < b.z) || (p2 - m > b.w);
+    }
+    // one survivor of the scan: pre-filter, then the exact test
+    __device__ __forceinline__ bool candidate(const DevScene& S, uint2 c, float lo, float hi, TravCount& cnt) {
+        const bool out = outside_bounds(S, c.x, __uint_as_float(c.y));
+        if (COUNT) {                                  // counting instantiation: also proves the filter right
+            if (__ldg(S.refs + c.x) == ignore) return false;
+            if (out) cnt.prefiltered++; else cnt.exact++;
+            const bool acc = exact_test(S, c.x, lo, hi);
+            if (acc && out) cnt.wrong++;
+            return acc;
+        }
+        if (out) return false;
+        return exact_test(S, c.x, lo, hi);
     }
 
     // Triangle::TestIntersection proper for the reference at position p of the reference list that survived the
@@ -182,23 +213,24 @@ struct Traverser {
         float lo, hi, lo_c, hi_c;
         leaf_bounds(eps, lo, hi, lo_c, hi_c);
         const uint32_t pend = w.x + (w.y >> 2);
-        uint32_t cand[RGK_CAND_CAP];
+        uint2 cand[RGK_CAND_CAP];
         int nc = 0;
         bool hit = false;
         for (uint32_t p = w.x; p < pend; p++) {
             if (COUNT) { cnt.refs++; if (__ldg(S.refs + p) != ignore) cnt.tests++; }
-            if (prescreen(__ldg(S.ref_planes + p), eps, lo_c, hi_c)) {
-                cand[nc++] = p;
+            float t32;
+            if (prescreen(__ldg(S.ref_planes + p), eps, lo_c, hi_c, t32)) {
+                cand[nc++] = make_uint2(p, __float_as_uint(t32));
                 if (nc == RGK_CAND_CAP) {          // list full: evaluate what we have, in order
                     for (int k = 0; k < RGK_CAND_CAP; k++) {
-                        if (exact_test(S, cand[k], lo, hi)) { if (ANY) return true; hit = true; }
+                        if (candidate(S, cand[k], lo, hi, cnt)) { if (ANY) return true; hit = true; }
                     }
                     nc = 0;
                 }
             }
         }
         for (int k = 0; k < nc; k++) {
-            if (exact_test(S, cand[k], lo, hi)) { if (ANY) return true; hit = true; }
+            if (candidate(S, cand[k], lo, hi, cnt)) { if (ANY) return true; hit = true; }
         }
         return hit;
     }
@@ -272,7 +304,7 @@ __device__ __forceinline__ void trace_phased(const DevScene& S, uint32_t count, 
     const float eps = S.epsilon;
     bool active = false, exhausted = false, in_leaf = false, hit = false;
     uint32_t item = 0, p = 0, pend = 0;
-    uint32_t cand[RGK_CAND_CAP];
+    uint2 cand[RGK_CAND_CAP];                  // (position in the reference list, bits of its approximate t)
     int nc = 0;
     float lo = 0.0f, hi = 0.0f, lo_c = 0.0f, hi_c = 0.0f;
     for (;;) {
@@ -305,18 +337,29 @@ __device__ __forceinline__ void trace_phased(const DevScene& S, uint32_t count, 
         __syncwarp();
         // ---- phase 2: scan the leaf's references with the conservative pre-rejection
         if (active) {
-            while (p < pend && nc < RGK_CAND_CAP) {
-                const float4 r0 = __ldg(S.ref_planes + p);
-                if (COUNT) { cnt.refs++; if (__ldg(S.refs + p) != T.ignore) cnt.tests++; }
-                if (T.prescreen(r0, eps, lo_c, hi_c)) cand[nc++] = p;
-                ++p;
+            // two references per trip (both planes requested before either is used); the second one is a harmless
+            // repeat of the first when the leaf has an odd number left
+            while (p < pend && nc <= RGK_CAND_CAP - 2) {
+                const bool two = p + 1u < pend;
+                const uint32_t p2 = two ? p + 1u : p;
+                const float4 ra = __ldg(S.ref_planes + p), rb = __ldg(S.ref_planes + p2);
+                if (COUNT) {
+                    cnt.refs += two ? 2u : 1u;
+                    if (__ldg(S.refs + p) != T.ignore) cnt.tests++;
+                    if (two && __ldg(S.refs + p2) != T.ignore) cnt.tests++;
+                }
+                float ta, tb;
+                const bool sa = T.prescreen(ra, eps, lo_c, hi_c, ta), sb = T.prescreen(rb, eps, lo_c, hi_c, tb) && two;
+                if (sa) cand[nc++] = make_uint2(p, __float_as_uint(ta));
+                if (sb) cand[nc++] = make_uint2(p2, __float_as_uint(tb));
+                p = p2 + 1u;
             }
         }
         __syncwarp();
         // ---- phase 3: exact tests of the survivors (leaf order), together
         if (active && nc > 0) {
             for (int k = 0; k < nc; k++)
-                if (T.exact_test(S, cand[k], lo, hi)) { hit = true; if (ANY) break; }
+                if (T.candidate(S, cand[k], lo, hi, cnt)) { hit = true; if (ANY) break; }
             nc = 0;
         }
         if (active && (p == pend || (ANY && hit))) {             // leaf finished (src/scene_intersect.cpp:290-292)

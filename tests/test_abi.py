@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(abi.Material) == 64 and C.sizeof(abi.Ray) == 32 and C.sizeof(abi.Hit) == 20
     assert C.sizeof(abi.Mesh) == 16 and C.sizeof(abi.PointLight) == 32 and C.sizeof(abi.Task) == 16
-    assert C.sizeof(abi.Camera) == 8 * 12 + 12 and C.sizeof(abi.TravStats) == 40
+    assert C.sizeof(abi.Camera) == 8 * 12 + 12 and C.sizeof(abi.TravStats) == 64
 
 
 def test_host_only_entry_points_work_without_gpu():

@@ -53,3 +53,4 @@ def test_dragon_sponza_standin_two_million_triangles(gpu_ctx, oracle):
     hits, sg = gpu_ctx.trace_closest(rays, want_stats=True)
     ho_hits, so = oracle.trace_closest(ho, rays, want_stats=True)
     assert hits.tobytes() == ho_hits.tobytes() and sg.as_dict() == so.as_dict()
+    assert sg.prefilter_wrong == 0

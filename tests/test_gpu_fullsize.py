@@ -30,6 +30,7 @@ def test_full_hd_primary_and_shadow_properties(gpu_ctx, oracle, sponza):
     hits, st = gpu_ctx.trace_closest(rays, want_stats=True)
     ok = hits["triangle"] != 0xFFFFFFFF
     assert 0.5 < ok.mean() < 1.0 and int(st.rays) == len(rays)
+    assert st.prefilter_wrong == 0 and st.prefiltered > st.exact     # the pre-filter settles most candidates, never wrongly
     a = pack.arrays()
     P, I = a["positions"].astype(np.float64), a["indices"]
     h, r = hits[ok], rays[ok]

@@ -38,6 +38,7 @@ def test_cornell_tree_and_primary_hits(gpu_ctx, oracle, cornell, use_oracle_tree
     ho_hits, so = oracle.trace_closest(ho, rays, want_stats=True)
     assert hg.tobytes() == ho_hits.tobytes()
     assert sg.as_dict() == so.as_dict()                  # same nodes / refs / tests visited: same algorithm
+    assert sg.prefilter_wrong == 0 and sg.prefiltered > 0   # the 2-D bounds pre-filter only rejects what the exact test rejects
     assert (hg["triangle"] != 0xFFFFFFFF).mean() > 0.99
 
 
@@ -68,7 +69,7 @@ def test_cornell_bounce_and_shadow(gpu_ctx, oracle, cornell):
     a, b = raybatches.shadow_segments(rays, hits, (-0.005, 1.97, -0.03))
     vg, sg = gpu_ctx.trace_shadow(a, b, want_stats=True)
     vc = oracle.trace_shadow(ho, a, b)
-    assert np.array_equal(vg, vc)
+    assert np.array_equal(vg, vc) and sg.prefilter_wrong == 0
     assert 0.05 < vg.mean() < 0.95
 
 

@@ -320,7 +320,10 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
 
 constexpr int TRACE_THREADS = 128;
 #ifndef RGK_INCOH_MINB
-#define RGK_INCOH_MINB 12   // CTAs/SM the incoherent-bounce instantiations are compiled for (register budget)
+#define RGK_INCOH_MINB 10   // CTAs/SM the incoherent-bounce instantiations are compiled for (48 registers; 12 = 40 registers spills)
+#endif
+#ifndef RGK_COH_MINB
+#define RGK_COH_MINB 9      // camera rays: 56 registers
 #endif
 #ifndef RGK_RENDER_VARIANT
 #define RGK_RENDER_VARIANT 6   // phase-synchronised traversal (trace_device.cuh)
@@ -782,7 +785,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
 
     // chunking: whole tiles, every multisample of a pixel in the same chunk
-    const size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)16 << 20);
+    const size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)32 << 20);
     const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
     const size_t max_table_bytes = env_size("RGK_TABLE_BYTES", (size_t)24 << 30);
     std::vector<uint4> h_tiles; std::vector<uint2> h_tiles2;
@@ -860,7 +863,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             // two register budgets of the same kernel: 56 registers (9 CTAs/SM) for the issue-bound coherent camera rays,
             // 40 registers (12 CTAs/SM) for later bounces, which are latency-bound and gain from the extra warps
             if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
-            else if (bounce == 0) k_closest<false, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
+            else if (bounce == 0) k_closest<false, RGK_COH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             else k_closest<false, RGK_INCOH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             pool.end(ctx->stream);
             pool.begin(ctx->stream, T_SHADE);

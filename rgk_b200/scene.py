@@ -252,6 +252,92 @@ class ScenePack:
         return d
 
 
+    # -- on-disk form (RGKPACK1, little endian; read by rgkb::PackFile in include/rgk_b200_host.hpp and load_pack below)
+    def save(self, path, cfg):
+        """Writes the flattened scene, the LTC tables, the render configuration and the Camera constructor arguments."""
+        a = self.arrays()
+        ltc = load_ltc_tables()
+        d = self.desc()
+        ca = cfg.camera_args()
+        with open(path, "wb") as f:
+            f.write(b"RGKPACK1")
+            f.write(np.array([len(a["positions"]), len(a["indices"]), len(a["mesh_ranges"]), len(self.materials), len(self.textures),
+                              len(self.point_lights), int(self.thinglass), 0], np.uint32).tobytes())
+            for k in ("positions", "normals", "tangents", "texcoords", "indices"):
+                f.write(a[k].tobytes())
+            f.write(bytes(C.string_at(d.meshes, C.sizeof(abi.Mesh) * d.n_meshes)))
+            f.write(bytes(C.string_at(d.materials, C.sizeof(abi.Material) * d.n_materials)))
+            for kind, val in self.textures:
+                if kind == "solid":
+                    f.write(np.array([0, 0, 0], np.uint32).tobytes()); f.write(np.array(val, F).tobytes())
+                else:
+                    f.write(np.array([1, val.shape[1], val.shape[0]], np.uint32).tobytes()); f.write(np.zeros(3, F).tobytes())
+                    f.write(np.ascontiguousarray(val, F).tobytes())
+            f.write(bytes(C.string_at(d.point_lights, C.sizeof(abi.PointLight) * d.n_point_lights)))
+            f.write(bytes(d.sky))
+            for k in ("ggx_M", "ggx_amp", "beckmann_M", "beckmann_amp"):
+                f.write(np.ascontiguousarray(ltc[k], F).tobytes())
+            f.write(np.array([cfg.xres, cfg.yres, cfg.multisample, cfg.recursion_level, cfg.rounds, int(cfg.force_fresnell), cfg.reverse, 0],
+                             np.uint32).tobytes())
+            f.write(np.array([cfg.clamp, cfg.russian, cfg.bumpmap_scale, cfg.output_scale], F).tobytes())
+            f.write(np.array(list(ca["pos"]) + list(ca["lookat"]) + list(ca["up"]) + [ca["yview"], ca["xview"], ca["focus_plane"], ca["lens_size"]], F).tobytes())
+
+
+def load_pack(path):
+    """Reads an RGKPACK1 file back into (ScenePack, RenderConfig); the config's camera is returned as ready-made
+    Camera constructor arguments (cfg.camera_args() gives them back unchanged)."""
+    raw = open(path, "rb").read()
+    if raw[:8] != b"RGKPACK1":
+        raise ValueError("not an RGKPACK1 file: " + path)
+    off = 8
+
+    def take(dtype, n):
+        nonlocal off
+        arr = np.frombuffer(raw, dtype=dtype, count=n, offset=off).copy()
+        off += arr.nbytes
+        return arr
+    nv, nt, nm, nmat, ntex, npl, thinglass, _ = (int(x) for x in take(np.uint32, 8))
+    pos, nrm, tan = take(F, 3 * nv).reshape(-1, 3), take(F, 3 * nv).reshape(-1, 3), take(F, 3 * nv).reshape(-1, 3)
+    uv, idx = take(F, 2 * nv).reshape(-1, 2), take(np.uint32, 3 * nt).reshape(-1, 3)
+    meshes = take(np.uint32, 4 * nm).reshape(-1, 4)
+    mats = (abi.Material * max(1, nmat)).from_buffer_copy(raw[off:off + 64 * nmat].ljust(64, b"\0")); off += 64 * nmat
+    pack = ScenePack()
+    pack.thinglass = thinglass
+    for i in range(nmat):
+        m = mats[i]
+        pack.add_material("m%d" % i, int(m.bxdf), tuple(m.emission), bool(m.no_russian), float(m.roughness), float(m.ior), float(m.amount),
+                          int(m.mix_a), int(m.mix_b), int(m.tex_diffuse), int(m.tex_color), int(m.tex_bump))
+    for _ in range(ntex):
+        kind, w, h = (int(x) for x in take(np.uint32, 3))
+        col = take(F, 3)
+        if kind == 0:
+            pack.textures.append(("solid", tuple(float(c) for c in col)))
+        else:
+            pack.textures.append(("image", take(F, 3 * w * h).reshape(h, w, 3)))
+    pls = take(F, 8 * npl).reshape(-1, 8)
+    for q in pls:
+        pack.point_lights.append((tuple(float(x) for x in q[0:3]), tuple(float(x) for x in q[3:6]), float(q[6]), float(q[7])))
+    sky = abi.Sky.from_buffer_copy(raw[off:off + C.sizeof(abi.Sky)]); off += C.sizeof(abi.Sky)
+    pack.sky = dict(mode=int(sky.mode), color=tuple(sky.color), intensity=float(sky.intensity), rotate=float(sky.rotate), envmap=int(sky.envmap))
+    off += 4 * (2 * 4096 * 9 + 2 * 4096)          # LTC tables: load_ltc_tables() supplies the same data
+    for first, n, mat, _ in meshes:
+        first, n = int(first), int(n)
+        tri = idx[first:first + n]
+        lo, hi = (int(tri.min()), int(tri.max()) + 1) if n else (0, 0)
+        pack.meshes.append((pos[lo:hi], nrm[lo:hi], uv[lo:hi], tan[lo:hi], (tri - np.uint32(lo)).astype(np.uint32), int(mat)))
+    c = take(np.uint32, 8)
+    cf = take(F, 4)
+    ca = take(F, 13)
+    cfg = RenderConfig()
+    cfg.xres, cfg.yres, cfg.multisample, cfg.recursion_level, cfg.rounds = (int(x) for x in c[:5])
+    cfg.force_fresnell, cfg.reverse = bool(c[5]), int(c[6])
+    cfg.clamp, cfg.russian, cfg.bumpmap_scale, cfg.output_scale = (float(x) for x in cf)
+    args = dict(pos=ca[0:3].copy(), lookat=ca[3:6].copy(), up=ca[6:9].copy(), yview=float(ca[9]), xview=float(ca[10]),
+                xres=cfg.xres, yres=cfg.yres, focus_plane=float(ca[11]), lens_size=float(ca[12]))
+    cfg.camera_args = lambda: dict(args)
+    return pack, cfg
+
+
 # ---------------------------------------------------------------- JSON config (src/config.cpp:260-558)
 class ConfigFileException(RuntimeError):
     pass

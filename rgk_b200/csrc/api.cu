@@ -37,7 +37,7 @@ void free_scene(rgk_context* ctx) {
 template <class T>
 rgk_status upload(rgk_context* ctx, const std::vector<T>& h, const T** d) {
     *d = nullptr;
-    const size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
+    const size_t bytes = std::max<size_t>(h.size() * sizeof(T), 64);   // never empty: element 0 is always readable
     void* p = nullptr;
     RGK_CUDA(ctx, cudaMalloc(&p, bytes));
     ctx->scene_allocs.push_back(p);

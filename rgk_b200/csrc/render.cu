@@ -484,6 +484,16 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
         const V3 ro = v3(ro4), rd = v3(rd4);
         float4 cum4 = B.cum[slot];
         uint32_t n = __float_as_uint(cum4.w) + 1u;
+        // everything else that is addressed by the slot alone is requested here, ahead of the dependent chain
+        // triangle -> vertices / material -> textures -> LTC taps (the kernel is latency-bound): the sample's light and
+        // the two sampler values this vertex may consume (continuation direction, Russian roulette)
+        const float4 lp4 = B.light_pos[slot];
+        const float4 lc = B.light_col[slot];
+        const uint32_t c1 = B.cur1[slot];
+        const uint32_t pixel = slot % R.npix, set = slot / R.npix;
+        const uint32_t seed = B.pix_seed[pixel];
+        const V2 sample = smp.get2d(pixel, seed, set, R.base2 + (n - 1u));
+        const float roulette = smp.get1d(pixel, seed, set, c1 < R.n1d ? c1 : 0u);
         const RGB contribution = rgb(cum4.x, cum4.y, cum4.z);
         const V3 Vr = -rd;
         if (tri == RGK_NO_TRIANGLE) {
@@ -506,8 +516,9 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                 const float2 ta = __ldg(S.texcoords + tv.x), tb = __ldg(S.texcoords + tv.y), tc = __ldg(S.texcoords + tv.z);
                 const V2 uv = V2{ia * ta.x + ib * tb.x + ic * tc.x, ia * ta.y + ib * tb.y + ic * tc.y};
                 V3 lightN = faceN;
+                float right, bottom;
+                const TexPre pre = vertex_textures(S, mat, uv, right, bottom);
                 if (mat.tex_bump >= 0) {
-                    float right, bottom; tex_slopes(S, mat.tex_bump, uv, right, bottom);
                     V3 tangent = ia * v3(__ldg(S.tangents + tv.x)) + ib * v3(__ldg(S.tangents + tv.y)) + ic * v3(__ldg(S.tangents + tv.z));
                     if (!(tangent.x * tangent.x + tangent.y * tangent.y + tangent.z * tangent.z < 0.001f)) {
                         tangent = normalize(tangent);
@@ -517,17 +528,14 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                         if (isnan(lightN.x)) lightN = faceN;
                     }
                 }
-                const TexPre pre = tex_prefetch(S, mat, uv);
                 const Frame fr = system_transform_z(lightN);
                 const V3 VrL = qrot(fr.g2l, Vr);
                 // ---- next-event estimation set-up (the visibility test runs in k_shadow)
-                const float4 lp4 = B.light_pos[slot];
                 const uint32_t lflags = __float_as_uint(lp4.w);
                 RGB emis = rgb(0.0f, 0.0f, 0.0f);
                 if (dot(faceN, Vr) > 0) emis = rgb(mat.emission[0], mat.emission[1], mat.emission[2]);
                 if (lflags & 1u) {
                     const V3 lpos = v3(lp4);
-                    const float4 lc = B.light_col[slot];
                     const V3 Vi = normalize(lpos - pos);
                     const RGB f = bxdf_value(S, tv.w, mat, qrot(fr.g2l, Vi), VrL, uv, pre);
                     const V3 dlt = lpos - pos;
@@ -558,9 +566,6 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                     B.tot[slot] = t;
                 }
                 // ---- continuation
-                const uint32_t pixel = slot % R.npix, set = slot / R.npix;
-                const uint32_t seed = B.pix_seed[pixel];
-                const V2 sample = smp.get2d(pixel, seed, set, R.base2 + (n - 1u));
                 V3 dir; RGB tcf; bool may_leak;
                 bxdf_sample(S, mat, VrL, uv, sample, dir, tcf, may_leak, pre);
                 const bool inside = dir.z < 0;
@@ -572,9 +577,8 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                 cont = true;
                 if (gmax(gmax(cum.r, cum.g), cum.b) < 0.001f) cont = false;
                 if (cont && !mat.no_russian && R.russian >= 0.0f) {
-                    const uint32_t c1 = B.cur1[slot];
                     B.cur1[slot] = c1 + 1u;
-                    if (smp.get1d(pixel, seed, set, c1) > R.russian) cont = false;
+                    if (roulette > R.russian) cont = false;
                 }
                 if (cont && n > R.depth) cont = false;
                 if (cont && !(n < R.depth)) cont = false;          // while (n < depth)

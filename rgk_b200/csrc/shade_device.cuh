@@ -110,43 +110,62 @@ __device__ __forceinline__ bool decide_and_rescale(float& sample, float probabil
 
 // ---- textures (src/texture.cpp:35-102; manual fp32 bilinear)
 __device__ __forceinline__ float frepeat(float x) { return x - floorf(x); }
-__device__ __forceinline__ RGB tex_fetch(const DevScene& S, int32_t id, V2 uv) {
-    if (id < 0) return rgb(0.0f, 0.0f, 0.0f);
-    const DevTexture t = S.textures[id];
-    if (t.kind == 0) return rgb(t.color[0], t.color[1], t.color[2]);
+// Address part and arithmetic part of FileTexture::GetPixelInterpolated (src/texture.cpp:35-76), split so that several
+// fetches of one vertex can issue all their loads before any of them is consumed.
+struct BilinearTaps { uint32_t i00, i01, i10, i11; float fx, fy; };
+__device__ __forceinline__ BilinearTaps bilinear_taps(const DevTexture& t, V2 uv) {
     const int W = (int)t.width, H = (int)t.height;
     const float x = frepeat(uv.x) * t.width - 0.5f, y = frepeat(uv.y) * t.height - 0.5f;
     float ix0f, iy0f;
-    float fx = modff(x, &ix0f), fy = modff(y, &iy0f);
+    BilinearTaps a;
+    a.fx = modff(x, &ix0f); a.fy = modff(y, &iy0f);
     int ix0 = (int)ix0f, iy0 = (int)iy0f;
     const int ix1 = (ix0 != W - 1) ? ix0 + 1 : ix0;
     const int iy1 = (iy0 != H - 1) ? iy0 + 1 : iy0;
     if (ix0 == -1) ix0 = 0;
     if (iy0 == -1) iy0 = 0;
-    const float4* px = S.texels + t.offset;
-    const float4 c00 = __ldg(px + (size_t)iy0 * W + ix0), c01 = __ldg(px + (size_t)iy0 * W + ix1);
-    const float4 c10 = __ldg(px + (size_t)iy1 * W + ix0), c11 = __ldg(px + (size_t)iy1 * W + ix1);
-    fy = 1.0f - fy; fx = 1.0f - fx;
+    a.i00 = t.offset + (uint32_t)(iy0 * W + ix0); a.i01 = t.offset + (uint32_t)(iy0 * W + ix1);
+    a.i10 = t.offset + (uint32_t)(iy1 * W + ix0); a.i11 = t.offset + (uint32_t)(iy1 * W + ix1);
+    return a;
+}
+__device__ __forceinline__ RGB bilinear_mix(const BilinearTaps& a, float4 c00, float4 c01, float4 c10, float4 c11) {
+    const float fy = 1.0f - a.fy, fx = 1.0f - a.fx;
     const float gx = 1.0f - fx, gy = 1.0f - fy;
     const RGB c0s = rgb(fx * c00.x + gx * c01.x, fx * c00.y + gx * c01.y, fx * c00.z + gx * c01.z);
     const RGB c1s = rgb(fx * c10.x + gx * c11.x, fx * c10.y + gx * c11.y, fx * c10.z + gx * c11.z);
     return rgb(fy * c0s.r + gy * c1s.r, fy * c0s.g + gy * c1s.g, fy * c0s.b + gy * c1s.b);
+}
+__device__ __forceinline__ RGB tex_fetch(const DevScene& S, int32_t id, V2 uv) {
+    if (id < 0) return rgb(0.0f, 0.0f, 0.0f);
+    const DevTexture t = S.textures[id];
+    if (t.kind == 0) return rgb(t.color[0], t.color[1], t.color[2]);
+    const BilinearTaps a = bilinear_taps(t, uv);
+    return bilinear_mix(a, __ldg(S.texels + a.i00), __ldg(S.texels + a.i01), __ldg(S.texels + a.i10), __ldg(S.texels + a.i11));
+}
+// FileTexture::GetSlopeRight / GetSlopeBottom (src/texture.cpp:78-102)
+struct SlopeTaps { uint32_t ih, ir, ib; };
+__device__ __forceinline__ SlopeTaps slope_taps(const DevTexture& t, V2 uv) {
+    const int W = (int)t.width, H = (int)t.height;
+    int x = (int)(frepeat(uv.x) * t.width - 0.5f), y = (int)(frepeat(uv.y) * t.height - 0.5f);
+    const int x2 = (x != W - 1) ? x + 1 : x, y2 = (y != H - 1) ? y + 1 : y;
+    if (x == -1) x = 0;
+    if (y == -1) y = 0;
+    SlopeTaps a;
+    a.ih = t.offset + (uint32_t)(y * W + x); a.ir = t.offset + (uint32_t)(y * W + x2); a.ib = t.offset + (uint32_t)(y2 * W + x);
+    return a;
+}
+__device__ __forceinline__ void slope_mix(float4 h, float4 r, float4 b, float& right, float& bottom) {
+    const float here = (h.x + h.y + h.z) / 3;
+    right = here - (r.x + r.y + r.z) / 3;
+    bottom = here - (b.x + b.y + b.z) / 3;
 }
 __device__ __forceinline__ void tex_slopes(const DevScene& S, int32_t id, V2 uv, float& right, float& bottom) {
     right = 0.0f; bottom = 0.0f;
     if (id < 0) return;
     const DevTexture t = S.textures[id];
     if (t.kind == 0) return;
-    const int W = (int)t.width, H = (int)t.height;
-    int x = (int)(frepeat(uv.x) * t.width - 0.5f), y = (int)(frepeat(uv.y) * t.height - 0.5f);
-    const int x2 = (x != W - 1) ? x + 1 : x, y2 = (y != H - 1) ? y + 1 : y;
-    if (x == -1) x = 0;
-    if (y == -1) y = 0;
-    const float4* px = S.texels + t.offset;
-    const float4 h = __ldg(px + (size_t)y * W + x), r = __ldg(px + (size_t)y * W + x2), b = __ldg(px + (size_t)y2 * W + x);
-    const float here = (h.x + h.y + h.z) / 3;
-    right = here - (r.x + r.y + r.z) / 3;
-    bottom = here - (b.x + b.y + b.z) / 3;
+    const SlopeTaps a = slope_taps(t, uv);
+    slope_mix(__ldg(S.texels + a.ih), __ldg(S.texels + a.ir), __ldg(S.texels + a.ib), right, bottom);
 }
 
 // ---- LTC (src/LTC/ltc.cpp:20-143); N is always +Z (BxDFUpVector)
@@ -224,14 +243,32 @@ __device__ __forceinline__ RGB tex_diffuse_of(const DevScene& S, const DevMateri
 __device__ __forceinline__ RGB tex_color_of(const DevScene& S, const DevMaterial& m, V2 uv, const TexPre& pre) {
     return pre.have ? pre.color : tex_fetch(S, m.tex_color, uv);
 }
-// which of the two a material kind reads at all (the others never call the texture)
-__device__ __forceinline__ TexPre tex_prefetch(const DevScene& S, const DevMaterial& m, V2 uv) {
+// Everything a vertex reads from textures, in one batch: the three descriptors first, then all eleven texels (four
+// diffuse, four colour, three bump) are requested before any is used -- the shading kernel is bound by the latency of
+// its dependent loads, not by their number.  Unused taps read texel 0 (always allocated) and are discarded; the
+// arithmetic is the very code of tex_fetch / tex_slopes.  `have` stays false for mix materials.
+__device__ __forceinline__ TexPre vertex_textures(const DevScene& S, const DevMaterial& m, V2 uv, float& right, float& bottom) {
     TexPre pre; pre.have = m.bxdf != RGK_BXDF_MIX; pre.diffuse = rgb(0, 0, 0); pre.color = rgb(0, 0, 0);
-    if (!pre.have) return pre;
+    right = 0.0f; bottom = 0.0f;
     const bool uses_diffuse = m.bxdf == RGK_BXDF_DIFFUSE || m.bxdf == RGK_BXDF_LTC_BECKMANN_DIFFUSE || m.bxdf == RGK_BXDF_LTC_GGX_DIFFUSE;
-    const bool uses_color = m.bxdf != RGK_BXDF_DIFFUSE && m.bxdf != RGK_BXDF_TRANSPARENT;
-    if (uses_diffuse) pre.diffuse = tex_fetch(S, m.tex_diffuse, uv);
-    if (uses_color) pre.color = tex_fetch(S, m.tex_color, uv);
+    const bool uses_color = m.bxdf != RGK_BXDF_DIFFUSE && m.bxdf != RGK_BXDF_TRANSPARENT && m.bxdf != RGK_BXDF_MIX;
+    const bool want_d = uses_diffuse && m.tex_diffuse >= 0, want_c = uses_color && m.tex_color >= 0, want_b = m.tex_bump >= 0;
+    const DevTexture td = S.textures[want_d ? m.tex_diffuse : 0], tc = S.textures[want_c ? m.tex_color : 0], tb = S.textures[want_b ? m.tex_bump : 0];
+    const bool img_d = want_d && td.kind == 1u, img_c = want_c && tc.kind == 1u, img_b = want_b && tb.kind == 1u;
+    BilinearTaps ad = bilinear_taps(td, uv), ac = bilinear_taps(tc, uv);
+    SlopeTaps ab = slope_taps(tb, uv);
+    if (!img_d) { ad.i00 = 0u; ad.i01 = 0u; ad.i10 = 0u; ad.i11 = 0u; }
+    if (!img_c) { ac.i00 = 0u; ac.i01 = 0u; ac.i10 = 0u; ac.i11 = 0u; }
+    if (!img_b) { ab.ih = 0u; ab.ir = 0u; ab.ib = 0u; }
+    const float4* __restrict__ px = S.texels;
+    const float4 d00 = __ldg(px + ad.i00), d01 = __ldg(px + ad.i01), d10 = __ldg(px + ad.i10), d11 = __ldg(px + ad.i11);
+    const float4 c00 = __ldg(px + ac.i00), c01 = __ldg(px + ac.i01), c10 = __ldg(px + ac.i10), c11 = __ldg(px + ac.i11);
+    const float4 bh = __ldg(px + ab.ih), br = __ldg(px + ab.ir), bb = __ldg(px + ab.ib);
+    if (img_d) pre.diffuse = bilinear_mix(ad, d00, d01, d10, d11);
+    else if (want_d) pre.diffuse = rgb(td.color[0], td.color[1], td.color[2]);
+    if (img_c) pre.color = bilinear_mix(ac, c00, c01, c10, c11);
+    else if (want_c) pre.color = rgb(tc.color[0], tc.color[1], tc.color[2]);
+    if (img_b) slope_mix(bh, br, bb, right, bottom);
     return pre;
 }
 

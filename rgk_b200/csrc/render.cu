@@ -566,45 +566,49 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                     B.tot[slot] = t;
                 }
                 // ---- continuation
-                V3 dir; RGB tcf; bool may_leak;
-                bxdf_sample(S, mat, VrL, uv, sample, dir, tcf, may_leak, pre);
-                const bool inside = dir.z < 0;
-                dir = qrot(fr.l2g, dir);
-                if (!(dot(dir, faceN) * dot(Vr, faceN) > 0) && !may_leak) n += 10000u;
-                const float rcoef = (!mat.no_russian && R.russian > 0.0f && n > 1u) ? 1.0f / R.russian : 1.0f;
-                RGB cum = rgb(rcoef * contribution.r, rcoef * contribution.g, rcoef * contribution.b);
-                cum = rgb(tcf.r * cum.r, tcf.g * cum.g, tcf.b * cum.b);
-                cont = true;
-                if (gmax(gmax(cum.r, cum.g), cum.b) < 0.001f) cont = false;
-                if (cont && !mat.no_russian && R.russian >= 0.0f) {
-                    B.cur1[slot] = c1 + 1u;
-                    if (roulette > R.russian) cont = false;
-                }
-                if (cont && n > R.depth) cont = false;
-                if (cont && !(n < R.depth)) cont = false;          // while (n < depth)
-                if (cont) {
-                    const V3 no = pos + faceN * S.epsilon * 10.0f * (inside ? -1.0f : 1.0f);
-                    const V3 nd = normalize(normalize(dir));
-                    B.ray_o[slot] = make_float4(no.x, no.y, no.z, 0.0f);
-                    B.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, 0.0f);
-                    B.cum[slot] = make_float4(cum.r, cum.g, cum.b, __uint_as_float(n));
-                    B.last_tri[slot] = tri;
+                // A path whose next vertex would exceed recursion-max ends here whatever BxDF::sample returns (the loop
+                // condition `n < depth`, src/path_tracer.cpp:122): nothing of the continuation is observable, skip it.
+                if (n < R.depth) {
+                    V3 dir; RGB tcf; bool may_leak;
+                    bxdf_sample(S, mat, VrL, uv, sample, dir, tcf, may_leak, pre);
+                    const bool inside = dir.z < 0;
+                    dir = qrot(fr.l2g, dir);
+                    if (!(dot(dir, faceN) * dot(Vr, faceN) > 0) && !may_leak) n += 10000u;
+                    const float rcoef = (!mat.no_russian && R.russian > 0.0f && n > 1u) ? 1.0f / R.russian : 1.0f;
+                    RGB cum = rgb(rcoef * contribution.r, rcoef * contribution.g, rcoef * contribution.b);
+                    cum = rgb(tcf.r * cum.r, tcf.g * cum.g, tcf.b * cum.b);
+                    cont = true;
+                    if (gmax(gmax(cum.r, cum.g), cum.b) < 0.001f) cont = false;
+                    if (cont && !mat.no_russian && R.russian >= 0.0f) {
+                        B.cur1[slot] = c1 + 1u;
+                        if (roulette > R.russian) cont = false;
+                    }
+                    if (cont && n > R.depth) cont = false;
+                    if (cont && !(n < R.depth)) cont = false;          // while (n < depth)
+                    if (cont) {
+                        const V3 no = pos + faceN * S.epsilon * 10.0f * (inside ? -1.0f : 1.0f);
+                        const V3 nd = normalize(normalize(dir));
+                        B.ray_o[slot] = make_float4(no.x, no.y, no.z, 0.0f);
+                        B.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+                        B.cum[slot] = make_float4(cum.r, cum.g, cum.b, __uint_as_float(n));
+                        B.last_tri[slot] = tri;
+                    }
                 }
             }
         }
     }
-    if (R.binning) {
-        // queues are built by k_bin from these keys: rays of one pixel block are reordered by direction so that the lanes
-        // of a traversal warp follow similar paths through the tree (the order of the queue never changes a result)
-        if (cont && R.binning == 1u) { const float4 d = B.ray_d[slot]; B.key_next[slot] = dir_bin(d.x, d.y, d.z); }
+    // queues: either built by k_bin from direction-bin keys (rays of one pixel block are reordered by direction so that
+    // the lanes of a traversal warp follow similar paths through the tree), or by warp-aggregated atomic compaction in
+    // path order.  R.binning bit 0: continuation rays, bit 1: shadow rays.  The order of a queue never changes a result.
+    if (R.binning & 1u) {
+        if (cont) { const float4 d = B.ray_d[slot]; B.key_next[slot] = dir_bin(d.x, d.y, d.z); }
+    } else push_queue(next_queue, counters + C_NEXT, cont, slot);
+    if (R.binning & 2u) {
         if (shadow) {
             const float4 a = B.light_pos[slot], b = B.sh_pos[slot];
             B.key_shadow[slot] = dir_bin(b.x - a.x, b.y - a.y, b.z - a.z);
         }
-    } else {
-        push_queue(next_queue, counters + C_NEXT, cont, slot);
-        push_queue(shadow_queue, counters + C_SHADOW, shadow, slot);
-    }
+    } else push_queue(shadow_queue, counters + C_SHADOW, shadow, slot);
     {   // Visibility queries of the reference that were provably irrelevant and therefore not traced
         const unsigned m = __ballot_sync(0xffffffffu, null_shadow);
         if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + C_SHADOW_SKIPPED, (unsigned long long)__popc(m));
@@ -783,6 +787,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const bool counting = ctx->counting;
     const uint32_t skip_null = env_flag("RGK_SKIP_NULL_SHADOW", true) ? 1u : 0u;
     const bool binning = env_flag("RGK_BIN", true) && P->depth > 1;
+    const bool bin_shadow0 = env_flag("RGK_BIN_SHADOW0", true);
     const size_t bin_items = env_size("RGK_BIN_ITEMS", 4096);   // path slots per reordering group
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 8);
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
@@ -872,16 +877,19 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             pool.end(ctx->stream);
             pool.begin(ctx->stream, T_SHADE);
             const bool last_bounce = bounce + 1 >= P->depth;       // no continuation rays: k_shade ends every path (n == depth)
-            if (binning) {
-                if (!last_bounce) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
-                RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
-            }
+            // camera-ray hit points are already in image order: their shadow rays are binned only on request
+            const bool bin_next = binning && !last_bounce, bin_shadow = binning && (bounce > 0 || bin_shadow0);
+            R.binning = (binning ? 1u : 0u) | (bin_shadow ? 2u : 0u);
+            if (bin_next) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
+            if (bin_shadow) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
             k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
-            if (binning) {
-                if (!last_bounce)
-                    k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, B.counters + C_NEXT);
+            if (bin_next) {
+                k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, B.counters + C_NEXT);
+                ctx->launches++;
+            }
+            if (bin_shadow) {
                 k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_shadow, (uint32_t)npix, ms, PG, SG, n_pgroups, B.queue_s, B.counters + C_SHADOW);
-                ctx->launches += 2;
+                ctx->launches++;
             }
             pool.end(ctx->stream);
             ctx->launches += 2; total.closest_launches++;

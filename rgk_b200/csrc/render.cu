@@ -788,8 +788,9 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const uint32_t skip_null = env_flag("RGK_SKIP_NULL_SHADOW", true) ? 1u : 0u;
     const bool binning = env_flag("RGK_BIN", true) && P->depth > 1;
     const bool bin_shadow0 = env_flag("RGK_BIN_SHADOW0", true);
-    const size_t bin_items = env_size("RGK_BIN_ITEMS", 4096);   // path slots per reordering group
-    const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 8);
+    const size_t bin_items = env_size("RGK_BIN_ITEMS", 2048);   // path slots per reordering group
+    const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 24);
+    const uint32_t refill_shadow = (uint32_t)env_size("RGK_REFILL_SHADOW", 12);   // any-hit rays end at very different times: refill sooner
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
 
@@ -835,7 +836,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         R.lens = lens; R.npix = (uint32_t)npix; R.skip_null_shadow = skip_null; R.binning = binning ? 1u : 0u;
         // reordering groups: SG samples x PG pixel positions (a multiple of the 32-pixel blocks of k_pixel_setup)
         const uint32_t SG = (uint32_t)std::min<size_t>(ms, 128);
-        const uint32_t PG = (uint32_t)std::max<size_t>(32, (bin_items / SG) / 32 * 32);
+        const uint32_t PG = (uint32_t)std::max<size_t>(8, (bin_items / SG) / 8 * 8);
         const uint32_t n_pgroups = (uint32_t)((npix + PG - 1) / PG), n_sgroups = (ms + SG - 1) / SG;
         SamplerView smp{B.t1, B.t2, (uint32_t)npix, ss, sq, P->sampler_mode};
         pool.begin(ctx->stream, T_SAMPLER);
@@ -898,6 +899,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             const uint32_t next_count = (uint32_t)B.h_counters[C_NEXT], shadow_count = (uint32_t)B.h_counters[C_SHADOW];
             total.closest_rays += count; total.shadow_rays += shadow_count; total.shadow_rays_skipped += B.h_counters[C_SHADOW_SKIPPED];
             if (shadow_count) {
+                dev.refill_threshold = bounce == 0 ? refill_coherent : refill_shadow;
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
                 if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1);

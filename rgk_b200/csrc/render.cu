@@ -788,6 +788,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const uint32_t skip_null = env_flag("RGK_SKIP_NULL_SHADOW", true) ? 1u : 0u;
     const bool binning = env_flag("RGK_BIN", true) && P->depth > 1;
     const bool bin_shadow0 = env_flag("RGK_BIN_SHADOW0", true);
+    const double bin_min_frac = std::getenv("RGK_BIN_MIN_FRAC") ? std::atof(std::getenv("RGK_BIN_MIN_FRAC")) : 0.25;
     const size_t bin_items = env_size("RGK_BIN_ITEMS", 2048);   // path slots per reordering group
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 24);
     const uint32_t refill_shadow = (uint32_t)env_size("RGK_REFILL_SHADOW", 12);   // any-hit rays end at very different times: refill sooner
@@ -879,8 +880,11 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             pool.begin(ctx->stream, T_SHADE);
             const bool last_bounce = bounce + 1 >= P->depth;       // no continuation rays: k_shade ends every path (n == depth)
             // camera-ray hit points are already in image order: their shadow rays are binned only on request
-            const bool bin_next = binning && !last_bounce, bin_shadow = binning && (bounce > 0 || bin_shadow0);
-            R.binning = (binning ? 1u : 0u) | (bin_shadow ? 2u : 0u);
+            // k_bin reads every slot of the chunk, the traversal only gains on the live ones: deep bounces with few
+            // survivors go back to the atomic compaction
+            const bool worth = binning && (double)count >= bin_min_frac * (double)npaths;
+            const bool bin_next = worth && !last_bounce, bin_shadow = worth && (bounce > 0 || bin_shadow0);
+            R.binning = (bin_next ? 1u : 0u) | (bin_shadow ? 2u : 0u);
             if (bin_next) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
             if (bin_shadow) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
             k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);

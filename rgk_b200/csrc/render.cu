@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include "trace_device.cuh"
 #include "shade_device.cuh"
 
@@ -58,30 +59,43 @@ template <class T> bool alloc_dev(T** p, size_t n) {
 // (src/sampler.cpp:5-36,85-116) over libstdc++'s mt19937 / generate_canonical / uniform_int_distribution (Lemire)
 // / std::shuffle (pairwise) -- SURVEY Appendix C.  One thread per pixel; the 624-word generator state lives in
 // global memory, interleaved across threads (state[k * stride + thread]) so every access is coalesced.
+constexpr int MT_LANES = 128;   // threads per CTA of the sampler kernels = width of a state block
 struct MT {
-    uint32_t* st; size_t stride; int k0, cur;
+    uint32_t* st;      // this thread's column of its CTA's state block: word k at st[k * MT_LANES] (32-bit offsets, coalesced)
+    int k0, cur;
     uint32_t buf[8];
     __device__ void seed(uint32_t s) {
         uint32_t prev = s; st[0] = s;
-        for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; st[(size_t)i * stride] = prev; }
+        for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; st[i * MT_LANES] = prev; }
         k0 = 0; cur = 8;
     }
     // The twist is done incrementally, eight words at a time, right before their tempered values are handed out (the
     // standard implementation twists all 624 words when the block is exhausted; word k only depends on old k, old k+1
     // -- new word 0 for k = 623 -- and word k+397 mod 624, old for k < 227 and already renewed for k >= 227, so doing
     // it in ascending batches yields identical words).  A batch first loads its 17 inputs, then stores its 8 outputs:
-    // one memory round trip per eight draws instead of one per draw.
+    // one memory round trip per eight draws instead of one per draw.  Only the batches at k0 = 224 (the k+397 window
+    // crosses the end of the state) and k0 = 616 (word k+1 of the last word is word 0) need per-word wrap-around;
+    // all others address their words at constant offsets from one pointer.
     __device__ void fill() {
         uint32_t own[9], far[8];
+        uint32_t* p = st + k0 * MT_LANES;
+        if (k0 != 224 && k0 != 616) {
+            const uint32_t* pf = (k0 < 224) ? p + 397 * MT_LANES : p - 227 * MT_LANES;
 #pragma unroll
-        for (int j = 0; j < 9; j++) { const int k = k0 + j; own[j] = st[(size_t)(k == 624 ? 0 : k) * stride]; }
+            for (int j = 0; j < 9; j++) own[j] = p[j * MT_LANES];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { const int k = k0 + j + 397; far[j] = st[(size_t)(k < 624 ? k : k - 624) * stride]; }
+            for (int j = 0; j < 8; j++) far[j] = pf[j * MT_LANES];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 9; j++) { const int k = k0 + j; own[j] = st[(k == 624 ? 0 : k) * MT_LANES]; }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const int k = k0 + j + 397; far[j] = st[(k < 624 ? k : k - 624) * MT_LANES]; }
+        }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const uint32_t y0 = (own[j] & 0x80000000u) | (own[j + 1] & 0x7fffffffu);
             uint32_t y = far[j] ^ (y0 >> 1) ^ ((y0 & 1u) ? 0x9908b0dfu : 0u);
-            st[(size_t)(k0 + j) * stride] = y;
+            p[j * MT_LANES] = y;
             y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
             buf[j] = y;
         }
@@ -110,14 +124,15 @@ struct MT {
     }
 };
 
-template <class T>
-__device__ __forceinline__ void dev_swap(T* base, size_t stride, uint32_t i, uint32_t j) {
-    const T a = base[(size_t)i * stride], b = base[(size_t)j * stride];
-    base[(size_t)i * stride] = b; base[(size_t)j * stride] = a;
+// I = index type of (entry * stride): 32-bit for the shared-memory tables, 64-bit for the global ones
+template <class T, class I>
+__device__ __forceinline__ void dev_swap(T* base, I stride, uint32_t i, uint32_t j) {
+    const T a = base[(I)i * stride], b = base[(I)j * stride];
+    base[(I)i * stride] = b; base[(I)j * stride] = a;
 }
 // std::shuffle, pairwise variant; `store` false only advances the generator
-template <class T>
-__device__ void dev_shuffle(T* base, size_t stride, uint32_t n, MT& g, bool store) {
+template <class T, class I>
+__device__ void dev_shuffle(T* base, I stride, uint32_t n, MT& g, bool store) {
     uint32_t i = 1;
     if ((n % 2) == 0) { const uint32_t d = g.lemire(2); if (store) dev_swap(base, stride, i, d); i++; }
     while (i != n) {
@@ -139,26 +154,27 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
                              float* __restrict__ t1, float2* __restrict__ t2, uint32_t* __restrict__ state) {
     extern __shared__ float sm[];
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
-    MT g; g.st = state + p; g.stride = npix;
-    g.seed(seeds[p]);
+    MT g; g.st = state + (size_t)blockIdx.x * (624 * MT_LANES) + threadIdx.x;
+    if (p < npix) g.seed(seeds[p]);
     const float len1 = 1.0f / (float)ss, len2 = 1.0f / (float)sq;
     const uint32_t last_dim = max(n1d, n2d);   // dims >= last_dim are never read: stop there (the stream is not reused)
-    const size_t bd = blockDim.x;
+    if (p >= npix) return;
+    typedef typename std::conditional<SMEM, uint32_t, size_t>::type I;
+    const I bd = (I)blockDim.x;
     float* s1 = sm + threadIdx.x;                                  // ss floats
-    float2* s2 = reinterpret_cast<float2*>(sm + (size_t)ss * bd) + threadIdx.x;   // ss float2 (8-byte lanes: 2-way, still cheap)
+    float2* s2 = reinterpret_cast<float2*>(sm + (size_t)ss * blockDim.x) + threadIdx.x;   // ss float2 (8-byte lanes: 2-way, still cheap)
     for (uint32_t dim = 0; dim < last_dim; dim++) {
         const bool keep1 = dim < n1d, keep2 = dim < n2d;
         float* out1 = t1 + ((size_t)(keep1 ? dim : n1d) * ss) * npix + p;
         float* a = SMEM ? s1 : out1;
-        const size_t as = SMEM ? bd : (size_t)npix;
+        const I as = SMEM ? bd : (I)npix;
         for (uint32_t k = 0; k < ss; k++) {
             const float begin = (float)k / (float)ss;
             const float v = begin + g.uniform_real(0.0f, len1);
-            if (keep1) a[(size_t)k * as] = v;
+            if (keep1) a[(I)k * as] = v;
         }
         dev_shuffle(a, as, ss, g, keep1);
-        if (SMEM && keep1) for (uint32_t k = 0; k < ss; k++) out1[(size_t)k * npix] = s1[(size_t)k * bd];
+        if (SMEM && keep1) { float* o = out1; for (uint32_t k = 0; k < ss; k++, o += npix) *o = s1[k * (uint32_t)bd]; }
         float2* out2 = t2 + ((size_t)(keep2 ? dim : n2d) * ss) * npix + p;
         float2* b = SMEM ? s2 : out2;
         for (uint32_t sy = 0; sy < sq; sy++)
@@ -166,10 +182,10 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
                 const float bx = (float)sx / (float)sq, by = (float)sy / (float)sq;
                 const float x = bx + g.uniform_real(0.0f, len2);
                 const float y = by + g.uniform_real(0.0f, len2);
-                if (keep2) b[(size_t)(sy * sq + sx) * as] = make_float2(x, y);
+                if (keep2) b[(I)(sy * sq + sx) * as] = make_float2(x, y);
             }
         dev_shuffle(b, as, ss, g, keep2);
-        if (SMEM && keep2) for (uint32_t k = 0; k < ss; k++) out2[(size_t)k * npix] = s2[(size_t)k * bd];
+        if (SMEM && keep2) { float2* o = out2; for (uint32_t k = 0; k < ss; k++, o += npix) *o = s2[k * (uint32_t)bd]; }
     }
 }
 
@@ -200,13 +216,13 @@ static void launch_sampler_mt(cudaStream_t stream, const uint32_t* seeds, uint32
     // per SM drops to one or two warps and the latency of the generator-state loads is no longer hidden (measured:
     // 2.4 s vs 1.2 s per 1080p x 256 spp x depth-40 round), so larger sets are shuffled in place in global memory
     if (use_smem) {
-        const size_t bytes = (size_t)128 * ss * 12;
+        const size_t bytes = (size_t)MT_LANES * ss * 12;
         if (bytes <= 100 * 1024) {
-            k_sampler_mt<true><<<(npix + 127) / 128, 128, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
+            k_sampler_mt<true><<<(npix + MT_LANES - 1) / MT_LANES, MT_LANES, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
             return;
         }
     }
-    k_sampler_mt<false><<<(npix + 127) / 128, 128, 0, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
+    k_sampler_mt<false><<<(npix + MT_LANES - 1) / MT_LANES, MT_LANES, 0, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
 }
 
 // Counter-based sampler with the same structure (jittered strata visited in a per-(pixel,dim) random order),
@@ -677,7 +693,7 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
         if (ok && B.mt_state) { cudaFree(B.mt_state); B.mt_state = nullptr; }
         B.cap_pixels = ok ? pixels : 0;
     }
-    if (ok && need_mt && !B.mt_state) ok = alloc_dev(&B.mt_state, B.cap_pixels * 624);
+    if (ok && need_mt && !B.mt_state) ok = alloc_dev(&B.mt_state, (B.cap_pixels + MT_LANES - 1) / MT_LANES * MT_LANES * 624);
     if (ok && t1_floats > B.cap_t1) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t1, t1_floats); B.cap_t1 = ok ? t1_floats : 0; }
     if (ok && t2_float2s > B.cap_t2) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t2, t2_float2s); B.cap_t2 = ok ? t2_float2s : 0; }
     if (ok && tiles > B.cap_tiles) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.tiles, tiles) && alloc_dev(&B.tiles2, tiles); B.cap_tiles = ok ? tiles : 0; }
@@ -730,7 +746,7 @@ rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint
     float* t1 = nullptr; float2* t2 = nullptr; uint32_t* st = nullptr;
     const size_t e1 = (size_t)(n1d + 1) * ss * n_seeds, e2 = (size_t)(n2d + 1) * ss * n_seeds;
     if (cudaMalloc((void**)&t1, e1 * 4) != cudaSuccess || cudaMalloc((void**)&t2, e2 * 8) != cudaSuccess ||
-        cudaMalloc((void**)&st, (size_t)n_seeds * 624 * 4) != cudaSuccess) {
+        cudaMalloc((void**)&st, ((size_t)n_seeds + MT_LANES - 1) / MT_LANES * MT_LANES * 624 * 4) != cudaSuccess) {
         cudaGetLastError(); if (t1) cudaFree(t1); if (t2) cudaFree(t2); if (st) cudaFree(st);
         return rgk_fail(ctx, RGK_ERR_NOMEM, "sampler table allocation failed");
     }

@@ -36,7 +36,31 @@ METRIC = "Mrays/s (closest-hit+shadow)"
 CROP = (960, 540)   # CPU baseline sample: centred crop of the full-resolution image, full spp (10-20 s on 16 cores)
 
 
+def real_asset_workload(name, spp):
+    """BASELINE configs on the real assets when $RGK_ASSETS points at a copy of the reference's scenes/ directory that
+    has the meshes (sponza.obj, sibenik.obj, ... are not distributed with the reference).  Returns None otherwise."""
+    root = os.environ.get("RGK_ASSETS")
+    sizes = {"sponza": (1920, 1080, 64), "sibenik": (1920, 1080, 256), "conference": (3840, 2160, 1024), "dragon-sponza": (3840, 2160, 512)}
+    if not root or name not in sizes:
+        return None
+    cfg_path = os.path.join(root, name + ".json")
+    if not os.path.exists(cfg_path):
+        return None
+    from rgk_b200 import assets, scene
+    w, h, ms = sizes[name]
+    try:
+        pack, cfg = scene.load_json_config(cfg_path, overrides={"output-width": w, "output-height": h, "multisample": spp or ms, "rounds": 1},
+                                           mesh_loader=assets.load_obj_into, texture_loader=assets.load_image)
+    except (scene.ConfigFileException, OSError) as e:
+        print("RGK_ASSETS: %s (%s); using the stand-in" % (cfg_path, e), file=sys.stderr)
+        return None
+    return pack, cfg, "scenes/%s.json %dx%d %dspp on the real asset (%d tris)" % (name, w, h, spp or ms, pack.n_triangles)
+
+
 def build_workload(name, spp=None):
+    real = real_asset_workload(name, spp)
+    if real is not None:
+        return real
     if name == "sponza":
         pack, cfg = standin.sponza(**({"multisample": spp} if spp else {}))
         label = "scenes/sponza.json 1920x1080 64spp NEE recursion-max 2 (atrium stand-in, %d tris)" % pack.n_triangles

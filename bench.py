@@ -6,7 +6,7 @@ scenes/sponza.json at 1920x1080, 64 spp, path tracing with next-event estimation
 seeded ~66-71 k-triangle atrium STAND-IN, because sponza.obj is not distributed with the reference
 (rgk_b200/standin.py).  One "step" = one RenderDriver round (every pixel, 64 spp) per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sponza|cornell|sibenik]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sponza|cornell|sibenik|conference|dragon-sponza]
                   [--sampler mt|fast] [--shard rounds|tiles]
 
 N > 1 (torchrun): rounds are sharded (GPU g renders round step*N+g with its own seed base, weak scaling) and the
@@ -67,6 +67,12 @@ def build_workload(name, spp=None):
     elif name == "sibenik":
         pack, cfg = standin.sibenik(**({"multisample": spp} if spp else {}))
         label = "scenes/sibenik.json 1920x1080 256spp lens+envmap (stand-in, %d tris)" % pack.n_triangles
+    elif name == "conference":
+        pack, cfg = standin.conference(**({"multisample": spp} if spp else {}))
+        label = "scenes/conference.json 3840x2160 1024spp 8 sphere lights recursion-max 4 (stand-in, %d tris)" % pack.n_triangles
+    elif name == "dragon-sponza":
+        pack, cfg = standin.dragon_sponza(**({"multisample": spp} if spp else {}))
+        label = "scenes/dragon-sponza.json 3840x2160 512spp (stand-in, %d tris)" % pack.n_triangles
     elif name == "cornell":
         pack, cfg = scenes.load_builtin("cornell-box", **({"multisample": spp} if spp else {}))
         label = "scenes/cornell-box.json 256x256 16spp recursion-max 40"

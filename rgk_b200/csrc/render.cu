@@ -160,9 +160,15 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
     const uint32_t last_dim = max(n1d, n2d);   // dims >= last_dim are never read: stop there (the stream is not reused)
     if (p >= npix) return;
     typedef typename std::conditional<SMEM, uint32_t, size_t>::type I;
-    const I bd = (I)blockDim.x;
-    float* s1 = sm + threadIdx.x;                                  // ss floats
-    float2* s2 = reinterpret_cast<float2*>(sm + (size_t)ss * blockDim.x) + threadIdx.x;   // ss float2 (8-byte lanes: 2-way, still cheap)
+    // Shared-memory tables are private to a warp (entry k of lane l at [k * 32 + l] of the warp's region: every swap of
+    // the shuffle is bank-conflict free whatever its random position).  The 2-D table reuses the storage of the 1-D one:
+    // a dimension's 1-D table is built, shuffled and copied out before its 2-D table is started, so only one of them is
+    // live (8 bytes x set size per thread instead of 12); the warp barriers keep a straggling lane's 1-D entries from
+    // being overwritten by its neighbours' 2-D ones.
+    const I bd = (I)32;
+    float* wbase = sm + (size_t)(threadIdx.x >> 5) * ss * 64;
+    float* s1 = wbase + (threadIdx.x & 31);                        // ss floats
+    float2* s2 = reinterpret_cast<float2*>(wbase) + (threadIdx.x & 31);   // ss float2 (8-byte lanes: 2-way, still cheap)
     for (uint32_t dim = 0; dim < last_dim; dim++) {
         const bool keep1 = dim < n1d, keep2 = dim < n2d;
         float* out1 = t1 + ((size_t)(keep1 ? dim : n1d) * ss) * npix + p;
@@ -175,6 +181,7 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
         }
         dev_shuffle(a, as, ss, g, keep1);
         if (SMEM && keep1) { float* o = out1; for (uint32_t k = 0; k < ss; k++, o += npix) *o = s1[k * (uint32_t)bd]; }
+        if (SMEM) __syncwarp();
         float2* out2 = t2 + ((size_t)(keep2 ? dim : n2d) * ss) * npix + p;
         float2* b = SMEM ? s2 : out2;
         for (uint32_t sy = 0; sy < sq; sy++)
@@ -186,6 +193,7 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
             }
         dev_shuffle(b, as, ss, g, keep2);
         if (SMEM && keep2) { float2* o = out2; for (uint32_t k = 0; k < ss; k++, o += npix) *o = s2[k * (uint32_t)bd]; }
+        if (SMEM) __syncwarp();
     }
 }
 
@@ -216,7 +224,7 @@ static void launch_sampler_mt(cudaStream_t stream, const uint32_t* seeds, uint32
     // per SM drops to one or two warps and the latency of the generator-state loads is no longer hidden (measured:
     // 2.4 s vs 1.2 s per 1080p x 256 spp x depth-40 round), so larger sets are shuffled in place in global memory
     if (use_smem) {
-        const size_t bytes = (size_t)MT_LANES * ss * 12;
+        const size_t bytes = (size_t)MT_LANES * ss * 8;
         if (bytes <= 100 * 1024) {
             k_sampler_mt<true><<<(npix + MT_LANES - 1) / MT_LANES, MT_LANES, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
             return;

@@ -522,6 +522,22 @@ inline V3 sphere_uniform(V2 s) { // :49-56
     float r = std::sqrt(1 - z * z);
     return v3(r * std::cos(a), r * std::sin(a), z);
 }
+inline V3 hemi_cos_y(V2 s) { // Sample2DToHemisphereCosine :32-36 (y up)
+    V2 p = disc_uniform(s);
+    float y = std::sqrt(gmax(0.00001f, 1 - p.x * p.x - p.y * p.y));
+    return v3(p.x, y, p.y);
+}
+// RotationFromY, src/glm.cpp:36-60
+inline Quat rotation_from_y(V3 dest) {
+    dest = normalize(dest);
+    const float cosTheta = dest.y;
+    if (cosTheta < -1 + 0.00001f) return angle_axis(PI_F, v3(1.0f, 0.0f, 0.0f));
+    const V3 axis = cross(v3(0.0f, 1.0f, 0.0f), dest);
+    const float s = std::sqrt((1 + cosTheta) * 2);
+    const float invs = 1 / s;
+    return Quat{s * 0.5f, axis.x * invs, axis.y * invs, axis.z * invs};
+}
+inline V3 hemi_cos_directed(V2 s, V3 direction) { return qrot(rotation_from_y(direction), hemi_cos_y(s)); } // :45-47,76-78
 inline bool decide_and_rescale(float& sample, float probability) { // :63-73
     if (probability == 0.0f) return false;
     if (probability == 1.0f) return true;
@@ -794,17 +810,19 @@ Ray camera_ray(const rgk_camera* c, int x, int y, int xres, int yres, V2 off, V2
 struct RenderCounters { uint64_t closest = 0, shadow = 0, samples = 0; Counters trav_closest, trav_shadow; };
 struct PathPoint {
     bool infinity = false; V3 pos, lightN, faceN; Frame fr; V3 Vr; uint32_t mat = 0; V2 uv; RGB emission; RGB contribution;
+    RGB light_from_source{0, 0, 0};   // light path only (src/path_tracer.hpp:57)
 };
+struct SideEffect { int x, y; RGB q; };   // PixelRenderResult::side_effects, src/tracer.hpp
 
 // PathTracer::GeneratePath, src/path_tracer.cpp:110-306
-void generate_path(const Scene& s, const rgk_render_params& P, Ray r, Sampler& smp, std::vector<PathPoint>& path, RenderCounters& rc) {
+void generate_path(const Scene& s, const rgk_render_params& P, Ray r, Sampler& smp, std::vector<PathPoint>& path, RenderCounters& rc,
+                   unsigned depth, float russian) {
     path.clear();
     RGB cum = rgb(1, 1, 1);
     Ray cur = r;
     unsigned n = 0;
     uint32_t last = RGK_NO_TRIANGLE;
-    const float russian = P.russian;
-    while (n < P.depth) {
+    while (n < depth) {
         n++;
         rc.closest++;
         Hit i = find_intersect(s, cur, last, &rc.trav_closest);
@@ -854,7 +872,7 @@ void generate_path(const Scene& s, const rgk_render_params& P, Ray r, Sampler& s
         path.push_back(p);
         if (rgbmax(cum) < 0.001f) break;
         if (!mat.no_russian && russian >= 0.0f && smp.get1d() > russian) break;
-        if (n > P.depth) break;
+        if (n > depth) break;
         Ray nr; nr.o = p.pos + p.faceN * s.epsilon * 10.0f * (inside ? -1.0f : 1.0f);
         nr.d = normalize(normalize(dir)); // glm::normalize(dir) then Ray(from,dir) normalises again
         cur = nr;
@@ -862,14 +880,66 @@ void generate_path(const Scene& s, const rgk_render_params& P, Ray r, Sampler& s
     }
 }
 
-// PathTracer::TracePath, src/path_tracer.cpp:308-512 (reverse == 0: the light path is empty)
-RGB trace_path(const Scene& s, const rgk_render_params& P, const Ray& r, Sampler& smp, std::vector<PathPoint>& path, RenderCounters& rc) {
+// Camera::GetCoordsFromDirection, src/camera.cpp:48-83
+bool coords_from_direction(const rgk_camera* c, V3 dir, int& x, int& y) {
+    const V3 N = v3(c->direction);
+    const float q = dot(dir, N);
+    if (q < 0.0001) return false;
+    const float t = dot(v3(c->viewscreen) - v3(c->origin), N) / q;
+    if (t <= 0) return false;
+    const V3 p = v3(c->origin) + dir * t;
+    const V3 v1 = v3(c->viewscreen_x), v2 = v3(c->viewscreen_y);
+    const V3 vp = p - v3(c->viewscreen);
+    const float plen = length(vp);
+    const float v1_cast_len = plen * dot(normalize(vp), normalize(v1));
+    const float v2_cast_len = plen * dot(normalize(vp), normalize(v2));
+    const float x_ratio = v1_cast_len / length(v1), y_ratio = v2_cast_len / length(v2);
+    if (x_ratio < 0.0f || x_ratio > 1.0f || y_ratio < 0.0f || y_ratio > 1.0f) return false;
+    x = (int)(c->xsize * x_ratio); y = (int)(c->ysize * y_ratio);
+    return true;
+}
+
+// PathTracer::TracePath, src/path_tracer.cpp:308-512.  reverse == 0: the light path is empty (GeneratePath with depth 0
+// draws nothing); reverse > 0: a light path of up to `reverse` vertices, its connections to the camera (side effects:
+// radiance splatted to other pixels with count 0) and to every vertex of the camera path.
+RGB trace_path(const Scene& s, const rgk_camera* cam, const rgk_render_params& P, const Ray& r, Sampler& smp, std::vector<PathPoint>& path,
+               std::vector<PathPoint>& light_path, std::vector<SideEffect>& side_effects, RenderCounters& rc) {
+    const V3 camerapos = r.o;
     V2 areal_sample = smp.get2d();
-    V2 lightdir_sample = smp.get2d(); (void)lightdir_sample;
+    V2 lightdir_sample = smp.get2d();
     V2 choice = smp.get2d(); float ls = smp.get1d();
     Light light = random_light(s, choice, ls, areal_sample);
-    generate_path(s, P, r, smp, path, rc);
-    if (light.type == 0) { V3 dir = sphere_uniform(areal_sample); light.pos = light.pos + light.size * dir; }
+    generate_path(s, P, r, smp, path, rc, P.depth, P.russian);
+    V3 main_light_dir = v3(0, 0, 0);
+    if (light.type == 0) {
+        V3 dir = sphere_uniform(areal_sample); light.pos = light.pos + light.size * dir;
+        if (P.reverse) main_light_dir = hemi_cos_directed(lightdir_sample, normalize(dir));
+    } else if (P.reverse) main_light_dir = hemi_cos_directed(lightdir_sample, light.normal);
+    light_path.clear();
+    if (P.reverse && light.valid) {
+        Ray light_ray; light_ray.o = light.pos + s.epsilon * light.normal * 100.0f; light_ray.d = normalize(main_light_dir);
+        generate_path(s, P, light_ray, smp, light_path, rc, P.reverse, -1.0f);
+        const float dfac = (light.type == 0) ? 1.0f : gmax(0.0f, dot(main_light_dir, light.normal));
+        const float k0 = light.intensity * dfac;
+        const RGB light_at_path_start = rgb(light.color.r * k0, light.color.g * k0, light.color.b * k0);
+        for (PathPoint& p : light_path) {
+            const RGB light_here = rgb(p.contribution.r * light_at_path_start.r, p.contribution.g * light_at_path_start.g, p.contribution.b * light_at_path_start.b);
+            p.light_from_source = light_here;
+            if (p.infinity) continue;
+            rc.shadow++;
+            if (!visibility(s, p.pos, camerapos, &rc.trav_shadow)) continue;
+            const V3 direction = normalize(p.pos - camerapos);
+            const RGB f = bxdf_value(s, p.mat, p.fr.toLocal(p.Vr), p.fr.toLocal(-direction), p.uv);
+            RGB q = rgb(light_here.r * f.r, light_here.g * f.g, light_here.b * f.b);
+            const float G = gmax(0.0f, dot(p.lightN, -direction)) / distance2(camerapos, p.pos);
+            if (G >= 0.00001f && !std::isnan(q.r)) {
+                q = rgb(q.r * G, q.g * G, q.b * G);
+                int x2, y2;
+                // (the reference accepts x_ratio == 1, which addresses one pixel past the row: dropped here)
+                if (coords_from_direction(cam, direction, x2, y2) && x2 < cam->xsize && y2 < cam->ysize) side_effects.push_back(SideEffect{x2, y2, q});
+            }
+        }
+    }
     RGB total = rgb(0, 0, 0);
     for (size_t n = 0; n < path.size(); n++) {
         const PathPoint& p = path[n];
@@ -892,6 +962,18 @@ RGB trace_path(const Scene& s, const rgk_render_params& P, const Ray& r, Sampler
                 here = rgb(here.r + inc.r * fg.r, here.g + inc.g * fg.g, here.b + inc.b * fg.b);
             }
         }
+        for (const PathPoint& l : light_path) {                       // "Reverse light", src/path_tracer.cpp:462-480
+            if (l.infinity) continue;
+            rc.shadow++;
+            if (!visibility(s, l.pos, p.pos, &rc.trav_shadow)) continue;
+            const V3 light_to_p = normalize(p.pos - l.pos), p_to_light = -light_to_p;
+            const RGB f_light = bxdf_value(s, l.mat, l.fr.toLocal(light_to_p), l.fr.toLocal(l.Vr), l.uv);
+            const RGB f_point = bxdf_value(s, p.mat, p.fr.toLocal(p.Vr), p.fr.toLocal(p_to_light), p.uv);
+            const float G = std::fabs(dot(p.lightN, p_to_light)) / distance2(l.pos, p.pos);
+            RGB ff = rgb(f_point.r * f_light.r, f_point.g * f_light.g, f_point.b * f_light.b);   // Spectrum * Spectrum: o.r * r
+            ff = rgb(G * ff.r, G * ff.g, G * ff.b);
+            here = rgb(here.r + l.light_from_source.r * ff.r, here.g + l.light_from_source.g * ff.g, here.b + l.light_from_source.b * ff.b);
+        }
         if (dot(p.faceN, p.Vr) > 0) here = rgb(here.r + p.emission.r, here.g + p.emission.g, here.b + p.emission.b);
         rgbclamp(here, P.clamp);
         total = rgb(total.r + here.r * p.contribution.r, total.g + here.g * p.contribution.g, total.b + here.b * p.contribution.b);
@@ -906,7 +988,8 @@ RGB trace_path(const Scene& s, const rgk_render_params& P, const Ray& r, Sampler
 // Tracer::Render + PathTracer::RenderPixel for one task, src/tracer.cpp:6-37, src/path_tracer.cpp:42-78
 void render_task(const Scene& s, const rgk_camera* cam, const rgk_render_params& P, const rgk_task& t, uint32_t seed,
                  float* rgb_sum, uint32_t* count, RenderCounters& rc) {
-    std::vector<PathPoint> path;
+    std::vector<PathPoint> path, light_path;
+    std::vector<SideEffect> side_effects;
     for (uint32_t y = t.y1; y < t.y2; y++)
         for (uint32_t x = t.x1; x < t.x2; x++) {
             seed += 0x42424242u;
@@ -918,13 +1001,18 @@ void render_task(const Scene& s, const rgk_camera* cam, const rgk_render_params&
                 V2 lens = V2{0, 0};
                 if (cam->lens_size != 0.0f) lens = smp.get2d();
                 Ray r = camera_ray(cam, x, y, P.xres, P.yres, coords, lens);
-                RGB q = trace_path(s, P, r, smp, path, rc);
+                RGB q = trace_path(s, cam, P, r, smp, path, light_path, side_effects, rc);
                 tot = rgb(tot.r + q.r, tot.g + q.g, tot.b + q.b);
                 rc.samples++;
             }
             const size_t px = (size_t)y * P.xres + x;
             rgb_sum[3 * px] += tot.r; rgb_sum[3 * px + 1] += tot.g; rgb_sum[3 * px + 2] += tot.b;
             count[px] += P.multisample;
+            for (const SideEffect& e : side_effects) {              // AddPixel(x2, y2, r, 0), src/tracer.cpp:20-26
+                const size_t q = (size_t)e.y * P.xres + e.x;
+                rgb_sum[3 * q] += e.q.r; rgb_sum[3 * q + 1] += e.q.g; rgb_sum[3 * q + 2] += e.q.b;
+            }
+            side_effects.clear();
         }
 }
 
@@ -1087,20 +1175,32 @@ int rgko_mt19937(uint32_t seed, uint32_t n, uint32_t* out) { MT19937 g(seed); fo
 int rgko_render_round(void* h, const rgk_camera* cam, const rgk_render_params* P, const rgk_task* tasks, uint32_t n_tasks,
                       uint32_t seedstart, uint32_t seedcount_base, float* rgb_sum, uint32_t* count, rgk_round_stats* st, int nthreads) {
     const Scene& s = *(Scene*)h;
-    if (P->reverse != 0) return RGK_ERR_UNSUPPORTED;
     nthreads = std::max(1, nthreads);
     std::vector<RenderCounters> rcs(nthreads);
     std::atomic<uint32_t> next(0);
     auto t0 = std::chrono::high_resolution_clock::now();
+    // reverse > 0: side effects land on pixels of other tasks, so every task renders into its own full-frame buffer which
+    // is then added to the total (EXRTexture::Accumulate, src/render_driver.cpp:176-181); buffers are added in task
+    // order, which is what the reference does with one worker thread (with more, its order is a race).
+    const size_t npx = (size_t)P->xres * P->yres;
+    std::vector<std::vector<float>> tsum; std::vector<std::vector<uint32_t>> tcnt;
+    if (P->reverse) { tsum.resize(n_tasks); tcnt.resize(n_tasks); }
     auto worker = [&](int tid) {
         for (;;) {
             uint32_t i = next.fetch_add(1);
             if (i >= n_tasks) break;
-            render_task(s, cam, *P, tasks[i], seedstart + seedcount_base + i, rgb_sum, count, rcs[tid]);
+            if (P->reverse) {
+                tsum[i].assign(3 * npx, 0.0f); tcnt[i].assign(npx, 0u);
+                render_task(s, cam, *P, tasks[i], seedstart + seedcount_base + i, tsum[i].data(), tcnt[i].data(), rcs[tid]);
+            } else render_task(s, cam, *P, tasks[i], seedstart + seedcount_base + i, rgb_sum, count, rcs[tid]);
         }
     };
     if (nthreads == 1) worker(0);
     else { std::vector<std::thread> th; for (int t = 0; t < nthreads; t++) th.emplace_back(worker, t); for (auto& t : th) t.join(); }
+    for (uint32_t i = 0; P->reverse && i < n_tasks; i++) {
+        for (size_t k = 0; k < 3 * npx; k++) rgb_sum[k] += tsum[i][k];
+        for (size_t k = 0; k < npx; k++) count[k] += tcnt[i][k];
+    }
     auto t1 = std::chrono::high_resolution_clock::now();
     if (st) {
         std::memset(st, 0, sizeof *st);

@@ -48,3 +48,20 @@ def test_render_rounds_bit_identical(oracle, ref):
         fo, co, so = oracle.render_round(ho, cam, p, tasks, seedcount_base=5, nthreads=4)
         assert np.array_equal(fr.view(np.uint32), fo.view(np.uint32)) and np.array_equal(cr, co)
         assert int(sr.closest_rays) == int(so.closest_rays)
+
+
+def test_bidirectional_rounds_bit_identical(oracle, ref):
+    """reverse > 0 with one worker thread (with more, the reference's own accumulation order is a race)."""
+    for (pack, cfg), rev in ((scenes.load_builtin("cornell-box", width=48, height=32, multisample=4), 2),
+                             (scenes.load_builtin("cornell-box", width=48, height=32, multisample=4), 4),
+                             (scenes.material_zoo(width=48, height=32, multisample=4), 3)):
+        cfg.reverse = rev
+        desc = pack.desc()
+        hr, ho = ref.scene_create(desc), oracle.scene_create(desc)
+        cam = _cam(oracle, cfg)
+        p = cfg.params()
+        tasks = oracle.generate_tasks(32, p.xres, p.yres)
+        fr, cr, sr = ref.render_round(hr, cam, p, tasks, nthreads=1)
+        fo, co, so = oracle.render_round(ho, cam, p, tasks, nthreads=1)
+        assert np.array_equal(fr.view(np.uint32), fo.view(np.uint32)) and np.array_equal(cr, co)
+        assert int(sr.closest_rays) == int(so.closest_rays)

@@ -56,6 +56,11 @@ fb, cnt, st = R.render_round(h, cam, p, tasks, nthreads=4)
 tl = np.array([[t.x1, t.x2, t.y1, t.y2] for t in R.generate_tasks(32, 1920, 1080)], np.uint32)
 np.savez_compressed(os.path.join(OUT, "cornell_render.npz"), fb=fb, cnt=cnt, closest_rays=int(st.closest_rays),
                     tasks_1080p=tl, tasks_64=np.array([[t.x1, t.x2, t.y1, t.y2] for t in tasks], np.uint32))
+# bidirectional mode (reverse = 3: light path, camera splats, vertex connections), one worker thread so that the
+# accumulation order of the per-task buffers is defined
+p.depth, p.reverse = 6, 3
+fbr, cntr, str_ = R.render_round(h, cam, p, tasks, nthreads=1)
+np.savez_compressed(os.path.join(OUT, "cornell_reverse.npz"), fb=fbr, cnt=cntr, closest_rays=int(str_.closest_rays))
 
 # ---- 2. StratifiedSampler tables
 sam = {}

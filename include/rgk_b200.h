@@ -27,7 +27,7 @@ typedef enum rgk_status {
     RGK_ERR_NOMEM = 3,
     RGK_ERR_NO_DEVICE = 4,   /* no CUDA device: the library never falls back to the CPU */
     RGK_ERR_NO_SCENE = 5,    /* compute call before rgk_scene_commit */
-    RGK_ERR_UNSUPPORTED = 6  /* e.g. reverse > 0 (bidirectional splats, out of scope) */
+    RGK_ERR_UNSUPPORTED = 6  /* e.g. recursion-max beyond the 64 tabulated sampler dimensions */
 } rgk_status;
 
 typedef struct rgk_context rgk_context;
@@ -196,7 +196,7 @@ typedef struct rgk_render_params {
     float russian;
     float bumpmap_scale;
     uint32_t force_fresnell;  /* stored, never used (as in the reference) */
-    uint32_t reverse;         /* must be 0 */
+    uint32_t reverse;         /* light-path vertices of the bidirectional mode (src/path_tracer.cpp:336-398,462-480); 0 = unidirectional */
     uint32_t sampler_mode;
 } rgk_render_params;
 

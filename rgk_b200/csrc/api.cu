@@ -454,7 +454,7 @@ static rgk_status check_render_args(rgk_context* ctx, const rgk_camera* cam, con
                                     uint32_t n_tasks, const void* rgb, const void* count) {
     if (!ctx || !cam || !p || (n_tasks && !tasks) || !rgb || !count) return RGK_ERR_INVALID;
     if (!ctx->has_scene) return rgk_fail(ctx, RGK_ERR_NO_SCENE, "rgk_scene_commit has not been called");
-    if (p->reverse != 0) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "reverse > 0 (bidirectional light path) is out of scope");
+    if (p->reverse > 16) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "reverse > 16 light-path vertices");
     if (p->xres == 0 || p->yres == 0 || p->multisample == 0) return rgk_fail(ctx, RGK_ERR_INVALID, "xres, yres and multisample must be positive");
     if (p->sampler_mode > RGK_SAMPLER_FAST) return rgk_fail(ctx, RGK_ERR_INVALID, "unknown sampler_mode");
     for (uint32_t i = 0; i < n_tasks; i++)

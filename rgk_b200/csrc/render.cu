@@ -21,6 +21,16 @@
 #include "shade_device.cuh"
 
 // ------------------------------------------------------------------ buffers
+// vertex storage of the bidirectional mode (reverse_device.cuh)
+struct ReverseBuffers {
+    float4 *cam_o = nullptr, *lstart = nullptr;                      // [slot] camera ray origin; light_at_path_start
+    uint32_t *nverts = nullptr, *nlverts = nullptr, *d2base = nullptr;   // [slot] camera / light vertex records; first light 2-D dim
+    // camera vertex n (0-based) of path slot at [n * npaths + slot]
+    float4 *vr_pos = nullptr, *vr_nrm = nullptr, *vr_vr = nullptr, *vr_uv = nullptr, *vr_con = nullptr, *vr_here = nullptr, *vr_emis = nullptr;
+    // light vertex b of path slot at [b * npaths + slot]
+    float4 *lr_pos = nullptr, *lr_nrm = nullptr, *lr_vr = nullptr, *lr_uv = nullptr, *lr_lfs = nullptr;
+    size_t cap_paths = 0, cap_cam = 0, cap_light = 0;
+};
 struct PathBuffers {
     size_t cap_paths = 0, cap_pixels = 0, cap_t1 = 0, cap_t2 = 0, cap_tiles = 0;
     float4 *ray_o = nullptr, *ray_d = nullptr, *hit = nullptr, *cum = nullptr, *tot = nullptr;
@@ -35,6 +45,7 @@ struct PathBuffers {
     unsigned long long *counters = nullptr;   // device
     unsigned long long *h_counters = nullptr; // pinned
     struct EventPool* events = nullptr;       // host only
+    ReverseBuffers* reverse = nullptr;        // host only (bidirectional mode)
 };
 
 enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_SHADOW_SKIPPED = 4, C_COUNT = 8 };
@@ -46,6 +57,8 @@ struct RenderConst {
     uint32_t set_size, n1d, n2d, base2, sampler_mode, lens, skip_null_shadow;
     uint32_t binning;       // 1: k_shade writes direction-bin keys and k_bin builds the queues (coherence reordering)
     uint32_t npix;          // pixels in the chunk
+    uint32_t reverse;       // light path length (bidirectional mode, reverse_device.cuh); 0 = unidirectional
+    uint32_t npaths;        // npix * ms
 };
 
 namespace {
@@ -313,7 +326,7 @@ __global__ void k_camera_rays(rgk_camera cam, uint32_t xres, uint32_t yres, cons
 }
 
 // RenderPixel's per-sample prologue (src/path_tracer.cpp:53-61) and TracePath's light pick (:315-322,337-346)
-__global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers B) {
+__global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, float4* __restrict__ cam_o) {
     const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t npaths = (size_t)R.npix * R.ms;
     if (slot >= npaths) return;
@@ -332,6 +345,7 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
     LightRec L = random_light(S, choice, ls, areal);
     if (L.valid && L.type == 0) { const V3 dir = sphere_uniform(areal); L.pos = L.pos + L.size * dir; }
     B.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+    if (cam_o) cam_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);             // camerapos of the sample (bidirectional mode)
     B.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
     B.cum[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));      // .w = n (bounces done)
     B.tot[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -639,6 +653,8 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
     }
 }
 
+#include "reverse_device.cuh"
+
 // TracePath's epilogue (clamp, NaN/negative guard, src/path_tracer.cpp:501-507), RenderPixel's in-order sum
 // over the samples (:64) and EXRTexture::AddPixel (src/texture.cpp:342-348)
 __global__ void k_finish(RenderConst R, PathBuffers B, float* __restrict__ fb, uint32_t* __restrict__ fb_count) {
@@ -713,6 +729,32 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
     return RGK_OK;
 }
 
+rgk_status ensure_reverse_buffers(rgk_context* ctx, size_t paths, uint32_t depth, uint32_t reverse) {
+    PathBuffers& B = *ctx->paths;
+    if (!B.reverse) B.reverse = new ReverseBuffers();
+    ReverseBuffers& V = *B.reverse;
+    bool ok = true;
+    if (paths > V.cap_paths) {
+        RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ok = alloc_dev(&V.cam_o, paths) && alloc_dev(&V.lstart, paths) && alloc_dev(&V.nverts, paths) && alloc_dev(&V.nlverts, paths) && alloc_dev(&V.d2base, paths);
+        V.cap_paths = ok ? paths : 0;
+    }
+    const size_t cam = paths * depth, light = paths * reverse;
+    if (ok && cam > V.cap_cam) {
+        RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ok = alloc_dev(&V.vr_pos, cam) && alloc_dev(&V.vr_nrm, cam) && alloc_dev(&V.vr_vr, cam) && alloc_dev(&V.vr_uv, cam) && alloc_dev(&V.vr_con, cam) &&
+             alloc_dev(&V.vr_here, cam) && alloc_dev(&V.vr_emis, cam);
+        V.cap_cam = ok ? cam : 0;
+    }
+    if (ok && light > V.cap_light) {
+        RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ok = alloc_dev(&V.lr_pos, light) && alloc_dev(&V.lr_nrm, light) && alloc_dev(&V.lr_vr, light) && alloc_dev(&V.lr_uv, light) && alloc_dev(&V.lr_lfs, light);
+        V.cap_light = ok ? light : 0;
+    }
+    if (!ok) { cudaGetLastError(); return rgk_fail(ctx, RGK_ERR_NOMEM, "bidirectional vertex storage allocation failed (lower RGK_REVERSE_BYTES)"); }
+    return RGK_OK;
+}
+
 } // namespace
 
 void free_event_pool(struct EventPool* p);
@@ -724,6 +766,13 @@ void free_path_buffers(rgk_context* ctx) {
                     B.tiles, B.tiles2, B.counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (B.h_counters) cudaFreeHost(B.h_counters);
+    if (B.reverse) {
+        ReverseBuffers& V = *B.reverse;
+        void* rp[] = {V.cam_o, V.lstart, V.nverts, V.nlverts, V.d2base, V.vr_pos, V.vr_nrm, V.vr_vr, V.vr_uv, V.vr_con, V.vr_here, V.vr_emis,
+                      V.lr_pos, V.lr_nrm, V.lr_vr, V.lr_uv, V.lr_lfs};
+        for (void* q : rp) if (q) cudaFree(q);
+        delete B.reverse;
+    }
     free_event_pool(B.events);
     delete ctx->paths;
     ctx->paths = nullptr;
@@ -793,7 +842,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const uint32_t sq = (uint32_t)(std::sqrt((double)ss) + 0.5f);
     const uint32_t lens = cam->lens_size != 0.0f ? 1u : 0u;
     const uint32_t base2 = 4u + lens;                  // 2-D dims: jitter, [lens], areal, lightdir, choice, then one per bounce
-    const uint32_t n2d = base2 + P->depth, n1d = 1u + P->depth;
+    const uint32_t n2d = base2 + P->depth + P->reverse, n1d = 1u + P->depth;   // the light path continues the camera path's 2-D dims
     const bool user_tables = P->sampler_mode == RGK_SAMPLER_TABLES;
     if (user_tables) {
         uint64_t need = 0;
@@ -820,7 +869,11 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
 
     // chunking: whole tiles, every multisample of a pixel in the same chunk
-    const size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)32 << 20);
+    size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)32 << 20);
+    if (P->reverse) {      // bidirectional mode keeps every vertex of the camera and light paths: 112 B and 80 B per vertex
+        const size_t per_path = 112 * (size_t)P->depth + 80 * (size_t)P->reverse + 64;
+        max_paths = std::max<size_t>(std::min(max_paths, env_size("RGK_REVERSE_BYTES", (size_t)8 << 30) / per_path), 4096);
+    }
     const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
     const size_t max_table_bytes = env_size("RGK_TABLE_BYTES", (size_t)24 << 30);
     std::vector<uint4> h_tiles; std::vector<uint2> h_tiles2;
@@ -859,6 +912,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         R.cam = *cam; R.xres = P->xres; R.yres = P->yres; R.ms = ms; R.depth = P->depth; R.clamp = P->clamp; R.russian = P->russian;
         R.bump_scale = P->bumpmap_scale; R.set_size = ss; R.n1d = n1d; R.n2d = n2d; R.base2 = base2; R.sampler_mode = P->sampler_mode;
         R.lens = lens; R.npix = (uint32_t)npix; R.skip_null_shadow = skip_null; R.binning = binning ? 1u : 0u;
+        R.reverse = P->reverse; R.npaths = (uint32_t)npaths;
+        if (P->reverse) { s = ensure_reverse_buffers(ctx, npaths, P->depth, P->reverse); if (s != RGK_OK) return s; }
         // reordering groups: SG samples x PG pixel positions (a multiple of the 32-pixel blocks of k_pixel_setup)
         const uint32_t SG = (uint32_t)std::min<size_t>(ms, 128);
         const uint32_t PG = (uint32_t)std::max<size_t>(8, (bin_items / SG) / 8 * 8);
@@ -878,7 +933,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         call_pixels += npix;
         pool.end(ctx->stream);
         pool.begin(ctx->stream, T_SHADE);
-        k_raygen<<<(unsigned)((npaths + 127) / 128), 128, 0, ctx->stream>>>(ctx->dev, R, smp, B);
+        k_raygen<<<(unsigned)((npaths + 127) / 128), 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, P->reverse ? B.reverse->cam_o : nullptr);
         pool.end(ctx->stream);
         ctx->launches++;
         RGK_CUDA(ctx, cudaGetLastError());
@@ -887,6 +942,80 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         uint32_t count = (uint32_t)npaths;
         const uint32_t* queue = nullptr;
         uint32_t* qnext = B.queue_a;
+        if (P->reverse) {
+            // ---- bidirectional mode (reverse_device.cuh): camera paths kept vertex by vertex, then the light paths,
+            // then the connections, then the per-vertex sums
+            const ReverseBuffers V = *B.reverse;
+            DevScene dev = ctx->dev;
+            RGK_CUDA(ctx, cudaMemsetAsync(V.nverts, 0, npaths * sizeof(uint32_t), ctx->stream));
+            auto counts = [&](uint32_t& next_count, uint32_t& shadow_count) -> rgk_status {
+                RGK_CUDA(ctx, cudaMemcpyAsync(B.h_counters, B.counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+                RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                next_count = (uint32_t)B.h_counters[C_NEXT]; shadow_count = (uint32_t)B.h_counters[C_SHADOW];
+                total.shadow_rays_skipped += B.h_counters[C_SHADOW_SKIPPED];
+                return RGK_OK;
+            };
+            auto closest = [&](const uint32_t* q, uint32_t n, bool coherent) {
+                dev.refill_threshold = coherent ? refill_coherent : refill_incoherent;
+                const int g = (int)std::min<uint64_t>(tgrid, ((uint64_t)n + TRACE_THREADS - 1) / TRACE_THREADS);
+                pool.begin(ctx->stream, T_CLOSEST);
+                if (coherent) k_closest<false, RGK_COH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, nullptr);
+                else k_closest<false, RGK_INCOH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, nullptr);
+                pool.end(ctx->stream);
+                ctx->launches++; total.closest_launches++; total.closest_rays += n;
+            };
+            for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {           // camera paths
+                RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
+                closest(queue, count, bounce == 0);
+                pool.begin(ctx->stream, T_SHADE);
+                k_shade_rev<false><<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, V, queue, count, qnext, B.queue_s, B.counters);
+                pool.end(ctx->stream);
+                ctx->launches++;
+                uint32_t next_count = 0, shadow_count = 0;
+                rgk_status cs = counts(next_count, shadow_count); if (cs != RGK_OK) return cs;
+                total.shadow_rays += shadow_count;
+                if (shadow_count) {
+                    dev.refill_threshold = bounce == 0 ? refill_coherent : refill_shadow;
+                    const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
+                    pool.begin(ctx->stream, T_SHADOW);
+                    k_shadow_rev<<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, R, B, V, B.queue_s, shadow_count, B.counters + C_WORK_B);
+                    pool.end(ctx->stream);
+                    ctx->launches++; total.shadow_launches++;
+                }
+                queue = qnext; qnext = (qnext == B.queue_a) ? B.queue_b : B.queue_a;
+                count = next_count;
+            }
+            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 5 * sizeof(unsigned long long), ctx->stream));   // light paths
+            pool.begin(ctx->stream, T_SHADE);
+            k_lightgen<<<(unsigned)((npaths + 127) / 128), 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, V, B.queue_a, B.counters);
+            pool.end(ctx->stream);
+            ctx->launches++;
+            uint32_t lcount = 0, dummy = 0;
+            rgk_status cs = counts(lcount, dummy); if (cs != RGK_OK) return cs;
+            const uint32_t* lq = B.queue_a; uint32_t* lnext = B.queue_b;
+            for (uint32_t b = 0; b < P->reverse && lcount > 0; b++) {
+                RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
+                closest(lq, lcount, false);
+                pool.begin(ctx->stream, T_SHADE);
+                k_shade_rev<true><<<(lcount + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, V, lq, lcount, lnext, B.queue_s, B.counters);
+                pool.end(ctx->stream);
+                ctx->launches++;
+                cs = counts(lcount, dummy); if (cs != RGK_OK) return cs;
+                lq = lnext; lnext = (lnext == B.queue_a) ? B.queue_b : B.queue_a;
+            }
+            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 5 * sizeof(unsigned long long), ctx->stream));   // connections
+            pool.begin(ctx->stream, T_SHADOW);
+            k_connect_camera<<<(unsigned)((npaths * P->reverse + 127) / 128), 128, 0, ctx->stream>>>(ctx->dev, R, B, V, d_rgb, B.counters);
+            k_connect_vertices<<<(unsigned)((npaths * P->depth + 127) / 128), 128, 0, ctx->stream>>>(ctx->dev, R, V, B.counters);
+            pool.end(ctx->stream);
+            pool.begin(ctx->stream, T_SHADE);
+            k_assemble<<<(unsigned)((npaths + 127) / 128), 128, 0, ctx->stream>>>(R, B, V);
+            pool.end(ctx->stream);
+            ctx->launches += 3;
+            cs = counts(dummy, lcount); if (cs != RGK_OK) return cs;
+            total.shadow_rays += lcount;                       // connection rays (Visibility calls of phases 2 and 3)
+            count = 0;
+        }
         for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {
             RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
             const int g1 = (int)std::min<uint64_t>(tgrid, ((uint64_t)count + TRACE_THREADS - 1) / TRACE_THREADS);

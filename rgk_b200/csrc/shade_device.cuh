@@ -94,6 +94,27 @@ __device__ __forceinline__ V3 hemi_cos_z(V2 s) {
     const float z = sqrtf(gmax(0.00001f, 1 - p.x * p.x - p.y * p.y));
     return v3(p.x, p.y, z);
 }
+// Sample2DToHemisphereCosine (y up) and Sample2DToHemisphereCosineDirected = RotationFromY(direction) * it
+// (src/random_utils.hpp:32-47,76-78, src/glm.cpp:36-60): the direction in which a light path leaves its light
+__device__ __forceinline__ V3 hemi_cos_directed(V2 s, V3 direction) {
+    const V2 p = disc_uniform(s);
+    const float y = sqrtf(gmax(0.00001f, 1 - p.x * p.x - p.y * p.y));
+    const V3 r = v3(p.x, y, p.y);
+    const V3 dest = normalize(direction);
+    const float cosTheta = dest.y;
+    Quat q;
+    if (cosTheta < -1 + 0.00001f) {
+        const float a = RGK_PI_F;
+        const float sn = sinf(a * 0.5f);
+        q = Quat{cosf(a * 0.5f), 1.0f * sn, 0.0f * sn, 0.0f * sn};
+    } else {
+        const V3 axis = cross(v3(0.0f, 1.0f, 0.0f), dest);
+        const float sq = sqrtf((1 + cosTheta) * 2);
+        const float invs = 1 / sq;
+        q = Quat{sq * 0.5f, axis.x * invs, axis.y * invs, axis.z * invs};
+    }
+    return qrot(q, r);
+}
 __device__ __forceinline__ V3 sphere_uniform(V2 s) {
     const float z = s.x * 2.0f - 1.0f;
     const float a = (float)((double)s.y * 6.283185);

@@ -90,10 +90,45 @@ def test_error_paths(gpu_ctx):
     gpu_ctx.commit(pack.desc())
     cam = gpu_ctx.camera(**cfg.camera_args())
     p = cfg.params()
-    p.reverse = 1
+    p.depth = 61                                   # leaves the 64 tabulated sampler dimensions
     with pytest.raises(RgkError) as e:
         gpu_ctx.render_round(cam, p, gpu_ctx.generate_tasks(32, 32, 32))
     assert e.value.status == 6
+    p = cfg.params()
+    p.reverse = 17
+    with pytest.raises(RgkError) as e:
+        gpu_ctx.render_round(cam, p, gpu_ctx.generate_tasks(32, 32, 32))
+    assert e.value.status == 6
+
+
+@pytest.mark.parametrize("scene_name,reverse,depth", [("cornell", 3, 6), ("cornell", 1, 40), ("zoo", 2, 5)])
+def test_bidirectional_round_matches_oracle(gpu_ctx, oracle, scene_name, reverse, depth):
+    """reverse > 0 (src/path_tracer.cpp:336-398,462-480): light path, camera splats (count 0), vertex connections.
+    Same sample sequence as the CPU; splats are summed with atomics, so the comparison is by tolerance."""
+    if scene_name == "cornell":
+        pack, cfg = scenes.load_builtin("cornell-box", width=64, height=64, multisample=4)
+    else:
+        pack, cfg = scenes.material_zoo(width=64, height=40, multisample=4, lens=0.03)
+    desc = pack.desc()
+    gpu_ctx.commit(desc)
+    cam = gpu_ctx.camera(**cfg.camera_args())
+    p = cfg.params()
+    p.depth, p.reverse = depth, reverse
+    tasks = gpu_ctx.generate_tasks(32, p.xres, p.yres)
+    fb, cnt, st = gpu_ctx.render_round(cam, p, tasks)
+    ho = oracle.scene_create(desc)
+    fo, co, so = oracle.render_round(ho, cam, p, tasks, nthreads=1)
+    assert np.array_equal(cnt, co) and np.all(cnt == 4)                 # splats add radiance, never samples
+    assert int(st.closest_rays) == int(so.closest_rays)                 # camera + light path segments
+    assert int(st.shadow_rays) + int(st.shadow_rays_skipped) == int(so.shadow_rays)   # NEE + both kinds of connection rays
+    mean = float(fo.mean())
+    assert abs(float(fb.mean()) - mean) / mean < 1e-3
+    assert float(np.sqrt(np.mean((fb - fo) ** 2))) / mean < 0.05
+    # and the unidirectional image differs from it (the mode is doing something)
+    p.reverse = 0
+    f0, _, _ = gpu_ctx.render_round(cam, p, tasks)
+    assert float(np.abs(f0 - fb).mean()) > 1e-3 * mean
+    oracle.scene_destroy(ho)
 
 
 def _pixel_seeds(tasks, seedstart=42, seedcount_base=0):

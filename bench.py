@@ -126,9 +126,10 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_sample(cfg, pack, desc, kind_pref, threads):
-    """Times the CPU renderer on the bounded crop.  Returns dict(value Mrays/s, cores, kind, sample, seconds, rays)."""
+def cpu_sample(cfg, pack, desc, kind_pref, threads, crop=None):
+    """Sets up the CPU renderer on a bounded sample (centred crop of the frame, full spp)."""
     import checkers
+    crop = crop or CROP
     use_ref = kind_pref == "reference" and checkers.have_ref()
     chk = checkers.ref() if use_ref else checkers.oracle()
     orc = checkers.oracle()
@@ -136,7 +137,7 @@ def cpu_sample(cfg, pack, desc, kind_pref, threads):
     ho = orc.scene_create(desc) if use_ref else h
     ca = cfg.camera_args()
     cam_full = orc.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
-    cw, ch = min(CROP[0], cfg.xres), min(CROP[1], cfg.yres)
+    cw, ch = min(crop[0], cfg.xres), min(crop[1], cfg.yres)
     cam = crop_camera(cam_full, cfg.xres, cfg.yres, cw, ch)
     p = cfg.params()
     p.xres, p.yres = cw, ch
@@ -160,7 +161,13 @@ def reference_arm(args):
     pack, cfg, label = build_workload(args.workload, args.spp)
     desc = pack.desc()
     threads = os.cpu_count() or 1
-    chk, orc, h, ho, cam, p, tasks, use_ref, (cw, ch) = cpu_sample(cfg, pack, desc, "reference", threads)
+    # size the per-step sample so that warmup + steps stay near two minutes on this box's cores: probe a small crop first
+    chk, orc, h, ho, cam, p, tasks, use_ref, _ = cpu_sample(cfg, pack, desc, "reference", threads, crop=(256, 144))
+    probe_dt, _, _, probe_samples = run_cpu(chk, h, cam, p, tasks, threads, 0)
+    budget_samples = (120.0 / max(1, args.steps + args.warmup + 1)) * probe_samples / max(probe_dt, 1e-3)
+    scale = min(1.0, (budget_samples / (CROP[0] * CROP[1] * max(1, cfg.multisample))) ** 0.5)
+    crop = (max(256, int(CROP[0] * scale) // 32 * 32), max(144, int(CROP[1] * scale) // 16 * 16))
+    chk, orc, h, ho, cam, p, tasks, use_ref, (cw, ch) = cpu_sample(cfg, pack, desc, "reference", threads, crop=crop)
     shadow = None
     if use_ref:   # the reference does not count shadow rays (src/path_tracer.cpp:126 counts closest only): take the
         # count of the bit-identical oracle run of the same sample, untimed

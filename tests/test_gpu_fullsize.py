@@ -76,3 +76,26 @@ def test_full_hd_round_linearity_and_counts(gpu_ctx, sponza):
     assert np.array_equal(acc[0], f1 + f2) and int(acc[1].min()) == 8
     assert not np.array_equal(f1, f2)                       # different seeds -> different noise
     assert abs(float(f1.mean()) - float(f2.mean())) < 0.05 * float(f1.mean())
+
+
+def test_queue_order_never_changes_a_result(gpu_ctx, sponza, monkeypatch):
+    """Direction-binned queues (k_bin) vs atomic compaction, different reordering group sizes and refill thresholds: the
+    order in which a launch processes its rays must not change one bit of the image."""
+    pack, cfg, desc, ho = sponza
+    cfg.multisample = 4
+    cam = gpu_ctx.camera(**cfg.camera_args())
+    p = cfg.params(abi.SAMPLER_MT19937)
+    tasks = gpu_ctx.generate_tasks(32, 1920, 1080)
+    ref_img = None
+    for env in ({"RGK_BIN": "0"}, {"RGK_BIN": "1"}, {"RGK_BIN": "1", "RGK_BIN_ITEMS": "8192", "RGK_REFILL_INCOHERENT": "4", "RGK_REFILL_SHADOW": "32"},
+                {"RGK_BIN": "1", "RGK_BIN_SHADOW0": "0", "RGK_CHUNK_PATHS": "3000000"}):
+        for k in ("RGK_BIN", "RGK_BIN_ITEMS", "RGK_REFILL_INCOHERENT", "RGK_REFILL_SHADOW", "RGK_BIN_SHADOW0", "RGK_CHUNK_PATHS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        f, c, st = gpu_ctx.render_round(cam, p, tasks, seedcount_base=7)
+        if ref_img is None:
+            ref_img, ref_rays = f, (int(st.closest_rays), int(st.shadow_rays))
+        else:
+            assert np.array_equal(f.view(np.uint32), ref_img.view(np.uint32)), env
+            assert (int(st.closest_rays), int(st.shadow_rays)) == ref_rays

@@ -231,8 +231,6 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
     D.n_areal_lights = hs.info.n_areal_lights;
     D.total_point_power = hs.info.total_point_power; D.total_areal_power = hs.info.total_areal_power;
     D.epsilon = hs.info.epsilon;
-    { const char* e = std::getenv("RGK_STEPS_INNER"); D.steps_inner = e ? (uint32_t)std::max(1, std::atoi(e)) : 4u; }
-    { const char* e = std::getenv("RGK_STEPS_LEAF"); D.steps_leaf = e ? (uint32_t)std::max(1, std::atoi(e)) : 4u; }
     { const char* e = std::getenv("RGK_REFILL"); const int v = e ? std::atoi(e) : 16; D.refill_threshold = (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v)); }
     for (int k = 0; k < 6; k++) D.bb[k] = hs.info.bbox[k];
     RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1025,7 +1025,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             dev.refill_threshold = bounce == 0 ? refill_coherent : refill_incoherent;
             pool.begin(ctx->stream, T_CLOSEST);
             // two register budgets of the same kernel: 56 registers (9 CTAs/SM) for the issue-bound coherent camera rays,
-            // 40 registers (12 CTAs/SM) for later bounces, which are latency-bound and gain from the extra warps
+            // 48 registers (10 CTAs/SM) for later bounces, which gain from the extra warps
             if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
             else if (bounce == 0) k_closest<false, RGK_COH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             else k_closest<false, RGK_INCOH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);

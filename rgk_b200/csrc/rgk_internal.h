@@ -67,7 +67,6 @@ struct DevScene {
     uint32_t sky_mode; float sky_color[3]; float sky_intensity, sky_rotate; int32_t sky_envmap;
     uint32_t has_ltc;
     uint32_t refill_threshold;   // idle lanes of a warp that trigger a refill (RGK_REFILL)
-    uint32_t steps_inner, steps_leaf;   // per-iteration budgets of the bounded-phase traversal (RGK_STEPS_INNER / RGK_STEPS_LEAF)
 };
 
 #define RGK_STACK_CAP 64  // traversal stack entries per ray (tree depth <= log2(n)+8, src/scene.cpp:409)

@@ -182,8 +182,11 @@ assert RAY_DT.itemsize == 32 and HIT_DT.itemsize == 20
 
 
 def oracle():
-    if not os.path.exists(ORACLE_SO):
-        raise RuntimeError(f"{ORACLE_SO} missing: run `make -C oracle oracle` (or __graft_entry__.build())")
+    if not os.path.exists(ORACLE_SO):      # normally built by __graft_entry__.build(); one g++ call if it did not travel
+        import subprocess
+        r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], capture_output=True, text=True)
+        if r.returncode != 0 or not os.path.exists(ORACLE_SO):
+            raise RuntimeError(f"{ORACLE_SO} missing and `make -C oracle oracle` failed: {r.stderr[-400:]}")
     return Checker(ORACLE_SO, "rgko")
 
 

@@ -14,10 +14,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "build", "host")
 
 
+SOURCES = {"rgk_render": os.path.join(ROOT, "rgk_b200", "host", "rgk_render.cpp"), "host_checks": os.path.join(ROOT, "tests", "host_cpp", "host_checks.cpp")}
+
+
 def _need(exe):
+    """The host programs are built by __graft_entry__.build(); if the build directory did not travel with the snapshot
+    they are compiled here against the in-tree library (g++ only, no nvcc needed)."""
     path = os.path.join(HOST, exe)
     if not os.path.exists(path):
-        pytest.fail(f"{path} missing: run python -c 'import __graft_entry__ as g; g.build()'")
+        os.makedirs(HOST, exist_ok=True)
+        cmd = ["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), SOURCES[exe], "-o", path,
+               "-L" + os.path.join(ROOT, "rgk_b200"), "-lrgk_b200", "-Wl,-rpath," + os.path.join(ROOT, "rgk_b200")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.fail(f"{path} missing and could not be built: {r.stderr[-500:]}")
     return path
 
 

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define RGK_ABI_VERSION 1
+#define RGK_ABI_VERSION 2   /* 2: rgk_trav_stats grew the pre-filter counters; rgk_host_scene_*; reverse > 0 */
 
 typedef enum rgk_status {
     RGK_OK = 0,

@@ -127,6 +127,8 @@ class RoundStats(C.Structure):
 assert C.sizeof(Material) == 64 and C.sizeof(Ray) == 32 and C.sizeof(Hit) == 20
 
 # Every symbol include/rgk_b200.h declares (tests check that the library exports all of them).
+ABI_VERSION = 2      # RGK_ABI_VERSION of include/rgk_b200.h these ctypes structures mirror
+
 EXPORTS = [
     "rgk_abi_version", "rgk_status_string", "rgk_context_create", "rgk_context_destroy", "rgk_last_error",
     "rgk_scene_commit", "rgk_scene_get_info", "rgk_scene_get_kdtree", "rgk_trace_closest", "rgk_trace_shadow",
@@ -149,6 +151,8 @@ def load_library(path=None):
     lib = C.CDLL(path)
     vp = C.c_void_p
     lib.rgk_abi_version.restype = C.c_uint32
+    if lib.rgk_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI version {lib.rgk_abi_version()}, this binding expects {ABI_VERSION} (rebuild: __graft_entry__.build())")
     lib.rgk_status_string.restype = C.c_char_p
     lib.rgk_status_string.argtypes = [C.c_int]
     lib.rgk_context_create.argtypes = [C.c_int, vp, C.POINTER(vp)]

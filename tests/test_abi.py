@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rgk_abi_version() == 1
+    assert lib.rgk_abi_version() == abi.ABI_VERSION
     assert lib.rgk_status_string(4).decode().startswith("no CUDA device")
 
 

@@ -77,10 +77,16 @@ struct MT {
     uint32_t* st;      // this thread's column of its CTA's state block: word k at st[k * MT_LANES] (32-bit offsets, coalesced)
     int k0, cur;
     uint32_t buf[8];
+    uint32_t la, lb;   // first generation only: seed-recurrence words k0 and k0 + 397, kept in registers
+    bool gen0;
+    static __device__ __forceinline__ uint32_t lcg(uint32_t prev, uint32_t i) { return 1812433253u * (prev ^ (prev >> 30)) + i; }
+    // mt19937::seed(s): word_0 = s, word_i = 1812433253 * (word_{i-1} ^ (word_{i-1} >> 30)) + i.  The seeded state is never
+    // written out: its words are only inputs of the first twist, and that reads them in ascending order at two places
+    // (k and k + 397), so two running registers replace the store pass and most loads of the first generation.
     __device__ void seed(uint32_t s) {
-        uint32_t prev = s; st[0] = s;
-        for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; st[i * MT_LANES] = prev; }
-        k0 = 0; cur = 8;
+        la = s; lb = s;
+        for (uint32_t i = 1; i <= 397; i++) lb = lcg(lb, i);
+        gen0 = true; k0 = 0; cur = 8;
     }
     // The twist is done incrementally, eight words at a time, right before their tempered values are handed out (the
     // standard implementation twists all 624 words when the block is exhausted; word k only depends on old k, old k+1
@@ -92,7 +98,27 @@ struct MT {
     __device__ void fill() {
         uint32_t own[9], far[8];
         uint32_t* p = st + k0 * MT_LANES;
-        if (k0 != 224 && k0 != 616) {
+        if (gen0) {
+            own[0] = la;
+#pragma unroll
+            for (int j = 1; j < 9; j++) own[j] = lcg(own[j - 1], (uint32_t)(k0 + j));
+            la = own[8];
+            if (k0 == 616) own[8] = st[0];                              // word "624" of the last batch is the NEW word 0
+            if (k0 < 224) {
+                far[0] = lb;
+#pragma unroll
+                for (int j = 1; j < 8; j++) far[j] = lcg(far[j - 1], (uint32_t)(k0 + 397 + j));
+                lb = lcg(far[7], (uint32_t)(k0 + 397 + 8));
+            } else if (k0 == 224) {                                     // old words 621..623, then new words 0..4
+                far[0] = lb; far[1] = lcg(far[0], 622u); far[2] = lcg(far[1], 623u);
+#pragma unroll
+                for (int j = 3; j < 8; j++) far[j] = st[(j - 3) * MT_LANES];
+            } else {
+                const uint32_t* pf = p - 227 * MT_LANES;
+#pragma unroll
+                for (int j = 0; j < 8; j++) far[j] = pf[j * MT_LANES];
+            }
+        } else if (k0 != 224 && k0 != 616) {
             const uint32_t* pf = (k0 < 224) ? p + 397 * MT_LANES : p - 227 * MT_LANES;
 #pragma unroll
             for (int j = 0; j < 9; j++) own[j] = p[j * MT_LANES];
@@ -112,7 +138,7 @@ struct MT {
             y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
             buf[j] = y;
         }
-        k0 = (k0 + 8 == 624) ? 0 : k0 + 8;
+        if (k0 + 8 == 624) { k0 = 0; gen0 = false; } else k0 += 8;
         cur = 0;
     }
     __device__ uint32_t next() {

@@ -37,6 +37,7 @@ struct PathBuffers {
     float4 *light_pos = nullptr, *light_col = nullptr, *light_nrm = nullptr;
     float4 *sh_pos = nullptr, *sh_direct = nullptr, *sh_emis = nullptr, *sh_contrib = nullptr;
     uint32_t *last_tri = nullptr, *cur1 = nullptr, *queue_a = nullptr, *queue_b = nullptr, *queue_s = nullptr;
+    uint32_t *queue_ua = nullptr, *queue_ub = nullptr;    // the live queue once more in path order (k_shade reads its state through it)
     uint8_t *key_next = nullptr, *key_shadow = nullptr;   // per-slot direction bin of the continuation / shadow ray, 0xFF = none (binned queues)
     uint32_t *pix_xy = nullptr, *pix_seed = nullptr, *pix_src = nullptr;   // pix_src: index of the pixel in call order (task order, y-major)
     uint32_t *mt_state = nullptr;
@@ -48,7 +49,7 @@ struct PathBuffers {
     ReverseBuffers* reverse = nullptr;        // host only (bidirectional mode)
 };
 
-enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_SHADOW_SKIPPED = 4, C_COUNT = 8 };
+enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_SHADOW_SKIPPED = 4, C_NEXT_U = 5, C_COUNT = 8 };
 
 struct RenderConst {
     rgk_camera cam;
@@ -536,7 +537,7 @@ __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* 
 #endif
 __global__ void __launch_bounds__(128, RGK_SHADE_MINB)
 k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count,
-        uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, unsigned long long* counters) {
+        uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ next_unsorted, unsigned long long* counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool cont = false, shadow = false, null_shadow = false;
     uint32_t slot = 0;
@@ -666,6 +667,9 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
     // path order.  R.binning bit 0: continuation rays, bit 1: shadow rays.  The order of a queue never changes a result.
     if (R.binning & 1u) {
         if (cont) { const float4 d = B.ray_d[slot]; B.key_next[slot] = dir_bin(d.x, d.y, d.z); }
+        // the same paths once more in path order: the next k_shade gathers its per-path state through this list
+        // (coalesced), the traversal goes through the direction-sorted one
+        push_queue(next_unsorted, counters + C_NEXT_U, cont, slot);
     } else push_queue(next_queue, counters + C_NEXT, cont, slot);
     if (R.binning & 2u) {
         if (shadow) {
@@ -733,7 +737,7 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
         ok = ok && alloc_dev(&B.ray_o, paths) && alloc_dev(&B.ray_d, paths) && alloc_dev(&B.hit, paths) && alloc_dev(&B.cum, paths) &&
              alloc_dev(&B.tot, paths) && alloc_dev(&B.light_pos, paths) && alloc_dev(&B.light_col, paths) && alloc_dev(&B.light_nrm, paths) &&
              alloc_dev(&B.sh_pos, paths) && alloc_dev(&B.sh_direct, paths) && alloc_dev(&B.sh_emis, paths) && alloc_dev(&B.sh_contrib, paths) &&
-             alloc_dev(&B.last_tri, paths) && alloc_dev(&B.cur1, paths) && alloc_dev(&B.queue_a, paths) && alloc_dev(&B.queue_b, paths) &&
+             alloc_dev(&B.last_tri, paths) && alloc_dev(&B.cur1, paths) && alloc_dev(&B.queue_a, paths) && alloc_dev(&B.queue_b, paths) && alloc_dev(&B.queue_ua, paths) && alloc_dev(&B.queue_ub, paths) &&
              alloc_dev(&B.queue_s, paths) && alloc_dev(&B.key_next, paths) && alloc_dev(&B.key_shadow, paths);
         B.cap_paths = ok ? paths : 0;
     }
@@ -788,7 +792,7 @@ void free_path_buffers(rgk_context* ctx) {
     if (!ctx->paths) return;
     PathBuffers& B = *ctx->paths;
     void* ptrs[] = {B.ray_o, B.ray_d, B.hit, B.cum, B.tot, B.light_pos, B.light_col, B.light_nrm, B.sh_pos, B.sh_direct, B.sh_emis,
-                    B.sh_contrib, B.last_tri, B.cur1, B.queue_a, B.queue_b, B.queue_s, B.key_next, B.key_shadow, B.pix_xy, B.pix_seed, B.pix_src, B.mt_state, B.t1, B.t2,
+                    B.sh_contrib, B.last_tri, B.cur1, B.queue_a, B.queue_b, B.queue_ua, B.queue_ub, B.queue_s, B.key_next, B.key_shadow, B.pix_xy, B.pix_seed, B.pix_src, B.mt_state, B.t1, B.t2,
                     B.tiles, B.tiles2, B.counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (B.h_counters) cudaFreeHost(B.h_counters);
@@ -887,6 +891,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const uint32_t skip_null = env_flag("RGK_SKIP_NULL_SHADOW", true) ? 1u : 0u;
     const bool binning = env_flag("RGK_BIN", true) && P->depth > 1;
     const bool bin_shadow0 = env_flag("RGK_BIN_SHADOW0", true);
+    const bool path_order_shade = env_flag("RGK_SHADE_PATH_ORDER", true);
     const double bin_min_frac = std::getenv("RGK_BIN_MIN_FRAC") ? std::atof(std::getenv("RGK_BIN_MIN_FRAC")) : 0.25;
     const size_t bin_items = env_size("RGK_BIN_ITEMS", 2048);   // path slots per reordering group
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 24);
@@ -1042,8 +1047,10 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             total.shadow_rays += lcount;                       // connection rays (Visibility calls of phases 2 and 3)
             count = 0;
         }
+        const uint32_t* shade_q = nullptr;          // the live queue in path order, when the traversal queue is direction-sorted
+        uint32_t* unext = B.queue_ua;
         for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {
-            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
+            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 6 * sizeof(unsigned long long), ctx->stream));
             const int g1 = (int)std::min<uint64_t>(tgrid, ((uint64_t)count + TRACE_THREADS - 1) / TRACE_THREADS);
             // camera rays (and the shadow rays of their hit points) are coherent: keep warps in lockstep (refill only
             // when the whole warp is done); later bounces are incoherent: refill as soon as a quarter of the warp idles
@@ -1066,7 +1073,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             R.binning = (bin_next ? 1u : 0u) | (bin_shadow ? 2u : 0u);
             if (bin_next) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
             if (bin_shadow) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
-            k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, count, qnext, B.queue_s, B.counters);
+            k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
             if (bin_next) {
                 k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, B.counters + C_NEXT);
                 ctx->launches++;
@@ -1091,6 +1098,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 ctx->launches++; total.shadow_launches++;
             }
             queue = qnext; qnext = (qnext == B.queue_a) ? B.queue_b : B.queue_a;
+            shade_q = (bin_next && path_order_shade) ? unext : nullptr;
+            unext = (unext == B.queue_ua) ? B.queue_ub : B.queue_ua;
             count = next_count;
         }
         pool.begin(ctx->stream, T_SHADE);

@@ -448,7 +448,15 @@ k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t
         },
         [&](uint32_t i, bool blocked, const HitRec&) {
             const uint32_t slot = __ldg(queue + i);
-            const float4 dr = B.sh_direct[slot], em = B.sh_emis[slot], cb = B.sh_contrib[slot];
+            const float4 dr = B.sh_direct[slot];
+            if (__float_as_uint(dr.w) == 0u) {                 // vertex without emission: dr = min(direct, clamp) * contribution
+                if (blocked) return;
+                float4 t = B.tot[slot];
+                t.x += dr.x; t.y += dr.y; t.z += dr.z;
+                B.tot[slot] = t;
+                return;
+            }
+            const float4 em = B.sh_emis[slot], cb = B.sh_contrib[slot];
             float hr = blocked ? 0.0f : dr.x, hg = blocked ? 0.0f : dr.y, hb = blocked ? 0.0f : dr.z;
             hr += em.x; hg += em.y; hb += em.z;
             if (hr > clampv) hr = clampv;
@@ -615,9 +623,20 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                     // Visibility query cannot change the pixel: it is not traced (R.skip_null_shadow, on by default).
                     if (!(R.skip_null_shadow && direct.r == 0.0f && direct.g == 0.0f && direct.b == 0.0f)) {
                         B.sh_pos[slot] = make_float4(pos.x, pos.y, pos.z, 0.0f);
-                        B.sh_direct[slot] = make_float4(direct.r, direct.g, direct.b, 0.0f);
-                        B.sh_emis[slot] = make_float4(emis.r, emis.g, emis.b, 0.0f);
-                        B.sh_contrib[slot] = make_float4(contribution.r, contribution.g, contribution.b, 0.0f);
+                        if (emis.r == 0.0f && emis.g == 0.0f && emis.b == 0.0f) {
+                            // no emission at this vertex (the usual case): what a visible light adds is already known,
+                            // min(direct, clamp) * contribution -- the very operations k_shadow would do -- and a blocked one
+                            // adds nothing, so the resolve touches one record instead of three (+ the radiance sum)
+                            float hr = direct.r, hg = direct.g, hb = direct.b;
+                            if (hr > R.clamp) hr = R.clamp;
+                            if (hg > R.clamp) hg = R.clamp;
+                            if (hb > R.clamp) hb = R.clamp;
+                            B.sh_direct[slot] = make_float4(hr * contribution.r, hg * contribution.g, hb * contribution.b, __uint_as_float(0u));
+                        } else {
+                            B.sh_direct[slot] = make_float4(direct.r, direct.g, direct.b, __uint_as_float(1u));
+                            B.sh_emis[slot] = make_float4(emis.r, emis.g, emis.b, 0.0f);
+                            B.sh_contrib[slot] = make_float4(contribution.r, contribution.g, contribution.b, 0.0f);
+                        }
                         shadow = true;
                     } else null_shadow = true;
                 }

@@ -202,6 +202,7 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
             pl[i].intensity = s.intensity; pl[i].size = s.size;
         }
         UP(pl, &D.point_lights);
+        ctx->first_point_light = pl.empty() ? DevPointLight{} : pl[0];
         UP(hs.areal_lights, &D.areal_lights);
         UP(hs.areal_tris, &D.areal_tris);
         const rgk_ltc_table* lt[2] = {&d->ltc_ggx, &d->ltc_beckmann};

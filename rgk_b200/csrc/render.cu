@@ -58,6 +58,8 @@ struct RenderConst {
     uint32_t set_size, n1d, n2d, base2, sampler_mode, lens, skip_null_shadow;
     uint32_t binning;       // 1: k_shade writes direction-bin keys and k_bin builds the queues (coherence reordering)
     uint32_t npix;          // pixels in the chunk
+    uint32_t const_light;   // 1: the scene's only light is one point light of size 0 -- every sample picks the same light record
+    float4 cl_pos, cl_col;  //    (position + flags, colour + intensity), read from here instead of per-path arrays
     uint32_t reverse;       // light path length (bidirectional mode, reverse_device.cuh); 0 = unidirectional
     uint32_t npaths;        // npix * ms
 };
@@ -369,8 +371,6 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
     d2++;                                                       // lightdir_sample: drawn, unused when reverse == 0
     const V2 choice = smp.get2d(pixel, seed, set, d2++);
     const float ls = smp.get1d(pixel, seed, set, 0);
-    LightRec L = random_light(S, choice, ls, areal);
-    if (L.valid && L.type == 0) { const V3 dir = sphere_uniform(areal); L.pos = L.pos + L.size * dir; }
     B.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
     if (cam_o) cam_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);             // camerapos of the sample (bidirectional mode)
     B.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
@@ -378,6 +378,9 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
     B.tot[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     B.last_tri[slot] = RGK_NO_TRIANGLE;
     B.cur1[slot] = 1u;
+    if (R.const_light) return;      // GetRandomLight can only return that one light, unjittered (size 0): kept in RenderConst
+    LightRec L = random_light(S, choice, ls, areal);
+    if (L.valid && L.type == 0) { const V3 dir = sphere_uniform(areal); L.pos = L.pos + L.size * dir; }
     B.light_pos[slot] = make_float4(L.pos.x, L.pos.y, L.pos.z, __uint_as_float((L.valid ? 1u : 0u) | ((uint32_t)L.type << 1)));
     B.light_col[slot] = make_float4(L.color.r, L.color.g, L.color.b, L.intensity);
     B.light_nrm[slot] = make_float4(L.normal.x, L.normal.y, L.normal.z, 0.0f);
@@ -433,13 +436,14 @@ k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_
 // shadow traversal fused with the NEE resolve (src/path_tracer.cpp:431-460,485-496)
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
-k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, rgk_trav_stats* stats) {
+k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, rgk_trav_stats* stats,
+         uint32_t const_light, float4 cl_pos) {
     TravCount cnt{0, 0, 0, 0, 0, 0, 0};
     uint32_t mine = 0;
     trace_rays<RGK_RENDER_VARIANT, true, COUNT>(S, count, work, cnt, mine,
         [&](uint32_t i, Traverser<true, COUNT>& T) {
             const uint32_t slot = __ldg(queue + i);
-            const float4 a = B.light_pos[slot], b = B.sh_pos[slot];
+            const float4 a = const_light ? cl_pos : B.light_pos[slot], b = B.sh_pos[slot];
             const float ex = b.x - a.x, ey = b.y - a.y, ez = b.z - a.z;
             const float d2 = ex * ex + ey * ey + ez * ez;
             const float inv = 1.0f / sqrtf(d2), len = sqrtf(d2);
@@ -560,8 +564,8 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
         // everything else that is addressed by the slot alone is requested here, ahead of the dependent chain
         // triangle -> vertices / material -> textures -> LTC taps (the kernel is latency-bound): the sample's light and
         // the two sampler values this vertex may consume (continuation direction, Russian roulette)
-        const float4 lp4 = B.light_pos[slot];
-        const float4 lc = B.light_col[slot];
+        const float4 lp4 = R.const_light ? R.cl_pos : B.light_pos[slot];
+        const float4 lc = R.const_light ? R.cl_col : B.light_col[slot];
         const uint32_t c1 = B.cur1[slot];
         const uint32_t pixel = slot % R.npix, set = slot / R.npix;
         const uint32_t seed = B.pix_seed[pixel];
@@ -692,7 +696,7 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
     } else push_queue(next_queue, counters + C_NEXT, cont, slot);
     if (R.binning & 2u) {
         if (shadow) {
-            const float4 a = B.light_pos[slot], b = B.sh_pos[slot];
+            const float4 a = R.const_light ? R.cl_pos : B.light_pos[slot], b = B.sh_pos[slot];
             B.key_shadow[slot] = dir_bin(b.x - a.x, b.y - a.y, b.z - a.z);
         }
     } else push_queue(shadow_queue, counters + C_SHADOW, shadow, slot);
@@ -963,6 +967,14 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         R.bump_scale = P->bumpmap_scale; R.set_size = ss; R.n1d = n1d; R.n2d = n2d; R.base2 = base2; R.sampler_mode = P->sampler_mode;
         R.lens = lens; R.npix = (uint32_t)npix; R.skip_null_shadow = skip_null; R.binning = binning ? 1u : 0u;
         R.reverse = P->reverse; R.npaths = (uint32_t)npaths;
+        {   // Scene::GetRandomLight with one point light and nothing else always returns it; with size 0 it is not jittered
+            const DevPointLight& l0 = ctx->first_point_light;
+            R.const_light = (!P->reverse && ctx->dev.n_point_lights == 1 && ctx->dev.n_areal_lights == 0 && l0.size == 0.0f && l0.intensity > 0.0f &&
+                             env_flag("RGK_CONST_LIGHT", true)) ? 1u : 0u;
+            const uint32_t flags = 1u; float fbits; std::memcpy(&fbits, &flags, 4);       // valid, FULL_SPHERE
+            R.cl_pos = make_float4(l0.pos[0], l0.pos[1], l0.pos[2], fbits);
+            R.cl_col = make_float4(l0.color[0], l0.color[1], l0.color[2], l0.intensity);
+        }
         if (P->reverse) { s = ensure_reverse_buffers(ctx, npaths, P->depth, P->reverse); if (s != RGK_OK) return s; }
         // reordering groups: SG samples x PG pixel positions (a multiple of the 32-pixel blocks of k_pixel_setup)
         const uint32_t SG = (uint32_t)std::min<size_t>(ms, 128);
@@ -1111,8 +1123,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 dev.refill_threshold = bounce == 0 ? refill_coherent : refill_shadow;
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
-                if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1);
-                else k_shadow<false, RGK_INCOH_MINB><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr);
+                if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1, R.const_light, R.cl_pos);
+                else k_shadow<false, RGK_INCOH_MINB><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr, R.const_light, R.cl_pos);
                 pool.end(ctx->stream);
                 ctx->launches++; total.shadow_launches++;
             }

@@ -108,6 +108,7 @@ struct rgk_context {
     bool counting = false;
     uint32_t shard_first = 0, shard_stride = 1;   // rgk_render_set_shard
     rgk_trav_stats last_closest{}, last_shadow{};
+    DevPointLight first_point_light{};            // host copy of point light 0 (single fixed light: no per-path light records)
 };
 
 rgk_status rgk_fail(rgk_context* ctx, rgk_status s, const std::string& msg);

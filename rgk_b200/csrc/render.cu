@@ -258,8 +258,9 @@ __global__ void k_tables_from_user(const float* __restrict__ u1, const float* __
 // launches the table generation with the best block size the set size allows
 static void launch_sampler_mt(cudaStream_t stream, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
                               float* t1, float2* t2, uint32_t* state) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_sampler_mt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    // per device (function attributes are), so set on every launch rather than once per process: contexts on several
+    // GPUs may live in one process
+    cudaFuncSetAttribute(k_sampler_mt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     static int use_smem = -1;
     if (use_smem < 0) { const char* e = std::getenv("RGK_SAMPLER_SMEM"); use_smem = (e && e[0] == '0') ? 0 : 1; }
     // shared-memory tables only while two 128-thread CTAs still fit an SM (set size <= 66); beyond that the CTA count

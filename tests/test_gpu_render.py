@@ -194,3 +194,24 @@ def test_chunking_does_not_change_the_image(gpu_ctx, monkeypatch):
     empty = (abi.Task * 0)()
     z, cz, sz = gpu_ctx.render_round(cam, p, empty)
     assert not z.any() and int(sz.samples) == 0
+
+
+def test_two_contexts_interleaved(gpu_ctx):
+    """Two contexts in one process (what a multi-GPU host would hold, here on one device) with different scenes,
+    called alternately: no state leaks between them."""
+    from rgk_b200 import device
+    pa, ca = scenes.load_builtin("cornell-box", width=64, height=48, multisample=4)
+    pb, cb = scenes.material_zoo(width=48, height=32, multisample=4)
+    other = device.Context(0)
+    try:
+        gpu_ctx.commit(pa.desc()); other.commit(pb.desc())
+        cam_a, cam_b = gpu_ctx.camera(**ca.camera_args()), other.camera(**cb.camera_args())
+        ta, tb = gpu_ctx.generate_tasks(32, 64, 48), other.generate_tasks(32, 48, 32)
+        a1, _, _ = gpu_ctx.render_round(cam_a, ca.params(), ta)
+        b1, _, _ = other.render_round(cam_b, cb.params(), tb)
+        a2, _, _ = gpu_ctx.render_round(cam_a, ca.params(), ta)
+        b2, _, _ = other.render_round(cam_b, cb.params(), tb)
+        assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32)) and np.array_equal(b1.view(np.uint32), b2.view(np.uint32))
+        assert a1.shape != b1.shape and other.scene_info().n_triangles != gpu_ctx.scene_info().n_triangles
+    finally:
+        other.close()

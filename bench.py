@@ -329,10 +329,12 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = cl_rays * b_closest / (cl_ms / 1e3) / 1e9 if cl_ms > 0 else 0.0
-        traffic = None     # DRAM bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json)
+        traffic, ncu = None, None     # DRAM bytes per launch + issue figures from the committed ncu --set full capture (profiles/r1_traffic.json)
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
             traffic = tj["dram_bytes_per_ray"] * cl_rays / cl_launches
+            ncu = {k: tj[k] for k in ("launches", "issue_slots_busy_pct", "active_lanes_per_instruction", "l1_hit_pct", "l2_hit_pct") if k in tj}
+            ncu["source"] = "profiles/r1_traffic.json (static, from the committed capture of this command at 16 spp)"
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "k_closest (kd-tree closest-hit traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -343,7 +345,7 @@ def main():
                     "note": "cache-fed: the tree, reference planes and triangle records (a few MB) live in L1/L2, so the algorithmic node/triangle "
                             "bytes are served ~70x from cache (compare `traffic`); frac > 1 against the HBM copy peak is expected, the kernel is "
                             "issue/divergence-bound (profiles/README.md)",
-                    "prefilter": tc.device_dict(),
+                    "prefilter": tc.device_dict(), "ncu": ncu,
                     "shadow_kernel": {"bytes_per_ray": b_shadow, "achieved": sh_rays * b_shadow / (sh_ms / 1e3) / 1e9 if sh_ms > 0 else 0.0,
                                       "Grays_per_s_in_kernel": sh_rays / (sh_ms / 1e3) / 1e9 if sh_ms > 0 else 0.0}}
         tot_ms = sum(float(s.gpu_ms) for s in stats)

@@ -924,13 +924,29 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
 
     // chunking: whole tiles, every multisample of a pixel in the same chunk
-    size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)32 << 20);
+    size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)128 << 20);   // ~27 GB of path state: sized for 180 GB of HBM
+    {   // never plan a chunk whose path state (~210 B per path, on top of what is already allocated) would not fit in 60 %
+        // of the memory that is free right now (other contexts, smaller parts)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t have = ctx->paths ? ctx->paths->cap_paths : 0;
+            const size_t fit = have + (size_t)(0.6 * (double)free_b / 210.0);
+            max_paths = std::min(max_paths, std::max<size_t>(fit, (size_t)1 << 20));
+        }
+    }
     if (P->reverse) {      // bidirectional mode keeps every vertex of the camera and light paths: 112 B and 80 B per vertex
         const size_t per_path = 112 * (size_t)P->depth + 80 * (size_t)P->reverse + 64;
         max_paths = std::max<size_t>(std::min(max_paths, env_size("RGK_REVERSE_BYTES", (size_t)8 << 30) / per_path), 4096);
     }
     const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
-    const size_t max_table_bytes = env_size("RGK_TABLE_BYTES", (size_t)24 << 30);
+    size_t max_table_bytes = env_size("RGK_TABLE_BYTES", (size_t)24 << 30);
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t have = ctx->paths ? (ctx->paths->cap_t1 * 4 + ctx->paths->cap_t2 * 8 + ctx->paths->cap_pixels * 624 * 4) : 0;
+            max_table_bytes = std::min(max_table_bytes, std::max<size_t>(have + (size_t)(0.25 * (double)free_b), (size_t)64 << 20));
+        }
+    }
     std::vector<uint4> h_tiles; std::vector<uint2> h_tiles2;
     rgk_round_stats total{};
     cudaEvent_t ev0 = ctx->ev[0], ev1 = ctx->ev[1];

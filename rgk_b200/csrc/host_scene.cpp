@@ -9,6 +9,7 @@
 // (left child = i+1, right child index stored in the parent), i.e. Scene::Compress's
 // output (src/scene.cpp:606-657), without building a pointer tree first.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -38,7 +39,9 @@ struct Builder {
     // child is built by another thread into its own arrays and stitched in afterwards (child indices and leaf
     // reference offsets shifted).  Every node is still split by the reference's procedure on the same triangle order,
     // so the arrays are byte-identical to the sequential build (tests compare them with the oracle's).
-    unsigned fork_depth = 0;
+    // A fork happens wherever both children are large and the shared budget of extra threads is not used up (not at a
+    // fixed depth: SAH splits are uneven, a fixed-depth fork leaves most of the work with one thread).
+    std::atomic<int>* spare_threads = nullptr;     // extra threads that may still be started
     size_t fork_min_tris = 20000;
 
     void emit_leaf(const std::vector<uint32_t>& tris) {
@@ -102,15 +105,20 @@ struct Builder {
         nodes.push_back(axis);
         float cb[3][2]; std::memcpy(cb, bb, sizeof cb);
         cb[axis][1] = best_pos;
-        if (depth < fork_depth && above.size() >= fork_min_tris && below.size() >= fork_min_tris) {
+        bool fork = false;
+        if (spare_threads && above.size() >= fork_min_tris && below.size() >= fork_min_tris) {
+            if (spare_threads->fetch_sub(1) > 0) fork = true; else spare_threads->fetch_add(1);
+        }
+        if (fork) {
             std::vector<uint32_t> rn, rr;
             Builder right{ev, rn, rr, max_depth};
-            right.fork_depth = fork_depth; right.fork_min_tris = fork_min_tris;
+            right.spare_threads = spare_threads; right.fork_min_tris = fork_min_tris;
             float rb[3][2]; std::memcpy(rb, bb, sizeof rb);
             rb[axis][0] = best_pos;
             std::thread worker([&] { right.build(above, rb, depth + 1); });
             build(below, cb, depth + 1);
             worker.join();
+            spare_threads->fetch_add(1);
             const uint32_t node_off = (uint32_t)(nodes.size() / 2), ref_off = (uint32_t)refs.size();
             nodes[me + 1] = axis | (node_off << 2);
             nodes.reserve(nodes.size() + rn.size());
@@ -308,13 +316,11 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
         deepest = measure_depth(hs.nodes);
     } else {
         Builder b{ev, hs.nodes, hs.refs, (unsigned)(int)(std::log2(nt) + 8)};
-        {   // up to 2^fork_depth threads; RGK_BUILD_THREADS=1 forces the sequential build
-            unsigned threads = std::thread::hardware_concurrency();
-            if (const char* e = std::getenv("RGK_BUILD_THREADS")) threads = (unsigned)std::max(1, std::atoi(e));
-            unsigned fd = 0;
-            while ((1u << fd) < threads && fd < 6) fd++;
-            b.fork_depth = fd;
-        }
+        // RGK_BUILD_THREADS threads in total (default: all cores, at most 64); 1 forces the sequential build
+        unsigned threads = std::min(64u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = std::getenv("RGK_BUILD_THREADS")) threads = (unsigned)std::min(64, std::max(1, std::atoi(e)));
+        std::atomic<int> spare((int)threads - 1);
+        if (threads > 1) b.spare_threads = &spare;
         std::vector<uint32_t> all(nt);
         for (uint32_t i = 0; i < nt; i++) all[i] = i;
         b.build(all, bb, 0);

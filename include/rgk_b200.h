@@ -253,6 +253,9 @@ const char* rgk_host_last_error(void);
 rgk_status rgk_host_scene_get_info(const rgk_host_scene* hs, rgk_scene_info* out);
 rgk_status rgk_host_scene_get_kdtree(const rgk_host_scene* hs, uint32_t* nodes, uint32_t* refs);
 rgk_status rgk_host_scene_get_records(const rgk_host_scene* hs, float* planes, float* records);
+/* The per-triangle bounds of the device's pre-filter (4 floats: lo1 | axis code in the two low mantissa bits, hi1, lo2,
+ * hi2, in the triangle's projection plane), for checking their conservativeness without a GPU. */
+rgk_status rgk_host_scene_get_bounds(const rgk_host_scene* hs, float* bounds);
 
 /* Replaces Scene::FindIntersectKdOtherThan (src/scene_intersect.cpp:211-327) over a
  * batch; ignore[i] = triangle index to skip or RGK_NO_TRIANGLE (then it is

@@ -137,7 +137,7 @@ EXPORTS = [
     "rgk_render_round_device", "rgk_render_frame", "rgk_render_set_tables", "rgk_synchronize",
     "rgk_render_set_counting", "rgk_render_get_trav_stats", "rgk_probe", "rgk_render_set_shard",
     "rgk_host_scene_create", "rgk_host_scene_destroy", "rgk_host_last_error", "rgk_host_scene_get_info",
-    "rgk_host_scene_get_kdtree", "rgk_host_scene_get_records",
+    "rgk_host_scene_get_kdtree", "rgk_host_scene_get_records", "rgk_host_scene_get_bounds",
 ]
 
 
@@ -192,6 +192,7 @@ def load_library(path=None):
     lib.rgk_host_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
     lib.rgk_host_scene_get_kdtree.argtypes = [vp, vp, vp]
     lib.rgk_host_scene_get_records.argtypes = [vp, vp, vp]
+    lib.rgk_host_scene_get_bounds.argtypes = [vp, vp]
     lib.rgk_render_set_counting.argtypes = [vp, C.c_int]
     lib.rgk_render_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.rgk_render_get_trav_stats.argtypes = [vp, C.POINTER(TravStats), C.POINTER(TravStats)]

@@ -293,6 +293,13 @@ rgk_status rgk_host_scene_get_records(const rgk_host_scene* h, float* planes, fl
     return RGK_OK;
 }
 
+// conservative 2-D bounds of every triangle (4 floats; the axis code rides in the two low mantissa bits of the first)
+rgk_status rgk_host_scene_get_bounds(const rgk_host_scene* h, float* bounds) {
+    if (!h || !bounds) return RGK_ERR_INVALID;
+    std::memcpy(bounds, h->hs.tri_bounds.data(), 4 * h->hs.tri_bounds.size());
+    return RGK_OK;
+}
+
 // ---- traversal -----------------------------------------------------------
 rgk_status rgk_trace_closest_device(rgk_context* ctx, const rgk_ray* d_rays, const uint32_t* d_ignore, uint64_t n,
                                     rgk_hit* d_hits, rgk_trav_stats* d_stats) {

@@ -217,6 +217,11 @@ class HostScene:
         self.lib.rgk_host_scene_get_records(self.h, _p(planes), _p(rec))
         return planes, rec
 
+    def bounds(self):
+        b = np.zeros((self.info().n_triangles, 4), np.float32)
+        self.lib.rgk_host_scene_get_bounds(self.h, _p(b))
+        return b
+
     def close(self):
         if self.h:
             self.lib.rgk_host_scene_destroy(self.h)

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "build", "host")
 
 
-SOURCES = {"rgk_render": os.path.join(ROOT, "rgk_b200", "host", "rgk_render.cpp"), "host_checks": os.path.join(ROOT, "tests", "host_cpp", "host_checks.cpp")}
+SOURCES = {"rgk_render": os.path.join(ROOT, "rgk_b200", "host", "rgk_render.cpp"), "host_checks": os.path.join(ROOT, "tests", "host_cpp", "host_checks.cpp"),
+           "rgk_render_multi": os.path.join(ROOT, "rgk_b200", "host", "rgk_render_multi.cpp")}
 
 
 def _need(exe):
@@ -25,6 +26,8 @@ def _need(exe):
         os.makedirs(HOST, exist_ok=True)
         cmd = ["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), SOURCES[exe], "-o", path,
                "-L" + os.path.join(ROOT, "rgk_b200"), "-lrgk_b200", "-Wl,-rpath," + os.path.join(ROOT, "rgk_b200")]
+        if exe == "rgk_render_multi":
+            cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl", "-lpthread", "-Wl,-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             pytest.fail(f"{path} missing and could not be built: {r.stderr[-500:]}")
@@ -145,3 +148,25 @@ def test_cpp_render_frame_matches_python_binding_and_resumes(tmp_path, gpu_ctx):
         mean = s_full / c_full[..., None]
         want = (mean / mean.max()).astype(np.float32) if cfg.output_scale <= 0 else mean * cfg.output_scale
         assert np.allclose(im[..., 2::-1], want.astype(np.float16).astype(np.float32), atol=2e-3)
+
+
+@pytest.mark.gpu
+def test_native_multi_gpu_driver_on_the_visible_gpus(tmp_path):
+    """rgk_render_multi (one thread + context per GPU, ncclReduce per super-round) against the single-GPU driver: same
+    counts, same sums.  Uses every visible GPU up to 2 (with one GPU the NCCL communicator has a single rank)."""
+    import torch
+    if not os.path.exists("/usr/include/nccl.h"):
+        pytest.skip("NCCL headers not installed")
+    multi, single = _need("rgk_render_multi"), _need("rgk_render")
+    n = min(2, torch.cuda.device_count())
+    pack, cfg = scenes.load_builtin("cornell-box", width=96, height=64, multisample=4)
+    ppath = str(tmp_path / "cornell.rgkpack")
+    pack.save(ppath, cfg)
+    subprocess.run([single, ppath, str(tmp_path / "s.exr"), "--rounds", "5", "--raw", str(tmp_path / "s.acc")], check=True, capture_output=True)
+    out = subprocess.run([multi, ppath, str(tmp_path / "m.exr"), "--gpus", str(n), "--rounds", "5", "--raw", str(tmp_path / "m.acc")],
+                         check=True, capture_output=True, text=True).stdout
+    st = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert st["gpus"] == n and st["rounds"] == 5 and st["samples"] == 5 * 96 * 64 * 4
+    s1, c1, r1 = read_acc(str(tmp_path / "s.acc"))
+    s2, c2, r2 = read_acc(str(tmp_path / "m.acc"))
+    assert r1 == r2 == 5 and np.array_equal(c1, c2) and np.allclose(s1, s2, rtol=1e-6, atol=1e-6)

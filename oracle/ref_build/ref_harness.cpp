@@ -57,6 +57,7 @@
 #undef protected
 
 #include "rgk_b200.h"
+#include "../../integration/gpu_bridge.hpp"   // the RGKrt-side binding, compiled here against the reference's own headers
 
 // src/render_driver.cpp:30 (free function, not declared in a header)
 std::vector<RenderTask> GenerateTaskList(unsigned int tile_size, unsigned int xres, unsigned int yres, glm::vec2 middle);
@@ -500,5 +501,27 @@ int rgkref_ltc_tables(int which, float* M, float* amp) {
     }
     return l.size;
 }
+
+
+// The bridge's Upload / RenderRound call into librgk_b200.so; this checker library must not depend on the product, so
+// the five entry points they use are satisfied by inert weak definitions here (the bridge is compiled in full, only
+// Describe() is executed by the tests).
+__attribute__((weak)) rgk_status rgk_context_create(int, void*, rgk_context**) { return RGK_ERR_NO_DEVICE; }
+__attribute__((weak)) void rgk_context_destroy(rgk_context*) {}
+__attribute__((weak)) const char* rgk_last_error(const rgk_context*) { return "checker build: librgk_b200 is not linked"; }
+__attribute__((weak)) rgk_status rgk_scene_commit(rgk_context*, const rgk_scene_desc*, const rgk_kdtree*) { return RGK_ERR_NO_DEVICE; }
+__attribute__((weak)) rgk_status rgk_render_round(rgk_context*, const rgk_camera*, const rgk_render_params*, const rgk_task*, uint32_t, uint32_t, uint32_t,
+                                                  float*, uint32_t*, rgk_round_stats*) { return RGK_ERR_NO_DEVICE; }
+
+// The integration bridge (integration/gpu_bridge.hpp) run on this reference Scene: returns a heap-allocated bridge whose
+// `desc` is what a RGKrt build would hand to rgk_scene_commit.  Test-only.
+void* rgkref_bridge_describe(void* h) {
+    RefScene* rs = (RefScene*)h;
+    RgkGpuBridge* b = new RgkGpuBridge();
+    try { b->Describe(rs->scene); } catch (const std::exception& e) { std::cerr << "bridge: " << e.what() << std::endl; delete b; return nullptr; }
+    return b;
+}
+const rgk_scene_desc* rgkref_bridge_desc(void* b) { return &((RgkGpuBridge*)b)->desc; }
+void rgkref_bridge_destroy(void* b) { delete (RgkGpuBridge*)b; }
 
 } // extern "C"

@@ -90,3 +90,72 @@ def test_reference_scene_files_bidirectional(oracle, ref):
         fr, cr, _ = ref.render_round(hr, cam, p, tasks, nthreads=1)
         fo, co, _ = oracle.render_round(ho, cam, p, tasks, nthreads=1)
         assert np.array_equal(fr.view(np.uint32), fo.view(np.uint32)) and np.array_equal(cr, co)
+
+
+def test_integration_bridge_describes_the_reference_scene(ref, oracle):
+    """integration/gpu_bridge.hpp (the binding a RGKrt maintainer adds) compiled against the reference's own headers:
+    RgkGpuBridge::Describe turns the reference's Scene back into the scene pack it was loaded from, and the library's
+    host commit of that description yields the reference's own flattened kd-tree."""
+    import ctypes as C
+    from rgk_b200 import abi, device
+    lib = ref.lib
+    lib.rgkref_bridge_describe.restype = C.c_void_p
+    lib.rgkref_bridge_describe.argtypes = [C.c_void_p]
+    lib.rgkref_bridge_desc.restype = C.POINTER(abi.SceneDesc)
+    lib.rgkref_bridge_desc.argtypes = [C.c_void_p]
+    lib.rgkref_bridge_destroy.argtypes = [C.c_void_p]
+
+    def arr(ptr, n, dt=np.float32):
+        return np.ctypeslib.as_array(ptr, (n,)).copy() if n else np.zeros(0, dt)
+
+    def tex_key(d, i):
+        if i < 0:
+            return None
+        t = d.textures[i]
+        if t.kind == 0:
+            return ("solid", tuple(t.color))
+        return ("image", t.width, t.height, arr(t.texels, 3 * t.width * t.height).tobytes())
+
+    for pack, cfg in (scenes.load_builtin("cornell-box", width=32, height=32, multisample=1),
+                      scenes.material_zoo(width=32, height=32, multisample=1),
+                      standin.sponza(width=32, height=32, multisample=1, target_tris=6000)):
+        d1 = pack.desc()
+        hr = ref.scene_create(d1)
+        b = lib.rgkref_bridge_describe(hr)
+        assert b
+        d2 = lib.rgkref_bridge_desc(b).contents
+        assert (d2.n_vertices, d2.n_triangles, d2.n_materials, d2.n_point_lights) == (d1.n_vertices, d1.n_triangles, d1.n_materials, d1.n_point_lights)
+        for name, k in (("positions", 3), ("normals", 3), ("tangents", 3), ("texcoords", 2)):
+            assert arr(getattr(d1, name), k * d1.n_vertices).tobytes() == arr(getattr(d2, name), k * d2.n_vertices).tobytes(), name
+        assert np.array_equal(arr(d1.indices, 3 * d1.n_triangles, np.uint32), arr(d2.indices, 3 * d2.n_triangles, np.uint32))
+        for i in range(d1.n_materials):
+            a, c = d1.materials[i], d2.materials[i]
+            assert (a.bxdf, a.no_russian, tuple(a.emission), a.mix_a, a.mix_b) == (c.bxdf, c.no_russian, tuple(c.emission), c.mix_a, c.mix_b), i
+            used = {abi.BXDF_DIFFUSE: ("tex_diffuse",), abi.BXDF_MIX: (), abi.BXDF_TRANSPARENT: (), abi.BXDF_MIRROR: ("tex_color",), abi.BXDF_DIELECTRIC: ("tex_color",)}.get(
+                a.bxdf, ("tex_color", "tex_diffuse") if a.bxdf in (abi.BXDF_LTC_GGX_DIFFUSE, abi.BXDF_LTC_BECKMANN_DIFFUSE) else ("tex_color",))
+            for slot in used + ("tex_bump",):
+                assert tex_key(d1, getattr(a, slot)) == tex_key(d2, getattr(c, slot)), (i, slot)
+            if a.bxdf == abi.BXDF_MIX:
+                assert a.amount == c.amount
+            if a.bxdf == abi.BXDF_DIELECTRIC:
+                assert a.ior == c.ior
+            if a.bxdf >= abi.BXDF_LTC_BECKMANN:
+                assert a.roughness == c.roughness
+        for i in range(d1.n_point_lights):
+            assert bytes(d1.point_lights[i]) == bytes(d2.point_lights[i])
+        assert (d1.sky.mode, d1.sky.intensity, d1.sky.rotate) == (d2.sky.mode, d2.sky.intensity, d2.sky.rotate)
+        assert tuple(d1.sky.color) == tuple(d2.sky.color) if d1.sky.mode == 0 else tex_key(d1, d1.sky.envmap) == tex_key(d2, d2.sky.envmap)
+        for t in ("ltc_ggx", "ltc_beckmann"):
+            assert arr(getattr(d1, t).M, 4096 * 9).tobytes() == arr(getattr(d2, t).M, 4096 * 9).tobytes()
+            assert arr(getattr(d1, t).amplitude, 4096).tobytes() == arr(getattr(d2, t).amplitude, 4096).tobytes()
+        # emissive meshes = areal lights: same grouping
+        lights1 = [(m.first_triangle, m.n_triangles) for m in (d1.meshes[i] for i in range(d1.n_meshes)) if any(x > 0 for x in d1.materials[m.material].emission)]
+        lights2 = [(m.first_triangle, m.n_triangles) for m in (d2.meshes[i] for i in range(d2.n_meshes)) if any(x > 0 for x in d2.materials[m.material].emission)]
+        assert lights1 == lights2
+        # the library's host commit of the bridged description == the reference's own flattened tree
+        hs = device.HostScene(d2)
+        n2, r2 = hs.kdtree()
+        nr, rr = ref.scene_kdtree(hr)
+        assert np.array_equal(n2, nr) and np.array_equal(r2, rr) and hs.info().n_areal_lights == ref.scene_info(hr).n_areal_lights
+        hs.close()
+        lib.rgkref_bridge_destroy(b)

@@ -494,7 +494,12 @@ def load_json_config(path, overrides=None, mesh_loader=None, texture_loader=None
 
 
 def load_config(root, cfgdir=".", overrides=None, mesh_loader=None, texture_loader=None):
-    """Same from an already-parsed config dict. `overrides` patches root keys (e.g. output-width)."""
+    """Same from an already-parsed config dict. `overrides` patches root keys (e.g. output-width).  Mesh files and
+    image textures go through rgk_b200.assets (OBJ / MTL, PNG / JPEG / HDR) unless other loaders are given."""
+    if mesh_loader is None or texture_loader is None:
+        from . import assets
+        mesh_loader = mesh_loader or assets.load_obj_into
+        texture_loader = texture_loader or assets.load_image
     root = dict(root)
     root.update(overrides or {})
     cfg = RenderConfig()

@@ -366,7 +366,9 @@ def _strip_comments(text):
         else:
             out.append(ch)
         i += 1
-    return re.sub(r",(\s*[\]}])", r"\1", "".join(out))
+    text = re.sub(r",(\s*[\]}])", r"\1", "".join(out))
+    # jsoncpp also reads numbers with leading zeros ("000.0" in scenes/conference.json:16); strict JSON does not
+    return re.sub(r'("(?:\\.|[^"\\])*")|(?<![\w.])(-?)0+(?=\d)', lambda m: m.group(1) if m.group(1) is not None else m.group(2), text)
 
 
 def _vec3(node, key, default=None, required=False):

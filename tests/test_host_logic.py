@@ -145,3 +145,9 @@ def test_host_scene_rejects_bad_input():
     bad.materials[0].bxdf = 99
     with pytest.raises(device.RgkError, match="Unsupported BRDF"):
         device.HostScene(bad)
+
+
+def test_json_reader_is_as_lenient_as_jsoncpp():
+    """Comments, trailing commas and numbers with leading zeros (scenes/conference.json:16 has `000.0`)."""
+    t = scene._strip_comments('{"a": [800.0, 400.0,  000.0, -007.5, 10.05, 100,], "s": "x 000.0 // y", /* c */ "b": 0.5, "d": 00, // e\n}')
+    assert json.loads(t) == {"a": [800.0, 400.0, 0.0, -7.5, 10.05, 100], "s": "x 000.0 // y", "b": 0.5, "d": 0}

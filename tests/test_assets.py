@@ -111,9 +111,11 @@ def test_reference_scene_files_load():
 
 
 @pytest.mark.gpu
-def test_obj_scene_parity_gpu(gpu_ctx, oracle):
-    """The fixture scene end to end: JSON -> OBJ / MTL / textures -> commit -> one round on the GPU vs the oracle."""
-    pack, cfg = load_room()
+@pytest.mark.parametrize("reverse", [0, 2])
+def test_obj_scene_parity_gpu(gpu_ctx, oracle, reverse):
+    """The fixture scene end to end: JSON -> OBJ / MTL / textures -> commit -> one round on the GPU vs the oracle, also in the
+    bidirectional mode (a sized point light: the light path leaves a jittered FULL_SPHERE light)."""
+    pack, cfg = load_room(reverse=reverse)
     desc = pack.desc()
     gpu_ctx.commit(desc)
     ho = oracle.scene_create(desc)
@@ -124,8 +126,9 @@ def test_obj_scene_parity_gpu(gpu_ctx, oracle):
     p = cfg.params()
     tasks = gpu_ctx.generate_tasks(32, cfg.xres, cfg.yres)
     fb, cnt, st = gpu_ctx.render_round(cam, p, tasks)
-    fo, co, so = oracle.render_round(ho, cam, p, tasks)
-    assert np.array_equal(cnt, co) and int(st.closest_rays) == int(so.closest_rays)
+    fo, co, so = oracle.render_round(ho, cam, p, tasks, nthreads=1)
+    assert p.reverse == reverse and np.array_equal(cnt, co) and int(st.closest_rays) == int(so.closest_rays)
+    assert int(st.shadow_rays) + int(st.shadow_rays_skipped) == int(so.shadow_rays)
     mean = float(fo.mean())
     assert abs(float(fb.mean()) - mean) / mean < 1e-3                       # stated bound: rel-mean <= 1e-3
     assert float(np.sqrt(np.mean((fb - fo) ** 2))) / mean < 0.05            # RMSE <= 5 % of the mean (specular chains)

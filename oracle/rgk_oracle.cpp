@@ -1221,6 +1221,143 @@ int rgko_render_round_counters(void* h, const rgk_camera* cam, const rgk_render_
     return 0;
 }
 
+// ---- design study (NOT a reference path): what a wide BVH would cost and how often its hit differs ----------------
+// A binned-SAH BVH over the same triangles, collapsed to `width` children per node, traversed front to back for the
+// GLOBAL closest hit with the same Triangle::TestIntersection arithmetic.  Reports, per ray, nodes visited, child boxes
+// tested and triangles tested, and how many rays end on a different triangle than FindIntersectKdOtherThan (exact ties
+// and epsilon cases at kd leaf boundaries).  Used by tools/bvh_study.py for DESIGN.md "Next"; never by a test gate.
+namespace {
+struct BNode { float lo[3], hi[3]; int left, right, first, count; };   // binary; count > 0 = leaf over order[first..]
+struct WNode { int nchild; float lo[8][3], hi[8][3]; int child[8]; int first[8], count[8]; };   // child < 0: leaf slot
+struct BvhStudy {
+    std::vector<BNode> b; std::vector<uint32_t> order; std::vector<WNode> w;
+};
+void tri_box(const Scene& s, uint32_t t, float lo[3], float hi[3]) {
+    const V3 v[3] = {s.pos[s.tris[t].va], s.pos[s.tris[t].vb], s.pos[s.tris[t].vc]};
+    for (int k = 0; k < 3; k++) { lo[k] = std::min(v[0][k], std::min(v[1][k], v[2][k])); hi[k] = std::max(v[0][k], std::max(v[1][k], v[2][k])); }
+}
+float half_area(const float lo[3], const float hi[3]) { const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2]; return x * y + y * z + z * x; }
+int build_binary(const Scene& s, BvhStudy& B, int first, int count, int leaf_size) {
+    BNode n; for (int k = 0; k < 3; k++) { n.lo[k] = 1e30f; n.hi[k] = -1e30f; }
+    float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = first; i < first + count; i++) {
+        float lo[3], hi[3]; tri_box(s, B.order[i], lo, hi);
+        for (int k = 0; k < 3; k++) { n.lo[k] = std::min(n.lo[k], lo[k]); n.hi[k] = std::max(n.hi[k], hi[k]); const float c = 0.5f * (lo[k] + hi[k]); clo[k] = std::min(clo[k], c); chi[k] = std::max(chi[k], c); }
+    }
+    n.left = n.right = -1; n.first = first; n.count = count;
+    const int me = (int)B.b.size(); B.b.push_back(n);
+    if (count <= leaf_size) return me;
+    int axis = 0; for (int k = 1; k < 3; k++) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+    if (!(chi[axis] > clo[axis])) return me;
+    const int NB = 16; int cnt[NB] = {0}; float blo[NB][3], bhi[NB][3];
+    for (int q = 0; q < NB; q++) for (int k = 0; k < 3; k++) { blo[q][k] = 1e30f; bhi[q][k] = -1e30f; }
+    const float scale = NB / (chi[axis] - clo[axis]);
+    auto bin_of = [&](uint32_t t) { float lo[3], hi[3]; tri_box(s, t, lo, hi); int q = (int)((0.5f * (lo[axis] + hi[axis]) - clo[axis]) * scale); return std::min(NB - 1, std::max(0, q)); };
+    for (int i = first; i < first + count; i++) {
+        const int q = bin_of(B.order[i]); float lo[3], hi[3]; tri_box(s, B.order[i], lo, hi); cnt[q]++;
+        for (int k = 0; k < 3; k++) { blo[q][k] = std::min(blo[q][k], lo[k]); bhi[q][k] = std::max(bhi[q][k], hi[k]); }
+    }
+    float best = 1e30f; int split = -1;
+    for (int sp = 1; sp < NB; sp++) {
+        float l0[3] = {1e30f, 1e30f, 1e30f}, h0[3] = {-1e30f, -1e30f, -1e30f}, l1[3] = {1e30f, 1e30f, 1e30f}, h1[3] = {-1e30f, -1e30f, -1e30f}; int c0 = 0, c1 = 0;
+        for (int q = 0; q < sp; q++) if (cnt[q]) { c0 += cnt[q]; for (int k = 0; k < 3; k++) { l0[k] = std::min(l0[k], blo[q][k]); h0[k] = std::max(h0[k], bhi[q][k]); } }
+        for (int q = sp; q < NB; q++) if (cnt[q]) { c1 += cnt[q]; for (int k = 0; k < 3; k++) { l1[k] = std::min(l1[k], blo[q][k]); h1[k] = std::max(h1[k], bhi[q][k]); } }
+        if (!c0 || !c1) continue;
+        const float cost = c0 * half_area(l0, h0) + c1 * half_area(l1, h1);
+        if (cost < best) { best = cost; split = sp; }
+    }
+    if (split < 0) return me;
+    auto mid = std::partition(B.order.begin() + first, B.order.begin() + first + count, [&](uint32_t t) { return bin_of(t) < split; });
+    const int nl = (int)(mid - (B.order.begin() + first));
+    if (nl == 0 || nl == count) return me;
+    const int l = build_binary(s, B, first, nl, leaf_size), r = build_binary(s, B, first + nl, count - nl, leaf_size);
+    B.b[me].left = l; B.b[me].right = r; B.b[me].count = 0;
+    return me;
+}
+int collapse(BvhStudy& B, int bn, int width) {
+    std::vector<int> kids = {bn};
+    for (;;) {          // open the child with the largest surface until `width` children
+        int pick = -1; float area = -1.0f;
+        for (size_t i = 0; i < kids.size(); i++) { const BNode& n = B.b[kids[i]]; if (n.count == 0) { const float a = half_area(n.lo, n.hi); if (a > area) { area = a; pick = (int)i; } } }
+        if (pick < 0 || (int)kids.size() >= width) break;
+        const BNode n = B.b[kids[pick]]; kids[pick] = n.left; kids.push_back(n.right);
+    }
+    const int me = (int)B.w.size(); B.w.emplace_back();
+    WNode wn{}; wn.nchild = (int)kids.size();
+    for (size_t i = 0; i < kids.size(); i++) {
+        const BNode& n = B.b[kids[i]];
+        for (int k = 0; k < 3; k++) { wn.lo[i][k] = n.lo[k]; wn.hi[i][k] = n.hi[k]; }
+        if (n.count > 0) { wn.child[i] = -1; wn.first[i] = n.first; wn.count[i] = n.count; }
+        else { wn.child[i] = 0; wn.first[i] = kids[i]; wn.count[i] = 0; }
+    }
+    B.w[me] = wn;
+    for (int i = 0; i < wn.nchild; i++) if (wn.child[i] == 0) { const int c = collapse(B, wn.first[i], width); B.w[me].child[i] = c; }
+    return me;
+}
+} // namespace
+
+// out[0..5] = rays, wide nodes visited, child boxes tested, triangles tested, rays whose triangle differs from the kd-tree's,
+// of those how many have |dt| <= 2 eps;  out[6] = wide nodes, out[7] = bytes of a 32-byte-per-child wide-node layout,
+// out[8] = rays with more than one hit within 2 eps of the closest (the ones an arbiter would hand to the kd traversal),
+// out[9] = rays that differ WITHOUT being flagged so (must be 0 for the arbiter plan to be bit-exact)
+int rgko_bvh_study(void* h, const rgk_ray* rays, const uint32_t* ignore, uint64_t n, int width, int leaf_size, double* out) {
+    const Scene& s = *(Scene*)h;
+    BvhStudy B; B.order.resize(s.tris.size());
+    for (size_t i = 0; i < B.order.size(); i++) B.order[i] = (uint32_t)i;
+    build_binary(s, B, 0, (int)B.order.size(), leaf_size);
+    collapse(B, 0, width);
+    uint64_t nodes = 0, boxes = 0, tests = 0, differ = 0, near_tie = 0, ambiguous = 0, differ_unflagged = 0;
+    const float window = 2.0f * s.epsilon;      // the arbiter's window: every hit within it of the closest one is kept
+    std::vector<std::pair<float, uint32_t>> found;
+    for (uint64_t i = 0; i < n; i++) {
+        found.clear();
+        Ray r; r.o = v3(rays[i].origin); r.d = v3(rays[i].direction); r.tnear = rays[i].tnear; r.tfar = rays[i].tfar;
+        const uint32_t ign = ignore ? ignore[i] : RGK_NO_TRIANGLE;
+        const float inv[3] = {1.f / r.d.x, 1.f / r.d.y, 1.f / r.d.z};
+        float best_t = r.tfar; uint32_t best = RGK_NO_TRIANGLE;
+        struct E { int node; float t; }; E stack[256]; int sp = 0; stack[sp++] = {0, r.tnear - s.epsilon};
+        while (sp) {
+            const E e = stack[--sp];
+            if (e.t > best_t + window) continue;
+            const WNode& wn = B.w[e.node]; nodes++;
+            E hitc[9]; int hc = 0; int leafc[8]; int lc = 0;
+            for (int c = 0; c < wn.nchild; c++) {
+                boxes++;
+                float t0 = r.tnear - s.epsilon, t1 = best_t + window;
+                for (int k = 0; k < 3; k++) { float a = (wn.lo[c][k] - r.o[k]) * inv[k], b = (wn.hi[c][k] - r.o[k]) * inv[k]; if (a > b) std::swap(a, b); t0 = std::max(t0, a - 1e-4f * std::fabs(a)); t1 = std::min(t1, b + 1e-4f * std::fabs(b)); }
+                if (t0 > t1) continue;
+                if (wn.child[c] < 0) leafc[lc++] = c; else hitc[hc++] = {wn.child[c], t0};
+            }
+            for (int q = 0; q < lc; q++) {
+                const int c = leafc[q];
+                for (int j = wn.first[c]; j < wn.first[c] + wn.count[c]; j++) {
+                    const uint32_t ti = B.order[j];
+                    if (ti == ign) continue;
+                    tests++;
+                    float t, a, b;
+                    if (test_intersection(s, s.tris[ti], r, t, a, b) && t >= r.tnear - s.epsilon && t <= r.tfar + s.epsilon) {
+                        if (t <= best_t + window) found.push_back({t, ti});
+                        if (t < best_t || (t == best_t && ti < best)) { best_t = t; best = ti; }
+                    }
+                }
+            }
+            for (int a = 1; a < hc; a++) { const E x = hitc[a]; int b = a; while (b > 0 && hitc[b - 1].t < x.t) { hitc[b] = hitc[b - 1]; b--; } hitc[b] = x; }   // far first: nearest popped first
+            for (int q = 0; q < hc; q++) stack[sp++] = hitc[q];
+        }
+        int close = 0;
+        for (const auto& f : found) if (f.first <= best_t + window) close++;
+        const bool amb = close > 1 || (best != RGK_NO_TRIANGLE && best_t < r.tnear + s.epsilon);   // also: a hit behind / at the offset origin
+        if (amb) ambiguous++;
+        const Hit k = find_intersect(s, r, ign, nullptr);
+        if (k.tri != best && !amb) differ_unflagged++;
+        if (k.tri != best) { if (getenv("RGKO_BVH_VERBOSE")) std::fprintf(stderr, "ray %llu: kd tri %u t %.9g | bvh tri %u t %.9g\n", (unsigned long long)i, k.tri, (double)k.t, best, (double)best_t);
+            differ++; if (k.tri != RGK_NO_TRIANGLE && best != RGK_NO_TRIANGLE && std::fabs(k.t - best_t) <= 2 * s.epsilon) near_tie++; }
+    }
+    out[0] = (double)n; out[1] = (double)nodes; out[2] = (double)boxes; out[3] = (double)tests; out[4] = (double)differ; out[5] = (double)near_tie;
+    out[6] = (double)B.w.size(); out[7] = (double)B.w.size() * width * 32.0; out[8] = (double)ambiguous; out[9] = (double)differ_unflagged;
+    return 0;
+}
+
 // ---- unit-level probes (same layouts as the rgkref_* probes)
 int rgko_bxdf_sample(void* h, uint32_t material, const float* Vi, const float* uv, const float* sample, uint64_t n, float* out) {
     const Scene& s = *(Scene*)h;

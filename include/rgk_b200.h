@@ -257,6 +257,20 @@ rgk_status rgk_host_scene_get_records(const rgk_host_scene* hs, float* planes, f
  * hi2, in the triangle's projection plane), for checking their conservativeness without a GPU. */
 rgk_status rgk_host_scene_get_bounds(const rgk_host_scene* hs, float* bounds);
 
+/* Opt-in wide BVH (environment RGK_WIDE_BVH=1 at commit time; no reference counterpart -- RGKrt only has the kd-tree,
+ * src/scene.cpp:294-429).  A candidate generator: the traversal entry points find the globally closest hit through it with
+ * the same Triangle::TestIntersection arithmetic, and every ray whose answer could depend on the kd-tree's per-leaf
+ * +-epsilon accept rule (more than one hit within 2 epsilon of the closest, or a hit within epsilon of the ray's ends) is
+ * re-traced through the kd-tree, which stays the authority.  Sizes are 0 when it is off (or the tree was too deep).
+ * nodes: 32 floats each -- lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4], 4 child codes (uint32 bits: inner = node
+ * index, leaf = 1<<31 | (count-1)<<29 | first slot, empty = 0x7fffffff), 4 zeros; order[slot] = triangle. */
+rgk_status rgk_host_scene_get_bvh_size(const rgk_host_scene* hs, uint32_t* n_nodes, uint32_t* n_slots, uint32_t* depth);
+rgk_status rgk_host_scene_get_bvh(const rgk_host_scene* hs, float* nodes, uint32_t* order);
+/* Counters of the wide-BVH traversal launches since the previous call (synchronises the stream): out[0] rays, out[1]
+ * ambiguous rays handed to the kd-tree, out[2] wide nodes visited, out[3] exact triangle tests (2-3 only while
+ * rgk_render_set_counting is on).  All zero when the BVH is off. */
+rgk_status rgk_bvh_stats(rgk_context* ctx, uint64_t out[4]);
+
 /* Replaces Scene::FindIntersectKdOtherThan (src/scene_intersect.cpp:211-327) over a
  * batch; ignore[i] = triangle index to skip or RGK_NO_TRIANGLE (then it is
  * Scene::FindIntersectKd, :4-116); ignore may be NULL.  Host buffers. */

@@ -1221,6 +1221,7 @@ int rgko_render_round_counters(void* h, const rgk_camera* cam, const rgk_render_
     return 0;
 }
 
+#define RGK_ORACLE_BVH_STACK 256
 // ---- design study (NOT a reference path): what a wide BVH would cost and how often its hit differs ----------------
 // A binned-SAH BVH over the same triangles, collapsed to `width` children per node, traversed front to back for the
 // GLOBAL closest hit with the same Triangle::TestIntersection arithmetic.  Reports, per ray, nodes visited, child boxes
@@ -1355,6 +1356,113 @@ int rgko_bvh_study(void* h, const rgk_ray* rays, const uint32_t* ignore, uint64_
     }
     out[0] = (double)n; out[1] = (double)nodes; out[2] = (double)boxes; out[3] = (double)tests; out[4] = (double)differ; out[5] = (double)near_tie;
     out[6] = (double)B.w.size(); out[7] = (double)B.w.size() * width * 32.0; out[8] = (double)ambiguous; out[9] = (double)differ_unflagged;
+    return 0;
+}
+
+// ---- CPU mirror of the product's opt-in wide-BVH traversal (rgk_b200/csrc/bvh_device.cuh) -------------------------
+// Walks the PRODUCT-built node / order arrays (rgk_host_scene_get_bvh) with the decision logic of BvhTraverser -- per-ray
+// box margin, widened interval bounds, sorted child order, accept interval, 2-epsilon ambiguity rule -- and the oracle's
+// TestIntersection.  tests/test_bvh_host.py uses it to check, without a GPU, that every ray the BVH pass would COMMIT has
+// exactly the kd-tree's answer and that the deferred fraction is small.  Not a reference path.
+namespace {
+struct Bvh4Out { bool deferred, found; Hit hit; };
+Bvh4Out bvh4_trace(const Scene& s, const float* nodes, const uint32_t* order, const Ray& r, uint32_t ignore, bool any, uint64_t* counters) {
+    Bvh4Out out{}; out.hit.tri = RGK_NO_TRIANGLE; out.hit.t = std::numeric_limits<float>::infinity(); out.hit.a = out.hit.b = out.hit.c = 0;
+    const float INF = std::numeric_limits<float>::infinity();
+    // a zero (or NaN / reciprocal-overflowing) direction component: the kd traversal's plane distance can be 0 * inf = NaN (origin exactly on a split plane),
+    // and a NaN interval bound accepts hits anywhere along the line (src/scene_intersect.cpp:272,308-318) -- kd rule only
+    const float inv[3] = {1.f / r.d.x, 1.f / r.d.y, 1.f / r.d.z};
+    if (!(std::fabs(inv[0]) < INF) || !(std::fabs(inv[1]) < INF) || !(std::fabs(inv[2]) < INF)) { out.deferred = true; return out; }
+    float t0 = r.tnear, t1 = r.tfar;
+    for (int k = 0; k < 3; k++) {
+        float tn = (s.bb[k][0] - r.o[k]) * inv[k], tf = (s.bb[k][1] - r.o[k]) * inv[k];
+        if (tn > tf) std::swap(tn, tf);
+        t0 = tn > t0 ? tn : t0; t1 = tf < t1 ? tf : t1;
+        if (t0 > t1) return out;
+    }
+    if (r.tfar < t0) return out;
+    const float eps = s.epsilon;
+    const float lo_t = t0 - eps, hi_t = t1 + eps, firm_lo = t0 + eps, firm_hi = t1 - eps;
+    const float m = (((std::fabs(r.o.x) + std::fabs(r.o.y)) + std::fabs(r.o.z)) + std::fabs(t1)) * 7.62939453125e-6f;
+    const float op[3] = {r.o.x + m, r.o.y + m, r.o.z + m}, om[3] = {r.o.x - m, r.o.y - m, r.o.z - m};
+    const float low_w = (lo_t - std::fabs(lo_t) * 9.5367431640625e-7f) - 1e-30f;
+    float best_t = INF, second_t = INF, limit;
+    auto set_limit = [&]() { float l = hi_t; if (!any) { const float w = best_t + 2.0f * eps; l = w < l ? w : l; } limit = (l + std::fabs(l) * 9.5367431640625e-7f) + 1e-30f; };
+    set_limit();
+    bool border = false, stop = false;
+    struct E { uint32_t code; float t; }; E stack[RGK_ORACLE_BVH_STACK]; int sp = 0;
+    auto pop = [&]() -> uint32_t { while (sp > 0) { --sp; if (stack[sp].t <= limit) return stack[sp].code; } return 0x7fffffffu; };
+    uint32_t cur = 0;
+    while (cur != 0x7fffffffu) {
+        if (cur < 0x7fffffffu) {
+            if (counters) counters[0]++;
+            const float* n = nodes + 32 * (size_t)cur;
+            E e[4];
+            for (int c = 0; c < 4; c++) {
+                float tn = low_w, tf = limit;
+                float lo3[3], hi3[3];
+                for (int k = 0; k < 3; k++) { const float a = (n[8 * k + c] - op[k]) * inv[k], b = (n[8 * k + 4 + c] - om[k]) * inv[k]; lo3[k] = std::fmin(a, b); hi3[k] = std::fmax(a, b); }
+                tn = std::fmax(std::fmax(lo3[0], lo3[1]), std::fmax(lo3[2], low_w));
+                tf = std::fmin(std::fmin(hi3[0], hi3[1]), std::fmin(hi3[2], limit));
+                uint32_t code; std::memcpy(&code, n + 24 + c, 4);
+                e[c] = {code, tn <= tf ? tn : INF};
+            }
+            auto cswap = [&](int a, int b) { if (e[b].t < e[a].t) std::swap(e[a], e[b]); };
+            cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+            if (!(e[0].t < INF)) { cur = pop(); continue; }
+            for (int c = 3; c >= 1; c--) if (e[c].t < INF) { if (sp >= RGK_ORACLE_BVH_STACK) { out.deferred = true; return out; } stack[sp++] = e[c]; }
+            cur = e[0].code;
+            continue;
+        }
+        const uint32_t first = cur & 0x1fffffffu, cnt = ((cur >> 29) & 3u) + 1u;
+        for (uint32_t j = 0; j < cnt && !stop; j++) {
+            const uint32_t ti = order[first + j];
+            if (ti == ignore) continue;
+            if (counters) counters[1]++;
+            float t, a, b;
+            if (!test_intersection(s, s.tris[ti], r, t, a, b)) continue;
+            if (t < lo_t || t > hi_t) continue;
+            if (!any && t > best_t + 2.0f * eps) continue;
+            if (any) { if (t >= firm_lo && t <= firm_hi) stop = true; else border = true; continue; }
+            if (t < best_t) { second_t = best_t; best_t = t; out.hit.tri = ti; out.hit.t = t; out.hit.a = 1.0f - a - b; out.hit.b = a; out.hit.c = b; set_limit(); }
+            else if (t < second_t) second_t = t;
+        }
+        cur = stop ? 0x7fffffffu : pop();
+    }
+    if (any) { out.found = stop; out.deferred = !stop && border; return out; }
+    out.found = out.hit.tri != RGK_NO_TRIANGLE;
+    out.deferred = out.found && (second_t <= best_t + 2.0f * eps || best_t < firm_lo || best_t > firm_hi);
+    return out;
+}
+} // namespace
+
+// closest: status[i] = 1 when the BVH pass defers ray i to the kd-tree, else hits[i] is what it commits.
+// counters: [0] wide nodes visited, [1] exact tests
+int rgko_bvh4_closest(void* h, const float* nodes, const uint32_t* order, const rgk_ray* rays, const uint32_t* ignore, uint64_t n,
+                      rgk_hit* hits, uint8_t* status, uint64_t* counters) {
+    const Scene& s = *(Scene*)h;
+    for (uint64_t i = 0; i < n; i++) {
+        Ray r; r.o = v3(rays[i].origin); r.d = v3(rays[i].direction); r.tnear = rays[i].tnear; r.tfar = rays[i].tfar;
+        const Bvh4Out o = bvh4_trace(s, nodes, order, r, ignore ? ignore[i] : RGK_NO_TRIANGLE, false, counters);
+        status[i] = o.deferred ? 1 : 0;
+        hits[i].triangle = o.found ? o.hit.tri : RGK_NO_TRIANGLE; hits[i].t = o.hit.t; hits[i].a = o.hit.a; hits[i].b = o.hit.b; hits[i].c = o.hit.c;
+    }
+    return 0;
+}
+// shadow segments a -> b (3 floats each): visible[i] as Scene::Visibility would say, status[i] = 1 when deferred
+int rgko_bvh4_shadow(void* h, const float* nodes, const uint32_t* order, const float* a, const float* b, uint64_t n, uint8_t* visible,
+                     uint8_t* status, uint64_t* counters) {
+    const Scene& s = *(Scene*)h;
+    for (uint64_t i = 0; i < n; i++) {
+        Ray r; r.o = v3(a + 3 * i);
+        const V3 diff = v3(b + 3 * i) - r.o;
+        r.d = normalize(diff);
+        const float len = length(diff), e = s.epsilon * 20.0f;
+        r.tnear = 0.0f + e; r.tfar = len - e;
+        const Bvh4Out o = bvh4_trace(s, nodes, order, r, RGK_NO_TRIANGLE, true, counters);
+        status[i] = o.deferred ? 1 : 0;
+        visible[i] = o.found ? 0 : 1;
+    }
     return 0;
 }
 

@@ -138,6 +138,7 @@ EXPORTS = [
     "rgk_render_set_counting", "rgk_render_get_trav_stats", "rgk_probe", "rgk_render_set_shard",
     "rgk_host_scene_create", "rgk_host_scene_destroy", "rgk_host_last_error", "rgk_host_scene_get_info",
     "rgk_host_scene_get_kdtree", "rgk_host_scene_get_records", "rgk_host_scene_get_bounds",
+    "rgk_host_scene_get_bvh_size", "rgk_host_scene_get_bvh", "rgk_bvh_stats",
 ]
 
 
@@ -193,6 +194,9 @@ def load_library(path=None):
     lib.rgk_host_scene_get_kdtree.argtypes = [vp, vp, vp]
     lib.rgk_host_scene_get_records.argtypes = [vp, vp, vp]
     lib.rgk_host_scene_get_bounds.argtypes = [vp, vp]
+    lib.rgk_host_scene_get_bvh_size.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.rgk_host_scene_get_bvh.argtypes = [vp, vp, vp]
+    lib.rgk_bvh_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
     lib.rgk_render_set_counting.argtypes = [vp, C.c_int]
     lib.rgk_render_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.rgk_render_get_trav_stats.argtypes = [vp, C.POINTER(TravStats), C.POINTER(TravStats)]

@@ -32,6 +32,7 @@ void free_scene(rgk_context* ctx) {
     ctx->scene_allocs.clear();
     ctx->has_scene = false;
     ctx->dev = DevScene{};
+    ctx->d_bvh_stats = nullptr;
 }
 
 template <class T>
@@ -154,6 +155,22 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
                 rp[j] = make_float4(q[0], q[1], q[2], q[3]);
             }
             UP(rp, &D.ref_bounds);
+        }
+        if (!hs.bvh_nodes.empty()) {                 // opt-in wide BVH (RGK_WIDE_BVH=1)
+            std::vector<float4> bn(hs.bvh_nodes.size() / 4);
+            std::memcpy(bn.data(), hs.bvh_nodes.data(), hs.bvh_nodes.size() * 4);
+            UP(bn, &D.bvh_nodes);
+            UP(hs.bvh_order, &D.bvh_refs);
+            std::vector<float4> bp(hs.bvh_order.size());
+            for (size_t j = 0; j < bp.size(); j++) {
+                const float* q = &hs.planes[4 * (size_t)hs.bvh_order[j]];
+                bp[j] = make_float4(q[0], q[1], q[2], q[3]);
+            }
+            UP(bp, &D.bvh_planes);
+            std::vector<BvhStats> z(1, BvhStats{0, 0, 0, 0});
+            const BvhStats* dz = nullptr;
+            UP(z, &dz);
+            ctx->d_bvh_stats = const_cast<BvhStats*>(dz);
         }
         std::vector<float4> rec(hs.tri_isect.size() / 4);
         std::memcpy(rec.data(), hs.tri_isect.data(), hs.tri_isect.size() * 4);
@@ -297,6 +314,35 @@ rgk_status rgk_host_scene_get_records(const rgk_host_scene* h, float* planes, fl
 rgk_status rgk_host_scene_get_bounds(const rgk_host_scene* h, float* bounds) {
     if (!h || !bounds) return RGK_ERR_INVALID;
     std::memcpy(bounds, h->hs.tri_bounds.data(), 4 * h->hs.tri_bounds.size());
+    return RGK_OK;
+}
+
+// the opt-in wide BVH (RGK_WIDE_BVH=1 at commit): sizes (all 0 when it is off), then nodes (32 floats each) and leaf order
+rgk_status rgk_host_scene_get_bvh_size(const rgk_host_scene* h, uint32_t* n_nodes, uint32_t* n_slots, uint32_t* depth) {
+    if (!h) return RGK_ERR_INVALID;
+    if (n_nodes) *n_nodes = (uint32_t)(h->hs.bvh_nodes.size() / 32);
+    if (n_slots) *n_slots = (uint32_t)h->hs.bvh_order.size();
+    if (depth) *depth = h->hs.bvh_depth;
+    return RGK_OK;
+}
+rgk_status rgk_host_scene_get_bvh(const rgk_host_scene* h, float* nodes, uint32_t* order) {
+    if (!h || !nodes || !order) return RGK_ERR_INVALID;
+    std::memcpy(nodes, h->hs.bvh_nodes.data(), 4 * h->hs.bvh_nodes.size());
+    std::memcpy(order, h->hs.bvh_order.data(), 4 * h->hs.bvh_order.size());
+    return RGK_OK;
+}
+
+// counters of the wide-BVH traversal launches since the previous call: rays, ambiguous (re-traced through the kd-tree),
+// wide nodes visited and exact triangle tests (the last two only while rgk_set_counting is on).  Zeros when the BVH is off.
+rgk_status rgk_bvh_stats(rgk_context* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return RGK_ERR_INVALID;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!ctx->d_bvh_stats) return RGK_OK;
+    BvhStats h{};
+    RGK_CUDA(ctx, cudaMemcpyAsync(&h, ctx->d_bvh_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    RGK_CUDA(ctx, cudaMemsetAsync(ctx->d_bvh_stats, 0, sizeof(h), ctx->stream));
+    RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out[0] = h.rays; out[1] = h.ambiguous; out[2] = h.nodes; out[3] = h.tests;
     return RGK_OK;
 }
 

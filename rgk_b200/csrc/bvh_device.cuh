@@ -1,0 +1,253 @@
+// bvh_device.cuh -- opt-in wide-BVH traversal (RGK_WIDE_BVH=1), device side.
+//
+// No reference counterpart: RGKrt traverses its kd-tree only (src/scene_intersect.cpp:211-327).  This finds the
+// GLOBALLY closest hit of a ray through the 4-wide BVH of host_bvh.cpp with Triangle::TestIntersection's own arithmetic
+// (src/primitives.cpp:75-166, the same operation order as Traverser::exact_test), so whenever the kd-tree's answer is
+// the global closest hit the result is bit-identical.  The kd rule can differ from that in two ways only (DESIGN.md 8,
+// tools/bvh_study.py): it accepts a triangle inside [leaf tmin - eps, leaf tmax + eps] and stops at the first leaf that
+// accepts one, so (1) of two hits less than eps apart it may return the farther one, and (2) hits within eps of the ends
+// of the root interval are accepted or not depending on the leaf.  Both cases are detected here -- a second accepted hit
+// within 2 eps of the best, or a best hit within eps of the root interval's ends -- and such rays (~2e-4 of them) are
+// NOT committed: they are appended to a list that the kd kernels re-trace.  The kd-tree stays the authority.
+//
+// Boxes are exact triangle bounds; conservativeness against the exact test's rounding (the accepted hit point can lie
+// ~2^-22 (|o| + |t|) outside the true triangle) comes from a per-ray margin m = 2^-17 (|ox| + |oy| + |oz| + |t1|) added
+// to every box (folded into two shifted copies of the origin), and from widening the interval bounds by 2^-20 relative.
+#pragma once
+#include "trace_device.cuh"
+
+struct BvhCount { uint32_t nodes, tests; };
+constexpr uint32_t BVH_DONE = 0x7fffffffu;      // also the code of an empty child slot
+constexpr uint32_t BVH_LEAF = 0x80000000u;
+
+template <bool ANY, bool COUNT>
+struct BvhTraverser {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+    float opx, opy, opz, omx, omy, omz;          // o + m, o - m
+    float lo_t, hi_t;                            // accept interval of the exact test: root interval -+ eps
+    float firm_lo, firm_hi;                      // hits inside are beyond the reach of the kd rule's end effects
+    float low_w;                                 // lo_t widened (box test)
+    float limit;                                 // boxes entered only up to here: min(hi_t, best + 2 eps), widened
+    float second_t;                              // smallest t of an accepted hit other than the best
+    uint32_t ignore;
+    bool border;                                 // ANY: an accepted hit outside the firm interval was seen
+    bool degenerate;                             // set by init: the ray must go to the kd pass untouched
+    int sp;
+    HitRec res;
+
+    // Same root slab test as the kd traversal (src/scene_intersect.cpp:223-232): a ray the kd-tree rejects at the root is
+    // rejected here.  false: no hit.  Rays with a zero (or NaN, or reciprocal-overflowing) direction component are marked
+    // `degenerate` and left to the kd pass: with the origin exactly on a split plane the kd traversal's plane distance is
+    // 0 * inf = NaN, and a NaN interval bound makes its leaves accept hits anywhere along the line (:272,308-318) --
+    // reference behaviour that only the kd traversal itself reproduces.
+    __device__ __forceinline__ bool init(const DevScene& S, float ox_, float oy_, float oz_, float dx_, float dy_, float dz_,
+                                         float tnear, float tfar, uint32_t ignore_) {
+        ox = ox_; oy = oy_; oz = oz_; dx = dx_; dy = dy_; dz = dz_; ignore = ignore_;
+        res.tri = RGK_NO_TRIANGLE; res.t = __int_as_float(0x7f800000); res.alpha = 0.0f; res.beta = 0.0f;
+        second_t = __int_as_float(0x7f800000); border = false; sp = 0;
+        ix = 1.f / dx; iy = 1.f / dy; iz = 1.f / dz;
+        const float inf = __int_as_float(0x7f800000);
+        degenerate = !(fabsf(ix) < inf) || !(fabsf(iy) < inf) || !(fabsf(iz) < inf);
+        if (degenerate) return true;
+        float t0 = tnear, t1 = tfar;
+        {
+            float tn = (S.bb[0] - ox) * ix, tf = (S.bb[1] - ox) * ix;
+            if (tn > tf) { const float q = tn; tn = tf; tf = q; }
+            t0 = tn > t0 ? tn : t0; t1 = tf < t1 ? tf : t1;
+            if (t0 > t1) return false;
+        }
+        {
+            float tn = (S.bb[2] - oy) * iy, tf = (S.bb[3] - oy) * iy;
+            if (tn > tf) { const float q = tn; tn = tf; tf = q; }
+            t0 = tn > t0 ? tn : t0; t1 = tf < t1 ? tf : t1;
+            if (t0 > t1) return false;
+        }
+        {
+            float tn = (S.bb[4] - oz) * iz, tf = (S.bb[5] - oz) * iz;
+            if (tn > tf) { const float q = tn; tn = tf; tf = q; }
+            t0 = tn > t0 ? tn : t0; t1 = tf < t1 ? tf : t1;
+            if (t0 > t1) return false;
+        }
+        if (tfar < t0) return false;             // "if(r.far < tmin) break" on the root pop (:253)
+        const float eps = S.epsilon;
+        lo_t = t0 - eps; hi_t = t1 + eps;
+        firm_lo = t0 + eps; firm_hi = t1 - eps;
+        const float m = (((fabsf(ox) + fabsf(oy)) + fabsf(oz)) + fabsf(t1)) * 7.62939453125e-6f;
+        opx = ox + m; opy = oy + m; opz = oz + m;
+        omx = ox - m; omy = oy - m; omz = oz - m;
+        low_w = (lo_t - fabsf(lo_t) * 9.5367431640625e-7f) - 1e-30f;
+        set_limit(eps);
+        return true;
+    }
+    __device__ __forceinline__ void set_limit(float eps) {
+        float l = hi_t;
+        if (!ANY) { const float w = res.t + 2.0f * eps; l = w < l ? w : l; }
+        limit = (l + fabsf(l) * 9.5367431640625e-7f) + 1e-30f;
+    }
+
+    // entry distance of child c of the node (lo/hi rows already loaded), +inf on a miss
+    __device__ __forceinline__ float child_entry(float lx, float hx, float ly, float hy, float lz, float hz) const {
+        const float ax = (lx - opx) * ix, bx = (hx - omx) * ix;
+        const float ay = (ly - opy) * iy, by = (hy - omy) * iy;
+        const float az = (lz - opz) * iz, bz = (hz - omz) * iz;
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), low_w));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), limit));
+        return tn <= tf ? tn : __int_as_float(0x7f800000);
+    }
+
+    // next stack entry still inside the limit, or BVH_DONE
+    __device__ __forceinline__ uint32_t pop(const TravStack& K) {
+        while (sp > 0) {
+            --sp;
+            const uint2 e = K.e[sp];
+            if (__uint_as_float(e.y) <= limit) return e.x;
+        }
+        return BVH_DONE;
+    }
+
+    // One inner node: returns the next thing to visit (nearest entered child, else the next stack entry, else BVH_DONE).
+    __device__ __forceinline__ uint32_t step(const DevScene& S, uint32_t node, TravStack& K, BvhCount& cnt) {
+        if (COUNT) cnt.nodes++;
+        const float4* n = S.bvh_nodes + 8 * (size_t)node;
+        const float4 lx = __ldg(n), hx = __ldg(n + 1), ly = __ldg(n + 2), hy = __ldg(n + 3), lz = __ldg(n + 4), hz = __ldg(n + 5);
+        const float4 cf = __ldg(n + 6);
+        float t0 = child_entry(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x);
+        float t1 = child_entry(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y);
+        float t2 = child_entry(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z);
+        float t3 = child_entry(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w);
+        uint32_t c0 = __float_as_uint(cf.x), c1 = __float_as_uint(cf.y), c2 = __float_as_uint(cf.z), c3 = __float_as_uint(cf.w);
+        // sorting network (0,1)(2,3)(0,2)(1,3)(1,2): ascending entry distance, misses (+inf) last
+#define RGK_CSWAP(ta, ca, tb, cb) { const bool s_ = tb < ta; const float tt_ = s_ ? tb : ta; tb = s_ ? ta : tb; ta = tt_; \
+                                    const uint32_t cc_ = s_ ? cb : ca; cb = s_ ? ca : cb; ca = cc_; }
+        RGK_CSWAP(t0, c0, t1, c1) RGK_CSWAP(t2, c2, t3, c3) RGK_CSWAP(t0, c0, t2, c2) RGK_CSWAP(t1, c1, t3, c3) RGK_CSWAP(t1, c1, t2, c2)
+#undef RGK_CSWAP
+        const float inf = __int_as_float(0x7f800000);
+        if (!(t0 < inf)) return pop(K);
+        if (t3 < inf) { K.e[sp] = make_uint2(c3, __float_as_uint(t3)); ++sp; }
+        if (t2 < inf) { K.e[sp] = make_uint2(c2, __float_as_uint(t2)); ++sp; }
+        if (t1 < inf) { K.e[sp] = make_uint2(c1, __float_as_uint(t1)); ++sp; }
+        return c0;
+    }
+
+    // Triangle::TestIntersection for leaf slot p on the reference's operation order (src/primitives.cpp:85-164; the
+    // arithmetic of Traverser::exact_test), accepted inside [lo_t, hi_t].  Returns true when the traversal can stop
+    // (ANY: a firm hit).
+    __device__ __forceinline__ bool test(const DevScene& S, uint32_t p, float eps, BvhCount& cnt) {
+        const float4 r0 = __ldg(S.bvh_planes + p);
+        const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;
+        const float dot2f = ox * r0.x + oy * r0.y + oz * r0.z;
+        if (dtf != dtf) return false;                                    // std::isnan(dot)
+        if (fabsf(dtf) < eps) return false;                              // parallel (:91)
+        // conservative fp32 pre-rejection (see Traverser::leaf_bounds): |t32 - t| < 2^-21 |t|, bounds widened by 2^-20
+        {
+            float rcp;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(dtf));
+            const float t32 = -(r0.w + dot2f) * rcp;
+            if (t32 < low_w || t32 > limit) return false;
+        }
+        const uint32_t ti = __ldg(S.bvh_refs + p);
+        if (ti == ignore) return false;
+        if (COUNT) cnt.tests++;
+        const float t = (float)(-((double)r0.w + (double)dot2f) / (double)dtf);
+        if (t < lo_t || t > hi_t) return false;
+        if (!ANY && t > res.t + 2.0f * eps) return false;                // beyond the window of the best so far
+        const float4* rec = S.tri_isect + 3 * (size_t)ti;
+        const float4 r1 = __ldg(rec + 1);
+        const float4 r2 = __ldg(rec + 2);
+        const uint32_t flags = __float_as_uint(r2.w);
+        const uint32_t code = flags & 3u;
+        const float o1 = (code == 0u) ? oy : ox, d1 = (code == 0u) ? dy : dx;
+        const float o2 = (code == 2u) ? oy : oz, d2 = (code == 2u) ? dy : dz;
+        const float q0x = (o1 + d1 * t) - r1.x;
+        const float q0y = (o2 + d2 * t) - r1.y;
+        float alpha, beta;
+        if (flags & 4u) {
+            beta = q0x / r2.x;
+            if (beta < 0.0f || beta > 1.0f) return false;
+            alpha = (q0y - beta * r2.y) / r1.w;
+        } else {
+            beta = (q0y * r1.z - q0x * r1.w) / r2.z;
+            if (beta < 0.0f || beta > 1.0f) return false;
+            alpha = (q0x - beta * r2.x) / r1.z;
+        }
+        if (alpha < 0.0f || (alpha + beta) > 1.0f) return false;
+        if (ANY) {
+            if (t >= firm_lo && t <= firm_hi) return true;
+            border = true;
+            return false;
+        }
+        if (t < res.t) {
+            second_t = res.t;
+            res.tri = ti; res.t = t; res.alpha = alpha; res.beta = beta;
+            set_limit(eps);
+        } else if (t < second_t) second_t = t;
+        return false;
+    }
+
+    // the triangles of a leaf child code; true = stop (ANY with a firm hit)
+    __device__ __forceinline__ bool leaf(const DevScene& S, uint32_t code, BvhCount& cnt) {
+        const float eps = S.epsilon;
+        const uint32_t first = code & 0x1fffffffu, n = ((code >> 29) & 3u) + 1u;
+        for (uint32_t j = 0; j < n; j++)
+            if (test(S, first + j, eps, cnt)) return true;
+        return false;
+    }
+
+    // closest: does the answer depend on the kd rule?  (ANY: only border hits were found)
+    __device__ __forceinline__ bool ambiguous(float eps) const {
+        if (ANY) return border;
+        if (res.tri == RGK_NO_TRIANGLE) return false;
+        return second_t <= res.t + 2.0f * eps || res.t < firm_lo || res.t > firm_hi;
+    }
+};
+
+// Persistent-warp driver, same work distribution as trace_phased.  `fetch(i, T)` loads item i and calls T.init;
+// `commit(i, found, res)` stores a settled result; `defer(i)` hands an ambiguous item to the kd-tree pass.
+template <bool ANY, bool COUNT, class Fetch, class Commit, class Defer>
+__device__ __forceinline__ void trace_bvh(const DevScene& S, uint32_t count, unsigned long long* work, BvhCount& cnt, uint32_t& done,
+                                          uint32_t& deferred, Fetch fetch, Commit commit, Defer defer) {
+    BvhTraverser<ANY, COUNT> T;
+    TravStack K;
+    const unsigned lane = threadIdx.x & 31;
+    const float eps = S.epsilon;
+    bool active = false, exhausted = false, stop = false;
+    uint32_t item = 0, cur = BVH_DONE;
+    for (;;) {
+        __syncwarp();
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !exhausted && (__popc(idle) >= (int)S.refill_threshold || idle == 0xffffffffu)) {
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(work, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + __popc(idle) >= count) exhausted = true;
+            if (!active) {
+                const unsigned long long mine = base + __popc(idle & ((1u << lane) - 1u));
+                if (mine < count) {
+                    item = (uint32_t)mine;
+                    done++;
+                    if (fetch(item, T)) {
+                        if (T.degenerate) { defer(item); deferred++; }
+                        else { active = true; cur = 0u; stop = false; }
+                    } else commit(item, false, T.res);
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) { if (exhausted) break; else continue; }
+        // ---- phase 1: inner nodes until the next leaf (or the end)
+        if (active) {
+            while (cur < BVH_DONE) cur = T.step(S, cur, K, cnt);
+        }
+        __syncwarp();
+        // ---- phase 2: the leaf's triangles, together
+        if (active && cur != BVH_DONE) {
+            stop = T.leaf(S, cur, cnt);
+            cur = stop ? BVH_DONE : T.pop(K);
+        }
+        if (active && cur == BVH_DONE) {
+            if (!stop && T.ambiguous(eps)) { defer(item); deferred++; }
+            else commit(item, ANY ? stop : (T.res.tri != RGK_NO_TRIANGLE), T.res);
+            active = false;
+        }
+    }
+}

@@ -327,6 +327,8 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
         deepest = b.deepest;
     }
     if (deepest + 2 > RGK_STACK_CAP) throw std::runtime_error("kd-tree deeper than the traversal stack capacity");
+    hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0;
+    if (const char* e = std::getenv("RGK_WIDE_BVH")) if (std::atoi(e) > 0) host_bvh_build(ev, nt, hs);
 
     // intersection records: the ray-independent part of Triangle::TestIntersection (src/primitives.cpp:83,104-133,141,149)
     hs.tri_isect.resize(12 * (size_t)nt);

@@ -67,6 +67,10 @@ struct DevScene {
     uint32_t sky_mode; float sky_color[3]; float sky_intensity, sky_rotate; int32_t sky_envmap;
     uint32_t has_ltc;
     uint32_t refill_threshold;   // idle lanes of a warp that trigger a refill (RGK_REFILL)
+    // opt-in wide BVH (RGK_WIDE_BVH=1, host_bvh.cpp / bvh_device.cuh); bvh_nodes == nullptr: kd-tree only
+    const float4* bvh_nodes;     // 8 x float4 per node
+    const uint32_t* bvh_refs;    // [n_triangles] triangle of leaf slot j
+    const float4* bvh_planes;    // [n_triangles] plane record of the triangle in leaf slot j
 };
 
 #define RGK_STACK_CAP 64  // traversal stack entries per ray (tree depth <= log2(n)+8, src/scene.cpp:409)
@@ -80,12 +84,19 @@ struct HostScene {
     std::vector<uint32_t> tri_shade;            // 4 / triangle
     std::vector<DevArealLight> areal_lights;
     std::vector<DevArealTri> areal_tris;
+    std::vector<float> bvh_nodes;               // 32 / wide node (host_bvh.cpp); empty unless RGK_WIDE_BVH=1
+    std::vector<uint32_t> bvh_order;            // triangle of leaf slot j
+    unsigned bvh_depth = 0;
     rgk_scene_info info{};
 };
+// host_bvh.cpp: ev[axis][2 i], [2 i + 1] = min, max of triangle i along the axis
+void host_bvh_build(const std::vector<float> ev[3], uint32_t nt, HostScene& hs);
 // Scene::Commit (src/scene.cpp:294-429) on the host. Throws std::runtime_error on bad input.
 void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScene& out);
 
 // ------------------------------------------------------------------ context
+// counters of the wide-BVH launches since the last call (device buffer ctx->d_bvh_stats): rays, ambiguous, nodes, tests
+struct BvhStats { unsigned long long rays, ambiguous, nodes, tests; };
 struct PathBuffers;   // render.cu
 struct rgk_context {
     int device = 0;
@@ -97,8 +108,8 @@ struct rgk_context {
     DevScene dev{};
     std::vector<void*> scene_allocs;
     // scratch for host-buffer entry points
-    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_size[4] = {0, 0, 0, 0};
+    void* scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // 0-2 staging, 3 work counters, 4 deferred-ray list
+    size_t scratch_size[5] = {0, 0, 0, 0, 0};
     rgk_trav_stats* d_stats = nullptr;
     PathBuffers* paths = nullptr;
     uint64_t launches = 0;
@@ -108,6 +119,7 @@ struct rgk_context {
     bool counting = false;
     uint32_t shard_first = 0, shard_stride = 1;   // rgk_render_set_shard
     rgk_trav_stats last_closest{}, last_shadow{};
+    BvhStats* d_bvh_stats = nullptr;              // wide-BVH counters (allocated with the scene when the BVH is on)
     DevPointLight first_point_light{};            // host copy of point light 0 (single fixed light: no per-path light records)
 };
 

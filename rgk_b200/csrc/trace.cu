@@ -6,6 +6,7 @@
 // whole CTA's slot hostage.  Compiled with -fmad=false (see trace_device.cuh).
 #include <cstdlib>
 #include "trace_device.cuh"
+#include "bvh_device.cuh"
 
 namespace {
 
@@ -80,6 +81,108 @@ k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict
     flush_counts<COUNT>(cnt, mine, stats);
 }
 
+// ---- opt-in wide BVH (RGK_WIDE_BVH=1): BVH pass over all rays, kd pass over the deferred (ambiguous) ones ----------
+template <bool COUNT>
+__device__ __forceinline__ void flush_bvh(const BvhCount& c, uint32_t nrays, uint32_t deferred, BvhStats* stats) {
+    unsigned long long v[4] = {nrays, deferred, COUNT ? c.nodes : 0u, COUNT ? c.tests : 0u};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats->rays, v[0]);
+        if (v[1]) atomicAdd(&stats->ambiguous, v[1]);
+        if (COUNT) { atomicAdd(&stats->nodes, v[2]); atomicAdd(&stats->tests, v[3]); }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
+k_bvh_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, uint64_t n,
+              rgk_hit* __restrict__ hits, BvhStats* stats, unsigned long long* next, uint32_t* __restrict__ list, uint32_t* list_count) {
+    BvhCount cnt{0, 0};
+    uint32_t mine = 0, deferred = 0;
+    trace_bvh<false, COUNT>(S, (uint32_t)n, next, cnt, mine, deferred,
+        [&](uint32_t i, BvhTraverser<false, COUNT>& T) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(rays + i));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+            return T.init(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, ignore ? __ldg(ignore + i) : RGK_NO_TRIANGLE);
+        },
+        [&](uint32_t i, bool found, const HitRec& h) {
+            rgk_hit out;
+            out.triangle = found ? h.tri : RGK_NO_TRIANGLE; out.t = found ? h.t : __int_as_float(0x7f800000);
+            if (found) { out.a = 1.0f - h.alpha - h.beta; out.b = h.alpha; out.c = h.beta; }
+            else { out.a = 0.0f; out.b = 0.0f; out.c = 0.0f; }
+            hits[i] = out;
+        },
+        [&](uint32_t i) { list[atomicAdd(list_count, 1u)] = i; });
+    flush_bvh<COUNT>(cnt, mine, deferred, stats);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
+k_bvh_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, uint64_t n, uint8_t* __restrict__ visible,
+             BvhStats* stats, unsigned long long* next, uint32_t* __restrict__ list, uint32_t* list_count) {
+    BvhCount cnt{0, 0};
+    uint32_t mine = 0, deferred = 0;
+    trace_bvh<true, COUNT>(S, (uint32_t)n, next, cnt, mine, deferred,
+        [&](uint32_t i, BvhTraverser<true, COUNT>& T) {
+            const float ax = pa[3 * (size_t)i], ay = pa[3 * (size_t)i + 1], az = pa[3 * (size_t)i + 2];
+            const float ex = pb[3 * (size_t)i] - ax, ey = pb[3 * (size_t)i + 1] - ay, ez = pb[3 * (size_t)i + 2] - az;
+            const float d2 = ex * ex + ey * ey + ez * ez;
+            const float inv = 1.0f / sqrtf(d2), len = sqrtf(d2);
+            const float e20 = S.epsilon * 20.0f;
+            return T.init(S, ax, ay, az, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20, RGK_NO_TRIANGLE);
+        },
+        [&](uint32_t i, bool found, const HitRec&) { visible[i] = found ? 0 : 1; },
+        [&](uint32_t i) { list[atomicAdd(list_count, 1u)] = i; });
+    flush_bvh<COUNT>(cnt, mine, deferred, stats);
+}
+
+// the kd kernels over the deferred list (count read on the device: no host round trip between the two passes)
+template <int VARIANT>
+__global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
+k_trace_closest_list(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, const uint32_t* __restrict__ list,
+                     const uint32_t* __restrict__ list_count, rgk_hit* __restrict__ hits, unsigned long long* next) {
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
+    uint32_t mine = 0;
+    trace_rays<VARIANT, false, false>(S, *list_count, next, cnt, mine,
+        [&](uint32_t k, Traverser<false, false>& T) {
+            const uint32_t i = list[k];
+            const float4 a = __ldg(reinterpret_cast<const float4*>(rays + i));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+            return T.init(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, ignore ? __ldg(ignore + i) : RGK_NO_TRIANGLE);
+        },
+        [&](uint32_t k, bool found, const HitRec& h) {
+            const uint32_t i = list[k];
+            rgk_hit out;
+            out.triangle = found ? h.tri : RGK_NO_TRIANGLE; out.t = found ? h.t : __int_as_float(0x7f800000);
+            if (found) { out.a = 1.0f - h.alpha - h.beta; out.b = h.alpha; out.c = h.beta; }
+            else { out.a = 0.0f; out.b = 0.0f; out.c = 0.0f; }
+            hits[i] = out;
+        });
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
+k_trace_shadow_list(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, const uint32_t* __restrict__ list,
+                    const uint32_t* __restrict__ list_count, uint8_t* __restrict__ visible, unsigned long long* next) {
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
+    uint32_t mine = 0;
+    trace_rays<VARIANT, true, false>(S, *list_count, next, cnt, mine,
+        [&](uint32_t k, Traverser<true, false>& T) {
+            const uint32_t i = list[k];
+            const float ax = pa[3 * (size_t)i], ay = pa[3 * (size_t)i + 1], az = pa[3 * (size_t)i + 2];
+            const float ex = pb[3 * (size_t)i] - ax, ey = pb[3 * (size_t)i + 1] - ay, ez = pb[3 * (size_t)i + 2] - az;
+            const float d2 = ex * ex + ey * ey + ez * ez;
+            const float inv = 1.0f / sqrtf(d2), len = sqrtf(d2);
+            const float e20 = S.epsilon * 20.0f;
+            return T.init(S, ax, ay, az, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20, RGK_NO_TRIANGLE);
+        },
+        [&](uint32_t k, bool found, const HitRec&) { visible[list[k]] = found ? 0 : 1; });
+}
+
 } // namespace
 
 // RGK_TRAVERSAL=2|6 selects the traversal control structure of the batch entry points (A/B knob; results are identical)
@@ -109,10 +212,23 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
     if (n > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "more than 2^32 rays in one batch");
     unsigned long long* next = (unsigned long long*)rgk_scratch(ctx, 3, 256);
     if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
-    RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
+    RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 24, ctx->stream));
     const uint64_t warps = (n + 31) / 32;
     const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + trace_threads() / 32 - 1) / (trace_threads() / 32));
     const int variant = rgk_traversal_variant();
+    if (ctx->dev.bvh_nodes && !d_stats) {          // wide BVH for every ray, then the kd-tree for the deferred ones
+        uint32_t* list = (uint32_t*)rgk_scratch(ctx, 4, n * 4);
+        if (!list) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
+        uint32_t* list_count = (uint32_t*)(next + 2);
+        if (ctx->counting) k_bvh_closest<true><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, ctx->d_bvh_stats, next, list, list_count);
+        else k_bvh_closest<false><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, ctx->d_bvh_stats, next, list, list_count);
+        const int g2 = std::min(grid, 148);
+        if (variant == 2) k_trace_closest_list<2><<<g2, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, list, list_count, d_hits, next + 1);
+        else k_trace_closest_list<6><<<g2, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, list, list_count, d_hits, next + 1);
+        ctx->launches += 2;
+        RGK_CUDA(ctx, cudaGetLastError());
+        return RGK_OK;
+    }
     if (d_stats) k_trace_closest<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
     else if (variant == 6) k_trace_closest<false, 6><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     else if (variant == 2) k_trace_closest<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
@@ -127,10 +243,23 @@ rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* 
     if (n > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "more than 2^32 rays in one batch");
     unsigned long long* next = (unsigned long long*)rgk_scratch(ctx, 3, 256);
     if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
-    RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 8, ctx->stream));
+    RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 24, ctx->stream));
     const uint64_t warps = (n + 31) / 32;
     const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + trace_threads() / 32 - 1) / (trace_threads() / 32));
     const int variant = rgk_traversal_variant();
+    if (ctx->dev.bvh_nodes && !d_stats) {
+        uint32_t* list = (uint32_t*)rgk_scratch(ctx, 4, n * 4);
+        if (!list) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
+        uint32_t* list_count = (uint32_t*)(next + 2);
+        if (ctx->counting) k_bvh_shadow<true><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats, next, list, list_count);
+        else k_bvh_shadow<false><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats, next, list, list_count);
+        const int g2 = std::min(grid, 148);
+        if (variant == 2) k_trace_shadow_list<2><<<g2, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, list, list_count, d_visible, next + 1);
+        else k_trace_shadow_list<6><<<g2, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, list, list_count, d_visible, next + 1);
+        ctx->launches += 2;
+        RGK_CUDA(ctx, cudaGetLastError());
+        return RGK_OK;
+    }
     if (d_stats) k_trace_shadow<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
     else if (variant == 6) k_trace_shadow<false, 6><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     else if (variant == 2) k_trace_shadow<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);

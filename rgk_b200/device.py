@@ -185,6 +185,12 @@ class Context:
     def synchronize(self):
         self._check(self.lib.rgk_synchronize(self.h))
 
+    def bvh_stats(self):
+        """Counters of the opt-in wide-BVH launches since the previous call (all 0 when RGK_WIDE_BVH was not set at commit)."""
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.rgk_bvh_stats(self.h, C.byref(out)))
+        return {"rays": out[0], "ambiguous": out[1], "nodes": out[2], "tests": out[3]}
+
 
 class HostScene:
     """Host-only scene commit (rgk_host_scene_*): planes, areal lights, epsilon, bbox, kd-tree build + flatten -- what
@@ -221,6 +227,17 @@ class HostScene:
         b = np.zeros((self.info().n_triangles, 4), np.float32)
         self.lib.rgk_host_scene_get_bounds(self.h, _p(b))
         return b
+
+    def bvh(self):
+        """(nodes [n, 32] float32, order [n_triangles] uint32, depth) of the opt-in wide BVH; n == 0 unless the scene was
+        committed with RGK_WIDE_BVH=1 in the environment."""
+        n, slots, depth = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.lib.rgk_host_scene_get_bvh_size(self.h, C.byref(n), C.byref(slots), C.byref(depth))
+        nodes = np.zeros((max(1, n.value), 32), np.float32)
+        order = np.zeros(max(1, slots.value), np.uint32)
+        if n.value:
+            self.lib.rgk_host_scene_get_bvh(self.h, _p(nodes), _p(order))
+        return nodes[:n.value], order[:slots.value], depth.value
 
     def close(self):
         if self.h:

@@ -1,0 +1,136 @@
+"""The opt-in wide BVH (RGK_WIDE_BVH=1; rgk_b200/csrc/host_bvh.cpp + bvh_device.cuh), checked without a GPU: structure of
+the product-built nodes, and -- through the oracle's CPU mirror of the device traversal logic (rgko_bvh4_*) -- that every
+ray the BVH pass would commit has exactly the kd-tree's answer (Scene::FindIntersectKdOtherThan / Scene::Visibility,
+src/scene_intersect.cpp:211-327, src/scene.cpp:670-673) while only a tiny fraction is deferred to the kd pass."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import checkers
+import raybatches
+from rgk_b200 import device, standin, scenes
+
+
+@pytest.fixture(scope="module")
+def setup():
+    pack, cfg = standin.sponza(width=320, height=180, multisample=1)
+    os.environ["RGK_WIDE_BVH"] = "1"
+    try:
+        hs = device.HostScene(pack.desc())
+    finally:
+        del os.environ["RGK_WIDE_BVH"]
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    ca = cfg.camera_args()
+    cam = O.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
+    rays = raybatches.primary(O, cam, 320, 180, jitter_seed=5)
+    hits = O.trace_closest(h, rays)
+    yield pack, cfg, hs, O, h, rays, hits
+    hs.close()
+
+
+def test_off_by_default():
+    pack = scenes.load_builtin("cornell-box")[0]
+    hs = device.HostScene(pack.desc())
+    nodes, order, depth = hs.bvh()
+    assert len(nodes) == 0 and len(order) == 0 and depth == 0
+    hs.close()
+
+
+def test_structure(setup):
+    pack, cfg, hs, O, h, rays, hits = setup
+    nodes, order, depth = hs.bvh()
+    nt = hs.info().n_triangles
+    assert len(nodes) > 0 and 3 * depth + 1 <= 64
+    assert sorted(order.tolist()) == list(range(nt))                       # every triangle in exactly one leaf slot
+    codes = nodes[:, 24:28].view(np.uint32)
+    assert not nodes[:, 28:].any()
+    arr = pack.arrays()
+    pos = np.asarray(arr["positions"], np.float32).reshape(-1, 3)
+    tri = np.asarray(arr["indices"], np.uint32).reshape(-1, 3)
+    tlo, thi = pos[tri].min(1), pos[tri].max(1)
+    seen_inner, covered = set(), np.zeros(nt, bool)
+    # subtree bounds bottom-up: children always have larger indices than their parent (preorder emission)
+    sub_lo, sub_hi = np.zeros((len(nodes), 3), np.float32), np.zeros((len(nodes), 3), np.float32)
+    for i in range(len(nodes) - 1, -1, -1):
+        lo_i, hi_i = np.full(3, np.inf, np.float32), np.full(3, -np.inf, np.float32)
+        for c in range(4):
+            code = int(codes[i, c])
+            lo = nodes[i, [0 + c, 8 + c, 16 + c]]; hi = nodes[i, [4 + c, 12 + c, 20 + c]]
+            if code == 0x7FFFFFFF:
+                assert np.isposinf(lo).all() and np.isposinf(hi).all()
+                continue
+            if code & 0x80000000:
+                first, cnt = code & 0x1FFFFFFF, ((code >> 29) & 3) + 1
+                t = order[first:first + cnt]
+                assert not covered[t].any()
+                covered[t] = True
+                assert (tlo[t].min(0) == lo).all() and (thi[t].max(0) == hi).all()     # exact bounds of its triangles
+            else:
+                assert i < code < len(nodes) and code not in seen_inner
+                seen_inner.add(code)
+                assert (sub_lo[code] == lo).all() and (sub_hi[code] == hi).all()
+            lo_i, hi_i = np.minimum(lo_i, lo), np.maximum(hi_i, hi)
+        sub_lo[i], sub_hi[i] = lo_i, hi_i
+    assert covered.all() and len(seen_inner) == len(nodes) - 1
+
+
+def _mirror(O, h, nodes, order):
+    lib = O.lib
+    vp = C.c_void_p
+    lib.rgko_bvh4_closest.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp, vp, vp]
+    lib.rgko_bvh4_shadow.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp, vp, vp]
+    nodes = np.ascontiguousarray(nodes); order = np.ascontiguousarray(order)
+
+    def closest(rays, ignore=None):
+        hits = np.zeros(len(rays), checkers.HIT_DT); status = np.zeros(len(rays), np.uint8); cnt = np.zeros(2, np.uint64)
+        rays = np.ascontiguousarray(rays)
+        lib.rgko_bvh4_closest(h, nodes.ctypes.data, order.ctypes.data, rays.ctypes.data, None if ignore is None else ignore.ctypes.data,
+                              len(rays), hits.ctypes.data, status.ctypes.data, cnt.ctypes.data)
+        return hits, status.astype(bool), cnt
+
+    def shadow(a, b):
+        a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+        vis = np.zeros(len(a), np.uint8); status = np.zeros(len(a), np.uint8); cnt = np.zeros(2, np.uint64)
+        lib.rgko_bvh4_shadow(h, nodes.ctypes.data, order.ctypes.data, a.ctypes.data, b.ctypes.data, len(a), vis.ctypes.data, status.ctypes.data, cnt.ctypes.data)
+        return vis, status.astype(bool), cnt
+    return closest, shadow
+
+
+def _same(a, b):
+    return all((a[f].view(np.uint32) == b[f].view(np.uint32)).all() for f in ("triangle", "t", "a", "b", "c"))
+
+
+def test_committed_rays_match_the_kdtree(setup):
+    pack, cfg, hs, O, h, rays, hits = setup
+    nodes, order, _ = hs.bvh()
+    closest, shadow = _mirror(O, h, nodes, order)
+    # primary rays
+    got, deferred, cnt = closest(rays)
+    assert deferred.mean() < 1e-3
+    assert _same(got[~deferred], hits[~deferred])
+    assert cnt[0] / len(rays) < 25 and cnt[1] / len(rays) < 12
+    # incoherent bounce rays with the hit triangle ignored
+    eps = O.scene_info(h).epsilon
+    brays, ign = raybatches.bounce(rays, hits, O.scene_planes(h)[:, :3], eps)
+    want = O.trace_closest(h, brays, ign)
+    got, deferred, cnt = closest(brays, ign)
+    assert deferred.mean() < 1e-3
+    assert _same(got[~deferred], want[~deferred])
+    # shadow segments from the light to the first hits, and between random pairs of hit points (mostly blocked)
+    light = np.asarray(pack.point_lights[0][0], np.float32)
+    a, b = raybatches.shadow_segments(rays, hits, light)
+    # The second batch has segments lying exactly in the floor plane (a zero direction component on a kd split plane:
+    # the reference's NaN-interval case, where its leaves accept hits anywhere along the line) -- all of them must defer.
+    for aa, bb, max_deferred in ((a, b, 1e-3), (b[np.random.default_rng(2).permutation(len(b))], b, 0.2)):
+        keep = np.linalg.norm(aa - bb, axis=1) > 1e-3
+        aa, bb = aa[keep], bb[keep]
+        want = O.trace_shadow(h, aa, bb)
+        vis, deferred, _ = shadow(aa, bb)
+        assert deferred.mean() < max_deferred
+        assert (vis[~deferred] == want[~deferred]).all()
+        assert 0 < want.mean() < 1
+        in_plane = ((bb - aa) == 0).any(1)
+        assert deferred[in_plane].all()

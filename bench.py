@@ -204,6 +204,9 @@ def main():
     ap.add_argument("--sampler", default="mt", choices=["mt", "fast"])
     ap.add_argument("--shard", default="rounds", choices=["rounds", "tiles"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--traversal", default="bvh", choices=["bvh", "kd"],
+                    help="bvh: the wide-BVH traversal with the kd-tree arbiter pass (RGK_WIDE_BVH=1; results bit-identical to the kd path, "
+                         "tests/test_gpu_bvh.py); kd: the reference's kd-tree for every ray")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -225,6 +228,10 @@ def main():
     desc = pack.desc()
     stream = torch.cuda.current_stream().cuda_stream
     ctx = device.Context(local, stream=stream)
+    if args.traversal == "bvh":
+        os.environ["RGK_WIDE_BVH"] = "1"       # read by rgk_scene_commit
+    else:
+        os.environ.pop("RGK_WIDE_BVH", None)
     t0 = time.perf_counter()
     ctx.commit(desc)
     commit_s = time.perf_counter() - t0
@@ -311,6 +318,8 @@ def main():
     # ---- roofline of the dominant kernel (closest-hit traversal), untimed counting pass for the algorithmic bytes
     roofline, extra = None, {}
     if rank == 0:
+        bvh = ctx.bvh_stats()                  # every wide-BVH launch so far (warm-up, timed and e2e steps); zeros on the kd path
+        bvh_on = bvh["rays"] > 0
         ctx.set_counting(True)
         ctx.set_shard(0, 1)
         ctx.render_round_device(cam, p, all_tasks, fb.data_ptr(), cnt.data_ptr(), 42, 100 * ntasks)
@@ -331,20 +340,24 @@ def main():
         achieved = cl_rays * b_closest / (cl_ms / 1e3) / 1e9 if cl_ms > 0 else 0.0
         traffic, ncu = None, None     # DRAM bytes per launch + issue figures from the committed ncu --set full capture (profiles/r1_traffic.json)
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tname = "r1_traffic_bvh.json" if bvh_on else "r1_traffic.json"
+            tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
             traffic = tj["dram_bytes_per_ray"] * cl_rays / cl_launches
             ncu = {k: tj[k] for k in ("launches", "issue_slots_busy_pct", "active_lanes_per_instruction", "l1_hit_pct", "l2_hit_pct") if k in tj}
-            ncu["source"] = "profiles/r1_traffic.json (static, from the committed capture of this command at 16 spp)"
+            ncu["source"] = "profiles/%s (static, from the committed ncu --set full capture)" % tname
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "k_closest (kd-tree closest-hit traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        kname = ("k_closest_bvh + k_closest_arb (closest hit through the wide BVH, kd-tree arbiter for the deferred rays)" if bvh_on
+                 else "k_closest (kd-tree closest-hit traversal)")
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write per ray x rays per launch)",
                     "algorithmic_bytes_per_launch": cl_rays * b_closest / cl_launches, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "bytes_per_ray": b_closest, "avg_launch_ms": cl_ms / cl_launches, "launches_per_step": cl_launches / max(1, args.steps),
                     "Grays_per_s_in_kernel": cl_rays / (cl_ms / 1e3) / 1e9 if cl_ms > 0 else 0.0,
-                    "note": "cache-fed: the tree, reference planes and triangle records (a few MB) live in L1/L2, so the algorithmic node/triangle "
-                            "bytes are served ~70x from cache (compare `traffic`); frac > 1 against the HBM copy peak is expected, the kernel is "
-                            "issue/divergence-bound (profiles/README.md)",
+                    "note": "algorithmic bytes are those of the REFERENCE algorithm (kd-tree counters of an untimed counting pass: SURVEY 8d); "
+                            "cache-fed: the tree, planes and triangle records (a few MB) live in L1/L2, so those bytes are served ~70x from cache "
+                            "(compare `traffic`); frac > 1 against the HBM copy peak is expected, the kernel is issue/divergence-bound "
+                            "(profiles/README.md)" + ("; the wide-BVH pass does the same job in 4x fewer node visits" if bvh_on else ""),
                     "prefilter": tc.device_dict(), "ncu": ncu,
                     "shadow_kernel": {"bytes_per_ray": b_shadow, "achieved": sh_rays * b_shadow / (sh_ms / 1e3) / 1e9 if sh_ms > 0 else 0.0,
                                       "Grays_per_s_in_kernel": sh_rays / (sh_ms / 1e3) / 1e9 if sh_ms > 0 else 0.0}}
@@ -352,6 +365,8 @@ def main():
         extra = {"kernel_share_of_step": {"closest": cl_ms / tot_ms, "shadow": sh_ms / tot_ms,
                                           "sampler": sum(float(s.sampler_ms) for s in stats) / tot_ms,
                                           "shade": sum(float(s.shade_ms) for s in stats) / tot_ms},
+                 "traversal": {"mode": "bvh4 + kd arbiter" if bvh_on else "kd", "bvh_rays": bvh["rays"],
+                               "deferred_to_kd_frac": bvh["ambiguous"] / max(1, bvh["rays"])},
                  "closest_Mrays_per_s": cl_rays / (ms / 1e3) / 1e6 if world == 1 else None,
                  "shadow_Mrays_per_s": sh_rays / (ms / 1e3) / 1e6 if world == 1 else None,
                  "trav_counters_per_closest_ray": {k: v / max(1, tc.rays) for k, v in tc.as_dict().items() if k != "rays"},
@@ -379,6 +394,8 @@ def main():
             "config": {"workload": label, "sampler": "mt19937 replica (same sequence as the CPU reference)" if mode == abi.SAMPLER_MT19937 else "fast counter-based",
                        "parallelism": ("1 GPU" if world == 1 else ("round-sharded x%d + NCCL reduce per round" % world if args.shard == "rounds"
                                                                    else "tile-sharded x%d + NCCL reduce per round" % world)),
+                       "traversal": ("wide BVH candidate pass + kd-tree arbiter pass (RGK_WIDE_BVH=1): bit-identical to the kd-tree path"
+                                     if args.traversal == "bvh" else "kd-tree (reference structure) for every ray"),
                        "l2": "no flush: per-step path state and sampler tables (GBs) exceed the 126 MB L2; the scene (a few MB) is the working set"},
             "samples_per_s": samples / (ms / 1e3), "gpu_launches": int(launches),
             "rays_note": "value counts rays actually traced; %d shadow queries per step whose direct term is exactly 0 are resolved without "

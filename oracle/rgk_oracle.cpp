@@ -1389,7 +1389,7 @@ Bvh4Out bvh4_trace(const Scene& s, const float* nodes, const uint32_t* order, co
     float best_t = INF, second_t = INF, limit;
     auto set_limit = [&]() { float l = hi_t; if (!any) { const float w = best_t + 2.0f * eps; l = w < l ? w : l; } limit = (l + std::fabs(l) * 9.5367431640625e-7f) + 1e-30f; };
     set_limit();
-    bool border = false, stop = false;
+    bool border = false, stop = false, best_edge = false;
     struct E { uint32_t code; float t; }; E stack[RGK_ORACLE_BVH_STACK]; int sp = 0;
     auto pop = [&]() -> uint32_t { while (sp > 0) { --sp; if (stack[sp].t <= limit) return stack[sp].code; } return 0x7fffffffu; };
     uint32_t cur = 0;
@@ -1423,15 +1423,16 @@ Bvh4Out bvh4_trace(const Scene& s, const float* nodes, const uint32_t* order, co
             if (!test_intersection(s, s.tris[ti], r, t, a, b)) continue;
             if (t < lo_t || t > hi_t) continue;
             if (!any && t > best_t + 2.0f * eps) continue;
-            if (any) { if (t >= firm_lo && t <= firm_hi) stop = true; else border = true; continue; }
-            if (t < best_t) { second_t = best_t; best_t = t; out.hit.tri = ti; out.hit.t = t; out.hit.a = 1.0f - a - b; out.hit.b = a; out.hit.c = b; set_limit(); }
+            const bool edge = a < 3.0517578125e-5f || b < 3.0517578125e-5f || (a + b) > 0.999969482421875f;
+            if (any) { if (!edge && t >= firm_lo && t <= firm_hi) stop = true; else border = true; continue; }
+            if (t < best_t) { second_t = best_t; best_t = t; best_edge = edge; out.hit.tri = ti; out.hit.t = t; out.hit.a = 1.0f - a - b; out.hit.b = a; out.hit.c = b; set_limit(); }
             else if (t < second_t) second_t = t;
         }
         cur = stop ? 0x7fffffffu : pop();
     }
     if (any) { out.found = stop; out.deferred = !stop && border; return out; }
     out.found = out.hit.tri != RGK_NO_TRIANGLE;
-    out.deferred = out.found && (second_t <= best_t + 2.0f * eps || best_t < firm_lo || best_t > firm_hi);
+    out.deferred = out.found && (best_edge || second_t <= best_t + 2.0f * eps || best_t < firm_lo || best_t > firm_hi);
     return out;
 }
 } // namespace

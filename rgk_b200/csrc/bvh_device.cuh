@@ -7,8 +7,11 @@
 // tools/bvh_study.py): it accepts a triangle inside [leaf tmin - eps, leaf tmax + eps] and stops at the first leaf that
 // accepts one, so (1) of two hits less than eps apart it may return the farther one, and (2) hits within eps of the ends
 // of the root interval are accepted or not depending on the leaf.  Both cases are detected here -- a second accepted hit
-// within 2 eps of the best, or a best hit within eps of the root interval's ends -- and such rays (~2e-4 of them) are
-// NOT committed: they are appended to a list that the kd kernels re-trace.  The kd-tree stays the authority.
+// within 2 eps of the best, or a best hit within eps of the root interval's ends.  A third case is (3) a hit on the very
+// edge of a triangle that only touches a kd cell: a ray running along that cell's face may never visit the leaf holding
+// the triangle, so the kd-tree reports nothing there; a best hit with a barycentric coordinate within 2^-15 of the
+// triangle's boundary is therefore treated the same way.  Such rays (~3e-4 of them) are NOT committed: they are appended
+// to a list that the kd kernels re-trace.  The kd-tree stays the authority.
 //
 // Boxes are exact triangle bounds; conservativeness against the exact test's rounding (the accepted hit point can lie
 // ~2^-22 (|o| + |t|) outside the true triangle) comes from a per-ray margin m = 2^-17 (|ox| + |oy| + |oz| + |t1|) added
@@ -30,7 +33,8 @@ struct BvhTraverser {
     float limit;                                 // boxes entered only up to here: min(hi_t, best + 2 eps), widened
     float second_t;                              // smallest t of an accepted hit other than the best
     uint32_t ignore;
-    bool border;                                 // ANY: an accepted hit outside the firm interval was seen
+    bool border;                                 // ANY: an accepted hit outside the firm interval (or on an edge) was seen
+    bool best_edge;                              // closest: the best hit lies on the boundary of its triangle
     bool degenerate;                             // set by init: the ray must go to the kd pass untouched
     int sp;
     HitRec res;
@@ -44,7 +48,7 @@ struct BvhTraverser {
                                          float tnear, float tfar, uint32_t ignore_) {
         ox = ox_; oy = oy_; oz = oz_; dx = dx_; dy = dy_; dz = dz_; ignore = ignore_;
         res.tri = RGK_NO_TRIANGLE; res.t = __int_as_float(0x7f800000); res.alpha = 0.0f; res.beta = 0.0f;
-        second_t = __int_as_float(0x7f800000); border = false; sp = 0;
+        second_t = __int_as_float(0x7f800000); border = false; best_edge = false; sp = 0;
         ix = 1.f / dx; iy = 1.f / dy; iz = 1.f / dz;
         const float inf = __int_as_float(0x7f800000);
         degenerate = !(fabsf(ix) < inf) || !(fabsf(iy) < inf) || !(fabsf(iz) < inf);
@@ -171,14 +175,16 @@ struct BvhTraverser {
             alpha = (q0x - beta * r2.x) / r1.z;
         }
         if (alpha < 0.0f || (alpha + beta) > 1.0f) return false;
+        const bool edge = alpha < 3.0517578125e-5f || beta < 3.0517578125e-5f || (alpha + beta) > 0.999969482421875f;
         if (ANY) {
-            if (t >= firm_lo && t <= firm_hi) return true;
+            if (!edge && t >= firm_lo && t <= firm_hi) return true;
             border = true;
             return false;
         }
         if (t < res.t) {
             second_t = res.t;
             res.tri = ti; res.t = t; res.alpha = alpha; res.beta = beta;
+            best_edge = edge;
             set_limit(eps);
         } else if (t < second_t) second_t = t;
         return false;
@@ -197,7 +203,7 @@ struct BvhTraverser {
     __device__ __forceinline__ bool ambiguous(float eps) const {
         if (ANY) return border;
         if (res.tri == RGK_NO_TRIANGLE) return false;
-        return second_t <= res.t + 2.0f * eps || res.t < firm_lo || res.t > firm_hi;
+        return best_edge || second_t <= res.t + 2.0f * eps || res.t < firm_lo || res.t > firm_hi;
     }
 };
 

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <type_traits>
 #include "trace_device.cuh"
+#include "bvh_device.cuh"
 #include "shade_device.cuh"
 
 // ------------------------------------------------------------------ buffers
@@ -472,6 +473,111 @@ k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t
             B.tot[slot] = t;
         });
     flush_counts<COUNT>(cnt, mine, stats);
+}
+
+// ---- opt-in wide BVH (RGK_WIDE_BVH=1, bvh_device.cuh): the same fetch / commit as k_closest and k_shadow, run through the
+// BVH; rays whose answer could depend on the kd rule are not committed but appended (as path slots) to `arb`, and the
+// *_arb kernels then run the kd traversal over that list (its length is read on the device).  A path's shadow resolve has
+// side effects (B.tot), so it is committed exactly once: by the BVH pass or by the arbiter pass.
+struct ClosestIO {
+    PathBuffers B;
+    __device__ __forceinline__ void commit(uint32_t slot, bool found, const HitRec& h) const {
+        B.hit[slot] = make_float4(h.t, h.alpha, h.beta, __uint_as_float(found ? h.tri : RGK_NO_TRIANGLE));
+    }
+};
+struct ShadowIO {
+    PathBuffers B; float clampv; uint32_t const_light; float4 cl_pos;
+    template <class T>
+    __device__ __forceinline__ bool fetch(const DevScene& S, uint32_t slot, T& tr) const {
+        const float4 a = const_light ? cl_pos : B.light_pos[slot], b = B.sh_pos[slot];
+        const float ex = b.x - a.x, ey = b.y - a.y, ez = b.z - a.z;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        const float inv = 1.0f / sqrtf(d2), len = sqrtf(d2);
+        const float e20 = S.epsilon * 20.0f;
+        return tr.init(S, a.x, a.y, a.z, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20, RGK_NO_TRIANGLE);
+    }
+    __device__ __forceinline__ void commit(uint32_t slot, bool blocked) const {       // the NEE resolve of k_shadow
+        const float4 dr = B.sh_direct[slot];
+        if (__float_as_uint(dr.w) == 0u) {
+            if (blocked) return;
+            float4 t = B.tot[slot];
+            t.x += dr.x; t.y += dr.y; t.z += dr.z;
+            B.tot[slot] = t;
+            return;
+        }
+        const float4 em = B.sh_emis[slot], cb = B.sh_contrib[slot];
+        float hr = blocked ? 0.0f : dr.x, hg = blocked ? 0.0f : dr.y, hb = blocked ? 0.0f : dr.z;
+        hr += em.x; hg += em.y; hb += em.z;
+        if (hr > clampv) hr = clampv;
+        if (hg > clampv) hg = clampv;
+        if (hb > clampv) hb = clampv;
+        float4 t = B.tot[slot];
+        t.x += hr * cb.x; t.y += hg * cb.y; t.z += hb * cb.z;
+        B.tot[slot] = t;
+    }
+};
+constexpr int BVH_MINB = 6;      // 128 threads x <= 80 registers
+
+__device__ __forceinline__ void flush_bvh_counts(uint32_t nrays, uint32_t deferred, BvhStats* stats) {
+    unsigned long long a = nrays, b = deferred;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&stats->rays, a); if (b) atomicAdd(&stats->ambiguous, b); }
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS, BVH_MINB)
+k_closest_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, BvhStats* stats,
+              uint32_t* __restrict__ arb, uint32_t* arb_count) {
+    BvhCount cnt{0, 0};
+    uint32_t mine = 0, deferred = 0;
+    const ClosestIO io{B};
+    trace_bvh<false, false>(S, count, work, cnt, mine, deferred,
+        [&](uint32_t i, BvhTraverser<false, false>& T) {
+            const uint32_t slot = queue ? __ldg(queue + i) : i;
+            const float4 o = B.ray_o[slot], d = B.ray_d[slot];
+            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot]);
+        },
+        [&](uint32_t i, bool found, const HitRec& h) { io.commit(queue ? __ldg(queue + i) : i, found, h); },
+        [&](uint32_t i) { arb[atomicAdd(arb_count, 1u)] = queue ? __ldg(queue + i) : i; });
+    flush_bvh_counts(mine, deferred, stats);
+}
+template <int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB)
+k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const uint32_t* __restrict__ arb_count, unsigned long long* work) {
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
+    uint32_t mine = 0;
+    const ClosestIO io{B};
+    trace_rays<RGK_RENDER_VARIANT, false, false>(S, *arb_count, work, cnt, mine,
+        [&](uint32_t i, Traverser<false, false>& T) {
+            const uint32_t slot = arb[i];
+            const float4 o = B.ray_o[slot], d = B.ray_d[slot];
+            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot]);
+        },
+        [&](uint32_t i, bool found, const HitRec& h) { io.commit(arb[i], found, h); });
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS, BVH_MINB)
+k_shadow_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, BvhStats* stats,
+             uint32_t const_light, float4 cl_pos, uint32_t* __restrict__ arb, uint32_t* arb_count) {
+    BvhCount cnt{0, 0};
+    uint32_t mine = 0, deferred = 0;
+    const ShadowIO io{B, clampv, const_light, cl_pos};
+    trace_bvh<true, false>(S, count, work, cnt, mine, deferred,
+        [&](uint32_t i, BvhTraverser<true, false>& T) { return io.fetch(S, __ldg(queue + i), T); },
+        [&](uint32_t i, bool blocked, const HitRec&) { io.commit(__ldg(queue + i), blocked); },
+        [&](uint32_t i) { arb[atomicAdd(arb_count, 1u)] = __ldg(queue + i); });
+    flush_bvh_counts(mine, deferred, stats);
+}
+template <int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB)
+k_shadow_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const uint32_t* __restrict__ arb_count, float clampv, unsigned long long* work,
+             uint32_t const_light, float4 cl_pos) {
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
+    uint32_t mine = 0;
+    const ShadowIO io{B, clampv, const_light, cl_pos};
+    trace_rays<RGK_RENDER_VARIANT, true, false>(S, *arb_count, work, cnt, mine,
+        [&](uint32_t i, Traverser<true, false>& T) { return io.fetch(S, arb[i], T); },
+        [&](uint32_t i, bool blocked, const HitRec&) { io.commit(arb[i], blocked); });
 }
 
 // Direction bin for the coherence reordering: octahedral map of the direction onto a 16x16 grid, cells numbered along
@@ -1095,6 +1201,16 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             total.shadow_rays += lcount;                       // connection rays (Visibility calls of phases 2 and 3)
             count = 0;
         }
+        // opt-in wide BVH (RGK_WIDE_BVH=1 at commit): BVH pass + kd arbiter pass per traversal launch; the counting
+        // instantiation and the bidirectional mode stay on the kd kernels
+        const bool use_bvh = ctx->dev.bvh_nodes != nullptr && !counting;
+        uint32_t* arb_list = nullptr; unsigned long long* arb_ctr = nullptr;
+        if (use_bvh) {
+            arb_list = (uint32_t*)rgk_scratch(ctx, 4, npaths * sizeof(uint32_t));
+            unsigned long long* s3 = (unsigned long long*)rgk_scratch(ctx, 3, 256);
+            if (!arb_list || !s3) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
+            arb_ctr = s3 + 8;               // [0] closest arbiter work, [1] its count, [2] shadow arbiter work, [3] its count
+        }
         const uint32_t* shade_q = nullptr;          // the live queue in path order, when the traversal queue is direction-sorted
         uint32_t* unext = B.queue_ua;
         for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {
@@ -1107,7 +1223,13 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             pool.begin(ctx->stream, T_CLOSEST);
             // two register budgets of the same kernel: 56 registers (9 CTAs/SM) for the issue-bound coherent camera rays,
             // 48 registers (10 CTAs/SM) for later bounces, which gain from the extra warps
-            if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
+            if (use_bvh) {
+                RGK_CUDA(ctx, cudaMemsetAsync(arb_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
+                k_closest_bvh<<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, 148), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
+                ctx->launches++;
+            }
+            else if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
             else if (bounce == 0) k_closest<false, RGK_COH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             else k_closest<false, RGK_INCOH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
             pool.end(ctx->stream);
@@ -1140,7 +1262,14 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 dev.refill_threshold = bounce == 0 ? refill_coherent : refill_shadow;
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
-                if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1, R.const_light, R.cl_pos);
+                if (use_bvh) {
+                    k_shadow_bvh<<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                                                                        R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
+                    k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, 148), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 3), P->clamp, arb_ctr + 2,
+                                                                                                     R.const_light, R.cl_pos);
+                    ctx->launches++;
+                }
+                else if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1, R.const_light, R.cl_pos);
                 else k_shadow<false, RGK_INCOH_MINB><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr, R.const_light, R.cl_pos);
                 pool.end(ctx->stream);
                 ctx->launches++; total.shadow_launches++;

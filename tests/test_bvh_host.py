@@ -109,7 +109,7 @@ def test_committed_rays_match_the_kdtree(setup):
     closest, shadow = _mirror(O, h, nodes, order)
     # primary rays
     got, deferred, cnt = closest(rays)
-    assert deferred.mean() < 1e-3
+    assert deferred.mean() < 3e-3
     assert _same(got[~deferred], hits[~deferred])
     assert cnt[0] / len(rays) < 25 and cnt[1] / len(rays) < 12
     # incoherent bounce rays with the hit triangle ignored
@@ -117,14 +117,18 @@ def test_committed_rays_match_the_kdtree(setup):
     brays, ign = raybatches.bounce(rays, hits, O.scene_planes(h)[:, :3], eps)
     want = O.trace_closest(h, brays, ign)
     got, deferred, cnt = closest(brays, ign)
-    assert deferred.mean() < 1e-3
+    assert deferred.mean() < 3e-3
     assert _same(got[~deferred], want[~deferred])
     # shadow segments from the light to the first hits, and between random pairs of hit points (mostly blocked)
     light = np.asarray(pack.point_lights[0][0], np.float32)
     a, b = raybatches.shadow_segments(rays, hits, light)
+    b2 = raybatches.shadow_segments(brays, want, light)[1]          # points on every wall, not just the visible ones
     # The second batch has segments lying exactly in the floor plane (a zero direction component on a kd split plane:
-    # the reference's NaN-interval case, where its leaves accept hits anywhere along the line) -- all of them must defer.
-    for aa, bb, max_deferred in ((a, b, 1e-3), (b[np.random.default_rng(2).permutation(len(b))], b, 0.2)):
+    # the reference's NaN-interval case, where its leaves accept hits anywhere along the line) -- all of them must defer --
+    # and the third has segments that run within an ulp of a wall and graze the edges of the triangles touching it, which
+    # the kd-tree sees or not depending on the side of the cell face the ray is on (the edge-hit deferral).
+    for aa, bb, max_deferred in ((a, b, 1e-3), (b[np.random.default_rng(2).permutation(len(b))], b, 0.2),
+                                 (b2[np.random.default_rng(3).permutation(len(b2))], b2, 0.2)):
         keep = np.linalg.norm(aa - bb, axis=1) > 1e-3
         aa, bb = aa[keep], bb[keep]
         want = O.trace_shadow(h, aa, bb)

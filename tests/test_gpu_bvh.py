@@ -10,9 +10,7 @@ import checkers
 import raybatches
 from rgk_b200 import device, standin
 
-# Opt-in path: not yet confirmed on a B200 at the time of writing, so the round-end suite (which stops at the first
-# failure) only runs it on request.
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("RGK_TEST_WIDE_BVH") != "1", reason="set RGK_TEST_WIDE_BVH=1 to test the opt-in wide-BVH path")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
@@ -44,14 +42,14 @@ def test_closest_and_shadow_match_the_oracle(setup):
     want = O.trace_closest(h, rays)
     got = ctx.trace_closest(rays)
     s = ctx.bvh_stats()
-    assert s["rays"] == len(rays) and s["ambiguous"] < 1e-3 * len(rays)
+    assert s["rays"] == len(rays) and s["ambiguous"] < 3e-3 * len(rays)
     assert _same(got, want)
     eps = O.scene_info(h).epsilon
     brays, ign = raybatches.bounce(rays, want, O.scene_planes(h)[:, :3], eps)
     wantb = O.trace_closest(h, brays, ign)
     gotb = ctx.trace_closest(brays, ign)
     s = ctx.bvh_stats()
-    assert s["rays"] == len(brays) and s["ambiguous"] < 1e-3 * len(brays)
+    assert s["rays"] == len(brays) and s["ambiguous"] < 3e-3 * len(brays)
     assert _same(gotb, wantb)
     light = np.asarray(pack.point_lights[0][0], np.float32)
     a, b = raybatches.shadow_segments(brays, wantb, light)
@@ -79,3 +77,31 @@ def test_counting_mode_and_empty_batch(setup):
     finally:
         ctx.set_counting(False)
     assert len(ctx.trace_closest(rays[:0])) == 0
+
+
+def test_render_round_is_bit_identical_to_the_kd_path():
+    """The whole wavefront (closest + shadow launches through the BVH, ambiguous rays through the kd arbiter) must produce
+    the same framebuffer, bit for bit, and the same ray counts as the kd-only context."""
+    pack, cfg = standin.sponza(width=256, height=144, multisample=4)
+    desc = pack.desc()
+    kd = device.Context(0); kd.commit(desc)
+    os.environ["RGK_WIDE_BVH"] = "1"
+    try:
+        bv = device.Context(0); bv.commit(desc)
+    finally:
+        del os.environ["RGK_WIDE_BVH"]
+    out = []
+    for ctx in (kd, bv):
+        cam = ctx.camera(**cfg.camera_args())
+        tasks = ctx.generate_tasks(64, 256, 144)
+        params = cfg.params()
+        params.depth = 3
+        ctx.bvh_stats()
+        rgb, cnt, stats = ctx.render_round(cam, params, tasks)
+        out.append(((rgb, cnt), stats, ctx.bvh_stats()))
+    (fb0, st0, b0), (fb1, st1, b1) = out
+    assert b0["rays"] == 0 and b1["rays"] == st1.closest_rays + st1.shadow_rays
+    assert b1["ambiguous"] < 3e-3 * b1["rays"]
+    assert st0.closest_rays == st1.closest_rays and st0.shadow_rays == st1.shadow_rays
+    assert (fb0[0].view(np.uint32) == fb1[0].view(np.uint32)).all() and (fb0[1] == fb1[1]).all()
+    kd.close(); bv.close()

@@ -36,6 +36,7 @@ class Cuda:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scene", default="sponza"); ap.add_argument("--res", default="1920x1080"); ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--render", type=int, default=2, help="also time N full render rounds of the bench workload (default scene config) on both contexts")
     args = ap.parse_args()
     from rgk_b200 import device, standin, abi
     import raybatches
@@ -94,6 +95,40 @@ def main():
     print(json.dumps({"batch": "shadow", "rays": len(sa), "kd_ms": ms_kd, "bvh_ms": ms_bv, "kd_mrays_s": len(sa) / ms_kd / 1e3, "bvh_mrays_s": len(sa) / ms_bv / 1e3,
                       "speedup": ms_kd / ms_bv, "deferred_frac": s["ambiguous"] / max(1, s["rays"]), "visible_frac": float(v1.mean()),
                       "mismatching_records": int((v1 != v2).sum()), "bvh_commit_s": t_commit}), flush=True)
+    for p in (d_a, d_b, d_v1, d_v2): cu.free(p)
+    if args.render > 0:
+        render_ab(cu, st, kd, bv, args.scene, args.render)
+
+
+def render_ab(cu, st, kd, bv, scene, rounds):
+    """ms per RenderDriver round of the bench workload (the stand-in's own resolution / spp / depth) through the kd-only and
+    the BVH context, the framebuffers compared bit for bit."""
+    from rgk_b200 import standin
+    pack, cfg = standin.BUILDERS[scene]()
+    params = cfg.params()
+    out = {}
+    for name, ctx in (("kd", kd), ("bvh", bv)):
+        cam = ctx.camera(**cfg.camera_args())
+        tasks = ctx.generate_tasks(64, params.xres, params.yres)
+        npx = params.xres * params.yres
+        d_rgb, d_cnt = cu.empty(npx * 12), cu.empty(npx * 4)
+        ms = []
+        for r in range(rounds + 1):
+            cu.ck(cu.rt.cudaMemset(C.c_void_p(d_rgb), 0, C.c_size_t(npx * 12))); cu.ck(cu.rt.cudaMemset(C.c_void_p(d_cnt), 0, C.c_size_t(npx * 4)))
+            ctx.bvh_stats()
+            stats = ctx.render_round_device(cam, params, tasks, d_rgb, d_cnt)
+            ctx.synchronize()
+            ms.append(stats.gpu_ms)
+        b = ctx.bvh_stats()
+        out[name] = {"ms": ms[1:], "closest_rays": stats.closest_rays, "shadow_rays": stats.shadow_rays, "bvh_rays": b["rays"], "bvh_deferred": b["ambiguous"],
+                     "fb": cu.to_host(d_rgb, np.uint32, npx * 3), "cnt": cu.to_host(d_cnt, np.uint32, npx)}
+        cu.free(d_rgb); cu.free(d_cnt)
+    k, b = out["kd"], out["bvh"]
+    print(json.dumps({"render": scene, "xres": params.xres, "yres": params.yres, "spp": params.multisample, "depth": params.depth,
+                      "kd_ms_per_round": k["ms"], "bvh_ms_per_round": b["ms"], "speedup": min(k["ms"]) / min(b["ms"]),
+                      "rays_equal": k["closest_rays"] == b["closest_rays"] and k["shadow_rays"] == b["shadow_rays"],
+                      "bvh_rays": b["bvh_rays"], "bvh_deferred_frac": b["bvh_deferred"] / max(1, b["bvh_rays"]),
+                      "framebuffer_words_differing": int((k["fb"] != b["fb"]).sum()), "counts_differing": int((k["cnt"] != b["cnt"]).sum())}), flush=True)
 
 
 if __name__ == "__main__":

@@ -516,7 +516,6 @@ struct ShadowIO {
         B.tot[slot] = t;
     }
 };
-constexpr int BVH_MINB = 6;      // 128 threads x <= 80 registers
 
 __device__ __forceinline__ void flush_bvh_counts(uint32_t nrays, uint32_t deferred, BvhStats* stats) {
     unsigned long long a = nrays, b = deferred;
@@ -525,7 +524,8 @@ __device__ __forceinline__ void flush_bvh_counts(uint32_t nrays, uint32_t deferr
     if ((threadIdx.x & 31) == 0) { atomicAdd(&stats->rays, a); if (b) atomicAdd(&stats->ambiguous, b); }
 }
 
-__global__ void __launch_bounds__(TRACE_THREADS, BVH_MINB)
+template <int MINB>       // 6: <= 80 registers (no spills, 7 CTAs/SM at the 72 it uses); 8: <= 64 (RGK_BVH_MINB A/B knob)
+__global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_closest_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, BvhStats* stats,
               uint32_t* __restrict__ arb, uint32_t* arb_count) {
     BvhCount cnt{0, 0};
@@ -556,7 +556,8 @@ k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const
         [&](uint32_t i, bool found, const HitRec& h) { io.commit(arb[i], found, h); });
 }
 
-__global__ void __launch_bounds__(TRACE_THREADS, BVH_MINB)
+template <int MINB>
+__global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_shadow_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, BvhStats* stats,
              uint32_t const_light, float4 cl_pos, uint32_t* __restrict__ arb, uint32_t* arb_count) {
     BvhCount cnt{0, 0};
@@ -1024,7 +1025,10 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const bool path_order_shade = env_flag("RGK_SHADE_PATH_ORDER", true);
     const double bin_min_frac = std::getenv("RGK_BIN_MIN_FRAC") ? std::atof(std::getenv("RGK_BIN_MIN_FRAC")) : 0.25;
     const size_t bin_items = env_size("RGK_BIN_ITEMS", 2048);   // path slots per reordering group
-    const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 24);
+    // the wide-BVH kernels' iterations are longer than the kd ones: refilling coherent warps at 24 idle lanes instead of 32
+    // measured -1.9 ms per round (profiles/r1_bvh_sweep.json); the other thresholds are flat
+    const bool bvh_round = ctx->dev.bvh_nodes != nullptr && !ctx->counting && !P->reverse;
+    const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", bvh_round ? 24 : 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 24);
     const uint32_t refill_shadow = (uint32_t)env_size("RGK_REFILL_SHADOW", 12);   // any-hit rays end at very different times: refill sooner
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
@@ -1204,6 +1208,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         // opt-in wide BVH (RGK_WIDE_BVH=1 at commit): BVH pass + kd arbiter pass per traversal launch; the counting
         // instantiation and the bidirectional mode stay on the kd kernels
         const bool use_bvh = ctx->dev.bvh_nodes != nullptr && !counting;
+        // the arbiter sees ~4e-4 of the rays, all of them long (grazing) traversals: spread them over many warps
+        const int arb_grid = 148 * (int)std::max<size_t>(1, env_size("RGK_ARB_GRID", 8)), bvh_minb = (int)env_size("RGK_BVH_MINB", 6);
         uint32_t* arb_list = nullptr; unsigned long long* arb_ctr = nullptr;
         if (use_bvh) {
             arb_list = (uint32_t*)rgk_scratch(ctx, 4, npaths * sizeof(uint32_t));
@@ -1225,8 +1231,9 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             // 48 registers (10 CTAs/SM) for later bounces, which gain from the extra warps
             if (use_bvh) {
                 RGK_CUDA(ctx, cudaMemsetAsync(arb_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
-                k_closest_bvh<<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
-                k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, 148), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
+                if (bvh_minb >= 8) k_closest_bvh<8><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                else k_closest_bvh<6><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
                 ctx->launches++;
             }
             else if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
@@ -1263,9 +1270,11 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
                 if (use_bvh) {
-                    k_shadow_bvh<<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
-                                                                        R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, 148), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 3), P->clamp, arb_ctr + 2,
+                    if (bvh_minb >= 8) k_shadow_bvh<8><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                                                                                              R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
+                    else k_shadow_bvh<6><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                                                                                R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
+                    k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 3), P->clamp, arb_ctr + 2,
                                                                                                      R.const_light, R.cl_pos);
                     ctx->launches++;
                 }

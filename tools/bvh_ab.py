@@ -37,6 +37,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scene", default="sponza"); ap.add_argument("--res", default="1920x1080"); ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--render", type=int, default=2, help="also time N full render rounds of the bench workload (default scene config) on both contexts")
+    ap.add_argument("--spp", type=int, default=None, help="override the samples per pixel of the render rounds")
+    ap.add_argument("--render-only", action="store_true", help="skip the ray-batch A/B (for ncu runs)")
+    ap.add_argument("--sweep", action="store_true", help="render-only: time the BVH context under a list of environment knob settings")
     args = ap.parse_args()
     from rgk_b200 import device, standin, abi
     import raybatches
@@ -50,6 +53,11 @@ def main():
     os.environ["RGK_WIDE_BVH"] = "1"
     t0 = time.time(); bv = device.Context(0, stream=st.value); bv.commit(desc); t_commit = time.time() - t0
     os.environ.pop("RGK_WIDE_BVH")
+    if args.sweep:
+        return sweep(cu, bv, args.scene, args.render, args.spp)
+    if args.render_only:
+        render_ab(cu, st, kd, bv, args.scene, args.render, args.spp)
+        return
     info = kd.scene_info()
     cam = kd.camera(**cfg.camera_args())
     ys, xs = np.mgrid[0:h, 0:w]
@@ -97,14 +105,45 @@ def main():
                       "mismatching_records": int((v1 != v2).sum()), "bvh_commit_s": t_commit}), flush=True)
     for p in (d_a, d_b, d_v1, d_v2): cu.free(p)
     if args.render > 0:
-        render_ab(cu, st, kd, bv, args.scene, args.render)
+        render_ab(cu, st, kd, bv, args.scene, args.render, args.spp)
 
 
-def render_ab(cu, st, kd, bv, scene, rounds):
+SWEEP = [{}, {"RGK_ARB_GRID": "1"}, {"RGK_ARB_GRID": "4"}, {"RGK_BVH_MINB": "8"}, {"RGK_REFILL_INCOHERENT": "16"}, {"RGK_REFILL_INCOHERENT": "28"},
+         {"RGK_REFILL_INCOHERENT": "32"}, {"RGK_REFILL_COHERENT": "24"}, {"RGK_REFILL_SHADOW": "6"}, {"RGK_REFILL_SHADOW": "20"}, {"RGK_BIN": "0"},
+         {"RGK_BIN_SHADOW0": "1"}, {}]
+
+
+def sweep(cu, bv, scene, rounds, spp=None):
+    """ms per round of the BVH context under each knob setting (the knobs are read per render call)."""
+    from rgk_b200 import standin
+    pack, cfg = standin.BUILDERS[scene](**({"multisample": spp} if spp else {}))
+    params = cfg.params()
+    cam = bv.camera(**cfg.camera_args())
+    tasks = bv.generate_tasks(64, params.xres, params.yres)
+    npx = params.xres * params.yres
+    d_rgb, d_cnt = cu.empty(npx * 12), cu.empty(npx * 4)
+    ref = None
+    for knobs in SWEEP:
+        for k, v in knobs.items(): os.environ[k] = v
+        ms = []
+        for r in range(rounds + 1):
+            cu.ck(cu.rt.cudaMemset(C.c_void_p(d_rgb), 0, C.c_size_t(npx * 12))); cu.ck(cu.rt.cudaMemset(C.c_void_p(d_cnt), 0, C.c_size_t(npx * 4)))
+            stats = bv.render_round_device(cam, params, tasks, d_rgb, d_cnt)
+            bv.synchronize()
+            ms.append((stats.gpu_ms, stats.closest_ms, stats.shadow_ms, stats.shade_ms, stats.sampler_ms))
+        for k in knobs: os.environ.pop(k)
+        fb = cu.to_host(d_rgb, np.uint32, npx * 3)
+        if ref is None: ref = fb
+        best = min(ms[1:])
+        print(json.dumps({"knobs": knobs, "ms": best[0], "closest_ms": best[1], "shadow_ms": best[2], "shade_ms": best[3], "sampler_ms": best[4],
+                          "same_framebuffer": bool((fb == ref).all())}), flush=True)
+
+
+def render_ab(cu, st, kd, bv, scene, rounds, spp=None):
     """ms per RenderDriver round of the bench workload (the stand-in's own resolution / spp / depth) through the kd-only and
     the BVH context, the framebuffers compared bit for bit."""
     from rgk_b200 import standin
-    pack, cfg = standin.BUILDERS[scene]()
+    pack, cfg = standin.BUILDERS[scene](**({"multisample": spp} if spp else {}))
     params = cfg.params()
     out = {}
     for name, ctx in (("kd", kd), ("bvh", bv)):

@@ -138,3 +138,39 @@ def test_committed_rays_match_the_kdtree(setup):
         assert 0 < want.mean() < 1
         in_plane = ((bb - aa) == 0).any(1)
         assert deferred[in_plane].all()
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "material-zoo"])
+def test_small_scenes_through_the_mirror(name):
+    """Few, large, axis-aligned triangles (Cornell box: pixel-centre rays with zero direction components, hits on shared
+    edges) and the material zoo: committed rays equal the kd-tree's answer over primary rays and three bounces."""
+    pack, cfg = scenes.load_builtin("cornell-box", width=128, height=128, multisample=1) if name == "cornell-box" else scenes.material_zoo(width=128, height=96)
+    os.environ["RGK_WIDE_BVH"] = "1"
+    try:
+        hs = device.HostScene(pack.desc())
+    finally:
+        del os.environ["RGK_WIDE_BVH"]
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    ca = cfg.camera_args()
+    cam = O.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
+    nodes, order, _ = hs.bvh()
+    closest, shadow = _mirror(O, h, nodes, order)
+    eps = O.scene_info(h).epsilon
+    light = np.asarray(pack.point_lights[0][0], np.float32) if pack.point_lights else np.array([0, 0.9, 0], np.float32)
+    for jitter in (None, 3):
+        cur = raybatches.primary(O, cam, cfg.xres, cfg.yres, jitter_seed=jitter)
+        ign = None
+        for bounce in range(4):
+            want = O.trace_closest(h, cur, ign)
+            got, deferred, _ = closest(cur, ign)
+            assert deferred.mean() < 0.05
+            assert _same(got[~deferred], want[~deferred])
+            a, b = raybatches.shadow_segments(cur, want, light)
+            if len(a):
+                vis, dfs, _ = shadow(a, b)
+                assert (vis[~dfs] == O.trace_shadow(h, a, b)[~dfs]).all()
+            cur, ign = raybatches.bounce(cur, want, O.scene_planes(h)[:, :3], eps, seed=7 + bounce)
+            if len(cur) == 0:
+                break
+    hs.close()

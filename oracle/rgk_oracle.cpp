@@ -1226,7 +1226,7 @@ int rgko_render_round_counters(void* h, const rgk_camera* cam, const rgk_render_
 // A binned-SAH BVH over the same triangles, collapsed to `width` children per node, traversed front to back for the
 // GLOBAL closest hit with the same Triangle::TestIntersection arithmetic.  Reports, per ray, nodes visited, child boxes
 // tested and triangles tested, and how many rays end on a different triangle than FindIntersectKdOtherThan (exact ties
-// and epsilon cases at kd leaf boundaries).  Used by tools/bvh_study.py for DESIGN.md "Next"; never by a test gate.
+// and epsilon cases at kd leaf boundaries).  Used by tests/bvh_study.py for DESIGN.md "Next"; never by a test gate.
 namespace {
 struct BNode { float lo[3], hi[3]; int left, right, first, count; };   // binary; count > 0 = leaf over order[first..]
 struct WNode { int nchild; float lo[8][3], hi[8][3]; int child[8]; int first[8], count[8]; };   // child < 0: leaf slot

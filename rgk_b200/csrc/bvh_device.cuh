@@ -4,7 +4,7 @@
 // GLOBALLY closest hit of a ray through the 4-wide BVH of host_bvh.cpp with Triangle::TestIntersection's own arithmetic
 // (src/primitives.cpp:75-166, the same operation order as Traverser::exact_test), so whenever the kd-tree's answer is
 // the global closest hit the result is bit-identical.  The kd rule can differ from that in two ways only (DESIGN.md 8,
-// tools/bvh_study.py): it accepts a triangle inside [leaf tmin - eps, leaf tmax + eps] and stops at the first leaf that
+// tests/bvh_study.py): it accepts a triangle inside [leaf tmin - eps, leaf tmax + eps] and stops at the first leaf that
 // accepts one, so (1) of two hits less than eps apart it may return the farther one, and (2) hits within eps of the ends
 // of the root interval are accepted or not depending on the leaf.  Both cases are detected here -- a second accepted hit
 // within 2 eps of the best, or a best hit within eps of the root interval's ends.  A third case is (3) a hit on the very

@@ -4,7 +4,7 @@
 // for the traversal kernels in bvh_device.cuh -- it finds the globally closest hit with the reference's own
 // Triangle::TestIntersection arithmetic in 4-6x fewer dependent steps than the kd-tree, flags the rare rays
 // (~2e-4) whose answer could depend on the kd-tree's per-leaf +-epsilon accept rule, and those are re-traced by the
-// kd kernels (tools/bvh_study.py).  The kd-tree stays the authority for every result.
+// kd kernels (tests/bvh_study.py).  The kd-tree stays the authority for every result.
 //
 // Build: binned SAH (16 bins on the centroid of the longest axis) down to leaves of <= 4 triangles, then collapsed to
 // 4 children per node by repeatedly opening the inner child with the largest surface.  Deterministic, single-threaded

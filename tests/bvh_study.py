@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Design study for DESIGN.md "Next": work per ray of a wide BVH (binned SAH, collapsed to 4 / 8 children) against the
 reference kd-tree on the stand-in scene, and how often its closest hit lands on a different triangle.  CPU only (the
-oracle library); nothing here is a product path or a test gate.   python tools/bvh_study.py [--scene sponza] [--rays 200000]"""
+oracle library); nothing here is a product path or a test gate.   python tests/bvh_study.py [--scene sponza] [--rays 200000]"""
 import argparse, ctypes as C, json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

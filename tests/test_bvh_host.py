@@ -174,3 +174,53 @@ def test_small_scenes_through_the_mirror(name):
             if len(cur) == 0:
                 break
     hs.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_triangle_soup_stress(seed):
+    """Goes looking for trouble: a soup of well-shaped, tiny (smaller than epsilon), huge, sliver, far-from-origin and
+    axis-aligned triangles plus exact coplanar duplicates, with rays aimed at vertices, edges and interiors from inside and
+    far outside the scene.  Whatever the BVH pass would commit must be the kd-tree's answer; everything else must defer."""
+    from test_prefilter_bounds import _scene, _triangles
+    rng = np.random.default_rng(seed)
+    tris = _triangles(rng, 3000)
+    tris = np.concatenate([tris, tris[:200], tris[:100] + np.float32(1e-6)])          # exact and near-exact duplicates
+    pack = _scene(tris)
+    os.environ["RGK_WIDE_BVH"] = "1"
+    try:
+        hs = device.HostScene(pack.desc())
+    finally:
+        del os.environ["RGK_WIDE_BVH"]
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    nodes, order, depth = hs.bvh()
+    assert len(nodes) > 0
+    closest, shadow = _mirror(O, h, nodes, order)
+    n = 60000
+    pick = rng.integers(0, len(tris), n)
+    w = rng.dirichlet([0.3, 0.3, 0.3], n).astype(np.float32)                          # clusters near vertices and edges
+    kind = rng.integers(0, 4, n)
+    w[kind == 0] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, (kind == 0).sum())]     # exactly a vertex
+    e = kind == 1                                                                       # exactly on an edge
+    w[e, 2] = 0; w[e, :2] /= w[e, :2].sum(1, keepdims=True)
+    target = np.einsum("nk,nkd->nd", w, tris[pick]).astype(np.float32)
+    origin = np.where(rng.random((n, 1)) < 0.5, rng.uniform(-1.5, 1.5, (n, 3)), rng.uniform(-2000, 2000, (n, 3))).astype(np.float32)
+    d = target - origin
+    keep = np.linalg.norm(d, axis=1) > 1e-6
+    rays = np.zeros(int(keep.sum()), checkers.RAY_DT)
+    rays["origin"] = origin[keep]
+    rays["direction"] = (d[keep] / np.linalg.norm(d[keep], axis=1, keepdims=True)).astype(np.float32)
+    rays["tnear"] = 0.0
+    rays["tfar"] = 10000.0
+    ax = rng.random(len(rays)) < 0.05                                                   # some axis-aligned directions
+    rays["direction"][ax] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, ax.sum())] * np.where(rng.random((ax.sum(), 1)) < 0.5, 1, -1).astype(np.float32)
+    ign = np.where(rng.random(len(rays)) < 0.3, pick[keep], 0xFFFFFFFF).astype(np.uint32)
+    want = O.trace_closest(h, rays, ign)
+    got, deferred, _ = closest(rays, ign)
+    assert deferred.mean() < 0.6 and (want["triangle"] != 0xFFFFFFFF).mean() > 0.3
+    assert _same(got[~deferred], want[~deferred])
+    a, b = rays["origin"], target[keep]
+    far_enough = np.linalg.norm(a - b, axis=1) > 0.1
+    vis, dfs, _ = shadow(a[far_enough], b[far_enough])
+    assert (vis[~dfs] == O.trace_shadow(h, a[far_enough], b[far_enough])[~dfs]).all()
+    hs.close()

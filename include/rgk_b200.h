@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define RGK_ABI_VERSION 2   /* 2: rgk_trav_stats grew the pre-filter counters; rgk_host_scene_*; reverse > 0 */
+#define RGK_ABI_VERSION 3   /* 2: rgk_trav_stats grew the pre-filter counters; rgk_host_scene_*; reverse > 0.  3: wide-BVH entry points */
 
 typedef enum rgk_status {
     RGK_OK = 0,

@@ -127,7 +127,7 @@ class RoundStats(C.Structure):
 assert C.sizeof(Material) == 64 and C.sizeof(Ray) == 32 and C.sizeof(Hit) == 20
 
 # Every symbol include/rgk_b200.h declares (tests check that the library exports all of them).
-ABI_VERSION = 2      # RGK_ABI_VERSION of include/rgk_b200.h these ctypes structures mirror
+ABI_VERSION = 3      # RGK_ABI_VERSION of include/rgk_b200.h these ctypes structures mirror
 
 EXPORTS = [
     "rgk_abi_version", "rgk_status_string", "rgk_context_create", "rgk_context_destroy", "rgk_last_error",

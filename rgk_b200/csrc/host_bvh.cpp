@@ -10,7 +10,8 @@
 // collapse of Ylitie, Karras and Laine (2017, section 3.1) into 4-wide nodes whose leaves hold <= 4 triangles (node visit
 // cost 1, triangle cost 0.3).  Against the first version (16 bins on the longest axis, leaves of <= 4 fixed by the binary
 // build, greedy largest-surface collapse) the CPU mirror counts 14 % fewer node visits and 27 % fewer exact tests per ray
-// (tests/bvh_quality.py).  RGK_BVH_BINS / _AXES / _LEAF / _COLLAPSE=greedy / _CPRIM are study knobs.  Deterministic,
+// (tests/bvh_quality.py).  RGK_BVH_BINS / _AXES / _LEAF / _COLLAPSE=greedy / _CPRIM are study knobs; so is RGK_BVH_REINSERT=n
+// (insertion-based optimisation of the binary tree: 2-3 % fewer node visits on the atrium stand-in, not monotonic in n -- off).  Deterministic,
 // single-threaded (2 M triangles in ~5 s).
 //
 // Node layout (32 floats = 128 bytes = one cache line / L2 sector group):
@@ -26,6 +27,7 @@
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include "rgk_internal.h"
 
 namespace {
@@ -104,6 +106,72 @@ struct BvhBuilder {
         bin[me].left = l; bin[me].right = r; bin[me].count = 0;      // total stays
         return me;
     }
+    // ---- insertion-based optimisation of the binary tree (after Bittner, Hapala, Havran 2013): take an inner node out,
+    // re-insert its two children where they add the least surface (branch and bound over induced + direct cost).  Needs
+    // single-triangle leaves; the triangle order is re-linearised afterwards.  Returns the (possibly new) root.
+    int find_best(int root, int X, std::vector<std::pair<float, int>>& heap) const {
+        const Box bx = bin[X].box; const float ax = bx.half_area();
+        float best = std::numeric_limits<float>::infinity(); int best_y = root;
+        heap.clear(); heap.push_back({0.0f, root});
+        auto cmp = [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; };
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            const float ci = heap.back().first; const int Y = heap.back().second; heap.pop_back();
+            if (ci + ax >= best) break;
+            Box u = bin[Y].box; u.grow(bx);
+            const float tot = ci + u.half_area();
+            if (tot < best) { best = tot; best_y = Y; }
+            const float cc = tot - bin[Y].box.half_area();
+            if (bin[Y].count == 0 && cc + ax < best) {
+                heap.push_back({cc, bin[Y].left}); std::push_heap(heap.begin(), heap.end(), cmp);
+                heap.push_back({cc, bin[Y].right}); std::push_heap(heap.begin(), heap.end(), cmp);
+            }
+        }
+        return best_y;
+    }
+    int reinsert(int root, int iterations, float fraction) {
+        const int n = (int)bin.size();
+        std::vector<int> parent(n, -1);
+        for (int i = 0; i < n; i++) if (bin[i].count == 0) { parent[bin[i].left] = i; parent[bin[i].right] = i; }
+        auto refit_up = [&](int i) {
+            while (i >= 0) { Box b = bin[bin[i].left].box; b.grow(bin[bin[i].right].box); bin[i].box = b; i = parent[i]; }
+        };
+        std::vector<int> cand; std::vector<std::pair<float, int>> heap;
+        for (int it = 0; it < iterations; it++) {
+            cand.clear();
+            for (int i = 0; i < n; i++) if (bin[i].count == 0 && i != root && parent[i] != root) cand.push_back(i);
+            std::sort(cand.begin(), cand.end(), [&](int a, int b) { const float x = bin[a].box.half_area(), y = bin[b].box.half_area(); return x > y || (x == y && a < b); });
+            cand.resize(std::max<size_t>(1, (size_t)(cand.size() * fraction)));
+            for (int N : cand) {
+                const int P = parent[N];
+                if (bin[N].count != 0 || N == root || P < 0 || P == root) continue;       // the tree changes during the pass
+                const int G = parent[P], S = bin[P].left == N ? bin[P].right : bin[P].left;
+                (bin[G].left == P ? bin[G].left : bin[G].right) = S; parent[S] = G; refit_up(G);
+                int L = bin[N].left, R = bin[N].right;
+                if (bin[L].box.half_area() < bin[R].box.half_area()) std::swap(L, R);
+                const int slot[2] = {N, P}, sub[2] = {L, R};
+                for (int q = 0; q < 2; q++) {
+                    const int X = sub[q], Y = find_best(root, X, heap), NP = slot[q], YP = parent[Y];
+                    bin[NP].left = Y; bin[NP].right = X; bin[NP].count = 0;
+                    parent[Y] = NP; parent[X] = NP; parent[NP] = YP;
+                    if (YP < 0) root = NP; else (bin[YP].left == Y ? bin[YP].left : bin[YP].right) = NP;
+                    refit_up(NP);
+                }
+            }
+        }
+        // re-linearise: subtree = contiguous range of `order` again
+        std::vector<uint32_t> fresh; fresh.reserve(order.size());
+        std::vector<std::pair<int, int>> st; st.push_back({root, 0});
+        while (!st.empty()) {
+            const int i = st.back().first; const int phase = st.back().second; st.pop_back();
+            if (bin[i].count > 0) { const uint32_t t = order[bin[i].first]; bin[i].first = (int)fresh.size(); bin[i].total = 1; fresh.push_back(t); continue; }
+            if (phase == 0) { bin[i].first = (int)fresh.size(); st.push_back({i, 1}); st.push_back({bin[i].right, 0}); st.push_back({bin[i].left, 0}); }
+            else bin[i].total = bin[bin[i].left].total + bin[bin[i].right].total;
+        }
+        order.swap(fresh);
+        return root;
+    }
+
     // ---- SAH-optimal collapse of the binary tree into 4-wide nodes with leaves of <= 4 triangles
     std::vector<Dp> dp;
     float c_node = 1.0f, c_prim = 0.3f;
@@ -216,7 +284,11 @@ void host_bvh_build(const std::vector<float> ev[3], uint32_t nt, HostScene& hs) 
     if (const char* e = std::getenv("RGK_BVH_COLLAPSE")) greedy = std::string(e) == "greedy";
     if (const char* e = std::getenv("RGK_BVH_CPRIM")) b.c_prim = (float)std::atof(e);
     if (!greedy && !std::getenv("RGK_BVH_LEAF")) b.leaf_max = 1;        // the collapse chooses the leaves (<= 4 triangles) itself
-    const int root = b.build(0, (int)nt);
+    int root = b.build(0, (int)nt);
+    int reinsert_iters = 0; float reinsert_frac = 0.25f;
+    if (const char* e = std::getenv("RGK_BVH_REINSERT")) reinsert_iters = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("RGK_BVH_REINSERT_FRAC")) reinsert_frac = (float)std::atof(e);
+    if (reinsert_iters > 0 && b.leaf_max == 1 && nt > 8) root = b.reinsert(root, reinsert_iters, reinsert_frac);
     if (greedy) b.collapse(root, 1);
     else { b.dp.resize(b.bin.size()); b.solve(root); b.emit(root, 1); }
     hs.bvh_order.swap(b.order);

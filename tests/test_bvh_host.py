@@ -41,6 +41,34 @@ def test_off_by_default():
 
 def test_structure(setup):
     pack, cfg, hs, O, h, rays, hits = setup
+    _check_structure(pack, hs)
+
+
+@pytest.mark.parametrize("knobs", [{"RGK_BVH_REINSERT": "1"}, {"RGK_BVH_COLLAPSE": "greedy", "RGK_BVH_AXES": "1", "RGK_BVH_BINS": "16"}])
+def test_structure_under_the_builder_knobs(knobs):
+    """The study knobs of host_bvh.cpp (insertion-based optimisation, the first version's greedy collapse) still produce a
+    valid tree whose committed rays match the kd-tree."""
+    pack, cfg = standin.sponza(width=160, height=90, multisample=1)
+    os.environ.update(knobs); os.environ["RGK_WIDE_BVH"] = "1"
+    try:
+        hs = device.HostScene(pack.desc())
+    finally:
+        for k in list(knobs) + ["RGK_WIDE_BVH"]:
+            del os.environ[k]
+    _check_structure(pack, hs)
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    ca = cfg.camera_args()
+    cam = O.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
+    rays = raybatches.primary(O, cam, 160, 90, jitter_seed=4)
+    nodes, order, _ = hs.bvh()
+    closest, _ = _mirror(O, h, nodes, order)
+    got, deferred, _ = closest(rays)
+    assert _same(got[~deferred], O.trace_closest(h, rays)[~deferred])
+    hs.close()
+
+
+def _check_structure(pack, hs):
     nodes, order, depth = hs.bvh()
     nt = hs.info().n_triangles
     assert len(nodes) > 0 and 3 * depth + 1 <= 64

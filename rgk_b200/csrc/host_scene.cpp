@@ -15,6 +15,7 @@
 #include <limits>
 #include <cstdlib>
 #include <stdexcept>
+#include <exception>
 #include <thread>
 #include "rgk_internal.h"
 
@@ -302,6 +303,13 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
     float bb[3][2];
     for (int ax = 0; ax < 3; ax++) { bb[ax][0] = mn[ax] - eps; bb[ax][1] = mx[ax] + eps; }
 
+    // the opt-in wide BVH (RGK_WIDE_BVH=1) is independent of the kd-tree: built on its own thread meanwhile
+    hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0;
+    std::thread bvh_thread; std::exception_ptr bvh_error;
+    if (const char* e = std::getenv("RGK_WIDE_BVH")) if (std::atoi(e) > 0)
+        bvh_thread = std::thread([&] { try { host_bvh_build(ev, nt, hs); } catch (...) { bvh_error = std::current_exception(); } });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{bvh_thread};     // also on the throwing paths below
+
     // kd-tree
     unsigned deepest;
     if (tree) {
@@ -327,8 +335,8 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
         deepest = b.deepest;
     }
     if (deepest + 2 > RGK_STACK_CAP) throw std::runtime_error("kd-tree deeper than the traversal stack capacity");
-    hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0;
-    if (const char* e = std::getenv("RGK_WIDE_BVH")) if (std::atoi(e) > 0) host_bvh_build(ev, nt, hs);
+    if (bvh_thread.joinable()) bvh_thread.join();
+    if (bvh_error) std::rethrow_exception(bvh_error);
 
     // intersection records: the ray-independent part of Triangle::TestIntersection (src/primitives.cpp:83,104-133,141,149)
     hs.tri_isect.resize(12 * (size_t)nt);

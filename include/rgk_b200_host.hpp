@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -249,8 +250,14 @@ public:
     Scene& operator=(const Scene&) = delete;
     // Scene::Commit (src/scene.cpp:294-429): planes, areal lights, epsilon, bbox, kd-tree; tree != nullptr installs a
     // given flattened tree instead.  Throws like the reference's loader does on inconsistent input.
-    void Commit(const rgk_scene_desc& desc, const rgk_kdtree* tree = nullptr) {
-        check(rgk_scene_commit(ctx, &desc, tree), "rgk_scene_commit");
+    // wide_bvh: also build the 4-wide BVH and trace through it first, kd-tree as arbiter (RGK_WIDE_BVH=1; same results)
+    void Commit(const rgk_scene_desc& desc, const rgk_kdtree* tree = nullptr, bool wide_bvh = false) {
+        const char* was = std::getenv("RGK_WIDE_BVH");
+        const std::string saved = was ? was : "";
+        if (wide_bvh) setenv("RGK_WIDE_BVH", "1", 1);
+        const rgk_status st = rgk_scene_commit(ctx, &desc, tree);
+        if (wide_bvh) { if (was) setenv("RGK_WIDE_BVH", saved.c_str(), 1); else unsetenv("RGK_WIDE_BVH"); }
+        check(st, "rgk_scene_commit");
         check(rgk_scene_get_info(ctx, &info), "rgk_scene_get_info");
     }
     // Scene::FindIntersectKdOtherThan (src/scene_intersect.cpp:211-327); ignored = RGK_NO_TRIANGLE: FindIntersectKd

@@ -4,7 +4,7 @@
 // (SURVEY 8e).  The library itself stays NCCL-free: the collective is issued here, on the stream each context was
 // created with, so it is ordered after that GPU's round without a host synchronisation.
 //
-//   rgk_render_multi scene.rgkpack out.exr --gpus N [--rounds R] [--raw file]
+//   rgk_render_multi scene.rgkpack out.exr --gpus N [--rounds R] [--raw file] [--bvh]
 //
 // build: g++ -std=c++17 -O2 -Iinclude -I/usr/local/cuda/include rgk_b200/host/rgk_render_multi.cpp -o rgk_render_multi
 //        -Lrgk_b200 -lrgk_b200 -L/usr/local/cuda/lib64 -lcudart -lnccl -lpthread
@@ -34,7 +34,7 @@ struct Gpu {
 };
 
 int main(int argc, char** argv) {
-    if (argc < 3) { std::fprintf(stderr, "usage: rgk_render_multi scene.rgkpack out.exr --gpus N [--rounds R] [--raw f]\n"); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: rgk_render_multi scene.rgkpack out.exr --gpus N [--rounds R] [--raw f] [--bvh]\n"); return 2; }
     try {
         rgkb::PackFile pack(argv[1]);
         const std::string out = argv[2];
@@ -46,6 +46,7 @@ int main(int argc, char** argv) {
             if (a == "--gpus" && i + 1 < argc) n = std::atoi(argv[++i]);
             else if (a == "--rounds" && i + 1 < argc) cfg.render_rounds = (unsigned)std::atoi(argv[++i]);
             else if (a == "--raw" && i + 1 < argc) raw = argv[++i];
+            else if (a == "--bvh") setenv("RGK_WIDE_BVH", "1", 1);          // read by every rgk_scene_commit below
             else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
         }
         int have = 0;

@@ -1,5 +1,5 @@
 """GPU parity of the opt-in wide-BVH traversal (RGK_WIDE_BVH=1 at commit; bvh_device.cuh + the kd arbiter pass) against the
-oracle, through the C ABI: hit records and visibility flags bit-exact, like the kd path (test_gpu_traversal.py), with the
+oracle, through the C ABI: hit records and visibility flags bit-exact, like the kd path (test_gpu_trace.py), with the
 BVH counters proving that the BVH kernels -- not the kd ones -- produced them."""
 import os
 

@@ -1,6 +1,7 @@
 """Loaders for the two CPU checkers (test infrastructure): the oracle restatement
 (oracle/_build/librgk_oracle.so, prefix rgko_) and the reference build
 (oracle/_ref/librgk_ref.so, prefix rgkref_).  Product code never imports this."""
+import contextlib
 import ctypes as C
 import os
 
@@ -12,6 +13,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "librgk_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "librgk_ref.so")
 vp = C.c_void_p
+
+
+@contextlib.contextmanager
+def scoped_env(**kv):
+    """Set environment variables for the duration of a block (None = unset) and restore what was there before."""
+    old = {k: os.environ.get(k) for k in kv}
+    try:
+        for k, v in kv.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def _ptr(a):

@@ -12,6 +12,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # RGK_TEST_TRAVERSAL=bvh runs the whole GPU suite with every scene committed under RGK_WIDE_BVH=1 (the wide-BVH
+    # candidate pass + kd-tree arbiter): the gate for making that path the library default.  The tests that set or clear
+    # RGK_WIDE_BVH themselves (test_gpu_bvh.py, test_bvh_host.py) are unaffected.
+    if os.environ.get("RGK_TEST_TRAVERSAL") == "bvh":
+        os.environ["RGK_WIDE_BVH"] = "1"
 
 
 @pytest.fixture(scope="session")

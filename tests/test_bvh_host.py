@@ -16,11 +16,8 @@ from rgk_b200 import device, standin, scenes
 @pytest.fixture(scope="module")
 def setup():
     pack, cfg = standin.sponza(width=320, height=180, multisample=1)
-    os.environ["RGK_WIDE_BVH"] = "1"
-    try:
+    with checkers.scoped_env(RGK_WIDE_BVH=1):
         hs = device.HostScene(pack.desc())
-    finally:
-        del os.environ["RGK_WIDE_BVH"]
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
     ca = cfg.camera_args()
@@ -33,7 +30,8 @@ def setup():
 
 def test_off_by_default():
     pack = scenes.load_builtin("cornell-box")[0]
-    hs = device.HostScene(pack.desc())
+    with checkers.scoped_env(RGK_WIDE_BVH=None):
+        hs = device.HostScene(pack.desc())
     nodes, order, depth = hs.bvh()
     assert len(nodes) == 0 and len(order) == 0 and depth == 0
     hs.close()
@@ -49,12 +47,8 @@ def test_structure_under_the_builder_knobs(knobs):
     """The study knobs of host_bvh.cpp (insertion-based optimisation, the first version's greedy collapse) still produce a
     valid tree whose committed rays match the kd-tree."""
     pack, cfg = standin.sponza(width=160, height=90, multisample=1)
-    os.environ.update(knobs); os.environ["RGK_WIDE_BVH"] = "1"
-    try:
+    with checkers.scoped_env(RGK_WIDE_BVH=1, **knobs):
         hs = device.HostScene(pack.desc())
-    finally:
-        for k in list(knobs) + ["RGK_WIDE_BVH"]:
-            del os.environ[k]
     _check_structure(pack, hs)
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
@@ -173,11 +167,8 @@ def test_small_scenes_through_the_mirror(name):
     """Few, large, axis-aligned triangles (Cornell box: pixel-centre rays with zero direction components, hits on shared
     edges) and the material zoo: committed rays equal the kd-tree's answer over primary rays and three bounces."""
     pack, cfg = scenes.load_builtin("cornell-box", width=128, height=128, multisample=1) if name == "cornell-box" else scenes.material_zoo(width=128, height=96)
-    os.environ["RGK_WIDE_BVH"] = "1"
-    try:
+    with checkers.scoped_env(RGK_WIDE_BVH=1):
         hs = device.HostScene(pack.desc())
-    finally:
-        del os.environ["RGK_WIDE_BVH"]
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
     ca = cfg.camera_args()
@@ -214,11 +205,8 @@ def test_triangle_soup_stress(seed):
     tris = _triangles(rng, 3000)
     tris = np.concatenate([tris, tris[:200], tris[:100] + np.float32(1e-6)])          # exact and near-exact duplicates
     pack = _scene(tris)
-    os.environ["RGK_WIDE_BVH"] = "1"
-    try:
+    with checkers.scoped_env(RGK_WIDE_BVH=1):
         hs = device.HostScene(pack.desc())
-    finally:
-        del os.environ["RGK_WIDE_BVH"]
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
     nodes, order, depth = hs.bvh()

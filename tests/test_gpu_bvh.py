@@ -16,12 +16,9 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def setup():
     pack, cfg = standin.sponza(width=480, height=270, multisample=1)
-    os.environ["RGK_WIDE_BVH"] = "1"
-    try:
+    with checkers.scoped_env(RGK_WIDE_BVH=1):
         ctx = device.Context(0)
         ctx.commit(pack.desc())
-    finally:
-        del os.environ["RGK_WIDE_BVH"]
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
     cam = ctx.camera(**cfg.camera_args())
@@ -84,12 +81,10 @@ def test_render_round_is_bit_identical_to_the_kd_path():
     the same framebuffer, bit for bit, and the same ray counts as the kd-only context."""
     pack, cfg = standin.sponza(width=256, height=144, multisample=4)
     desc = pack.desc()
-    kd = device.Context(0); kd.commit(desc)
-    os.environ["RGK_WIDE_BVH"] = "1"
-    try:
+    with checkers.scoped_env(RGK_WIDE_BVH=None):
+        kd = device.Context(0); kd.commit(desc)
+    with checkers.scoped_env(RGK_WIDE_BVH=1):
         bv = device.Context(0); bv.commit(desc)
-    finally:
-        del os.environ["RGK_WIDE_BVH"]
     out = []
     for ctx in (kd, bv):
         cam = ctx.camera(**cfg.camera_args())

@@ -144,9 +144,7 @@ struct BvhTraverser {
         if (fabsf(dtf) < eps) return false;                              // parallel (:91)
         // conservative fp32 pre-rejection (see Traverser::leaf_bounds): |t32 - t| < 2^-21 |t|, bounds widened by 2^-20
         {
-            float rcp;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(dtf));
-            const float t32 = -(r0.w + dot2f) * rcp;
+            const float t32 = -(r0.w + dot2f) * rcp_approx(dtf);
             if (t32 < low_w || t32 > limit) return false;
         }
         const uint32_t ti = __ldg(S.bvh_refs + p);

@@ -27,11 +27,25 @@ struct HitRec { uint32_t tri; float t, alpha, beta; };  // alpha/beta as returne
 // x, y or z by axis code as two predicated selects (the ternary chain compiles to a branch diamond with its own
 // reconvergence barrier otherwise; this sits in the innermost loop of the issue-bound traversal)
 __device__ __forceinline__ float sel_axis(uint32_t axis, float x, float y, float z) {
+#ifdef __CUDA_ARCH__
     float r;
     asm("{\n\t.reg .pred p0, p1;\n\tsetp.eq.u32 p0, %1, 0;\n\tsetp.eq.u32 p1, %1, 1;\n\t"
         "selp.f32 %0, %3, %4, p1;\n\tselp.f32 %0, %2, %0, p0;\n\t}"
         : "=f"(r) : "r"(axis), "f"(x), "f"(y), "f"(z));
     return r;
+#else
+    return axis == 0u ? x : (axis == 1u ? y : z);      // host build of this header (tests/host_cpp/device_on_host.cpp)
+#endif
+}
+// approximate reciprocal of the conservative pre-rejections (never part of a result)
+__device__ __forceinline__ float rcp_approx(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
 }
 
 template <bool ANY, bool COUNT>
@@ -116,8 +130,7 @@ struct Traverser {
     __device__ __forceinline__ bool prescreen(const float4 r0, float eps, float lo_c, float hi_c, float& t32) const {
         const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;
         const float dot2f = ox * r0.x + oy * r0.y + oz * r0.z;
-        float rcp;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(dtf));
+        const float rcp = rcp_approx(dtf);
         t32 = -(r0.w + dot2f) * rcp;
         return !((fabsf(dtf) < eps) || (t32 < lo_c) || (t32 > hi_c));
     }

@@ -1,0 +1,119 @@
+// device_on_host.cpp -- the product's traversal headers compiled for the host (device_shim.h) behind a small C interface:
+// the kd-tree traversal in both control structures (trace_persistent / trace_phased) and the wide-BVH candidate pass with
+// its deferral rules, driven by the SAME persistent-warp drivers the kernels use, over arrays produced by the product's own
+// host scene commit (rgk_host_scene_*).  tests/test_device_on_host.py compares the results with the oracle.
+//
+// build: g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -I/usr/local/cuda/include -Irgk_b200/csrc -Iinclude
+//        tests/host_cpp/device_on_host.cpp -o build/host/libdevice_on_host.so      (-ffp-contract=off = nvcc -fmad=false)
+#include "device_shim.h"
+#include <vector>
+const uint3 threadIdx = {0, 0, 0};
+#include "bvh_device.cuh"          // includes trace_device.cuh and rgk_internal.h
+
+namespace {
+struct Scene {
+    std::vector<uint2> nodes; std::vector<uint32_t> refs; std::vector<float4> ref_planes, ref_bounds, tri_isect, bvh_nodes, bvh_planes;
+    std::vector<uint32_t> bvh_refs;
+    DevScene S{};
+};
+}
+
+extern "C" {
+
+// nodes: 2 words / kd node; planes 4, records 12, bounds 4 floats / triangle; bvh_nodes 32 floats / wide node (may be empty)
+void* doh_scene_create(const uint32_t* nodes, uint32_t n_nodes, const uint32_t* refs, uint32_t n_refs, const float* planes, const float* records,
+                       const float* bounds, uint32_t n_tris, const float* bvh_nodes, uint32_t n_bvh_nodes, const uint32_t* bvh_order, float epsilon,
+                       const float* bbox) {
+    Scene* s = new Scene();
+    s->nodes.resize(n_nodes);
+    for (uint32_t i = 0; i < n_nodes; i++) s->nodes[i] = make_uint2(nodes[2 * i], nodes[2 * i + 1]);
+    s->refs.assign(refs, refs + n_refs);
+    s->ref_planes.resize(n_refs + 1); s->ref_bounds.resize(n_refs + 1);
+    for (uint32_t j = 0; j < n_refs; j++) {
+        const float* p = planes + 4 * (size_t)refs[j]; const float* b = bounds + 4 * (size_t)refs[j];
+        s->ref_planes[j] = make_float4(p[0], p[1], p[2], p[3]); s->ref_bounds[j] = make_float4(b[0], b[1], b[2], b[3]);
+    }
+    s->tri_isect.resize(3 * (size_t)n_tris);
+    std::memcpy(s->tri_isect.data(), records, 48 * (size_t)n_tris);
+    DevScene& S = s->S;
+    S.nodes = s->nodes.data(); S.refs = s->refs.data(); S.ref_planes = s->ref_planes.data(); S.ref_bounds = s->ref_bounds.data();
+    S.tri_isect = s->tri_isect.data();
+    if (n_bvh_nodes) {
+        s->bvh_nodes.resize(8 * (size_t)n_bvh_nodes);
+        std::memcpy(s->bvh_nodes.data(), bvh_nodes, 128 * (size_t)n_bvh_nodes);
+        s->bvh_refs.assign(bvh_order, bvh_order + n_tris);
+        s->bvh_planes.resize(n_tris);
+        for (uint32_t j = 0; j < n_tris; j++) { const float* p = planes + 4 * (size_t)bvh_order[j]; s->bvh_planes[j] = make_float4(p[0], p[1], p[2], p[3]); }
+        S.bvh_nodes = s->bvh_nodes.data(); S.bvh_refs = s->bvh_refs.data(); S.bvh_planes = s->bvh_planes.data();
+    }
+    S.n_nodes = n_nodes; S.n_refs = n_refs; S.n_triangles = n_tris; S.epsilon = epsilon;
+    for (int k = 0; k < 6; k++) S.bb[k] = bbox[k];
+    S.refill_threshold = 1;             // a one-lane warp refills after every ray
+    return s;
+}
+void doh_scene_destroy(void* h) { delete (Scene*)h; }
+
+static void store_hit(rgk_hit& out, bool found, const HitRec& h) {
+    out.triangle = found ? h.tri : RGK_NO_TRIANGLE; out.t = found ? h.t : __int_as_float(0x7f800000);
+    if (found) { out.a = 1.0f - h.alpha - h.beta; out.b = h.alpha; out.c = h.beta; }
+    else { out.a = 0.0f; out.b = 0.0f; out.c = 0.0f; }
+}
+
+// variant 2 / 6: the kd traversal (status untouched); variant 4: the wide-BVH pass, status[i] = 1 for a deferred ray
+int doh_closest(void* h, int variant, const rgk_ray* rays, const uint32_t* ignore, uint64_t n, rgk_hit* hits, uint8_t* status, uint64_t* counters) {
+    const DevScene& S = ((Scene*)h)->S;
+    unsigned long long work = 0; uint32_t done = 0;
+    if (variant == 4) {
+        if (!S.bvh_nodes) return 1;
+        BvhCount cnt{0, 0}; uint32_t deferred = 0;
+        trace_bvh<false, true>(S, (uint32_t)n, &work, cnt, done, deferred,
+            [&](uint32_t i, BvhTraverser<false, true>& T) {
+                const rgk_ray& r = rays[i];
+                return T.init(S, r.origin[0], r.origin[1], r.origin[2], r.direction[0], r.direction[1], r.direction[2], r.tnear, r.tfar, ignore ? ignore[i] : RGK_NO_TRIANGLE);
+            },
+            [&](uint32_t i, bool found, const HitRec& hr) { store_hit(hits[i], found, hr); status[i] = 0; },
+            [&](uint32_t i) { status[i] = 1; });
+        if (counters) { counters[0] = cnt.nodes; counters[1] = cnt.tests; }
+        return done == n ? 0 : 2;
+    }
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
+    auto fetch = [&](uint32_t i, Traverser<false, true>& T) {
+        const rgk_ray& r = rays[i];
+        return T.init(S, r.origin[0], r.origin[1], r.origin[2], r.direction[0], r.direction[1], r.direction[2], r.tnear, r.tfar, ignore ? ignore[i] : RGK_NO_TRIANGLE);
+    };
+    auto commit = [&](uint32_t i, bool found, const HitRec& hr) { store_hit(hits[i], found, hr); };
+    if (variant == 6) trace_phased<false, true>(S, (uint32_t)n, &work, cnt, done, fetch, commit);
+    else trace_persistent<false, true>(S, (uint32_t)n, &work, cnt, done, fetch, commit);
+    if (counters) { counters[0] = cnt.inner; counters[1] = cnt.leaf; counters[2] = cnt.refs; counters[3] = cnt.tests; counters[4] = cnt.exact; counters[5] = cnt.prefiltered; counters[6] = cnt.wrong; }
+    return done == n ? 0 : 2;
+}
+
+int doh_shadow(void* h, int variant, const float* pa, const float* pb, uint64_t n, uint8_t* visible, uint8_t* status) {
+    const DevScene& S = ((Scene*)h)->S;
+    unsigned long long work = 0; uint32_t done = 0;
+    auto init = [&](uint32_t i, auto& T) {          // Ray(from, to, eps) + Scene::Visibility, as k_trace_shadow does
+        const float ax = pa[3 * (size_t)i], ay = pa[3 * (size_t)i + 1], az = pa[3 * (size_t)i + 2];
+        const float ex = pb[3 * (size_t)i] - ax, ey = pb[3 * (size_t)i + 1] - ay, ez = pb[3 * (size_t)i + 2] - az;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        const float inv = 1.0f / sqrtf(d2), len = sqrtf(d2);
+        const float e20 = S.epsilon * 20.0f;
+        return T.init(S, ax, ay, az, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20, RGK_NO_TRIANGLE);
+    };
+    if (variant == 4) {
+        if (!S.bvh_nodes) return 1;
+        BvhCount cnt{0, 0}; uint32_t deferred = 0;
+        trace_bvh<true, false>(S, (uint32_t)n, &work, cnt, done, deferred,
+            [&](uint32_t i, BvhTraverser<true, false>& T) { return init(i, T); },
+            [&](uint32_t i, bool found, const HitRec&) { visible[i] = found ? 0 : 1; status[i] = 0; },
+            [&](uint32_t i) { status[i] = 1; });
+        return done == n ? 0 : 2;
+    }
+    TravCount cnt{0, 0, 0, 0, 0, 0, 0};
+    auto fetch = [&](uint32_t i, Traverser<true, false>& T) { return init(i, T); };
+    auto commit = [&](uint32_t i, bool found, const HitRec&) { visible[i] = found ? 0 : 1; };
+    if (variant == 6) trace_phased<true, false>(S, (uint32_t)n, &work, cnt, done, fetch, commit);
+    else trace_persistent<true, false>(S, (uint32_t)n, &work, cnt, done, fetch, commit);
+    return done == n ? 0 : 2;
+}
+
+}

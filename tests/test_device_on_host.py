@@ -1,0 +1,159 @@
+"""The DEVICE SOURCE of the traversal (rgk_b200/csrc/trace_device.cuh, bvh_device.cuh) compiled for the host
+(tests/host_cpp/device_shim.h, device_on_host.cpp) and run against the oracle -- not a restatement of it: the kd-tree
+traversal in both control structures with its two conservative pre-filters (bit-exact hit records, oracle-identical
+counters, prefilter_wrong == 0) and the wide-BVH candidate pass with its deferral rules, through the same persistent-warp
+drivers the kernels use (one-lane warps).  Scene arrays come from the product's host commit (rgk_host_scene_*).
+Covers what nvcc compiles except the two inline-PTX helpers (host branches) and real warp divergence."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import checkers
+import raybatches
+from rgk_b200 import device, scenes, standin
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "build", "host", "libdevice_on_host.so")
+vp = C.c_void_p
+
+
+@pytest.fixture(scope="module")
+def doh():
+    if not os.path.exists(SO):
+        import __graft_entry__ as g
+        g.build()
+    lib = C.CDLL(SO)
+    lib.doh_scene_create.restype = vp
+    lib.doh_scene_create.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_float, vp]
+    lib.doh_scene_destroy.argtypes = [vp]
+    lib.doh_closest.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, vp, vp, vp]
+    lib.doh_shadow.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, vp, vp]
+    return lib
+
+
+class Scene:
+    def __init__(self, lib, pack):
+        with checkers.scoped_env(RGK_WIDE_BVH=1):
+            hs = device.HostScene(pack.desc())
+        info = hs.info()
+        self.keep = [np.ascontiguousarray(a) for a in (*hs.kdtree(), *hs.records(), hs.bounds(), *hs.bvh()[:2], np.array(list(info.bbox), np.float32))]
+        nodes, refs, planes, rec, bounds, bnodes, border, bbox = self.keep
+        p = lambda a: a.ctypes.data
+        self.lib = lib
+        self.h = vp(lib.doh_scene_create(p(nodes), len(nodes) // 2, p(refs), len(refs), p(planes), p(rec), p(bounds), info.n_triangles,
+                                         p(bnodes), len(bnodes), p(border), info.epsilon, p(bbox)))
+        hs.close()
+
+    def closest(self, variant, rays, ignore=None):
+        rays = np.ascontiguousarray(rays)
+        hits = np.zeros(len(rays), checkers.HIT_DT); status = np.zeros(len(rays), np.uint8); cnt = np.zeros(8, np.uint64)
+        rc = self.lib.doh_closest(self.h, variant, rays.ctypes.data, None if ignore is None else ignore.ctypes.data, len(rays), hits.ctypes.data,
+                                  status.ctypes.data, cnt.ctypes.data)
+        assert rc == 0
+        return hits, status.astype(bool), cnt
+
+    def shadow(self, variant, a, b):
+        a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+        vis = np.zeros(len(a), np.uint8); status = np.zeros(len(a), np.uint8)
+        assert self.lib.doh_shadow(self.h, variant, a.ctypes.data, b.ctypes.data, len(a), vis.ctypes.data, status.ctypes.data) == 0
+        return vis, status.astype(bool)
+
+    def close(self):
+        self.lib.doh_scene_destroy(self.h)
+
+
+def _same(a, b):
+    return all((a[f].view(np.uint32) == b[f].view(np.uint32)).all() for f in ("triangle", "t", "a", "b", "c"))
+
+
+def _batches(O, h, pack, cfg, w, hgt):
+    ca = cfg.camera_args()
+    cam = O.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
+    rays = raybatches.primary(O, cam, w, hgt, jitter_seed=21)
+    hits, st = O.trace_closest(h, rays, want_stats=True)
+    eps = O.scene_info(h).epsilon
+    brays, ign = raybatches.bounce(rays, hits, O.scene_planes(h)[:, :3], eps, seed=5)
+    bhits, bst = O.trace_closest(h, brays, ign, want_stats=True)
+    light = np.asarray(pack.point_lights[0][0], np.float32) if pack.point_lights else np.array([0, 0.9, 0], np.float32)
+    a, b = raybatches.shadow_segments(brays, bhits, light)
+    return (rays, None, hits, st), (brays, ign, bhits, bst), (a, b, O.trace_shadow(h, a, b))
+
+
+@pytest.mark.parametrize("name", ["sponza", "cornell-box", "material-zoo"])
+def test_device_source_on_the_host(doh, name):
+    if name == "sponza":
+        pack, cfg = standin.sponza(width=240, height=135, multisample=1)
+    elif name == "cornell-box":
+        pack, cfg = scenes.load_builtin("cornell-box", width=128, height=128, multisample=1)
+    else:
+        pack, cfg = scenes.material_zoo(width=128, height=96)
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    S = Scene(doh, pack)
+    prim, bounce, (a, b, want_vis) = _batches(O, h, pack, cfg, cfg.xres, cfg.yres)
+    for rays, ign, want, st in (prim, bounce):
+        for variant in (2, 6):                                   # trace_persistent / trace_phased
+            got, _, cnt = S.closest(variant, rays, ign)
+            assert _same(got, want)
+            # counters of the counting instantiation: the oracle's, and the second pre-filter never wrong
+            assert (int(cnt[0]), int(cnt[1]), int(cnt[2]), int(cnt[3])) == (st.inner, st.leaf, st.refs, st.tests)
+            assert int(cnt[6]) == 0 and int(cnt[4]) + int(cnt[5]) > 0
+        got, deferred, cnt = S.closest(4, rays, ign)             # wide-BVH pass
+        assert deferred.mean() < 0.05
+        assert _same(got[~deferred], want[~deferred])
+        assert 0 < cnt[0] < 40 * len(rays)
+    for variant in (2, 6):
+        vis, _ = S.shadow(variant, a, b)
+        assert (vis == want_vis).all()
+    vis, deferred = S.shadow(4, a, b)
+    assert deferred.mean() < 0.05 and (vis[~deferred] == want_vis[~deferred]).all()
+    S.close()
+
+
+def test_device_source_on_a_triangle_soup(doh):
+    """The stress scene of test_bvh_host.py (tiny, huge, sliver, far, axis-aligned and duplicated triangles; rays aimed at
+    vertices and edges from inside and far outside) through the device source: kd traversal bit-exact with
+    prefilter_wrong == 0, wide-BVH pass equal on everything it would commit."""
+    from test_prefilter_bounds import _scene, _triangles
+    rng = np.random.default_rng(11)
+    tris = _triangles(rng, 2500)
+    tris = np.concatenate([tris, tris[:150], tris[:80] + np.float32(1e-6)])
+    pack = _scene(tris)
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    S = Scene(doh, pack)
+    n = 40000
+    pick = rng.integers(0, len(tris), n)
+    w = rng.dirichlet([0.3, 0.3, 0.3], n).astype(np.float32)
+    kind = rng.integers(0, 4, n)
+    w[kind == 0] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, (kind == 0).sum())]
+    e = kind == 1
+    w[e, 2] = 0; w[e, :2] /= w[e, :2].sum(1, keepdims=True)
+    target = np.einsum("nk,nkd->nd", w, tris[pick]).astype(np.float32)
+    origin = np.where(rng.random((n, 1)) < 0.5, rng.uniform(-1.5, 1.5, (n, 3)), rng.uniform(-2000, 2000, (n, 3))).astype(np.float32)
+    d = target - origin
+    keep = np.linalg.norm(d, axis=1) > 1e-6
+    rays = np.zeros(int(keep.sum()), checkers.RAY_DT)
+    rays["origin"] = origin[keep]
+    rays["direction"] = (d[keep] / np.linalg.norm(d[keep], axis=1, keepdims=True)).astype(np.float32)
+    rays["tfar"] = 10000.0
+    ax = rng.random(len(rays)) < 0.05
+    rays["direction"][ax] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, ax.sum())]
+    ign = np.where(rng.random(len(rays)) < 0.3, pick[keep], 0xFFFFFFFF).astype(np.uint32)
+    want, st = O.trace_closest(h, rays, ign, want_stats=True)
+    for variant in (2, 6):
+        got, _, cnt = S.closest(variant, rays, ign)
+        assert _same(got, want)
+        assert (int(cnt[0]), int(cnt[1]), int(cnt[2]), int(cnt[3])) == (st.inner, st.leaf, st.refs, st.tests) and int(cnt[6]) == 0
+    got, deferred, _ = S.closest(4, rays, ign)
+    assert deferred.mean() < 0.6 and _same(got[~deferred], want[~deferred])
+    a, b = rays["origin"], target[keep]
+    far = np.linalg.norm(a - b, axis=1) > 0.1
+    want_vis = O.trace_shadow(h, a[far], b[far])
+    for variant in (2, 6):
+        assert (S.shadow(variant, a[far], b[far])[0] == want_vis).all()
+    vis, dfs = S.shadow(4, a[far], b[far])
+    assert (vis[~dfs] == want_vis[~dfs]).all()
+    S.close()

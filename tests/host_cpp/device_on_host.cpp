@@ -9,8 +9,25 @@
 #include <vector>
 const uint3 threadIdx = {0, 0, 0};
 #include "bvh_device.cuh"          // includes trace_device.cuh and rgk_internal.h
+#include "probe_device.cuh"        // includes shade_device.cuh
 
 namespace {
+// the shading side of DevScene, prepared from the scene description the way rgk_scene_commit prepares its uploads
+// (rgk_b200/csrc/api.cu); areal lights and scene constants come from the product's own host_scene_commit
+struct ShadeScene {
+    HostScene hs;
+    std::vector<float4> positions, normals, tangents, texels, ltc_M[2];
+    std::vector<float2> texcoords;
+    std::vector<uint4> tri_shade;
+    std::vector<DevMaterial> materials; std::vector<DevTexture> textures; std::vector<DevPointLight> point_lights;
+    std::vector<float> ltc_amp[2];
+    DevScene S{};
+};
+std::vector<float4> pad3(const float* src, uint32_t n) {
+    std::vector<float4> v(n + 1);
+    for (uint32_t i = 0; i < n; i++) v[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.0f);
+    return v;
+}
 struct Scene {
     std::vector<uint2> nodes; std::vector<uint32_t> refs; std::vector<float4> ref_planes, ref_bounds, tri_isect, bvh_nodes, bvh_planes;
     std::vector<uint32_t> bvh_refs;
@@ -52,6 +69,68 @@ void* doh_scene_create(const uint32_t* nodes, uint32_t n_nodes, const uint32_t* 
     return s;
 }
 void doh_scene_destroy(void* h) { delete (Scene*)h; }
+
+void* doh_shade_scene_create(const rgk_scene_desc* d) {
+    ShadeScene* s = new ShadeScene();
+    try { host_scene_commit(d, nullptr, s->hs); } catch (...) { delete s; return nullptr; }
+    DevScene& D = s->S;
+    s->positions = pad3(d->positions, d->n_vertices); s->normals = pad3(d->normals, d->n_vertices); s->tangents = pad3(d->tangents, d->n_vertices);
+    s->texcoords.resize(d->n_vertices + 1);
+    for (uint32_t i = 0; i < d->n_vertices; i++) s->texcoords[i] = make_float2(d->texcoords[2 * i], d->texcoords[2 * i + 1]);
+    s->tri_shade.resize(s->hs.tri_shade.size() / 4 + 1);
+    std::memcpy(s->tri_shade.data(), s->hs.tri_shade.data(), s->hs.tri_shade.size() * 4);
+    s->materials.resize(d->n_materials + 1);
+    std::memcpy(s->materials.data(), d->materials, sizeof(DevMaterial) * d->n_materials);
+    s->textures.resize(d->n_textures + 1);
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const rgk_texture& t = d->textures[i];
+        DevTexture& o = s->textures[i];
+        o.kind = t.kind; o.width = t.width; o.height = t.height; o._pad = 0;
+        o.color[0] = t.color[0]; o.color[1] = t.color[1]; o.color[2] = t.color[2];
+        o.offset = (uint32_t)s->texels.size();
+        if (t.kind == 1) for (size_t k = 0; k < (size_t)t.width * t.height; k++) s->texels.push_back(make_float4(t.texels[3 * k], t.texels[3 * k + 1], t.texels[3 * k + 2], 0.0f));
+    }
+    s->texels.push_back(make_float4(0, 0, 0, 0));
+    s->point_lights.resize(d->n_point_lights + 1);
+    for (uint32_t i = 0; i < d->n_point_lights; i++) {
+        const rgk_point_light& q = d->point_lights[i];
+        for (int k = 0; k < 3; k++) { s->point_lights[i].pos[k] = q.position[k]; s->point_lights[i].color[k] = q.color[k]; }
+        s->point_lights[i].intensity = q.intensity; s->point_lights[i].size = q.size;
+    }
+    const rgk_ltc_table* lt[2] = {&d->ltc_ggx, &d->ltc_beckmann};
+    D.has_ltc = 1;
+    for (int k = 0; k < 2; k++) {
+        if (lt[k]->M && lt[k]->amplitude) {
+            s->ltc_M[k].resize(4096 * 3); s->ltc_amp[k].assign(lt[k]->amplitude, lt[k]->amplitude + 4096);
+            for (int i = 0; i < 4096; i++) {
+                const float* m = lt[k]->M + 9 * i;
+                s->ltc_M[k][3 * i] = make_float4(m[0], m[1], m[2], m[3]); s->ltc_M[k][3 * i + 1] = make_float4(m[4], m[5], m[6], m[7]);
+                s->ltc_M[k][3 * i + 2] = make_float4(m[8], 0.0f, 0.0f, 0.0f);
+            }
+        } else { D.has_ltc = 0; s->ltc_M[k].resize(1); s->ltc_amp[k].resize(1); }
+        D.ltc_M[k] = s->ltc_M[k].data(); D.ltc_amp[k] = s->ltc_amp[k].data();
+    }
+    if (s->hs.areal_lights.empty()) s->hs.areal_lights.resize(1);
+    if (s->hs.areal_tris.empty()) s->hs.areal_tris.resize(1);
+    D.positions = s->positions.data(); D.normals = s->normals.data(); D.tangents = s->tangents.data(); D.texcoords = s->texcoords.data();
+    D.tri_shade = s->tri_shade.data(); D.materials = s->materials.data(); D.textures = s->textures.data(); D.texels = s->texels.data();
+    D.point_lights = s->point_lights.data(); D.areal_lights = s->hs.areal_lights.data(); D.areal_tris = s->hs.areal_tris.data();
+    D.sky_mode = d->sky.mode; D.sky_intensity = d->sky.intensity; D.sky_rotate = d->sky.rotate; D.sky_envmap = d->sky.envmap;
+    for (int k = 0; k < 3; k++) D.sky_color[k] = d->sky.color[k];
+    const rgk_scene_info& in = s->hs.info;
+    D.n_triangles = in.n_triangles; D.n_vertices = d->n_vertices; D.n_materials = d->n_materials; D.n_textures = d->n_textures;
+    D.n_point_lights = d->n_point_lights; D.n_areal_lights = in.n_areal_lights;
+    D.total_point_power = in.total_point_power; D.total_areal_power = in.total_areal_power; D.epsilon = in.epsilon;
+    return s;
+}
+void doh_shade_scene_destroy(void* h) { delete (ShadeScene*)h; }
+// rgk_probe on the host: the same probe_one the k_probe kernel runs per row
+int doh_probe(void* h, uint32_t kind, uint32_t index, const float* in, uint64_t n, float* out) {
+    const DevScene& S = ((ShadeScene*)h)->S;
+    if (kind > RGK_PROBE_FRAME) return 1;
+    for (uint64_t i = 0; i < n; i++) probe_one(S, kind, index, in, i, out);
+    return 0;
+}
 
 static void store_hit(rgk_hit& out, bool found, const HitRec& h) {
     out.triangle = found ? h.tri : RGK_NO_TRIANGLE; out.t = found ? h.t : __int_as_float(0x7f800000);

@@ -17,6 +17,8 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#undef __noinline__
+#define __noinline__
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }

@@ -30,6 +30,10 @@ def doh():
     lib.doh_scene_destroy.argtypes = [vp]
     lib.doh_closest.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, vp, vp, vp]
     lib.doh_shadow.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, vp, vp]
+    lib.doh_shade_scene_create.restype = vp
+    lib.doh_shade_scene_create.argtypes = [vp]
+    lib.doh_shade_scene_destroy.argtypes = [vp]
+    lib.doh_probe.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
     return lib
 
 
@@ -157,3 +161,38 @@ def test_device_source_on_a_triangle_soup(doh):
     vis, dfs = S.shadow(4, a[far], b[far])
     assert (vis[~dfs] == want_vis[~dfs]).all()
     S.close()
+
+
+class HostProber:
+    """Stands in for device.Context in the shading unit tests: .probe() runs probe_one (probe_device.cuh) on the host."""
+
+    def __init__(self, lib, desc):
+        self.lib, self.desc = lib, desc
+        self.h = vp(lib.doh_shade_scene_create(C.byref(desc)))
+        assert self.h.value
+
+    def probe(self, kind, index, rows):
+        from rgk_b200 import abi
+        rows = np.ascontiguousarray(rows, np.float32)
+        win, wout = abi.PROBE_WIDTHS[kind]
+        assert rows.ndim == 2 and rows.shape[1] == win
+        out = np.zeros((len(rows), wout), np.float32)
+        assert self.lib.doh_probe(self.h, kind, index, rows.ctypes.data, len(rows), out.ctypes.data) == 0
+        return out
+
+    def close(self):
+        self.lib.doh_shade_scene_destroy(self.h)
+
+
+def test_shading_device_source_on_the_host(doh, oracle):
+    """The unit-level shading parity tests of test_gpu_shading.py (every live BxDF incl. the LTC lobes, textures and bump
+    slopes, light picking, envmap sky, local frames) with shade_device.cuh compiled for the host instead of the GPU: same
+    inputs, same golden fixture, same tolerances."""
+    import test_gpu_shading as T
+    pack, cfg = scenes.material_zoo(width=48, height=32, multisample=4, lens=0.05)
+    desc = pack.desc()
+    ctx = HostProber(doh, desc)
+    zoo = (pack, cfg, desc, oracle.scene_create(desc), np.load(os.path.join(T.G, "zoo.npz")))
+    T.test_bxdf_value_and_sample_all_kinds(ctx, oracle, zoo)
+    T.test_textures_lights_sky_frames(ctx, oracle, zoo)
+    ctx.close()

@@ -3,13 +3,26 @@
 // its deferral rules, driven by the SAME persistent-warp drivers the kernels use, over arrays produced by the product's own
 // host scene commit (rgk_host_scene_*).  tests/test_device_on_host.py compares the results with the oracle.
 //
-// build: g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -I/usr/local/cuda/include -Irgk_b200/csrc -Iinclude
+// build (__graft_entry__.build): python tests/host_cpp/gen_host_sources.py rgk_b200/csrc build/host/gen, then
+//        g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -I/usr/local/cuda/include -Ibuild/host/gen -Iinclude
 //        tests/host_cpp/device_on_host.cpp -o build/host/libdevice_on_host.so      (-ffp-contract=off = nvcc -fmad=false)
 #include "device_shim.h"
+#include <algorithm>
+#include <cstdio>
+#include <string>
 #include <vector>
-const uint3 threadIdx = {0, 0, 0};
 #include "bvh_device.cuh"          // includes trace_device.cuh and rgk_internal.h
 #include "probe_device.cuh"        // includes shade_device.cuh
+#include "render_host.inc"         // render.cu with its launches rewritten (gen_host_sources.py): kernels + host loop
+
+// the two helpers of api.cu that render.cu calls, for the host build
+rgk_status rgk_fail(rgk_context* ctx, rgk_status s, const std::string& msg) { if (ctx) ctx->last_error = msg; return s; }
+void* rgk_scratch(rgk_context* ctx, int slot, size_t bytes) {
+    if (ctx->scratch_size[slot] >= bytes && ctx->scratch[slot]) return ctx->scratch[slot];
+    std::free(ctx->scratch[slot]);
+    ctx->scratch[slot] = std::calloc(std::max<size_t>(bytes, 256), 1); ctx->scratch_size[slot] = std::max<size_t>(bytes, 256);
+    return ctx->scratch[slot];
+}
 
 namespace {
 // the shading side of DevScene, prepared from the scene description the way rgk_scene_commit prepares its uploads
@@ -21,6 +34,8 @@ struct ShadeScene {
     std::vector<uint4> tri_shade;
     std::vector<DevMaterial> materials; std::vector<DevTexture> textures; std::vector<DevPointLight> point_lights;
     std::vector<float> ltc_amp[2];
+    std::vector<uint2> nodes; std::vector<float4> ref_planes, ref_bounds, tri_isect, bvh_nodes, bvh_planes;
+    BvhStats bvh_stats{};
     DevScene S{};
 };
 std::vector<float4> pad3(const float* src, uint32_t n) {
@@ -117,6 +132,27 @@ void* doh_shade_scene_create(const rgk_scene_desc* d) {
     D.point_lights = s->point_lights.data(); D.areal_lights = s->hs.areal_lights.data(); D.areal_tris = s->hs.areal_tris.data();
     D.sky_mode = d->sky.mode; D.sky_intensity = d->sky.intensity; D.sky_rotate = d->sky.rotate; D.sky_envmap = d->sky.envmap;
     for (int k = 0; k < 3; k++) D.sky_color[k] = d->sky.color[k];
+    // traversal arrays, as rgk_scene_commit lays them out
+    const HostScene& hs = s->hs;
+    s->nodes.resize(hs.nodes.size() / 2);
+    for (size_t i = 0; i < s->nodes.size(); i++) s->nodes[i] = make_uint2(hs.nodes[2 * i], hs.nodes[2 * i + 1]);
+    s->ref_planes.resize(hs.refs.size() + 1); s->ref_bounds.resize(hs.refs.size() + 1);
+    for (size_t j = 0; j < hs.refs.size(); j++) {
+        const float* q = &hs.planes[4 * (size_t)hs.refs[j]]; const float* b = &hs.tri_bounds[4 * (size_t)hs.refs[j]];
+        s->ref_planes[j] = make_float4(q[0], q[1], q[2], q[3]); s->ref_bounds[j] = make_float4(b[0], b[1], b[2], b[3]);
+    }
+    s->tri_isect.resize(hs.tri_isect.size() / 4 + 1);
+    std::memcpy(s->tri_isect.data(), hs.tri_isect.data(), hs.tri_isect.size() * 4);
+    D.nodes = s->nodes.data(); D.refs = hs.refs.data(); D.ref_planes = s->ref_planes.data(); D.ref_bounds = s->ref_bounds.data(); D.tri_isect = s->tri_isect.data();
+    if (!hs.bvh_nodes.empty()) {
+        s->bvh_nodes.resize(hs.bvh_nodes.size() / 4);
+        std::memcpy(s->bvh_nodes.data(), hs.bvh_nodes.data(), hs.bvh_nodes.size() * 4);
+        s->bvh_planes.resize(hs.bvh_order.size());
+        for (size_t j = 0; j < hs.bvh_order.size(); j++) { const float* q = &hs.planes[4 * (size_t)hs.bvh_order[j]]; s->bvh_planes[j] = make_float4(q[0], q[1], q[2], q[3]); }
+        D.bvh_nodes = s->bvh_nodes.data(); D.bvh_refs = hs.bvh_order.data(); D.bvh_planes = s->bvh_planes.data();
+    }
+    for (int k = 0; k < 6; k++) D.bb[k] = hs.info.bbox[k];
+    D.n_nodes = hs.info.n_nodes; D.n_refs = hs.info.n_refs; D.refill_threshold = 1;
     const rgk_scene_info& in = s->hs.info;
     D.n_triangles = in.n_triangles; D.n_vertices = d->n_vertices; D.n_materials = d->n_materials; D.n_textures = d->n_textures;
     D.n_point_lights = d->n_point_lights; D.n_areal_lights = in.n_areal_lights;
@@ -124,6 +160,32 @@ void* doh_shade_scene_create(const rgk_scene_desc* d) {
     return s;
 }
 void doh_shade_scene_destroy(void* h) { delete (ShadeScene*)h; }
+
+// One RenderDriver round through render_round_impl -- the product's own host loop and kernels -- with caller-supplied
+// sampler tables (RGK_SAMPLER_TABLES; t1[pixel][dim][set], t2[pixel][dim][set][2]).  out_bvh: rays through the wide-BVH
+// kernels and how many of them were deferred to the kd arbiter (both 0 when the scene was committed without RGK_WIDE_BVH).
+int doh_render_round(void* h, const rgk_camera* cam, const rgk_render_params* p, const rgk_task* tasks, uint32_t n_tasks, uint32_t seedstart,
+                     uint32_t seedcount_base, const float* t1, const float* t2, uint32_t n1d, uint32_t n2d, uint64_t n_pixels, float* rgb,
+                     uint32_t* count, rgk_round_stats* stats, uint64_t* out_bvh) {
+    ShadeScene* s = (ShadeScene*)h;
+    rgk_context ctx;
+    ctx.dev = s->S; ctx.has_scene = true;
+    ctx.dev.refill_threshold = 1;
+    if (s->S.n_point_lights) ctx.first_point_light = s->point_lights[0];
+    s->bvh_stats = BvhStats{0, 0, 0, 0};
+    ctx.d_bvh_stats = s->S.bvh_nodes ? &s->bvh_stats : nullptr;
+    if (t1 && t2) {
+        ctx.d_user_t1 = const_cast<float*>(t1); ctx.d_user_t2 = const_cast<float*>(t2);
+        ctx.user_n1d = n1d; ctx.user_n2d = n2d; ctx.user_ss = host_sampler_set_size(p->multisample); ctx.user_npix = n_pixels;
+    }
+    rgk_round_stats local{};
+    const rgk_status st = render_round_impl(&ctx, cam, p, tasks, n_tasks, seedstart, seedcount_base, rgb, count, stats ? stats : &local);
+    if (st != RGK_OK) std::fprintf(stderr, "doh_render_round: %s\n", ctx.last_error.c_str());
+    if (out_bvh) { out_bvh[0] = s->bvh_stats.rays; out_bvh[1] = s->bvh_stats.ambiguous; }
+    free_path_buffers(&ctx);
+    for (auto& q : ctx.scratch) if (q) std::free(q);
+    return (int)st;
+}
 // rgk_probe on the host: the same probe_one the k_probe kernel runs per row
 int doh_probe(void* h, uint32_t kind, uint32_t index, const float* in, uint64_t n, float* out) {
     const DevScene& S = ((ShadeScene*)h)->S;

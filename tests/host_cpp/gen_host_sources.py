@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Host build of the wavefront renderer for the CPU tests: copies rgk_b200/csrc/{*.cuh,*.h,render.cu} into build/host/gen/
+with three textual changes that g++ needs -- the product sources are not touched:
+  * `kernel<<<grid, block, smem, stream>>>(args)`  ->  `doh_launch(kernel, grid, block, smem, stream, args)`  (device_shim.h runs
+    the kernel as a loop over blocks and threads);
+  * `threadIdx.x & 31` -> `0u`: a warp has one lane in the emulation (ballots return bit 0, shuffles their argument);
+  * `extern __shared__ T name[];` -> `static T name[1];` (the two kernels that cooperate through shared memory, k_sampler_mt and
+    k_bin, are compiled but never run: the tests feed caller-supplied sampler tables and switch the binning off).
+usage: gen_host_sources.py <csrc dir> <out dir>"""
+import os, re, sys
+
+src, out = sys.argv[1], sys.argv[2]
+os.makedirs(out, exist_ok=True)
+launch = re.compile(r'(\bk_\w+(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\(', re.S)
+n_launch = 0
+for name in sorted(os.listdir(src)):
+    if not (name.endswith((".cuh", ".h")) or name == "render.cu"):
+        continue
+    s = open(os.path.join(src, name)).read()
+    s, k = launch.subn(lambda m: "doh_launch(%s, %s, " % (m.group(1), m.group(2)), s)
+    n_launch += k
+    s = s.replace("(threadIdx.x & 31)", "(0u)").replace("threadIdx.x & 31", "0u")
+    s = re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'static \1 \2[1];', s)
+    dst = os.path.join(out, name if name != "render.cu" else "render_host.inc")
+    if not os.path.exists(dst) or open(dst).read() != s:
+        open(dst, "w").write(s)
+assert n_launch >= 30, n_launch

@@ -34,6 +34,7 @@ def doh():
     lib.doh_shade_scene_create.argtypes = [vp]
     lib.doh_shade_scene_destroy.argtypes = [vp]
     lib.doh_probe.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
+    lib.doh_render_round.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
     return lib
 
 
@@ -196,3 +197,72 @@ def test_shading_device_source_on_the_host(doh, oracle):
     T.test_bxdf_value_and_sample_all_kinds(ctx, oracle, zoo)
     T.test_textures_lights_sky_frames(ctx, oracle, zoo)
     ctx.close()
+
+
+def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=False, reverse=None):
+    """One round of render_round_impl compiled for the host (kernels + host loop of render.cu), fed with the oracle's
+    StratifiedSampler tables, next to the oracle's own round."""
+    from rgk_b200 import abi
+    from test_gpu_render import _pixel_seeds
+    desc = pack.desc()
+    # one-lane warps: refill after every ray; no k_bin (it cooperates through shared memory)
+    with checkers.scoped_env(RGK_WIDE_BVH=1 if wide_bvh else None, RGK_BIN=0, RGK_REFILL_COHERENT=1, RGK_REFILL_INCOHERENT=1, RGK_REFILL_SHADOW=1):
+        h = vp(doh.doh_shade_scene_create(C.byref(desc)))
+        assert h.value
+        ho = oracle.scene_create(desc)
+        ca = cfg.camera_args()
+        cam = oracle.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
+        p = cfg.params(abi.SAMPLER_TABLES)
+        if depth is not None:
+            p.depth = depth
+        if reverse is not None:
+            p.reverse = reverse
+        tasks = oracle.generate_tasks(32, p.xres, p.yres)
+        lens = 1 if ca["lens_size"] != 0.0 else 0
+        n1d, n2d = 1 + p.depth, 4 + lens + p.depth + p.reverse
+        seeds = _pixel_seeds(tasks, 42, seedcount_base)
+        t1, t2 = oracle.sampler_tables(seeds, p.multisample, n1d, n2d)
+        t1 = np.ascontiguousarray(t1, np.float32); t2 = np.ascontiguousarray(t2, np.float32)
+        rgb = np.zeros((p.yres, p.xres, 3), np.float32); cnt = np.zeros((p.yres, p.xres), np.uint32)
+        st = abi.RoundStats(); bvh = np.zeros(2, np.uint64)
+        rc = doh.doh_render_round(h, C.byref(cam), C.byref(p), tasks, len(tasks), 42, seedcount_base, t1.ctypes.data, t2.ctypes.data, n1d, n2d,
+                                  len(seeds), rgb.ctypes.data, cnt.ctypes.data, C.byref(st), bvh.ctypes.data)
+        assert rc == 0
+        po = cfg.params(abi.SAMPLER_MT19937); po.depth = p.depth; po.reverse = p.reverse
+        fo, co, so = oracle.render_round(ho, cam, po, tasks, seedcount_base=seedcount_base)
+        doh.doh_shade_scene_destroy(h)
+    return (rgb, cnt, st, bvh), (fo, co, so)
+
+
+def _zoo():
+    return scenes.material_zoo(width=40, height=24, multisample=4, recursion_max=3, lens=0.04)
+
+
+def _cornell():
+    return scenes.load_builtin("cornell-box", width=48, height=48, multisample=4)          # recursion-max 40, Russian roulette
+
+
+def _sponza():
+    return standin.sponza(width=64, height=36, multisample=4)
+
+
+@pytest.mark.parametrize("scene,wide_bvh,reverse", [(_zoo, False, 0), (_zoo, True, 0), (_cornell, False, 0), (_cornell, True, 0),
+                                                    (_sponza, True, 0), (_cornell, False, 2), (_zoo, False, 1)])
+def test_wavefront_device_source_on_the_host(doh, oracle, scene, wide_bvh, reverse):
+    """The whole wavefront -- render.cu's kernels AND its host loop -- on the CPU, with the oracle's sampler tables: pixel
+    setup, camera rays, closest-hit (kd, or wide BVH + arbiter), k_shade (BxDFs, textures, NEE, roulette), shadow resolve,
+    accumulation; with reverse > 0 the bidirectional mode's light paths, splats and connections.  The libm is the oracle's
+    here, so the framebuffer must be the oracle's BIT FOR BIT: whatever the GPU image differs by is CUDA's sinf/cosf."""
+    pack, cfg = scene()
+    (rgb, cnt, st, bvh), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=7, wide_bvh=wide_bvh, reverse=reverse)
+    assert np.array_equal(cnt, co)
+    assert int(st.closest_rays) == int(so.closest_rays)
+    assert int(st.shadow_rays) + int(st.shadow_rays_skipped) == int(so.shadow_rays)
+    assert (bvh[0] > 0) == wide_bvh
+    if reverse:
+        # splats and per-vertex sums are accumulated in another order than the reference's sequential loop (atomics, one
+        # thread per connection): float addition does not associate, a few ulps of the pixel sum remain
+        assert (np.abs(rgb - fo) <= 2e-5 * np.maximum(np.abs(fo), float(fo.mean()))).all()
+        return
+    same = rgb.view(np.uint32) == fo.view(np.uint32)
+    assert same.all(), f"{(~same).sum()} of {same.size} framebuffer words differ; max abs diff {np.abs(rgb - fo).max()}"

@@ -266,3 +266,36 @@ def test_wavefront_device_source_on_the_host(doh, oracle, scene, wide_bvh, rever
         return
     same = rgb.view(np.uint32) == fo.view(np.uint32)
     assert same.all(), f"{(~same).sum()} of {same.size} framebuffer words differ; max abs diff {np.abs(rgb - fo).max()}"
+
+
+def test_reference_scene_files_through_the_wavefront_on_the_host(doh, oracle):
+    """Every scene file of the reference that loads here (its own JSON configs: OBJ meshes, MTL materials, image and bump
+    textures, point / sphere / areal lights, envmap and colour skies, thin-glass flag, unidirectional and bidirectional) at
+    32x24x2: the device source on the host against the oracle -- bit for bit where reverse == 0, 2e-5 otherwise.
+    Needs /root/reference (this container only)."""
+    import glob
+    import warnings
+    from rgk_b200 import scene
+    done = []
+    for path in sorted(glob.glob("/root/reference/scenes/*.json")):
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                pack, cfg = scene.load_json_config(path, overrides={"output-width": 32, "output-height": 24, "multisample": 2})
+        except (scene.ConfigFileException, FileNotFoundError):
+            continue
+        if cfg.recursion_level + cfg.reverse > 59:
+            continue
+        for wide_bvh in (False, True):
+            (rgb, cnt, st, bvh), (fo, co, so) = _host_round(doh, oracle, pack, cfg, wide_bvh=wide_bvh)
+            name = (os.path.basename(path), wide_bvh)
+            assert np.array_equal(cnt, co), name
+            assert int(st.closest_rays) == int(so.closest_rays), name
+            if cfg.reverse:
+                assert (np.abs(rgb - fo) <= 2e-5 * np.maximum(np.abs(fo), float(fo.mean()) + 1e-6)).all(), name
+            else:
+                assert np.array_equal(rgb.view(np.uint32), fo.view(np.uint32)), name
+        done.append((os.path.basename(path), cfg.reverse))
+    if not done:
+        pytest.skip("no reference scenes here")
+    assert len(done) >= 15

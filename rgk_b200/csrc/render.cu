@@ -1027,7 +1027,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const size_t bin_items = env_size("RGK_BIN_ITEMS", 2048);   // path slots per reordering group
     // the wide-BVH kernels' iterations are longer than the kd ones: refilling coherent warps at 24 idle lanes instead of 32
     // measured -1.9 ms per round (profiles/r1_bvh_sweep.json); the other thresholds are flat
-    const bool bvh_round = ctx->dev.bvh_nodes != nullptr && !ctx->counting && !P->reverse;
+    const bool bvh_round = ctx->dev.bvh_nodes != nullptr && !ctx->counting;
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", bvh_round ? 24 : 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 24);
     const uint32_t refill_shadow = (uint32_t)env_size("RGK_REFILL_SHADOW", 12);   // any-hit rays end at very different times: refill sooner
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
@@ -1131,6 +1131,19 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         uint32_t count = (uint32_t)npaths;
         const uint32_t* queue = nullptr;
         uint32_t* qnext = B.queue_a;
+        // opt-in wide BVH (RGK_WIDE_BVH=1 at commit): BVH pass + kd arbiter pass per closest-hit / shadow launch.  The counting
+        // instantiation stays on the kd kernels, and so do the bidirectional mode's shadow resolves and connection segments
+        // (its closest-hit launches use the BVH)
+        const bool use_bvh = ctx->dev.bvh_nodes != nullptr && !counting;
+        // the arbiter sees ~4e-4 of the rays, all of them long (grazing) traversals: spread them over many warps
+        const int arb_grid = 148 * (int)std::max<size_t>(1, env_size("RGK_ARB_GRID", 8)), bvh_minb = (int)env_size("RGK_BVH_MINB", 6);
+        uint32_t* arb_list = nullptr; unsigned long long* arb_ctr = nullptr;
+        if (use_bvh) {
+            arb_list = (uint32_t*)rgk_scratch(ctx, 4, npaths * sizeof(uint32_t));
+            unsigned long long* s3 = (unsigned long long*)rgk_scratch(ctx, 3, 256);
+            if (!arb_list || !s3) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
+            arb_ctr = s3 + 8;               // [0] closest arbiter work, [1] its count, [2] shadow arbiter work, [3] its count
+        }
         if (P->reverse) {
             // ---- bidirectional mode (reverse_device.cuh): camera paths kept vertex by vertex, then the light paths,
             // then the connections, then the per-vertex sums
@@ -1148,7 +1161,14 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 dev.refill_threshold = coherent ? refill_coherent : refill_incoherent;
                 const int g = (int)std::min<uint64_t>(tgrid, ((uint64_t)n + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_CLOSEST);
-                if (coherent) k_closest<false, RGK_COH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, nullptr);
+                if (use_bvh) {
+                    cudaMemsetAsync(arb_ctr, 0, 2 * sizeof(unsigned long long), ctx->stream);
+                    if (bvh_minb >= 8) k_closest_bvh<8><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                    else k_closest_bvh<6><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                    k_closest_arb<RGK_INCOH_MINB><<<std::min(g, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
+                    ctx->launches++;
+                }
+                else if (coherent) k_closest<false, RGK_COH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, nullptr);
                 else k_closest<false, RGK_INCOH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, nullptr);
                 pool.end(ctx->stream);
                 ctx->launches++; total.closest_launches++; total.closest_rays += n;
@@ -1204,18 +1224,6 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             cs = counts(dummy, lcount); if (cs != RGK_OK) return cs;
             total.shadow_rays += lcount;                       // connection rays (Visibility calls of phases 2 and 3)
             count = 0;
-        }
-        // opt-in wide BVH (RGK_WIDE_BVH=1 at commit): BVH pass + kd arbiter pass per traversal launch; the counting
-        // instantiation and the bidirectional mode stay on the kd kernels
-        const bool use_bvh = ctx->dev.bvh_nodes != nullptr && !counting;
-        // the arbiter sees ~4e-4 of the rays, all of them long (grazing) traversals: spread them over many warps
-        const int arb_grid = 148 * (int)std::max<size_t>(1, env_size("RGK_ARB_GRID", 8)), bvh_minb = (int)env_size("RGK_BVH_MINB", 6);
-        uint32_t* arb_list = nullptr; unsigned long long* arb_ctr = nullptr;
-        if (use_bvh) {
-            arb_list = (uint32_t*)rgk_scratch(ctx, 4, npaths * sizeof(uint32_t));
-            unsigned long long* s3 = (unsigned long long*)rgk_scratch(ctx, 3, 256);
-            if (!arb_list || !s3) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
-            arb_ctr = s3 + 8;               // [0] closest arbiter work, [1] its count, [2] shadow arbiter work, [3] its count
         }
         const uint32_t* shade_q = nullptr;          // the live queue in path order, when the traversal queue is direction-sorted
         uint32_t* unext = B.queue_ua;

@@ -247,7 +247,7 @@ def _sponza():
 
 
 @pytest.mark.parametrize("scene,wide_bvh,reverse", [(_zoo, False, 0), (_zoo, True, 0), (_cornell, False, 0), (_cornell, True, 0),
-                                                    (_sponza, True, 0), (_cornell, False, 2), (_zoo, False, 1)])
+                                                    (_sponza, True, 0), (_cornell, False, 2), (_zoo, False, 1), (_cornell, True, 2), (_zoo, True, 1)])
 def test_wavefront_device_source_on_the_host(doh, oracle, scene, wide_bvh, reverse):
     """The whole wavefront -- render.cu's kernels AND its host loop -- on the CPU, with the oracle's sampler tables: pixel
     setup, camera rays, closest-hit (kd, or wide BVH + arbiter), k_shade (BxDFs, textures, NEE, roulette), shadow resolve,

@@ -299,3 +299,13 @@ def test_reference_scene_files_through_the_wavefront_on_the_host(doh, oracle):
     if not done:
         pytest.skip("no reference scenes here")
     assert len(done) >= 15
+
+
+def test_host_loop_chunking_on_the_host(doh, oracle):
+    """render_round_impl's chunk loop (RGK_CHUNK_PATHS far below the paths of the call: many chunks, tiles split across
+    them) gives the same bits as one chunk -- the host loop of render.cu itself, run on the CPU."""
+    pack, cfg = _zoo()
+    with checkers.scoped_env(RGK_CHUNK_PATHS=700):
+        (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=3, wide_bvh=True)
+    assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
+    assert int(st.closest_launches) > cfg.recursion_level                          # more than one chunk was traced

@@ -146,6 +146,11 @@ def test_device_source_on_a_triangle_soup(doh):
     rays["tfar"] = 10000.0
     ax = rng.random(len(rays)) < 0.05
     rays["direction"][ax] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, ax.sum())]
+    # a third of the rays with a bounded [tnear, tfar] that often ends on or just before the target
+    bounded = rng.random(len(rays)) < 0.33
+    dist = np.linalg.norm(d[keep], axis=1).astype(np.float32)
+    rays["tnear"][bounded] = (dist[bounded] * rng.uniform(0.0, 0.6, bounded.sum())).astype(np.float32)
+    rays["tfar"][bounded] = (dist[bounded] * rng.choice([0.8, 1.0, 1.0, 1.2], bounded.sum())).astype(np.float32)
     ign = np.where(rng.random(len(rays)) < 0.3, pick[keep], 0xFFFFFFFF).astype(np.uint32)
     want, st = O.trace_closest(h, rays, ign, want_stats=True)
     for variant in (2, 6):

@@ -655,6 +655,9 @@ __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* 
 #ifndef RGK_SHADE_MINB
 #define RGK_SHADE_MINB 5   // <= 102 registers: 5 CTAs of 128 threads per SM
 #endif
+// LAST: the launch of the last bounce (every vertex of the queue has n == depth, so no continuation is ever sampled): the same
+// results from a kernel without the BxDF sampling code (A/B knob RGK_SHADE_LAST=1; off until it is measured)
+template <bool LAST>
 __global__ void __launch_bounds__(128, RGK_SHADE_MINB)
 k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count,
         uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ next_unsorted, unsigned long long* counters) {
@@ -764,7 +767,7 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                 // ---- continuation
                 // A path whose next vertex would exceed recursion-max ends here whatever BxDF::sample returns (the loop
                 // condition `n < depth`, src/path_tracer.cpp:122): nothing of the continuation is observable, skip it.
-                if (n < R.depth) {
+                if (!LAST && n < R.depth) {
                     V3 dir; RGB tcf; bool may_leak;
                     bxdf_sample(S, mat, VrL, uv, sample, dir, tcf, may_leak, pre);
                     const bool inside = dir.z < 0;
@@ -1029,6 +1032,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     // measured -1.9 ms per round (profiles/r1_bvh_sweep.json); the other thresholds are flat
     const bool bvh_round = ctx->dev.bvh_nodes != nullptr && !ctx->counting;
     const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", bvh_round ? 24 : 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 24);
+    const bool shade_last = env_size("RGK_SHADE_LAST", 0) != 0;
     const uint32_t refill_shadow = (uint32_t)env_size("RGK_REFILL_SHADOW", 12);   // any-hit rays end at very different times: refill sooner
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
@@ -1258,7 +1262,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             R.binning = (bin_next ? 1u : 0u) | (bin_shadow ? 2u : 0u);
             if (bin_next) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
             if (bin_shadow) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
-            k_shade<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
+            if (last_bounce && shade_last) k_shade<true><<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
+            else k_shade<false><<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
             if (bin_next) {
                 k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, B.counters + C_NEXT);
                 ctx->launches++;

@@ -11,7 +11,7 @@ import os, re, sys
 
 src, out = sys.argv[1], sys.argv[2]
 os.makedirs(out, exist_ok=True)
-launch = re.compile(r'(\bk_\w+(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\(', re.S)
+launch = re.compile(r'(\bk_\w+(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\(', re.S)     # kernel, optional template arguments, launch configuration
 n_launch = 0
 for name in sorted(os.listdir(src)):
     if not (name.endswith((".cuh", ".h")) or name == "render.cu"):

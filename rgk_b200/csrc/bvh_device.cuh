@@ -23,7 +23,9 @@ struct BvhCount { uint32_t nodes, tests; };
 constexpr uint32_t BVH_DONE = 0x7fffffffu;      // also the code of an empty child slot
 constexpr uint32_t BVH_LEAF = 0x80000000u;
 
-template <bool ANY, bool COUNT>
+// SORT = false (any-hit only, A/B knob RGK_BVH_SHADOW_NOSORT): children are entered in slot order instead of by entry
+// distance -- the answer of an any-hit query does not depend on the order (a firm hit anywhere blocks, border hits alone defer)
+template <bool ANY, bool COUNT, bool SORT = true>
 struct BvhTraverser {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz;
     float opx, opy, opz, omx, omy, omz;          // o + m, o - m
@@ -120,12 +122,19 @@ struct BvhTraverser {
         float t2 = child_entry(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z);
         float t3 = child_entry(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w);
         uint32_t c0 = __float_as_uint(cf.x), c1 = __float_as_uint(cf.y), c2 = __float_as_uint(cf.z), c3 = __float_as_uint(cf.w);
+        const float inf = __int_as_float(0x7f800000);
+        if (!SORT) {
+            uint32_t nx = BVH_DONE; float tx = inf;
+#define RGK_ENTER(t, c) if (t < inf) { if (nx != BVH_DONE) { K.e[sp] = make_uint2(nx, __float_as_uint(tx)); ++sp; } nx = c; tx = t; }
+            RGK_ENTER(t0, c0) RGK_ENTER(t1, c1) RGK_ENTER(t2, c2) RGK_ENTER(t3, c3)
+#undef RGK_ENTER
+            return nx != BVH_DONE ? nx : pop(K);
+        }
         // sorting network (0,1)(2,3)(0,2)(1,3)(1,2): ascending entry distance, misses (+inf) last
 #define RGK_CSWAP(ta, ca, tb, cb) { const bool s_ = tb < ta; const float tt_ = s_ ? tb : ta; tb = s_ ? ta : tb; ta = tt_; \
                                     const uint32_t cc_ = s_ ? cb : ca; cb = s_ ? ca : cb; ca = cc_; }
         RGK_CSWAP(t0, c0, t1, c1) RGK_CSWAP(t2, c2, t3, c3) RGK_CSWAP(t0, c0, t2, c2) RGK_CSWAP(t1, c1, t3, c3) RGK_CSWAP(t1, c1, t2, c2)
 #undef RGK_CSWAP
-        const float inf = __int_as_float(0x7f800000);
         if (!(t0 < inf)) return pop(K);
         if (t3 < inf) { K.e[sp] = make_uint2(c3, __float_as_uint(t3)); ++sp; }
         if (t2 < inf) { K.e[sp] = make_uint2(c2, __float_as_uint(t2)); ++sp; }
@@ -207,10 +216,10 @@ struct BvhTraverser {
 
 // Persistent-warp driver, same work distribution as trace_phased.  `fetch(i, T)` loads item i and calls T.init;
 // `commit(i, found, res)` stores a settled result; `defer(i)` hands an ambiguous item to the kd-tree pass.
-template <bool ANY, bool COUNT, class Fetch, class Commit, class Defer>
+template <bool ANY, bool COUNT, bool SORT = true, class Fetch, class Commit, class Defer>
 __device__ __forceinline__ void trace_bvh(const DevScene& S, uint32_t count, unsigned long long* work, BvhCount& cnt, uint32_t& done,
                                           uint32_t& deferred, Fetch fetch, Commit commit, Defer defer) {
-    BvhTraverser<ANY, COUNT> T;
+    BvhTraverser<ANY, COUNT, SORT> T;
     TravStack K;
     const unsigned lane = threadIdx.x & 31;
     const float eps = S.epsilon;

@@ -556,15 +556,15 @@ k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const
         [&](uint32_t i, bool found, const HitRec& h) { io.commit(arb[i], found, h); });
 }
 
-template <int MINB>
+template <int MINB, bool SORT>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_shadow_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, BvhStats* stats,
              uint32_t const_light, float4 cl_pos, uint32_t* __restrict__ arb, uint32_t* arb_count) {
     BvhCount cnt{0, 0};
     uint32_t mine = 0, deferred = 0;
     const ShadowIO io{B, clampv, const_light, cl_pos};
-    trace_bvh<true, false>(S, count, work, cnt, mine, deferred,
-        [&](uint32_t i, BvhTraverser<true, false>& T) { return io.fetch(S, __ldg(queue + i), T); },
+    trace_bvh<true, false, SORT>(S, count, work, cnt, mine, deferred,
+        [&](uint32_t i, BvhTraverser<true, false, SORT>& T) { return io.fetch(S, __ldg(queue + i), T); },
         [&](uint32_t i, bool blocked, const HitRec&) { io.commit(__ldg(queue + i), blocked); },
         [&](uint32_t i) { arb[atomicAdd(arb_count, 1u)] = __ldg(queue + i); });
     flush_bvh_counts(mine, deferred, stats);
@@ -1141,6 +1141,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         const bool use_bvh = ctx->dev.bvh_nodes != nullptr && !counting;
         // the arbiter sees ~4e-4 of the rays, all of them long (grazing) traversals: spread them over many warps
         const int arb_grid = 148 * (int)std::max<size_t>(1, env_size("RGK_ARB_GRID", 8)), bvh_minb = (int)env_size("RGK_BVH_MINB", 6);
+        const bool bvh_shadow_nosort = env_size("RGK_BVH_SHADOW_NOSORT", 0) != 0;     // A/B knob: any-hit children in slot order
         uint32_t* arb_list = nullptr; unsigned long long* arb_ctr = nullptr;
         if (use_bvh) {
             arb_list = (uint32_t*)rgk_scratch(ctx, 4, npaths * sizeof(uint32_t));
@@ -1283,9 +1284,11 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
                 if (use_bvh) {
-                    if (bvh_minb >= 8) k_shadow_bvh<8><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                    if (bvh_shadow_nosort) k_shadow_bvh<6, false><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                                                                                                R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
+                    else if (bvh_minb >= 8) k_shadow_bvh<8, true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
                                                                                               R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    else k_shadow_bvh<6><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                    else k_shadow_bvh<6, true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
                                                                                 R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
                     k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 3), P->clamp, arb_ctr + 2,
                                                                                                      R.const_light, R.cl_pos);

@@ -22,6 +22,8 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#undef __shared__
+#undef __launch_bounds__
 #define __shared__ static
 #define __launch_bounds__(...)
 #undef __noinline__

@@ -21,7 +21,6 @@
 
 struct BvhCount { uint32_t nodes, tests; };
 constexpr uint32_t BVH_DONE = 0x7fffffffu;      // also the code of an empty child slot
-constexpr uint32_t BVH_LEAF = 0x80000000u;
 
 // SORT = false (any-hit only, A/B knob RGK_BVH_SHADOW_NOSORT): children are entered in slot order instead of by entry
 // distance -- the answer of an any-hit query does not depend on the order (a firm hit anywhere blocks, border hits alone defer)

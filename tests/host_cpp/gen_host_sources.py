@@ -4,8 +4,9 @@ with three textual changes that g++ needs -- the product sources are not touched
   * `kernel<<<grid, block, smem, stream>>>(args)`  ->  `doh_launch(kernel, grid, block, smem, stream, args)`  (device_shim.h runs
     the kernel as a loop over blocks and threads);
   * `threadIdx.x & 31` -> `0u`: a warp has one lane in the emulation (ballots return bit 0, shuffles their argument);
-  * `extern __shared__ T name[];` -> `static T name[1];` (the two kernels that cooperate through shared memory, k_sampler_mt and
-    k_bin, are compiled but never run: the tests feed caller-supplied sampler tables and switch the binning off).
+  * `extern __shared__ T name[];` -> `static T name[65536];` (k_sampler_mt's tables are private to a lane, so it runs thread by
+    thread like the rest; only k_bin, whose threads cooperate through shared memory, is compiled but never run: the tests
+    switch the binning off).
 usage: gen_host_sources.py <csrc dir> <out dir>"""
 import os, re, sys
 
@@ -20,7 +21,7 @@ for name in sorted(os.listdir(src)):
     s, k = launch.subn(lambda m: "doh_launch(%s, %s, " % (m.group(1), m.group(2)), s)
     n_launch += k
     s = s.replace("(threadIdx.x & 31)", "(0u)").replace("threadIdx.x & 31", "0u")
-    s = re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'static \1 \2[1];', s)
+    s = re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'static \1 \2[65536];', s)      # 256 KB: more than any launch asks for
     dst = os.path.join(out, name if name != "render.cu" else "render_host.inc")
     if not os.path.exists(dst) or open(dst).read() != s:
         open(dst, "w").write(s)

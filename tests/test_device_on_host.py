@@ -3,7 +3,9 @@
 traversal in both control structures with its two conservative pre-filters (bit-exact hit records, oracle-identical
 counters, prefilter_wrong == 0) and the wide-BVH candidate pass with its deferral rules, through the same persistent-warp
 drivers the kernels use (one-lane warps).  Scene arrays come from the product's host commit (rgk_host_scene_*).
-Covers what nvcc compiles except the two inline-PTX helpers (host branches) and real warp divergence."""
+Further down: the shading functions, and whole rounds of the wavefront (render.cu's kernels and host loop, the device sampler
+included) against the oracle's framebuffer.  Covers what nvcc compiles except the two inline-PTX helpers (host branches),
+k_bin (queue order only) and real warp divergence."""
 import ctypes as C
 import os
 
@@ -204,7 +206,7 @@ def test_shading_device_source_on_the_host(doh, oracle):
     ctx.close()
 
 
-def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=False, reverse=None):
+def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=False, reverse=None, device_sampler=False):
     """One round of render_round_impl compiled for the host (kernels + host loop of render.cu), fed with the oracle's
     StratifiedSampler tables, next to the oracle's own round."""
     from rgk_b200 import abi
@@ -217,7 +219,7 @@ def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=F
         ho = oracle.scene_create(desc)
         ca = cfg.camera_args()
         cam = oracle.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
-        p = cfg.params(abi.SAMPLER_TABLES)
+        p = cfg.params(abi.SAMPLER_MT19937 if device_sampler else abi.SAMPLER_TABLES)
         if depth is not None:
             p.depth = depth
         if reverse is not None:
@@ -230,7 +232,8 @@ def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=F
         t1 = np.ascontiguousarray(t1, np.float32); t2 = np.ascontiguousarray(t2, np.float32)
         rgb = np.zeros((p.yres, p.xres, 3), np.float32); cnt = np.zeros((p.yres, p.xres), np.uint32)
         st = abi.RoundStats(); bvh = np.zeros(2, np.uint64)
-        rc = doh.doh_render_round(h, C.byref(cam), C.byref(p), tasks, len(tasks), 42, seedcount_base, t1.ctypes.data, t2.ctypes.data, n1d, n2d,
+        rc = doh.doh_render_round(h, C.byref(cam), C.byref(p), tasks, len(tasks), 42, seedcount_base, None if device_sampler else t1.ctypes.data,
+                                  None if device_sampler else t2.ctypes.data, n1d, n2d,
                                   len(seeds), rgb.ctypes.data, cnt.ctypes.data, C.byref(st), bvh.ctypes.data)
         assert rc == 0
         po = cfg.params(abi.SAMPLER_MT19937); po.depth = p.depth; po.reverse = p.reverse
@@ -326,3 +329,13 @@ def test_ab_knob_kernels_on_the_host(doh, oracle, scene):
         (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=5, wide_bvh=True)
     assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
     assert int(st.closest_rays) == int(so.closest_rays)
+
+
+@pytest.mark.parametrize("multisample", [4, 9, 121])
+def test_device_sampler_in_the_wavefront_on_the_host(doh, oracle, multisample):
+    """RGK_SAMPLER_MT19937: k_sampler_mt (the device replica of StratifiedSampler over libstdc++'s mt19937 / shuffle) inside
+    the host-compiled wavefront instead of caller-supplied tables -- still the oracle's framebuffer bit for bit.  Set size
+    121 exceeds the shared-memory budget and takes the in-place global-memory instantiation."""
+    pack, cfg = scenes.material_zoo(width=16, height=12, multisample=multisample, recursion_max=3, lens=0.04)
+    (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=2, wide_bvh=True, device_sampler=True)
+    assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))

@@ -72,6 +72,7 @@ static inline cudaError_t doh_cudaMemcpyAsync(void* d, const void* s, size_t n, 
 static inline cudaError_t doh_cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t doh_ok() { return cudaSuccess; }
 static inline cudaError_t doh_cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+static inline cudaError_t doh_cudaEventOp(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }     // arguments are evaluated
 static inline cudaError_t doh_cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
 static inline cudaError_t doh_cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)512 << 20; return cudaSuccess; }
 static inline cudaError_t doh_cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }
@@ -87,9 +88,9 @@ template <class F> static inline cudaError_t doh_cudaFuncSetAttribute(F, cudaFun
 #define cudaStreamSynchronize(s) doh_ok()
 #define cudaGetLastError() doh_ok()
 #define cudaEventCreate doh_cudaEventCreate
-#define cudaEventRecord(e, s) doh_ok()
-#define cudaEventSynchronize(e) doh_ok()
-#define cudaEventDestroy(e) doh_ok()
+#define cudaEventRecord doh_cudaEventOp
+#define cudaEventSynchronize doh_cudaEventOp
+#define cudaEventDestroy doh_cudaEventOp
 #define cudaEventElapsedTime doh_cudaEventElapsedTime
 #define cudaMemGetInfo doh_cudaMemGetInfo
 #define cudaDeviceGetAttribute doh_cudaDeviceGetAttribute

@@ -17,7 +17,7 @@ import raybatches
 from rgk_b200 import device, scenes, standin
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SO = os.path.join(ROOT, "build", "host", "libdevice_on_host.so")
+SO = os.environ.get("RGK_DEVICE_ON_HOST_SO") or os.path.join(ROOT, "build", "host", "libdevice_on_host.so")    # tools/asan_device_on_host.sh
 vp = C.c_void_p
 
 

@@ -22,9 +22,12 @@
 struct BvhCount { uint32_t nodes, tests; };
 constexpr uint32_t BVH_DONE = 0x7fffffffu;      // also the code of an empty child slot
 
-// SORT = false (any-hit only, A/B knob RGK_BVH_SHADOW_NOSORT): children are entered in slot order instead of by entry
-// distance -- the answer of an any-hit query does not depend on the order (a firm hit anywhere blocks, border hits alone defer)
-template <bool ANY, bool COUNT, bool SORT = true>
+// SORT: 1 = children entered by ascending entry distance (sorting network).  A/B knobs, results identical: 0 = slot order
+// (RGK_BVH_SHADOW_NOSORT; the answer of an any-hit query does not depend on the order: a firm hit anywhere blocks, border
+// hits alone defer), 2 = nearest child first, the others pushed in slot order (RGK_BVH_CLOSEST_NEAREST; a closest-hit answer
+// does not depend on the order either: a node holding a hit inside the final 2-eps window is never culled, because its
+// entry distance is below every limit the traversal ever had).
+template <bool ANY, bool COUNT, int SORT = 1>
 struct BvhTraverser {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz;
     float opx, opy, opz, omx, omy, omz;          // o + m, o - m
@@ -122,7 +125,20 @@ struct BvhTraverser {
         float t3 = child_entry(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w);
         uint32_t c0 = __float_as_uint(cf.x), c1 = __float_as_uint(cf.y), c2 = __float_as_uint(cf.z), c3 = __float_as_uint(cf.w);
         const float inf = __int_as_float(0x7f800000);
-        if (!SORT) {
+        if (SORT == 2) {
+            // nearest entered child (first of equals), then the rest in slot order
+            float tm = t0; uint32_t cm = c0; int im = 0;
+            if (t1 < tm) { tm = t1; cm = c1; im = 1; }
+            if (t2 < tm) { tm = t2; cm = c2; im = 2; }
+            if (t3 < tm) { tm = t3; cm = c3; im = 3; }
+            if (!(tm < inf)) return pop(K);
+            if (im != 0 && t0 < inf) { K.e[sp] = make_uint2(c0, __float_as_uint(t0)); ++sp; }
+            if (im != 1 && t1 < inf) { K.e[sp] = make_uint2(c1, __float_as_uint(t1)); ++sp; }
+            if (im != 2 && t2 < inf) { K.e[sp] = make_uint2(c2, __float_as_uint(t2)); ++sp; }
+            if (im != 3 && t3 < inf) { K.e[sp] = make_uint2(c3, __float_as_uint(t3)); ++sp; }
+            return cm;
+        }
+        if (SORT == 0) {
             uint32_t nx = BVH_DONE; float tx = inf;
 #define RGK_ENTER(t, c) if (t < inf) { if (nx != BVH_DONE) { K.e[sp] = make_uint2(nx, __float_as_uint(tx)); ++sp; } nx = c; tx = t; }
             RGK_ENTER(t0, c0) RGK_ENTER(t1, c1) RGK_ENTER(t2, c2) RGK_ENTER(t3, c3)
@@ -215,7 +231,7 @@ struct BvhTraverser {
 
 // Persistent-warp driver, same work distribution as trace_phased.  `fetch(i, T)` loads item i and calls T.init;
 // `commit(i, found, res)` stores a settled result; `defer(i)` hands an ambiguous item to the kd-tree pass.
-template <bool ANY, bool COUNT, bool SORT = true, class Fetch, class Commit, class Defer>
+template <bool ANY, bool COUNT, int SORT = 1, class Fetch, class Commit, class Defer>
 __device__ __forceinline__ void trace_bvh(const DevScene& S, uint32_t count, unsigned long long* work, BvhCount& cnt, uint32_t& done,
                                           uint32_t& deferred, Fetch fetch, Commit commit, Defer defer) {
     BvhTraverser<ANY, COUNT, SORT> T;

@@ -524,15 +524,15 @@ __device__ __forceinline__ void flush_bvh_counts(uint32_t nrays, uint32_t deferr
     if ((threadIdx.x & 31) == 0) { atomicAdd(&stats->rays, a); if (b) atomicAdd(&stats->ambiguous, b); }
 }
 
-template <int MINB>       // 6: <= 80 registers (no spills, 7 CTAs/SM at the 72 it uses); 8: <= 64 (RGK_BVH_MINB A/B knob)
+template <int MINB, int SORT = 1>       // MINB 6: <= 80 registers (no spills, 7 CTAs/SM at the 72 it uses); 8: <= 64 (RGK_BVH_MINB A/B knob)
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_closest_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, BvhStats* stats,
               uint32_t* __restrict__ arb, uint32_t* arb_count) {
     BvhCount cnt{0, 0};
     uint32_t mine = 0, deferred = 0;
     const ClosestIO io{B};
-    trace_bvh<false, false>(S, count, work, cnt, mine, deferred,
-        [&](uint32_t i, BvhTraverser<false, false>& T) {
+    trace_bvh<false, false, SORT>(S, count, work, cnt, mine, deferred,
+        [&](uint32_t i, BvhTraverser<false, false, SORT>& T) {
             const uint32_t slot = queue ? __ldg(queue + i) : i;
             const float4 o = B.ray_o[slot], d = B.ray_d[slot];
             return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot]);
@@ -556,7 +556,7 @@ k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const
         [&](uint32_t i, bool found, const HitRec& h) { io.commit(arb[i], found, h); });
 }
 
-template <int MINB, bool SORT>
+template <int MINB, int SORT>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_shadow_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, BvhStats* stats,
              uint32_t const_light, float4 cl_pos, uint32_t* __restrict__ arb, uint32_t* arb_count) {
@@ -1142,6 +1142,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         // the arbiter sees ~4e-4 of the rays, all of them long (grazing) traversals: spread them over many warps
         const int arb_grid = 148 * (int)std::max<size_t>(1, env_size("RGK_ARB_GRID", 8)), bvh_minb = (int)env_size("RGK_BVH_MINB", 6);
         const bool bvh_shadow_nosort = env_size("RGK_BVH_SHADOW_NOSORT", 0) != 0;     // A/B knob: any-hit children in slot order
+        const bool bvh_closest_nearest = env_size("RGK_BVH_CLOSEST_NEAREST", 0) != 0; // A/B knob: nearest child first, no full sort
         uint32_t* arb_list = nullptr; unsigned long long* arb_ctr = nullptr;
         if (use_bvh) {
             arb_list = (uint32_t*)rgk_scratch(ctx, 4, npaths * sizeof(uint32_t));
@@ -1244,7 +1245,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             // 48 registers (10 CTAs/SM) for later bounces, which gain from the extra warps
             if (use_bvh) {
                 RGK_CUDA(ctx, cudaMemsetAsync(arb_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
-                if (bvh_minb >= 8) k_closest_bvh<8><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                if (bvh_closest_nearest) k_closest_bvh<6, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                else if (bvh_minb >= 8) k_closest_bvh<8><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                 else k_closest_bvh<6><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                 k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
                 ctx->launches++;
@@ -1284,11 +1286,11 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
                 if (use_bvh) {
-                    if (bvh_shadow_nosort) k_shadow_bvh<6, false><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                    if (bvh_shadow_nosort) k_shadow_bvh<6, 0><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
                                                                                                 R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    else if (bvh_minb >= 8) k_shadow_bvh<8, true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                    else if (bvh_minb >= 8) k_shadow_bvh<8, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
                                                                                               R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    else k_shadow_bvh<6, true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                    else k_shadow_bvh<6, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
                                                                                 R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
                     k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 3), P->clamp, arb_ctr + 2,
                                                                                                      R.const_light, R.cl_pos);

@@ -323,9 +323,10 @@ def test_host_loop_chunking_on_the_host(doh, oracle):
 def test_ab_knob_kernels_on_the_host(doh, oracle, scene):
     """The A/B candidates that are built but off by default give the same bits: RGK_SHADE_LAST=1 (the last bounce through
     k_shade<true>, the instantiation without the BxDF sampling code, 4016 instead of 7352 SASS instructions) and
-    RGK_BVH_SHADOW_NOSORT=1 (any-hit BVH traversal entering the children in slot order)."""
+    RGK_BVH_SHADOW_NOSORT=1 (any-hit BVH traversal entering the children in slot order) and RGK_BVH_CLOSEST_NEAREST=1
+    (closest-hit BVH traversal entering the nearest child first without sorting the others)."""
     pack, cfg = scene()
-    with checkers.scoped_env(RGK_SHADE_LAST=1, RGK_BVH_SHADOW_NOSORT=1):
+    with checkers.scoped_env(RGK_SHADE_LAST=1, RGK_BVH_SHADOW_NOSORT=1, RGK_BVH_CLOSEST_NEAREST=1):
         (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=5, wide_bvh=True)
     assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
     assert int(st.closest_rays) == int(so.closest_rays)

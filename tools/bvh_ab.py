@@ -110,7 +110,8 @@ def main():
 
 SWEEP = [{}, {"RGK_ARB_GRID": "1"}, {"RGK_ARB_GRID": "4"}, {"RGK_BVH_MINB": "8"}, {"RGK_REFILL_INCOHERENT": "16"}, {"RGK_REFILL_INCOHERENT": "28"},
          {"RGK_REFILL_INCOHERENT": "32"}, {"RGK_REFILL_COHERENT": "24"}, {"RGK_REFILL_SHADOW": "6"}, {"RGK_REFILL_SHADOW": "20"}, {"RGK_BIN": "0"},
-         {"RGK_BIN_SHADOW0": "1"}, {"RGK_SHADE_LAST": "1"}, {"RGK_BVH_SHADOW_NOSORT": "1"}, {}]
+         {"RGK_BIN_SHADOW0": "1"}, {"RGK_SHADE_LAST": "1"}, {"RGK_BVH_SHADOW_NOSORT": "1"}, {"RGK_BVH_CLOSEST_NEAREST": "1"},
+         {"RGK_SHADE_LAST": "1", "RGK_BVH_SHADOW_NOSORT": "1", "RGK_BVH_CLOSEST_NEAREST": "1"}, {}]
 
 
 def sweep(cu, bv, scene, rounds, spp=None):

@@ -240,3 +240,32 @@ def test_triangle_soup_stress(seed):
     vis, dfs, _ = shadow(a[far_enough], b[far_enough])
     assert (vis[~dfs] == O.trace_shadow(h, a[far_enough], b[far_enough])[~dfs]).all()
     hs.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 9])
+def test_tiny_scenes(n):
+    """One wide node with a single leaf, a full leaf, the first split: structure and committed rays on scenes of 1-9 triangles."""
+    from test_prefilter_bounds import _scene
+    rng = np.random.default_rng(n)
+    base = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
+    tris = (base + rng.normal(scale=0.5, size=(n, 3, 3))).astype(np.float32)
+    pack = _scene(tris)
+    with checkers.scoped_env(RGK_WIDE_BVH=1):
+        hs = device.HostScene(pack.desc())
+    _check_structure(pack, hs)
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    nodes, order, depth = hs.bvh()
+    closest, shadow = _mirror(O, h, nodes, order)
+    m = 4000
+    rays = np.zeros(m, checkers.RAY_DT)
+    rays["origin"] = rng.uniform(-3, 3, (m, 3)).astype(np.float32)
+    target = tris[rng.integers(0, n, m)].mean(1) + rng.normal(scale=0.05, size=(m, 3)).astype(np.float32)
+    d = target - rays["origin"]
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tfar"] = 10000.0
+    want = O.trace_closest(h, rays)
+    got, deferred, _ = closest(rays)
+    assert (want["triangle"] != 0xFFFFFFFF).mean() > 0.05 and deferred.mean() < 0.2
+    assert _same(got[~deferred], want[~deferred])
+    hs.close()

@@ -340,3 +340,18 @@ def test_device_sampler_in_the_wavefront_on_the_host(doh, oracle, multisample):
     pack, cfg = scenes.material_zoo(width=16, height=12, multisample=multisample, recursion_max=3, lens=0.04)
     (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=2, wide_bvh=True, device_sampler=True)
     assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_material_parameters_on_the_host(doh, oracle, seed):
+    """The material zoo with random roughness / ior / mix amounts (including the 0 and 1 ends), with and without lens and
+    envmap sky, recursion-max 5, device sampler: the wavefront's device source against the oracle, bit for bit."""
+    rng = np.random.default_rng(100 + seed)
+    pack, cfg = scenes.material_zoo(width=32, height=20, multisample=4, recursion_max=5, lens=0.04 if seed % 2 else 0.0, envmap_sky=bool(seed % 3))
+    for m in pack.materials:
+        m["roughness"] = float(np.float32(rng.choice([0.0, 0.01, 0.05, 0.3, 0.7, 1.0]) if rng.random() < 0.5 else rng.uniform(0.0, 1.0)))
+        m["ior"] = float(np.float32(rng.uniform(1.0, 2.6)))
+        m["amount"] = float(np.float32(rng.uniform(0.0, 1.0)))
+    (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=seed, wide_bvh=bool(seed % 2), device_sampler=True)
+    assert np.array_equal(cnt, co) and int(st.closest_rays) == int(so.closest_rays)
+    assert np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))

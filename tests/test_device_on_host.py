@@ -355,3 +355,27 @@ def test_random_material_parameters_on_the_host(doh, oracle, seed):
     (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=seed, wide_bvh=bool(seed % 2), device_sampler=True)
     assert np.array_equal(cnt, co) and int(st.closest_rays) == int(so.closest_rays)
     assert np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_cameras_on_the_host(doh, oracle, seed):
+    """Cameras dropped at random inside the scene's bounding box (often inside or behind geometry, looking anywhere), Cornell
+    box / material zoo / cathedral stand-in, BVH path, device sampler, odd seeds also in the bidirectional mode."""
+    rng = np.random.default_rng(1000 + seed)
+    if seed % 3 == 0:
+        pack, cfg = scenes.load_builtin("cornell-box", width=32, height=32, multisample=4, recursion_max=8)
+    elif seed % 3 == 1:
+        pack, cfg = scenes.material_zoo(width=32, height=20, multisample=4, recursion_max=4)
+    else:
+        pack, cfg = standin.sibenik(width=32, height=20, multisample=2)
+    a = pack.arrays()
+    lo, hi = a["positions"].min(0), a["positions"].max(0)
+    cfg.camera["position"] = [float(x) for x in (lo + (hi - lo) * rng.uniform(0.05, 0.95, 3)).astype(np.float32)]
+    cfg.camera["lookat"] = [float(x) for x in (lo + (hi - lo) * rng.uniform(0.0, 1.0, 3)).astype(np.float32)]
+    for rev in ((0, 1) if seed % 2 else (0,)):
+        (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=seed, wide_bvh=True, device_sampler=True, reverse=rev)
+        assert np.array_equal(cnt, co) and int(st.closest_rays) == int(so.closest_rays)
+        if rev:
+            assert (np.abs(rgb - fo) <= 2e-5 * np.maximum(np.abs(fo), float(fo.mean()) + 1e-6)).all()
+        else:
+            assert np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))

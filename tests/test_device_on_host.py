@@ -379,3 +379,21 @@ def test_random_cameras_on_the_host(doh, oracle, seed):
             assert (np.abs(rgb - fo) <= 2e-5 * np.maximum(np.abs(fo), float(fo.mean()) + 1e-6)).all()
         else:
             assert np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
+
+
+@pytest.mark.parametrize("reverse", [0, 2])
+def test_obj_fixture_scene_on_the_host(doh, oracle, reverse):
+    """tests/golden/objscene/room.json (OBJ mesh with quads and n-gons, MTL materials, PNG texture, JPEG bump map) through the
+    importers and then the host-compiled wavefront -- travels with the repo, unlike the reference's own scene files."""
+    import warnings
+    from rgk_b200 import scene
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pack, cfg = scene.load_json_config(os.path.join(ROOT, "tests", "golden", "objscene", "room.json"),
+                                           overrides={"output-width": 40, "output-height": 30, "multisample": 4})
+    (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, wide_bvh=True, device_sampler=True, reverse=reverse)
+    assert np.array_equal(cnt, co) and int(st.closest_rays) == int(so.closest_rays)
+    if reverse:
+        assert (np.abs(rgb - fo) <= 2e-5 * np.maximum(np.abs(fo), float(fo.mean()) + 1e-6)).all()
+    else:
+        assert np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))

@@ -269,3 +269,40 @@ def test_tiny_scenes(n):
     assert (want["triangle"] != 0xFFFFFFFF).mean() > 0.05 and deferred.mean() < 0.2
     assert _same(got[~deferred], want[~deferred])
     hs.close()
+
+
+@pytest.mark.parametrize("case", ["identical", "zero-area", "collinear-centroids"])
+def test_degenerate_inputs(case):
+    """200 copies of one triangle (every hit is an exact tie: all must defer), zero-area triangles among ordinary ones, and a
+    row of triangles with collinear centroids: valid tree, committed rays equal to the kd-tree's answer."""
+    from test_prefilter_bounds import _scene
+    rng = np.random.default_rng(0)
+    if case == "identical":
+        tris = np.repeat(rng.normal(size=(1, 3, 3)).astype(np.float32), 200, 0)
+    elif case == "zero-area":
+        tris = np.concatenate([rng.normal(size=(50, 3, 3)).astype(np.float32), np.repeat(rng.normal(size=(20, 1, 3)).astype(np.float32), 3, 1)])
+    else:
+        tris = np.stack([np.stack([[i, 0, 0], [i + 0.5, 1, 0], [i + 0.5, 0, 1]]) for i in range(300)]).astype(np.float32)
+    pack = _scene(tris)
+    with checkers.scoped_env(RGK_WIDE_BVH=1):
+        hs = device.HostScene(pack.desc())
+    _check_structure(pack, hs)
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    nodes, order, _ = hs.bvh()
+    closest, _ = _mirror(O, h, nodes, order)
+    m = 5000
+    rays = np.zeros(m, checkers.RAY_DT)
+    rays["origin"] = rng.uniform(-3, 3, (m, 3)).astype(np.float32)
+    d = tris[rng.integers(0, len(tris), m)].mean(1) + rng.normal(scale=0.05, size=(m, 3)).astype(np.float32) - rays["origin"]
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tfar"] = 10000.0
+    want = O.trace_closest(h, rays)
+    got, deferred, _ = closest(rays)
+    hit = want["triangle"] != 0xFFFFFFFF
+    assert hit.mean() > 0.5 and _same(got[~deferred], want[~deferred])
+    if case == "identical":
+        assert deferred[hit].all()
+    else:
+        assert deferred.mean() < 0.02
+    hs.close()

@@ -1423,7 +1423,20 @@ Bvh4Out bvh4_trace(const Scene& s, const float* nodes, const uint32_t* order, co
             if (!test_intersection(s, s.tris[ti], r, t, a, b)) continue;
             if (t < lo_t || t > hi_t) continue;
             if (!any && t > best_t + 2.0f * eps) continue;
-            const bool edge = a < 3.0517578125e-5f || b < 3.0517578125e-5f || (a + b) > 0.999969482421875f;
+            bool edge;
+            {   // as BvhTraverser::test: boundary width from the ray's margin over the triangle's smallest projected height
+                const Tri& tr = s.tris[ti];
+                const V3 pn = v3(tr.p[0], tr.p[1], tr.p[2]);
+                const float px = std::fabs(pn.x), py = std::fabs(pn.y), pz = std::fabs(pn.z);
+                int i1, i2;
+                if (px > py && px > pz) { i1 = 1; i2 = 2; } else if (py > pz) { i1 = 0; i2 = 2; } else { i1 = 0; i2 = 1; }
+                const V3 v0 = s.pos[tr.va], v1 = s.pos[tr.vb], v2 = s.pos[tr.vc];
+                const float q1x = v1[i1] - v0[i1], q1y = v1[i2] - v0[i2], q2x = v2[i1] - v0[i1], q2y = v2[i2] - v0[i2];
+                const float den = q2y * q1x - q2x * q1y;
+                const float longest = std::fmax(std::fmax(std::fabs(q1x), std::fabs(q1y)), std::fmax(std::fabs(q2x), std::fabs(q2y)));
+                const float delta = std::fmax(3.0517578125e-5f, 0.125f * m * longest / std::fabs(den));
+                edge = !(a >= delta) || !(b >= delta) || !((a + b) <= 1.0f - delta);
+            }
             if (any) { if (!edge && t >= firm_lo && t <= firm_hi) stop = true; else border = true; continue; }
             if (t < best_t) { second_t = best_t; best_t = t; best_edge = edge; out.hit.tri = ti; out.hit.t = t; out.hit.a = 1.0f - a - b; out.hit.b = a; out.hit.c = b; set_limit(); }
             else if (t < second_t) second_t = t;

@@ -10,7 +10,8 @@
 // within 2 eps of the best, or a best hit within eps of the root interval's ends.  A third case is (3) a hit on the very
 // edge of a triangle that only touches a kd cell: a ray running along that cell's face may never visit the leaf holding
 // the triangle, so the kd-tree reports nothing there; a best hit with a barycentric coordinate within 2^-15 of the
-// triangle's boundary is therefore treated the same way.  Such rays (~3e-4 of them) are NOT committed: they are appended
+// triangle's boundary (more when the ray's own position uncertainty is larger than that against the triangle's size: far
+// origins, tiny triangles) is therefore treated the same way.  Such rays (~3e-4 of them) are NOT committed: they are appended
 // to a list that the kd kernels re-trace.  The kd-tree stays the authority.
 //
 // Boxes are exact triangle bounds; conservativeness against the exact test's rounding (the accepted hit point can lie
@@ -36,6 +37,7 @@ struct BvhTraverser {
     float low_w;                                 // lo_t widened (box test)
     float limit;                                 // boxes entered only up to here: min(hi_t, best + 2 eps), widened
     float second_t;                              // smallest t of an accepted hit other than the best
+    float marg;                                  // the per-ray box margin m (also scales the edge test)
     uint32_t ignore;
     bool border;                                 // ANY: an accepted hit outside the firm interval (or on an edge) was seen
     bool best_edge;                              // closest: the best hit lies on the boundary of its triangle
@@ -81,6 +83,7 @@ struct BvhTraverser {
         lo_t = t0 - eps; hi_t = t1 + eps;
         firm_lo = t0 + eps; firm_hi = t1 - eps;
         const float m = (((fabsf(ox) + fabsf(oy)) + fabsf(oz)) + fabsf(t1)) * 7.62939453125e-6f;
+        marg = m;
         opx = ox + m; opy = oy + m; opz = oz + m;
         omx = ox - m; omy = oy - m; omz = oz - m;
         low_w = (lo_t - fabsf(lo_t) * 9.5367431640625e-7f) - 1e-30f;
@@ -197,7 +200,11 @@ struct BvhTraverser {
             alpha = (q0x - beta * r2.x) / r1.z;
         }
         if (alpha < 0.0f || (alpha + beta) > 1.0f) return false;
-        const bool edge = alpha < 3.0517578125e-5f || beta < 3.0517578125e-5f || (alpha + beta) > 0.999969482421875f;
+        // "on the boundary" in units of this ray's position uncertainty: an eighth of the margin m (8x the rounding of o + d t) over the
+        // triangle's smallest projected height |denom| / longest projected edge, and never less than 2^-15
+        const float longest = fmaxf(fmaxf(fabsf(r1.z), fabsf(r1.w)), fmaxf(fabsf(r2.x), fabsf(r2.y)));
+        const float delta = fmaxf(3.0517578125e-5f, 0.125f * marg * longest / fabsf(r2.z));
+        const bool edge = !(alpha >= delta) || !(beta >= delta) || !((alpha + beta) <= 1.0f - delta);
         if (ANY) {
             if (!edge && t >= firm_lo && t <= firm_hi) return true;
             border = true;

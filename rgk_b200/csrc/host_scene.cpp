@@ -303,10 +303,49 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
     float bb[3][2];
     for (int ax = 0; ax < 3; ax++) { bb[ax][0] = mn[ax] - eps; bb[ax][1] = mx[ax] + eps; }
 
+    // intersection records: the ray-independent part of Triangle::TestIntersection (src/primitives.cpp:83,104-133,141,149)
+    hs.tri_isect.resize(12 * (size_t)nt);
+    hs.tri_bounds.resize(4 * (size_t)nt);
+    for (uint32_t i = 0; i < nt; i++) {
+        const float* p = &hs.planes[4 * (size_t)i];
+        const float px = std::fabs(p[0]), py = std::fabs(p[1]), pz = std::fabs(p[2]);
+        int i1, i2; uint32_t code;
+        if (px > py && px > pz) { i1 = 1; i2 = 2; code = 0; }
+        else if (py > pz) { i1 = 0; i2 = 2; code = 1; }
+        else { i1 = 0; i2 = 1; code = 2; }
+        const uint32_t* s = &hs.tri_shade[4 * (size_t)i];
+        const F3 v0 = ld3(d->positions + 3 * s[0]), v1 = ld3(d->positions + 3 * s[1]), v2 = ld3(d->positions + 3 * s[2]);
+        const float q1x = comp(v1, i1) - comp(v0, i1), q1y = comp(v1, i2) - comp(v0, i2);
+        const float q2x = comp(v2, i1) - comp(v0, i1), q2y = comp(v2, i2) - comp(v0, i2);
+        const float denom = q2y * q1x - q2x * q1y;
+        if (q1x > -eps && q1x < eps) code |= 4u;
+        float* r = &hs.tri_isect[12 * (size_t)i];
+        r[0] = p[0]; r[1] = p[1]; r[2] = p[2]; r[3] = p[3];
+        r[4] = comp(v0, i1); r[5] = comp(v0, i2); r[6] = q1x; r[7] = q1y;
+        r[8] = q2x; r[9] = q2y; r[10] = denom; std::memcpy(&r[11], &code, 4);
+        tri_prefilter_bounds(r, code, &hs.tri_bounds[4 * (size_t)i]);
+    }
+
+    // Triangles whose record can produce NaN barycentrics (projected edges exactly collinear: denom == 0, or q2.x == 0 /
+    // q1.y == 0 in the |q1.x| < eps branch) while their plane is finite: the reference's TestIntersection ACCEPTS such a hit
+    // (every comparison with NaN is false, src/primitives.cpp:141-164) wherever the ray crosses the triangle's plane inside a
+    // kd leaf that references it -- not a geometric event, so no bounding box can stand in for it.  Scenes that have one keep
+    // the kd-tree for every ray (the wide BVH is not built); exact zero-area triangles are harmless (NaN plane: rejected).
+    size_t nan_prone = 0;
+    for (uint32_t i = 0; i < nt; i++) {
+        const float* r = &hs.tri_isect[12 * (size_t)i];
+        uint32_t flags; std::memcpy(&flags, &r[11], 4);
+        const bool finite_plane = std::isfinite(r[0]) && std::isfinite(r[1]) && std::isfinite(r[2]) && std::isfinite(r[3]);
+        const bool degenerate = (flags & 4u) ? (r[8] == 0.0f || r[7] == 0.0f) : (r[10] == 0.0f);
+        bool finite_rec = true;
+        for (int k = 4; k < 11; k++) finite_rec = finite_rec && std::isfinite(r[k]);
+        if (finite_plane && (degenerate || !finite_rec)) nan_prone++;
+    }
+    hs.nan_prone_triangles = (uint32_t)std::min<size_t>(nan_prone, 0xFFFFFFFFu);
     // the opt-in wide BVH (RGK_WIDE_BVH=1) is independent of the kd-tree: built on its own thread meanwhile
     hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0;
     std::thread bvh_thread; std::exception_ptr bvh_error;
-    if (const char* e = std::getenv("RGK_WIDE_BVH")) if (std::atoi(e) > 0)
+    if (const char* e = std::getenv("RGK_WIDE_BVH")) if (std::atoi(e) > 0 && nan_prone == 0)
         bvh_thread = std::thread([&] { try { host_bvh_build(ev, nt, hs); } catch (...) { bvh_error = std::current_exception(); } });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{bvh_thread};     // also on the throwing paths below
 
@@ -337,29 +376,6 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
     if (deepest + 2 > RGK_STACK_CAP) throw std::runtime_error("kd-tree deeper than the traversal stack capacity");
     if (bvh_thread.joinable()) bvh_thread.join();
     if (bvh_error) std::rethrow_exception(bvh_error);
-
-    // intersection records: the ray-independent part of Triangle::TestIntersection (src/primitives.cpp:83,104-133,141,149)
-    hs.tri_isect.resize(12 * (size_t)nt);
-    hs.tri_bounds.resize(4 * (size_t)nt);
-    for (uint32_t i = 0; i < nt; i++) {
-        const float* p = &hs.planes[4 * (size_t)i];
-        const float px = std::fabs(p[0]), py = std::fabs(p[1]), pz = std::fabs(p[2]);
-        int i1, i2; uint32_t code;
-        if (px > py && px > pz) { i1 = 1; i2 = 2; code = 0; }
-        else if (py > pz) { i1 = 0; i2 = 2; code = 1; }
-        else { i1 = 0; i2 = 1; code = 2; }
-        const uint32_t* s = &hs.tri_shade[4 * (size_t)i];
-        const F3 v0 = ld3(d->positions + 3 * s[0]), v1 = ld3(d->positions + 3 * s[1]), v2 = ld3(d->positions + 3 * s[2]);
-        const float q1x = comp(v1, i1) - comp(v0, i1), q1y = comp(v1, i2) - comp(v0, i2);
-        const float q2x = comp(v2, i1) - comp(v0, i1), q2y = comp(v2, i2) - comp(v0, i2);
-        const float denom = q2y * q1x - q2x * q1y;
-        if (q1x > -eps && q1x < eps) code |= 4u;
-        float* r = &hs.tri_isect[12 * (size_t)i];
-        r[0] = p[0]; r[1] = p[1]; r[2] = p[2]; r[3] = p[3];
-        r[4] = comp(v0, i1); r[5] = comp(v0, i2); r[6] = q1x; r[7] = q1y;
-        r[8] = q2x; r[9] = q2y; r[10] = denom; std::memcpy(&r[11], &code, 4);
-        tri_prefilter_bounds(r, code, &hs.tri_bounds[4 * (size_t)i]);
-    }
 
     rgk_scene_info& in = hs.info;
     in.epsilon = eps;

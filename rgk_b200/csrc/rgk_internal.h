@@ -87,6 +87,7 @@ struct HostScene {
     std::vector<float> bvh_nodes;               // 32 / wide node (host_bvh.cpp); empty unless RGK_WIDE_BVH=1
     std::vector<uint32_t> bvh_order;            // triangle of leaf slot j
     unsigned bvh_depth = 0;
+    uint32_t nan_prone_triangles = 0;           // triangles that keep the scene on the kd path (host_scene.cpp)
     rgk_scene_info info{};
 };
 // host_bvh.cpp: ev[axis][2 i], [2 i + 1] = min, max of triangle i along the axis

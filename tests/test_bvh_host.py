@@ -306,3 +306,50 @@ def test_degenerate_inputs(case):
     else:
         assert deferred.mean() < 0.02
     hs.close()
+
+
+@pytest.mark.parametrize("seed", [5019, 5038, 5541, 5550])
+def test_campaign_regressions(seed):
+    """Seeds a randomized differential campaign (22 M rays) tripped over: rays from ~2000 units away aimed at vertices of small
+    triangles (the boundary width of the edge rule has to scale with the ray's position uncertainty over the triangle's
+    height), and soups moved to -5000 where tiny triangles collapse onto collinear float32 vertices (the reference accepts
+    their NaN-barycentric hits anywhere on the plane inside a referencing kd leaf: such scenes keep the kd-tree for every ray)."""
+    from test_prefilter_bounds import _scene, _triangles
+    rng = np.random.default_rng(seed)
+    n_t = int(rng.choice([50, 400, 3000]))
+    tris = _triangles(rng, n_t)
+    if seed % 2:
+        tris = np.concatenate([tris, tris[: n_t // 10]])
+    if seed % 3 == 0:
+        tris = (tris + np.float32(rng.choice([0, 100, -5000]))).astype(np.float32)
+    pack = _scene(tris)
+    with checkers.scoped_env(RGK_WIDE_BVH=1):
+        hs = device.HostScene(pack.desc())
+    nodes, order, _ = hs.bvh()
+    if seed in (5541, 5550):
+        assert len(nodes) == 0                       # NaN-prone triangles: no wide BVH for this scene
+        hs.close()
+        return
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    closest, _ = _mirror(O, h, nodes, order)
+    n = 20000
+    pick = rng.integers(0, len(tris), n)
+    w = rng.dirichlet([0.3, 0.3, 0.3], n).astype(np.float32)
+    kind = rng.integers(0, 4, n)
+    w[kind == 0] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, (kind == 0).sum())]
+    e = kind == 1
+    w[e, 2] = 0; w[e, :2] /= w[e, :2].sum(1, keepdims=True)
+    target = np.einsum("nk,nkd->nd", w, tris[pick]).astype(np.float32)
+    c = tris.reshape(-1, 3).mean(0)
+    origin = (c + np.where(rng.random((n, 1)) < 0.5, rng.uniform(-1.5, 1.5, (n, 3)), rng.uniform(-2000, 2000, (n, 3)))).astype(np.float32)
+    d = target - origin
+    keep = np.linalg.norm(d, axis=1) > 1e-6
+    rays = np.zeros(int(keep.sum()), checkers.RAY_DT)
+    rays["origin"] = origin[keep]
+    rays["direction"] = (d[keep] / np.linalg.norm(d[keep], axis=1, keepdims=True)).astype(np.float32)
+    rays["tfar"] = 10000.0
+    ign = np.where(rng.random(len(rays)) < 0.3, pick[keep], 0xFFFFFFFF).astype(np.uint32)
+    got, deferred, _ = closest(rays, ign)
+    assert _same(got[~deferred], O.trace_closest(h, rays, ign)[~deferred])
+    hs.close()

@@ -83,6 +83,14 @@ def build_workload(name, spp=None):
     return pack, cfg, label
 
 
+def parse_cfg(text):
+    out = {}
+    for item in filter(None, (text or "").split(",")):
+        k, v = item.split("=")
+        out[k.strip()] = float(v) if "." in v else int(v)
+    return out
+
+
 def crop_camera(cam, xres, yres, cw, ch):
     """Camera whose cw x ch image is the centred crop of cam's xres x yres image (same rays up to rounding)."""
     x0, y0 = (xres - cw) // 2, (yres - ch) // 2
@@ -205,8 +213,9 @@ def main():
     ap.add_argument("--shard", default="rounds", choices=["rounds", "tiles"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--traversal", default="bvh", choices=["bvh", "kd"],
-                    help="bvh: the wide-BVH traversal with the kd-tree arbiter pass (RGK_WIDE_BVH=1; results bit-identical to the kd path, "
-                         "tests/test_gpu_bvh.py); kd: the reference's kd-tree for every ray")
+                    help="bvh: the library default, the wide-BVH traversal with the kd-tree arbiter pass (results bit-identical to the kd "
+                         "path); kd: the reference's kd-tree for every ray")
+    ap.add_argument("--cfg", default="", help="rgk_device_cfg fields changed from the library defaults, e.g. binning=0,refill_shadow=20 (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -227,11 +236,7 @@ def main():
     pack, cfg, label = build_workload(args.workload, args.spp)
     desc = pack.desc()
     stream = torch.cuda.current_stream().cuda_stream
-    ctx = device.Context(local, stream=stream)
-    if args.traversal == "bvh":
-        os.environ["RGK_WIDE_BVH"] = "1"       # read by rgk_scene_commit
-    else:
-        os.environ.pop("RGK_WIDE_BVH", None)
+    ctx = device.Context(local, stream=stream, traversal=args.traversal, **parse_cfg(args.cfg))
     t0 = time.perf_counter()
     ctx.commit(desc)
     commit_s = time.perf_counter() - t0
@@ -394,7 +399,7 @@ def main():
             "config": {"workload": label, "sampler": "mt19937 replica (same sequence as the CPU reference)" if mode == abi.SAMPLER_MT19937 else "fast counter-based",
                        "parallelism": ("1 GPU" if world == 1 else ("round-sharded x%d + NCCL reduce per round" % world if args.shard == "rounds"
                                                                    else "tile-sharded x%d + NCCL reduce per round" % world)),
-                       "traversal": ("wide BVH candidate pass + kd-tree arbiter pass (RGK_WIDE_BVH=1): bit-identical to the kd-tree path"
+                       "traversal": ("wide BVH candidate pass + kd-tree arbiter pass (the library default): bit-identical to the kd-tree path"
                                      if args.traversal == "bvh" else "kd-tree (reference structure) for every ray"),
                        "l2": "no flush: per-step path state and sampler tables (GBs) exceed the 126 MB L2; the scene (a few MB) is the working set"},
             "samples_per_s": samples / (ms / 1e3), "gpu_launches": int(launches),

@@ -18,7 +18,8 @@
 extern "C" {
 #endif
 
-#define RGK_ABI_VERSION 3   /* 2: rgk_trav_stats grew the pre-filter counters; rgk_host_scene_*; reverse > 0.  3: wide-BVH entry points */
+#define RGK_ABI_VERSION 4   /* 2: rgk_trav_stats grew the pre-filter counters; rgk_host_scene_*; reverse > 0.  3: wide-BVH entry points.
+                               4: struct rgk_device_cfg -- the library reads no environment variable; the wide BVH is the default traversal */
 
 typedef enum rgk_status {
     RGK_OK = 0,
@@ -221,6 +222,56 @@ typedef struct rgk_round_stats {
                                      (the result cannot depend on them); shadow_rays counts traced rays only */
 } rgk_round_stats;
 
+/* ---- device configuration ----------------------------------------------- */
+
+/* How the library runs the path on the device.  The reference has no counterpart (its only knobs are the JSON
+ * config's, src/config.cpp, which arrive here as rgk_render_params); this replaces what round 1 read from RGK_*
+ * environment variables -- the library itself reads none.  Fill with rgk_device_cfg_init, change what you need, pass to
+ * rgk_context_configure BEFORE rgk_scene_commit (the traversal structure is built at commit) or to
+ * rgk_host_scene_create.  `traversal` selects the acceleration structure; every other field is scheduling or memory
+ * sizing and NEVER changes a result (tests/test_gpu_fullsize.py renders under several settings and compares bits). */
+enum {
+    RGK_TRAVERSAL_BVH = 0,   /* default: 4-wide BVH candidate pass for every ray + the reference's kd-tree as arbiter for the
+                                rays whose answer could depend on the kd rule (~1e-3 of them); bit-identical to RGK_TRAVERSAL_KD */
+    RGK_TRAVERSAL_KD = 1     /* the reference's kd-tree (src/scene_intersect.cpp:211-327) for every ray */
+};
+typedef struct rgk_device_cfg {
+    uint32_t struct_size;        /* sizeof(rgk_device_cfg), set by rgk_device_cfg_init */
+    uint32_t traversal;          /* RGK_TRAVERSAL_* */
+    /* host build */
+    uint32_t build_threads;      /* kd-tree build threads; 0 = all cores (at most 64) */
+    uint32_t bvh_bins;           /* binned-SAH bins per axis of the wide-BVH build (32) */
+    uint32_t bvh_all_axes;       /* 1: try the three axes at every split (default), 0: the longest only */
+    uint32_t bvh_leaf_max;       /* 0: the SAH-optimal collapse chooses the leaves (<= 4 triangles); 1-4: binary leaves of at most this size */
+    uint32_t bvh_greedy_collapse;/* 1: greedy collapse to 4 children instead of the SAH-optimal one */
+    float    bvh_c_prim;         /* SAH cost of one triangle test relative to one node visit; 0 = built-in */
+    uint32_t bvh_reinsert_iters; /* insertion-based re-optimisation passes over the binary tree (0 = off) */
+    float    bvh_reinsert_frac;  /* fraction of the nodes each pass re-inserts (0.25) */
+    /* memory sizing (bytes / paths); 0 = built-in, sized for 180 GB of HBM */
+    uint64_t chunk_paths;        /* paths per chunk of a round (128 Mi) */
+    uint64_t table_bytes;        /* sampler tables + generator states per chunk (24 GiB) */
+    uint64_t reverse_bytes;      /* vertex storage of the bidirectional mode per chunk (8 GiB) */
+    /* wavefront scheduling */
+    uint32_t refill_batch;       /* idle lanes of a warp that trigger a refill in the batch entry points rgk_trace_* (16) */
+    uint32_t refill_coherent;    /* ... camera-ray launches of a round (0 = built-in: 24 with the BVH, 32 kd) */
+    uint32_t refill_incoherent;  /* ... bounce launches (24) */
+    uint32_t refill_shadow;      /* ... shadow launches after the first bounce (12) */
+    uint32_t binning;            /* 1: direction-binned continuation / shadow queues (k_bin), 0: atomic compaction in path order */
+    uint32_t bin_shadow_first;   /* 1: also bin the shadow rays of the camera-ray hit points */
+    uint32_t bin_items;          /* path slots per reordering group (2048) */
+    float    bin_min_frac;       /* bounces with fewer live paths than this fraction of the chunk are not binned (0.25) */
+    uint32_t shade_path_order;   /* 1: k_shade gathers its per-path state through the path-ordered twin of the queue */
+    uint32_t skip_null_shadow;   /* 1: Visibility queries whose direct term is exactly 0 are not traced (counted in shadow_rays_skipped) */
+    uint32_t const_light;        /* 1: a scene whose only light is one point light of size 0 keeps it in launch constants */
+    uint32_t arb_grid;           /* CTAs per SM of the kd arbiter launches (8) */
+    uint32_t bvh_shadow_nosort;  /* 1: any-hit rays enter BVH children in slot order */
+    uint32_t bvh_closest_nearest;/* 1: closest-hit rays enter the nearest child first, the others in slot order */
+    uint32_t sampler_smem;       /* 1: sampler tables of small set sizes are shuffled in shared memory */
+    uint32_t trace_threads;      /* CTA size of the batch entry points: 64, 128 (default) or 256 */
+    uint32_t kd_variant;         /* control structure of the kd traversal in the batch entry points: 6 phased (default), 2 per-lane */
+    uint32_t _reserved[8];
+} rgk_device_cfg;
+
 /* ---- entry points ------------------------------------------------------- */
 
 uint32_t rgk_abi_version(void);
@@ -231,6 +282,11 @@ const char* rgk_status_string(rgk_status s);
 rgk_status rgk_context_create(int device, void* stream, rgk_context** out);
 void rgk_context_destroy(rgk_context* ctx);
 const char* rgk_last_error(const rgk_context* ctx);
+/* Defaults (see the struct); rgk_context_configure validates and stores a copy -- fields of the host-build and
+ * traversal groups take effect at the next rgk_scene_commit, the others at the next call. */
+void rgk_device_cfg_init(rgk_device_cfg* cfg);
+rgk_status rgk_context_configure(rgk_context* ctx, const rgk_device_cfg* cfg);
+rgk_status rgk_context_get_cfg(const rgk_context* ctx, rgk_device_cfg* out);
 
 /* Replaces Scene::Commit (src/scene.cpp:294-429): planes, areal lights, epsilon,
  * bbox, SAH kd-tree build + Compress on the host, flatten to the device layout,
@@ -243,11 +299,12 @@ rgk_status rgk_scene_get_kdtree(const rgk_context* ctx, uint32_t* nodes, uint32_
 
 /* Host-only half of rgk_scene_commit (no device needed): Triangle::CalculatePlane (src/primitives.cpp:24-36), areal
  * lights, epsilon, bbox (src/scene.cpp:294-429) and the SAH kd-tree build + Compress (src/scene.cpp:431-657), the
- * build forked over host threads (RGK_BUILD_THREADS, default = all cores; arrays are byte-identical to the
+ * build forked over host threads (rgk_device_cfg::build_threads, default = all cores; arrays are byte-identical to the
  * sequential reference procedure).  get_records copies the 4-float plane and the 12-float intersection record of
  * every triangle (either pointer may be NULL).  Errors: RGK_ERR_INVALID + rgk_host_last_error() (thread-local). */
 typedef struct rgk_host_scene rgk_host_scene;
-rgk_status rgk_host_scene_create(const rgk_scene_desc* desc, const rgk_kdtree* tree, rgk_host_scene** out);
+rgk_status rgk_host_scene_create(const rgk_scene_desc* desc, const rgk_kdtree* tree, const rgk_device_cfg* cfg /* NULL: defaults */,
+                                 rgk_host_scene** out);
 void rgk_host_scene_destroy(rgk_host_scene* hs);
 const char* rgk_host_last_error(void);
 rgk_status rgk_host_scene_get_info(const rgk_host_scene* hs, rgk_scene_info* out);
@@ -257,11 +314,13 @@ rgk_status rgk_host_scene_get_records(const rgk_host_scene* hs, float* planes, f
  * hi2, in the triangle's projection plane), for checking their conservativeness without a GPU. */
 rgk_status rgk_host_scene_get_bounds(const rgk_host_scene* hs, float* bounds);
 
-/* Opt-in wide BVH (environment RGK_WIDE_BVH=1 at commit time; no reference counterpart -- RGKrt only has the kd-tree,
+/* The wide BVH (rgk_device_cfg::traversal == RGK_TRAVERSAL_BVH, the default; no reference counterpart -- RGKrt only has the kd-tree,
  * src/scene.cpp:294-429).  A candidate generator: the traversal entry points find the globally closest hit through it with
  * the same Triangle::TestIntersection arithmetic, and every ray whose answer could depend on the kd-tree's per-leaf
  * +-epsilon accept rule (more than one hit within 2 epsilon of the closest, or a hit within epsilon of the ray's ends) is
- * re-traced through the kd-tree, which stays the authority.  Sizes are 0 when it is off (or the tree was too deep).
+ * re-traced through the kd-tree, which stays the authority.  Sizes are 0 when it is off, when the tree came out too deep for the
+ * traversal stack, or when the scene has a triangle whose exact test can produce NaN barycentrics (rgk_scene_info-independent;
+ * such scenes stay on the kd-tree, still on the GPU).
  * nodes: 32 floats each -- lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4], 4 child codes (uint32 bits: inner = node
  * index, leaf = 1<<31 | (count-1)<<29 | first slot, empty = 0x7fffffff), 4 zeros; order[slot] = triangle. */
 rgk_status rgk_host_scene_get_bvh_size(const rgk_host_scene* hs, uint32_t* n_nodes, uint32_t* n_slots, uint32_t* depth);
@@ -333,6 +392,13 @@ rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_r
  * 1 + depth 1-D dims and 4 (+1 with a lens) + depth 2-D dims.  Copied to the device at once. */
 rgk_status rgk_render_set_tables(rgk_context* ctx, uint32_t multisample, uint32_t n1d, uint32_t n2d,
                                  const float* t1d, const float* t2d, uint64_t n_pixels);
+
+/* Replaces EXRTexture::Accumulate (src/texture.cpp:403-412) for device-resident buffers: d_rgb_sum[i] += d_other_sum[i]
+ * for n_floats floats and, when both count pointers are given, d_count[j] += d_other_count[j] for n_floats / 3 pixels.
+ * `stream` = the cudaStream_t to run on (NULL: the context stream) -- multi-GPU drivers run it on their communication
+ * stream right after the NCCL reduce of a round, so that it overlaps the next round (rgk_b200/host/rgk_render_multi.cpp). */
+rgk_status rgk_accumulate_device(rgk_context* ctx, float* d_rgb_sum, const float* d_other_sum, uint64_t n_floats,
+                                 uint32_t* d_count, const uint32_t* d_other_count, void* stream);
 
 /* Tile sharding across GPUs: of every task list given to rgk_render_round*, this context renders only
  * tasks first, first+stride, first+2*stride, ...; each keeps the seed of its position in the full list, so the union

@@ -250,16 +250,17 @@ public:
     Scene& operator=(const Scene&) = delete;
     // Scene::Commit (src/scene.cpp:294-429): planes, areal lights, epsilon, bbox, kd-tree; tree != nullptr installs a
     // given flattened tree instead.  Throws like the reference's loader does on inconsistent input.
-    // wide_bvh: also build the 4-wide BVH and trace through it first, kd-tree as arbiter (RGK_WIDE_BVH=1; same results)
-    void Commit(const rgk_scene_desc& desc, const rgk_kdtree* tree = nullptr, bool wide_bvh = false) {
-        const char* was = std::getenv("RGK_WIDE_BVH");
-        const std::string saved = was ? was : "";
-        if (wide_bvh) setenv("RGK_WIDE_BVH", "1", 1);
-        const rgk_status st = rgk_scene_commit(ctx, &desc, tree);
-        if (wide_bvh) { if (was) setenv("RGK_WIDE_BVH", saved.c_str(), 1); else unsetenv("RGK_WIDE_BVH"); }
-        check(st, "rgk_scene_commit");
+    // traversal: RGK_TRAVERSAL_BVH (default: 4-wide BVH candidate pass, the kd-tree as arbiter) or RGK_TRAVERSAL_KD (the
+    // reference's kd-tree for every ray); same results either way
+    void Commit(const rgk_scene_desc& desc, const rgk_kdtree* tree = nullptr, uint32_t traversal = RGK_TRAVERSAL_BVH) {
+        rgk_device_cfg cfg;
+        check(rgk_context_get_cfg(ctx, &cfg), "rgk_context_get_cfg");
+        if (cfg.traversal != traversal) { cfg.traversal = traversal; Configure(cfg); }
+        check(rgk_scene_commit(ctx, &desc, tree), "rgk_scene_commit");
         check(rgk_scene_get_info(ctx, &info), "rgk_scene_get_info");
     }
+    // rgk_device_cfg: scheduling / memory sizing of the device path (before Commit for the traversal and build fields)
+    void Configure(const rgk_device_cfg& cfg) { check(rgk_context_configure(ctx, &cfg), "rgk_context_configure"); }
     // Scene::FindIntersectKdOtherThan (src/scene_intersect.cpp:211-327); ignored = RGK_NO_TRIANGLE: FindIntersectKd
     Intersection FindIntersectKdOtherThan(const Ray& r, uint32_t ignored = RGK_NO_TRIANGLE) const {
         rgk_ray rr; std::memcpy(rr.origin, r.origin, 12); std::memcpy(rr.direction, r.direction, 12); rr.tnear = r.tnear; rr.tfar = r.tfar;

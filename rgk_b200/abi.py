@@ -124,10 +124,42 @@ class RoundStats(C.Structure):
         return {k: (int(getattr(self, k)) if "ms" not in k else float(getattr(self, k))) for k, _ in self._fields_}
 
 
+TRAVERSAL_BVH, TRAVERSAL_KD = 0, 1
+
+
+class DeviceCfg(C.Structure):
+    """rgk_device_cfg: how the library runs the path on the device (the library reads no environment variable)."""
+    _fields_ = [("struct_size", C.c_uint32), ("traversal", C.c_uint32),
+                ("build_threads", C.c_uint32), ("bvh_bins", C.c_uint32), ("bvh_all_axes", C.c_uint32), ("bvh_leaf_max", C.c_uint32),
+                ("bvh_greedy_collapse", C.c_uint32), ("bvh_c_prim", C.c_float), ("bvh_reinsert_iters", C.c_uint32),
+                ("bvh_reinsert_frac", C.c_float),
+                ("chunk_paths", C.c_uint64), ("table_bytes", C.c_uint64), ("reverse_bytes", C.c_uint64),
+                ("refill_batch", C.c_uint32), ("refill_coherent", C.c_uint32), ("refill_incoherent", C.c_uint32),
+                ("refill_shadow", C.c_uint32), ("binning", C.c_uint32), ("bin_shadow_first", C.c_uint32), ("bin_items", C.c_uint32),
+                ("bin_min_frac", C.c_float), ("shade_path_order", C.c_uint32), ("skip_null_shadow", C.c_uint32),
+                ("const_light", C.c_uint32), ("arb_grid", C.c_uint32), ("bvh_shadow_nosort", C.c_uint32),
+                ("bvh_closest_nearest", C.c_uint32), ("sampler_smem", C.c_uint32), ("trace_threads", C.c_uint32),
+                ("kd_variant", C.c_uint32), ("_reserved", C.c_uint32 * 8)]
+
+
+def device_cfg(lib=None, **fields):
+    """The library's defaults (rgk_device_cfg_init) with `fields` changed; traversal may be 'bvh' / 'kd'."""
+    lib = lib or load_library()
+    cfg = DeviceCfg()
+    lib.rgk_device_cfg_init(C.byref(cfg))
+    for k, v in fields.items():
+        if k == "traversal" and isinstance(v, str):
+            v = {"bvh": TRAVERSAL_BVH, "kd": TRAVERSAL_KD}[v]
+        if not hasattr(cfg, k) or k.startswith("_") or k == "struct_size":
+            raise AttributeError("rgk_device_cfg has no field " + k)
+        setattr(cfg, k, v)
+    return cfg
+
+
 assert C.sizeof(Material) == 64 and C.sizeof(Ray) == 32 and C.sizeof(Hit) == 20
 
 # Every symbol include/rgk_b200.h declares (tests check that the library exports all of them).
-ABI_VERSION = 3      # RGK_ABI_VERSION of include/rgk_b200.h these ctypes structures mirror
+ABI_VERSION = 4      # RGK_ABI_VERSION of include/rgk_b200.h these ctypes structures mirror
 
 EXPORTS = [
     "rgk_abi_version", "rgk_status_string", "rgk_context_create", "rgk_context_destroy", "rgk_last_error",
@@ -139,12 +171,18 @@ EXPORTS = [
     "rgk_host_scene_create", "rgk_host_scene_destroy", "rgk_host_last_error", "rgk_host_scene_get_info",
     "rgk_host_scene_get_kdtree", "rgk_host_scene_get_records", "rgk_host_scene_get_bounds",
     "rgk_host_scene_get_bvh_size", "rgk_host_scene_get_bvh", "rgk_bvh_stats",
+    "rgk_device_cfg_init", "rgk_context_configure", "rgk_context_get_cfg", "rgk_accumulate_device",
 ]
+
+
+_LIBS = {}
 
 
 def load_library(path=None):
     """dlopen the CUDA library. Fails loudly when it has not been built (no CPU fallback exists)."""
     path = path or LIB_PATH
+    if path in _LIBS:
+        return _LIBS[path]
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
@@ -186,7 +224,12 @@ def load_library(path=None):
     lib.rgk_render_set_tables.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64]
     lib.rgk_synchronize.argtypes = [vp]
     lib.rgk_probe.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
-    lib.rgk_host_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(KdTree), C.POINTER(vp)]
+    lib.rgk_host_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(KdTree), C.POINTER(DeviceCfg), C.POINTER(vp)]
+    lib.rgk_device_cfg_init.argtypes = [C.POINTER(DeviceCfg)]
+    lib.rgk_device_cfg_init.restype = None
+    lib.rgk_context_configure.argtypes = [vp, C.POINTER(DeviceCfg)]
+    lib.rgk_context_get_cfg.argtypes = [vp, C.POINTER(DeviceCfg)]
+    lib.rgk_accumulate_device.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp]
     lib.rgk_host_scene_destroy.argtypes = [vp]
     lib.rgk_host_scene_destroy.restype = None
     lib.rgk_host_last_error.restype = C.c_char_p
@@ -200,4 +243,5 @@ def load_library(path=None):
     lib.rgk_render_set_counting.argtypes = [vp, C.c_int]
     lib.rgk_render_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.rgk_render_get_trav_stats.argtypes = [vp, C.POINTER(TravStats), C.POINTER(TravStats)]
+    _LIBS[path] = lib
     return lib

@@ -56,9 +56,51 @@ std::vector<float4> pad3(const float* src, uint32_t n) {
 
 } // namespace
 
+rgk_device_cfg default_device_cfg() {
+    rgk_device_cfg c;
+    std::memset(&c, 0, sizeof c);
+    c.struct_size = (uint32_t)sizeof(rgk_device_cfg);
+    c.traversal = RGK_TRAVERSAL_BVH;
+    c.bvh_bins = 32; c.bvh_all_axes = 1; c.bvh_reinsert_frac = 0.25f;
+    c.chunk_paths = (uint64_t)128 << 20; c.table_bytes = (uint64_t)24 << 30; c.reverse_bytes = (uint64_t)8 << 30;
+    c.refill_batch = 16; c.refill_coherent = 0; c.refill_incoherent = 24; c.refill_shadow = 12;
+    c.binning = 1; c.bin_shadow_first = 1; c.bin_items = 2048; c.bin_min_frac = 0.25f; c.shade_path_order = 1;
+    c.skip_null_shadow = 1; c.const_light = 1; c.arb_grid = 8;
+    c.sampler_smem = 1; c.trace_threads = 128; c.kd_variant = 6;
+    return c;
+}
+
 extern "C" {
 
 uint32_t rgk_abi_version(void) { return RGK_ABI_VERSION; }
+
+void rgk_device_cfg_init(rgk_device_cfg* cfg) { if (cfg) *cfg = default_device_cfg(); }
+
+static const char* check_cfg(const rgk_device_cfg& c) {
+    if (c.struct_size != sizeof(rgk_device_cfg)) return "rgk_device_cfg: struct_size mismatch (call rgk_device_cfg_init first)";
+    if (c.traversal > RGK_TRAVERSAL_KD) return "rgk_device_cfg: unknown traversal";
+    if (c.trace_threads != 64 && c.trace_threads != 128 && c.trace_threads != 256) return "rgk_device_cfg: trace_threads must be 64, 128 or 256";
+    if (c.kd_variant != 2 && c.kd_variant != 6) return "rgk_device_cfg: kd_variant must be 2 or 6";
+    if (c.refill_batch < 1 || c.refill_batch > 32 || c.refill_coherent > 32 || c.refill_incoherent < 1 || c.refill_incoherent > 32 ||
+        c.refill_shadow < 1 || c.refill_shadow > 32) return "rgk_device_cfg: refill thresholds are lane counts (1..32)";
+    if (c.bvh_leaf_max > 4) return "rgk_device_cfg: bvh_leaf_max > 4";
+    if (c.bin_items < 64 || c.arb_grid < 1) return "rgk_device_cfg: bin_items >= 64, arb_grid >= 1";
+    if (c.chunk_paths < 64 || c.table_bytes < ((uint64_t)1 << 20) || c.reverse_bytes < ((uint64_t)1 << 20)) return "rgk_device_cfg: memory sizes too small";
+    return nullptr;
+}
+
+rgk_status rgk_context_configure(rgk_context* ctx, const rgk_device_cfg* cfg) {
+    if (!ctx || !cfg) return RGK_ERR_INVALID;
+    if (const char* why = check_cfg(*cfg)) return rgk_fail(ctx, RGK_ERR_INVALID, why);
+    ctx->cfg = *cfg;
+    ctx->dev.refill_threshold = cfg->refill_batch;
+    return RGK_OK;
+}
+rgk_status rgk_context_get_cfg(const rgk_context* ctx, rgk_device_cfg* out) {
+    if (!ctx || !out) return RGK_ERR_INVALID;
+    *out = ctx->cfg;
+    return RGK_OK;
+}
 
 const char* rgk_status_string(rgk_status s) {
     switch (s) {
@@ -131,7 +173,7 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
     RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     free_scene(ctx);
     try {
-        host_scene_commit(d, tree, ctx->host);
+        host_scene_commit(d, tree, ctx->cfg, ctx->host);
     } catch (const std::exception& e) {
         return rgk_fail(ctx, RGK_ERR_INVALID, e.what());
     }
@@ -156,7 +198,7 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
             }
             UP(rp, &D.ref_bounds);
         }
-        if (!hs.bvh_nodes.empty()) {                 // opt-in wide BVH (RGK_WIDE_BVH=1)
+        if (!hs.bvh_nodes.empty()) {                 // wide BVH (RGK_TRAVERSAL_BVH)
             std::vector<float4> bn(hs.bvh_nodes.size() / 4);
             std::memcpy(bn.data(), hs.bvh_nodes.data(), hs.bvh_nodes.size() * 4);
             UP(bn, &D.bvh_nodes);
@@ -249,7 +291,7 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
     D.n_areal_lights = hs.info.n_areal_lights;
     D.total_point_power = hs.info.total_point_power; D.total_areal_power = hs.info.total_areal_power;
     D.epsilon = hs.info.epsilon;
-    { const char* e = std::getenv("RGK_REFILL"); const int v = e ? std::atoi(e) : 16; D.refill_threshold = (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v)); }
+    D.refill_threshold = ctx->cfg.refill_batch;
     for (int k = 0; k < 6; k++) D.bb[k] = hs.info.bbox[k];
     RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_scene = true;
@@ -275,12 +317,14 @@ rgk_status rgk_scene_get_kdtree(const rgk_context* ctx, uint32_t* nodes, uint32_
 struct rgk_host_scene { HostScene hs; std::string error; };
 thread_local std::string g_host_error;
 
-rgk_status rgk_host_scene_create(const rgk_scene_desc* d, const rgk_kdtree* tree, rgk_host_scene** out) {
+rgk_status rgk_host_scene_create(const rgk_scene_desc* d, const rgk_kdtree* tree, const rgk_device_cfg* cfg, rgk_host_scene** out) {
     if (!d || !out) return RGK_ERR_INVALID;
     *out = nullptr;
+    const rgk_device_cfg use = cfg ? *cfg : default_device_cfg();
+    if (const char* why = check_cfg(use)) { g_host_error = why; return RGK_ERR_INVALID; }
     rgk_host_scene* h = new rgk_host_scene();
     try {
-        host_scene_commit(d, tree, h->hs);
+        host_scene_commit(d, tree, use, h->hs);
     } catch (const std::exception& e) {
         g_host_error = e.what();
         delete h;
@@ -317,7 +361,7 @@ rgk_status rgk_host_scene_get_bounds(const rgk_host_scene* h, float* bounds) {
     return RGK_OK;
 }
 
-// the opt-in wide BVH (RGK_WIDE_BVH=1 at commit): sizes (all 0 when it is off), then nodes (32 floats each) and leaf order
+// the wide BVH (RGK_TRAVERSAL_BVH): sizes (all 0 when it is off), then nodes (32 floats each) and leaf order
 rgk_status rgk_host_scene_get_bvh_size(const rgk_host_scene* h, uint32_t* n_nodes, uint32_t* n_slots, uint32_t* depth) {
     if (!h) return RGK_ERR_INVALID;
     if (n_nodes) *n_nodes = (uint32_t)(h->hs.bvh_nodes.size() / 32);
@@ -508,6 +552,8 @@ static rgk_status check_render_args(rgk_context* ctx, const rgk_camera* cam, con
     if (!ctx->has_scene) return rgk_fail(ctx, RGK_ERR_NO_SCENE, "rgk_scene_commit has not been called");
     if (p->reverse > 16) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "reverse > 16 light-path vertices");
     if (p->xres == 0 || p->yres == 0 || p->multisample == 0) return rgk_fail(ctx, RGK_ERR_INVALID, "xres, yres and multisample must be positive");
+    // pixel coordinates travel packed as x | y << 16 (k_pixel_setup / k_raygen / k_finish)
+    if (p->xres > 65535u || p->yres > 65535u) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "image dimensions above 65535");
     if (p->sampler_mode > RGK_SAMPLER_FAST) return rgk_fail(ctx, RGK_ERR_INVALID, "unknown sampler_mode");
     for (uint32_t i = 0; i < n_tasks; i++)
         if (tasks[i].x1 > tasks[i].x2 || tasks[i].y1 > tasks[i].y2 || tasks[i].x2 > p->xres || tasks[i].y2 > p->yres)
@@ -578,6 +624,14 @@ rgk_status rgk_render_frame(rgk_context* ctx, const rgk_camera* cam, const rgk_r
     RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (stats) *stats = total;
     return RGK_OK;
+}
+
+rgk_status rgk_accumulate_device(rgk_context* ctx, float* d_rgb_sum, const float* d_other_sum, uint64_t n_floats, uint32_t* d_count,
+                                 const uint32_t* d_other_count, void* stream) {
+    if (!ctx || (n_floats && (!d_rgb_sum || !d_other_sum)) || ((d_count == nullptr) != (d_other_count == nullptr))) return RGK_ERR_INVALID;
+    if (n_floats == 0) return RGK_OK;
+    RGK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_accumulate(ctx, d_rgb_sum, d_other_sum, n_floats, d_count, d_other_count, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
 rgk_status rgk_render_set_shard(rgk_context* ctx, uint32_t first, uint32_t stride) {

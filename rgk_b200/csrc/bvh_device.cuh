@@ -1,4 +1,4 @@
-// bvh_device.cuh -- opt-in wide-BVH traversal (RGK_WIDE_BVH=1), device side.
+// bvh_device.cuh -- wide-BVH traversal (RGK_TRAVERSAL_BVH, the default), device side.
 //
 // No reference counterpart: RGKrt traverses its kd-tree only (src/scene_intersect.cpp:211-327).  This finds the
 // GLOBALLY closest hit of a ray through the 4-wide BVH of host_bvh.cpp with Triangle::TestIntersection's own arithmetic

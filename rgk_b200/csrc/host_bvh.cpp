@@ -1,4 +1,4 @@
-// host_bvh.cpp -- the opt-in wide BVH (RGK_WIDE_BVH=1) next to the reference's kd-tree.
+// host_bvh.cpp -- the wide BVH (RGK_TRAVERSAL_BVH, the default) next to the reference's kd-tree.
 //
 // Not a reference structure: RGKrt only has the kd-tree (src/scene.cpp:294-429).  The BVH is a *candidate generator*
 // for the traversal kernels in bvh_device.cuh -- it finds the globally closest hit with the reference's own
@@ -10,7 +10,7 @@
 // collapse of Ylitie, Karras and Laine (2017, section 3.1) into 4-wide nodes whose leaves hold <= 4 triangles (node visit
 // cost 1, triangle cost 0.3).  Against the first version (16 bins on the longest axis, leaves of <= 4 fixed by the binary
 // build, greedy largest-surface collapse) the CPU mirror counts 14 % fewer node visits and 27 % fewer exact tests per ray
-// (tests/bvh_quality.py).  RGK_BVH_BINS / _AXES / _LEAF / _COLLAPSE=greedy / _CPRIM are study knobs; so is RGK_BVH_REINSERT=n
+// (tests/bvh_quality.py).  rgk_device_cfg::bvh_bins / bvh_all_axes / bvh_leaf_max / bvh_greedy_collapse / bvh_c_prim are study knobs; so is bvh_reinsert_iters = n
 // (insertion-based optimisation of the binary tree: 2-3 % fewer node visits on the atrium stand-in, not monotonic in n -- off).  Deterministic,
 // single-threaded (2 M triangles in ~5 s).
 //
@@ -232,7 +232,7 @@ struct BvhBuilder {
         return (uint32_t)me;
     }
 
-    // greedy alternative (RGK_BVH_COLLAPSE=greedy): wide node for the binary subtree `b`, opening the largest child first
+    // greedy alternative (rgk_device_cfg::bvh_greedy_collapse): wide node for the binary subtree `b`, opening the largest child first
     uint32_t collapse(int b, unsigned depth) {
         if (depth > deepest) deepest = depth;
         int kids[4]; int nk = 1; kids[0] = b;
@@ -267,28 +267,25 @@ struct BvhBuilder {
 
 } // namespace
 
-void host_bvh_build(const std::vector<float> ev[3], uint32_t nt, HostScene& hs) {
+void host_bvh_build(const std::vector<float> ev[3], uint32_t nt, const rgk_device_cfg& cfg, HostScene& hs) {
     hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0;
     if (nt == 0) return;
     if (nt >= (1u << 29)) throw std::runtime_error("wide BVH: more than 2^29 triangles");
     BvhBuilder b;
     b.ev = ev; b.nodes = &hs.bvh_nodes;
-    if (const char* e = std::getenv("RGK_BVH_BINS")) b.nbins = std::min(256, std::max(4, std::atoi(e)));
-    if (const char* e = std::getenv("RGK_BVH_AXES")) b.all_axes = std::atoi(e) >= 3;
-    if (const char* e = std::getenv("RGK_BVH_LEAF")) b.leaf_max = std::min(4, std::max(1, std::atoi(e)));
+    if (cfg.bvh_bins) b.nbins = (int)std::min(256u, std::max(4u, cfg.bvh_bins));
+    b.all_axes = cfg.bvh_all_axes != 0;
+    const bool greedy = cfg.bvh_greedy_collapse != 0;
+    if (cfg.bvh_leaf_max) b.leaf_max = (int)std::min(4u, cfg.bvh_leaf_max);
+    else if (!greedy) b.leaf_max = 1;                      // the collapse chooses the leaves (<= 4 triangles) itself
+    if (cfg.bvh_c_prim > 0.0f) b.c_prim = cfg.bvh_c_prim;
     b.scratch_cnt.resize(b.nbins); b.scratch_sufc.resize(b.nbins); b.scratch_box.resize(b.nbins); b.scratch_suf.resize(b.nbins);
     b.order.resize(nt);
     for (uint32_t i = 0; i < nt; i++) b.order[i] = i;
     b.bin.reserve(2 * (size_t)nt);
-    bool greedy = false;
-    if (const char* e = std::getenv("RGK_BVH_COLLAPSE")) greedy = std::string(e) == "greedy";
-    if (const char* e = std::getenv("RGK_BVH_CPRIM")) b.c_prim = (float)std::atof(e);
-    if (!greedy && !std::getenv("RGK_BVH_LEAF")) b.leaf_max = 1;        // the collapse chooses the leaves (<= 4 triangles) itself
     int root = b.build(0, (int)nt);
-    int reinsert_iters = 0; float reinsert_frac = 0.25f;
-    if (const char* e = std::getenv("RGK_BVH_REINSERT")) reinsert_iters = std::max(0, std::atoi(e));
-    if (const char* e = std::getenv("RGK_BVH_REINSERT_FRAC")) reinsert_frac = (float)std::atof(e);
-    if (reinsert_iters > 0 && b.leaf_max == 1 && nt > 8) root = b.reinsert(root, reinsert_iters, reinsert_frac);
+    if (cfg.bvh_reinsert_iters > 0 && b.leaf_max == 1 && nt > 8)
+        root = b.reinsert(root, (int)cfg.bvh_reinsert_iters, cfg.bvh_reinsert_frac > 0.0f ? cfg.bvh_reinsert_frac : 0.25f);
     if (greedy) b.collapse(root, 1);
     else { b.dp.resize(b.bin.size()); b.solve(root); b.emit(root, 1); }
     hs.bvh_order.swap(b.order);

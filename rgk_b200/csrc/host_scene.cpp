@@ -116,10 +116,16 @@ struct Builder {
             right.spare_threads = spare_threads; right.fork_min_tris = fork_min_tris;
             float rb[3][2]; std::memcpy(rb, bb, sizeof rb);
             rb[axis][0] = best_pos;
-            std::thread worker([&] { right.build(above, rb, depth + 1); });
-            build(below, cb, depth + 1);
-            worker.join();
-            spare_threads->fetch_add(1);
+            // a throw on either side (bad_alloc on a multi-million-triangle scene) must not reach std::terminate: the worker's
+            // is carried over in an exception_ptr, the parent's unwinds through the joiner, and both surface from
+            // rgk_scene_commit as an error status
+            std::exception_ptr worker_error;
+            std::thread worker([&] { try { right.build(above, rb, depth + 1); } catch (...) { worker_error = std::current_exception(); } });
+            {
+                struct Joiner { std::thread& t; std::atomic<int>* spare; ~Joiner() { if (t.joinable()) t.join(); spare->fetch_add(1); } } joiner{worker, spare_threads};
+                build(below, cb, depth + 1);
+            }
+            if (worker_error) std::rethrow_exception(worker_error);
             const uint32_t node_off = (uint32_t)(nodes.size() / 2), ref_off = (uint32_t)refs.size();
             nodes[me + 1] = axis | (node_off << 2);
             nodes.reserve(nodes.size() + rn.size());
@@ -207,7 +213,7 @@ static void tri_prefilter_bounds(const float* r, uint32_t code, float* out) {
     out[0] = b[0]; out[1] = b[1]; out[2] = b[2]; out[3] = b[3];
 }
 
-void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScene& hs) {
+void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rgk_device_cfg& cfg, HostScene& hs) {
     hs = HostScene();
     const uint32_t nt = d->n_triangles, nv = d->n_vertices;
     if (nt == 0) throw std::runtime_error("scene has no triangles");
@@ -342,11 +348,12 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
         if (finite_plane && (degenerate || !finite_rec)) nan_prone++;
     }
     hs.nan_prone_triangles = (uint32_t)std::min<size_t>(nan_prone, 0xFFFFFFFFu);
-    // the opt-in wide BVH (RGK_WIDE_BVH=1) is independent of the kd-tree: built on its own thread meanwhile
+    // the wide BVH (rgk_device_cfg::traversal == RGK_TRAVERSAL_BVH, the default) is independent of the kd-tree: built on its
+    // own thread meanwhile
     hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0;
     std::thread bvh_thread; std::exception_ptr bvh_error;
-    if (const char* e = std::getenv("RGK_WIDE_BVH")) if (std::atoi(e) > 0 && nan_prone == 0)
-        bvh_thread = std::thread([&] { try { host_bvh_build(ev, nt, hs); } catch (...) { bvh_error = std::current_exception(); } });
+    if (cfg.traversal == RGK_TRAVERSAL_BVH && nan_prone == 0)
+        bvh_thread = std::thread([&] { try { host_bvh_build(ev, nt, cfg, hs); } catch (...) { bvh_error = std::current_exception(); } });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{bvh_thread};     // also on the throwing paths below
 
     // kd-tree
@@ -363,9 +370,9 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScen
         deepest = measure_depth(hs.nodes);
     } else {
         Builder b{ev, hs.nodes, hs.refs, (unsigned)(int)(std::log2(nt) + 8)};
-        // RGK_BUILD_THREADS threads in total (default: all cores, at most 64); 1 forces the sequential build
+        // rgk_device_cfg::build_threads threads in total (0 = all cores, at most 64); 1 forces the sequential build
         unsigned threads = std::min(64u, std::max(1u, std::thread::hardware_concurrency()));
-        if (const char* e = std::getenv("RGK_BUILD_THREADS")) threads = (unsigned)std::min(64, std::max(1, std::atoi(e)));
+        if (cfg.build_threads) threads = std::min(64u, cfg.build_threads);
         std::atomic<int> spare((int)threads - 1);
         if (threads > 1) b.spare_threads = &spare;
         std::vector<uint32_t> all(nt);

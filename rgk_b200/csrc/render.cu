@@ -257,13 +257,11 @@ __global__ void k_tables_from_user(const float* __restrict__ u1, const float* __
 }
 
 // launches the table generation with the best block size the set size allows
-static void launch_sampler_mt(cudaStream_t stream, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
+static void launch_sampler_mt(cudaStream_t stream, bool use_smem, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
                               float* t1, float2* t2, uint32_t* state) {
     // per device (function attributes are), so set on every launch rather than once per process: contexts on several
     // GPUs may live in one process
     cudaFuncSetAttribute(k_sampler_mt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    static int use_smem = -1;
-    if (use_smem < 0) { const char* e = std::getenv("RGK_SAMPLER_SMEM"); use_smem = (e && e[0] == '0') ? 0 : 1; }
     // shared-memory tables only while two 128-thread CTAs still fit an SM (set size <= 66); beyond that the CTA count
     // per SM drops to one or two warps and the latency of the generator-state loads is no longer hidden (measured:
     // 2.4 s vs 1.2 s per 1080p x 256 spp x depth-40 round), so larger sets are shuffled in place in global memory
@@ -475,7 +473,7 @@ k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t
     flush_counts<COUNT>(cnt, mine, stats);
 }
 
-// ---- opt-in wide BVH (RGK_WIDE_BVH=1, bvh_device.cuh): the same fetch / commit as k_closest and k_shadow, run through the
+// ---- wide BVH (RGK_TRAVERSAL_BVH, bvh_device.cuh): the same fetch / commit as k_closest and k_shadow, run through the
 // BVH; rays whose answer could depend on the kd rule are not committed but appended (as path slots) to `arb`, and the
 // *_arb kernels then run the kd traversal over that list (its length is read on the device).  A path's shadow resolve has
 // side effects (B.tot), so it is committed exactly once: by the BVH pass or by the arbiter pass.
@@ -656,7 +654,7 @@ __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* 
 #define RGK_SHADE_MINB 5   // <= 102 registers: 5 CTAs of 128 threads per SM
 #endif
 // LAST: the launch of the last bounce (every vertex of the queue has n == depth, so no continuation is ever sampled): the same
-// results from a kernel without the BxDF sampling code (A/B knob RGK_SHADE_LAST=1; off until it is measured)
+// results from a kernel without the BxDF sampling code (4016 instead of 7352 SASS instructions; measured -3 ms per headline round)
 template <bool LAST>
 __global__ void __launch_bounds__(128, RGK_SHADE_MINB)
 k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count,
@@ -842,24 +840,26 @@ __global__ void k_finish(RenderConst R, PathBuffers B, float* __restrict__ fb, u
     fb_count[px] += R.ms;
 }
 
+// EXRTexture::Accumulate (src/texture.cpp:403-412) on device buffers; grid-stride, 128-bit where the pointers allow
+__global__ void k_accumulate(float* __restrict__ dst, const float* __restrict__ src, uint64_t n, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ ocnt, uint64_t npx) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0) {
+        const uint64_t n4 = n / 4;
+        for (uint64_t i = i0; i < n4; i += stride) {
+            float4 a = reinterpret_cast<float4*>(dst)[i]; const float4 b = reinterpret_cast<const float4*>(src)[i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            reinterpret_cast<float4*>(dst)[i] = a;
+        }
+        for (uint64_t i = 4 * n4 + i0; i < n; i += stride) dst[i] += src[i];
+    } else for (uint64_t i = i0; i < n; i += stride) dst[i] += src[i];
+    if (cnt) for (uint64_t i = i0; i < npx; i += stride) cnt[i] += ocnt[i];
+}
+
 int machine_blocks(rgk_context* ctx, const void* kernel, int threads) {
     int sms = 148, per = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, threads, 0);
     return sms * std::max(per, 1);
-}
-
-bool env_flag(const char* name, bool def) {
-    const char* v = std::getenv(name);
-    if (!v || !*v) return def;
-    return v[0] != '0';
-}
-
-size_t env_size(const char* name, size_t def) {
-    const char* v = std::getenv(name);
-    if (!v || !*v) return def;
-    const double d = std::atof(v);
-    return d > 0 ? (size_t)d : def;
 }
 
 rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t t1_floats, size_t t2_float2s, size_t tiles, bool need_mt) {
@@ -889,7 +889,7 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
         ok = alloc_dev(&B.counters, (size_t)C_COUNT);
         ok = ok && cudaMallocHost((void**)&B.h_counters, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
     }
-    if (!ok) { cudaGetLastError(); return rgk_fail(ctx, RGK_ERR_NOMEM, "path-state allocation failed (lower RGK_CHUNK_PATHS)"); }
+    if (!ok) { cudaGetLastError(); return rgk_fail(ctx, RGK_ERR_NOMEM, "path-state allocation failed (lower rgk_device_cfg::chunk_paths)"); }
     return RGK_OK;
 }
 
@@ -915,7 +915,7 @@ rgk_status ensure_reverse_buffers(rgk_context* ctx, size_t paths, uint32_t depth
         ok = alloc_dev(&V.lr_pos, light) && alloc_dev(&V.lr_nrm, light) && alloc_dev(&V.lr_vr, light) && alloc_dev(&V.lr_uv, light) && alloc_dev(&V.lr_lfs, light);
         V.cap_light = ok ? light : 0;
     }
-    if (!ok) { cudaGetLastError(); return rgk_fail(ctx, RGK_ERR_NOMEM, "bidirectional vertex storage allocation failed (lower RGK_REVERSE_BYTES)"); }
+    if (!ok) { cudaGetLastError(); return rgk_fail(ctx, RGK_ERR_NOMEM, "bidirectional vertex storage allocation failed (lower rgk_device_cfg::reverse_bytes)"); }
     return RGK_OK;
 }
 
@@ -950,6 +950,15 @@ uint32_t host_sampler_set_size(uint32_t x) {
     return (uint32_t)((i + 1) * (i + 1));
 }
 
+rgk_status launch_accumulate(rgk_context* ctx, float* d_dst, const float* d_src, uint64_t n_floats, uint32_t* d_cnt, const uint32_t* d_ocnt, cudaStream_t stream) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    k_accumulate<<<sms * 8, 256, 0, stream>>>(d_dst, d_src, n_floats, d_cnt, d_ocnt, n_floats / 3);
+    ctx->launches++;
+    RGK_CUDA(ctx, cudaGetLastError());
+    return RGK_OK;
+}
+
 rgk_status launch_camera_rays(rgk_context* ctx, const rgk_camera* cam, uint32_t xres, uint32_t yres, const int32_t* d_xy,
                               const float* d_off, const float* d_lens, uint64_t n, rgk_ray* d_rays) {
     k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(*cam, xres, yres, d_xy, d_off, d_lens, n, d_rays);
@@ -971,7 +980,7 @@ rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint
         cudaGetLastError(); if (t1) cudaFree(t1); if (t2) cudaFree(t2); if (st) cudaFree(st);
         return rgk_fail(ctx, RGK_ERR_NOMEM, "sampler table allocation failed");
     }
-    launch_sampler_mt(ctx->stream, d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
+    launch_sampler_mt(ctx->stream, ctx->cfg.sampler_smem != 0, d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && n1d) e = cudaMemcpyAsync(d_out1, t1, (size_t)n1d * ss * n_seeds * 4, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1022,23 +1031,23 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const bool tables = mt || user_tables;
     size_t call_pixels = 0;
     const bool counting = ctx->counting;
-    const uint32_t skip_null = env_flag("RGK_SKIP_NULL_SHADOW", true) ? 1u : 0u;
-    const bool binning = env_flag("RGK_BIN", true) && P->depth > 1;
-    const bool bin_shadow0 = env_flag("RGK_BIN_SHADOW0", true);
-    const bool path_order_shade = env_flag("RGK_SHADE_PATH_ORDER", true);
-    const double bin_min_frac = std::getenv("RGK_BIN_MIN_FRAC") ? std::atof(std::getenv("RGK_BIN_MIN_FRAC")) : 0.25;
-    const size_t bin_items = env_size("RGK_BIN_ITEMS", 2048);   // path slots per reordering group
+    const rgk_device_cfg& cfg = ctx->cfg;              // scheduling and sizing only: none of it changes a result
+    const uint32_t skip_null = cfg.skip_null_shadow ? 1u : 0u;
+    const bool binning = cfg.binning && P->depth > 1;
+    const bool bin_shadow0 = cfg.bin_shadow_first != 0;
+    const bool path_order_shade = cfg.shade_path_order != 0;
+    const double bin_min_frac = cfg.bin_min_frac;
+    const size_t bin_items = cfg.bin_items;            // path slots per reordering group
     // the wide-BVH kernels' iterations are longer than the kd ones: refilling coherent warps at 24 idle lanes instead of 32
     // measured -1.9 ms per round (profiles/r1_bvh_sweep.json); the other thresholds are flat
     const bool bvh_round = ctx->dev.bvh_nodes != nullptr && !ctx->counting;
-    const uint32_t refill_coherent = (uint32_t)env_size("RGK_REFILL_COHERENT", bvh_round ? 24 : 32), refill_incoherent = (uint32_t)env_size("RGK_REFILL_INCOHERENT", 24);
-    const bool shade_last = env_size("RGK_SHADE_LAST", 0) != 0;
-    const uint32_t refill_shadow = (uint32_t)env_size("RGK_REFILL_SHADOW", 12);   // any-hit rays end at very different times: refill sooner
+    const uint32_t refill_coherent = cfg.refill_coherent ? cfg.refill_coherent : (bvh_round ? 24u : 32u), refill_incoherent = cfg.refill_incoherent;
+    const uint32_t refill_shadow = cfg.refill_shadow;  // any-hit rays end at very different times: refill sooner
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
 
     // chunking: whole tiles, every multisample of a pixel in the same chunk
-    size_t max_paths = env_size("RGK_CHUNK_PATHS", (size_t)128 << 20);   // ~27 GB of path state: sized for 180 GB of HBM
+    size_t max_paths = (size_t)cfg.chunk_paths;        // default 128 Mi paths ~ 27 GB of path state: sized for 180 GB of HBM
     {   // never plan a chunk whose path state (~210 B per path, on top of what is already allocated) would not fit in 60 %
         // of the memory that is free right now (other contexts, smaller parts)
         size_t free_b = 0, total_b = 0;
@@ -1050,10 +1059,10 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     }
     if (P->reverse) {      // bidirectional mode keeps every vertex of the camera and light paths: 112 B and 80 B per vertex
         const size_t per_path = 112 * (size_t)P->depth + 80 * (size_t)P->reverse + 64;
-        max_paths = std::max<size_t>(std::min(max_paths, env_size("RGK_REVERSE_BYTES", (size_t)8 << 30) / per_path), 4096);
+        max_paths = std::max<size_t>(std::min(max_paths, (size_t)cfg.reverse_bytes / per_path), 4096);
     }
     const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
-    size_t max_table_bytes = env_size("RGK_TABLE_BYTES", (size_t)24 << 30);
+    size_t max_table_bytes = (size_t)cfg.table_bytes;
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
@@ -1101,7 +1110,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         {   // Scene::GetRandomLight with one point light and nothing else always returns it; with size 0 it is not jittered
             const DevPointLight& l0 = ctx->first_point_light;
             R.const_light = (!P->reverse && ctx->dev.n_point_lights == 1 && ctx->dev.n_areal_lights == 0 && l0.size == 0.0f && l0.intensity > 0.0f &&
-                             env_flag("RGK_CONST_LIGHT", true)) ? 1u : 0u;
+                             cfg.const_light) ? 1u : 0u;
             const uint32_t flags = 1u; float fbits; std::memcpy(&fbits, &flags, 4);       // valid, FULL_SPHERE
             R.cl_pos = make_float4(l0.pos[0], l0.pos[1], l0.pos[2], fbits);
             R.cl_col = make_float4(l0.color[0], l0.color[1], l0.color[2], l0.intensity);
@@ -1116,7 +1125,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed, B.pix_src, (uint32_t)call_pixels);
         ctx->launches++;
         if (mt) {
-            launch_sampler_mt(ctx->stream, B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
+            launch_sampler_mt(ctx->stream, cfg.sampler_smem != 0, B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
             ctx->launches++;
         } else if (user_tables) {
             k_tables_from_user<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_user_t1, ctx->d_user_t2, ctx->user_n1d, ctx->user_n2d,
@@ -1135,14 +1144,14 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         uint32_t count = (uint32_t)npaths;
         const uint32_t* queue = nullptr;
         uint32_t* qnext = B.queue_a;
-        // opt-in wide BVH (RGK_WIDE_BVH=1 at commit): BVH pass + kd arbiter pass per closest-hit / shadow launch.  The counting
+        // wide BVH (RGK_TRAVERSAL_BVH at commit): BVH pass + kd arbiter pass per closest-hit / shadow launch.  The counting
         // instantiation stays on the kd kernels, and so do the bidirectional mode's shadow resolves and connection segments
         // (its closest-hit launches use the BVH)
         const bool use_bvh = ctx->dev.bvh_nodes != nullptr && !counting;
         // the arbiter sees ~4e-4 of the rays, all of them long (grazing) traversals: spread them over many warps
-        const int arb_grid = 148 * (int)std::max<size_t>(1, env_size("RGK_ARB_GRID", 8)), bvh_minb = (int)env_size("RGK_BVH_MINB", 6);
-        const bool bvh_shadow_nosort = env_size("RGK_BVH_SHADOW_NOSORT", 0) != 0;     // A/B knob: any-hit children in slot order
-        const bool bvh_closest_nearest = env_size("RGK_BVH_CLOSEST_NEAREST", 0) != 0; // A/B knob: nearest child first, no full sort
+        const int arb_grid = 148 * (int)std::max<uint32_t>(1u, cfg.arb_grid);
+        const bool bvh_shadow_nosort = cfg.bvh_shadow_nosort != 0;        // A/B knob: any-hit children in slot order
+        const bool bvh_closest_nearest = cfg.bvh_closest_nearest != 0;    // A/B knob: nearest child first, no full sort
         uint32_t* arb_list = nullptr; unsigned long long* arb_ctr = nullptr;
         if (use_bvh) {
             arb_list = (uint32_t*)rgk_scratch(ctx, 4, npaths * sizeof(uint32_t));
@@ -1169,8 +1178,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 pool.begin(ctx->stream, T_CLOSEST);
                 if (use_bvh) {
                     cudaMemsetAsync(arb_ctr, 0, 2 * sizeof(unsigned long long), ctx->stream);
-                    if (bvh_minb >= 8) k_closest_bvh<8><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
-                    else k_closest_bvh<6><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                    k_closest_bvh<6><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                     k_closest_arb<RGK_INCOH_MINB><<<std::min(g, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
                     ctx->launches++;
                 }
@@ -1246,7 +1254,6 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             if (use_bvh) {
                 RGK_CUDA(ctx, cudaMemsetAsync(arb_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
                 if (bvh_closest_nearest) k_closest_bvh<6, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
-                else if (bvh_minb >= 8) k_closest_bvh<8><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                 else k_closest_bvh<6><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                 k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
                 ctx->launches++;
@@ -1265,7 +1272,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             R.binning = (bin_next ? 1u : 0u) | (bin_shadow ? 2u : 0u);
             if (bin_next) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
             if (bin_shadow) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
-            if (last_bounce && shade_last) k_shade<true><<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
+            if (last_bounce) k_shade<true><<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
             else k_shade<false><<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
             if (bin_next) {
                 k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, B.counters + C_NEXT);
@@ -1288,8 +1295,6 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 if (use_bvh) {
                     if (bvh_shadow_nosort) k_shadow_bvh<6, 0><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
                                                                                                 R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    else if (bvh_minb >= 8) k_shadow_bvh<8, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
-                                                                                              R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
                     else k_shadow_bvh<6, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
                                                                                 R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
                     k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 3), P->clamp, arb_ctr + 2,

@@ -66,8 +66,8 @@ struct DevScene {
     float bb[6];
     uint32_t sky_mode; float sky_color[3]; float sky_intensity, sky_rotate; int32_t sky_envmap;
     uint32_t has_ltc;
-    uint32_t refill_threshold;   // idle lanes of a warp that trigger a refill (RGK_REFILL)
-    // opt-in wide BVH (RGK_WIDE_BVH=1, host_bvh.cpp / bvh_device.cuh); bvh_nodes == nullptr: kd-tree only
+    uint32_t refill_threshold;   // idle lanes of a warp that trigger a refill (rgk_device_cfg::refill_*)
+    // wide BVH (rgk_device_cfg::traversal == RGK_TRAVERSAL_BVH, host_bvh.cpp / bvh_device.cuh); bvh_nodes == nullptr: kd-tree only
     const float4* bvh_nodes;     // 8 x float4 per node
     const uint32_t* bvh_refs;    // [n_triangles] triangle of leaf slot j
     const float4* bvh_planes;    // [n_triangles] plane record of the triangle in leaf slot j
@@ -84,16 +84,17 @@ struct HostScene {
     std::vector<uint32_t> tri_shade;            // 4 / triangle
     std::vector<DevArealLight> areal_lights;
     std::vector<DevArealTri> areal_tris;
-    std::vector<float> bvh_nodes;               // 32 / wide node (host_bvh.cpp); empty unless RGK_WIDE_BVH=1
+    std::vector<float> bvh_nodes;               // 32 / wide node (host_bvh.cpp); empty on the kd-only traversal
     std::vector<uint32_t> bvh_order;            // triangle of leaf slot j
     unsigned bvh_depth = 0;
     uint32_t nan_prone_triangles = 0;           // triangles that keep the scene on the kd path (host_scene.cpp)
     rgk_scene_info info{};
 };
 // host_bvh.cpp: ev[axis][2 i], [2 i + 1] = min, max of triangle i along the axis
-void host_bvh_build(const std::vector<float> ev[3], uint32_t nt, HostScene& hs);
+void host_bvh_build(const std::vector<float> ev[3], uint32_t nt, const rgk_device_cfg& cfg, HostScene& hs);
 // Scene::Commit (src/scene.cpp:294-429) on the host. Throws std::runtime_error on bad input.
-void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, HostScene& out);
+void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rgk_device_cfg& cfg, HostScene& out);
+rgk_device_cfg default_device_cfg();          // api.cu: what rgk_device_cfg_init writes
 
 // ------------------------------------------------------------------ context
 // counters of the wide-BVH launches since the last call (device buffer ctx->d_bvh_stats): rays, ambiguous, nodes, tests
@@ -101,6 +102,7 @@ struct BvhStats { unsigned long long rays, ambiguous, nodes, tests; };
 struct PathBuffers;   // render.cu
 struct rgk_context {
     int device = 0;
+    rgk_device_cfg cfg = default_device_cfg();   // rgk_context_configure
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string last_error;
@@ -140,7 +142,6 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
                                 rgk_hit* d_hits, rgk_trav_stats* d_stats);
 rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* d_b, uint64_t n,
                                uint8_t* d_visible, rgk_trav_stats* d_stats);
-int rgk_traversal_variant();
 // render.cu
 rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_render_params* p, const rgk_task* tasks,
                              uint32_t n_tasks, uint32_t seedstart, uint32_t seedcount_base, float* d_rgb, uint32_t* d_count,
@@ -149,5 +150,6 @@ rgk_status launch_camera_rays(rgk_context* ctx, const rgk_camera* cam, uint32_t 
                               const float* d_off, const float* d_lens, uint64_t n, rgk_ray* d_rays);
 rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint32_t n_seeds, uint32_t multisample,
                                  uint32_t n1d, uint32_t n2d, float* d_out1, float* d_out2);
+rgk_status launch_accumulate(rgk_context* ctx, float* d_dst, const float* d_src, uint64_t n_floats, uint32_t* d_cnt, const uint32_t* d_ocnt, cudaStream_t stream);
 void free_path_buffers(rgk_context* ctx);
 uint32_t host_sampler_set_size(uint32_t multisample);

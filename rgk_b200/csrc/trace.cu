@@ -17,7 +17,6 @@ namespace {
 #define RGK_TRACE_THREADS_MAX 256
 #endif
 constexpr int TRACE_THREADS_MAX = RGK_TRACE_THREADS_MAX;
-static int trace_threads() { static int t = 0; if (!t) { const char* e = std::getenv("RGK_TRACE_THREADS"); t = e ? std::atoi(e) : 128; if (t != 64 && t != 128 && t != 256) t = 128; } return t; }
 
 template <bool COUNT>
 __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays, rgk_trav_stats* stats) {
@@ -81,7 +80,7 @@ k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict
     flush_counts<COUNT>(cnt, mine, stats);
 }
 
-// ---- opt-in wide BVH (RGK_WIDE_BVH=1): BVH pass over all rays, kd pass over the deferred (ambiguous) ones ----------
+// ---- wide BVH (RGK_TRAVERSAL_BVH, the default): BVH pass over all rays, kd pass over the deferred (ambiguous) ones ----------
 template <bool COUNT>
 __device__ __forceinline__ void flush_bvh(const BvhCount& c, uint32_t nrays, uint32_t deferred, BvhStats* stats) {
     unsigned long long v[4] = {nrays, deferred, COUNT ? c.nodes : 0u, COUNT ? c.tests : 0u};
@@ -185,23 +184,14 @@ k_trace_shadow_list(DevScene S, const float* __restrict__ pa, const float* __res
 
 } // namespace
 
-// RGK_TRAVERSAL=2|6 selects the traversal control structure of the batch entry points (A/B knob; results are identical)
-int rgk_traversal_variant() {
-    static int v = 0;
-    if (!v) { const char* e = std::getenv("RGK_TRAVERSAL"); v = (e && (e[0] == '2' || e[0] == '6')) ? (e[0] - '0') : 6; }
-    return v;
-}
-
 namespace {
-int trace_grid(rgk_context* ctx) {
-    static int blocks = 0;
-    if (!blocks) {
-        int sms = 148, per = 8;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_trace_closest<false, 2>, trace_threads(), 0);
-        blocks = sms * (per > 0 ? per : 1);
-    }
-    return blocks;
+// rgk_device_cfg::trace_threads / kd_variant select the CTA size and the kd control structure of the batch entry points
+// (A/B knobs; results are identical)
+int trace_grid(rgk_context* ctx, int threads) {
+    int sms = 148, per = 8;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_trace_closest<false, 2>, threads, 0);
+    return sms * (per > 0 ? per : 1);
 }
 
 } // namespace
@@ -214,24 +204,24 @@ rgk_status launch_trace_closest(rgk_context* ctx, const rgk_ray* d_rays, const u
     if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
     RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 24, ctx->stream));
     const uint64_t warps = (n + 31) / 32;
-    const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + trace_threads() / 32 - 1) / (trace_threads() / 32));
-    const int variant = rgk_traversal_variant();
+    const int threads = (int)ctx->cfg.trace_threads, variant = (int)ctx->cfg.kd_variant;
+    const int grid = (int)std::min<uint64_t>(trace_grid(ctx, threads), (warps + threads / 32 - 1) / (threads / 32));
     if (ctx->dev.bvh_nodes && !d_stats) {          // wide BVH for every ray, then the kd-tree for the deferred ones
         uint32_t* list = (uint32_t*)rgk_scratch(ctx, 4, n * 4);
         if (!list) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
         uint32_t* list_count = (uint32_t*)(next + 2);
-        if (ctx->counting) k_bvh_closest<true><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, ctx->d_bvh_stats, next, list, list_count);
-        else k_bvh_closest<false><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, ctx->d_bvh_stats, next, list, list_count);
+        if (ctx->counting) k_bvh_closest<true><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, ctx->d_bvh_stats, next, list, list_count);
+        else k_bvh_closest<false><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, ctx->d_bvh_stats, next, list, list_count);
         const int g2 = std::min(grid, 148);
-        if (variant == 2) k_trace_closest_list<2><<<g2, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, list, list_count, d_hits, next + 1);
-        else k_trace_closest_list<6><<<g2, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, list, list_count, d_hits, next + 1);
+        if (variant == 2) k_trace_closest_list<2><<<g2, threads, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, list, list_count, d_hits, next + 1);
+        else k_trace_closest_list<6><<<g2, threads, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, list, list_count, d_hits, next + 1);
         ctx->launches += 2;
         RGK_CUDA(ctx, cudaGetLastError());
         return RGK_OK;
     }
-    if (d_stats) k_trace_closest<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
-    else if (variant == 6) k_trace_closest<false, 6><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
-    else if (variant == 2) k_trace_closest<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
+    if (d_stats) k_trace_closest<true, 2><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, d_stats, next);
+    else if (variant == 6) k_trace_closest<false, 6><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
+    else if (variant == 2) k_trace_closest<false, 2><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_rays, d_ignore, n, d_hits, nullptr, next);
     ctx->launches++;
     RGK_CUDA(ctx, cudaGetLastError());
     return RGK_OK;
@@ -245,24 +235,24 @@ rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* 
     if (!next) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
     RGK_CUDA(ctx, cudaMemsetAsync(next, 0, 24, ctx->stream));
     const uint64_t warps = (n + 31) / 32;
-    const int grid = (int)std::min<uint64_t>(trace_grid(ctx), (warps + trace_threads() / 32 - 1) / (trace_threads() / 32));
-    const int variant = rgk_traversal_variant();
+    const int threads = (int)ctx->cfg.trace_threads, variant = (int)ctx->cfg.kd_variant;
+    const int grid = (int)std::min<uint64_t>(trace_grid(ctx, threads), (warps + threads / 32 - 1) / (threads / 32));
     if (ctx->dev.bvh_nodes && !d_stats) {
         uint32_t* list = (uint32_t*)rgk_scratch(ctx, 4, n * 4);
         if (!list) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
         uint32_t* list_count = (uint32_t*)(next + 2);
-        if (ctx->counting) k_bvh_shadow<true><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats, next, list, list_count);
-        else k_bvh_shadow<false><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats, next, list, list_count);
+        if (ctx->counting) k_bvh_shadow<true><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats, next, list, list_count);
+        else k_bvh_shadow<false><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats, next, list, list_count);
         const int g2 = std::min(grid, 148);
-        if (variant == 2) k_trace_shadow_list<2><<<g2, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, list, list_count, d_visible, next + 1);
-        else k_trace_shadow_list<6><<<g2, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, list, list_count, d_visible, next + 1);
+        if (variant == 2) k_trace_shadow_list<2><<<g2, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, list, list_count, d_visible, next + 1);
+        else k_trace_shadow_list<6><<<g2, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, list, list_count, d_visible, next + 1);
         ctx->launches += 2;
         RGK_CUDA(ctx, cudaGetLastError());
         return RGK_OK;
     }
-    if (d_stats) k_trace_shadow<true, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
-    else if (variant == 6) k_trace_shadow<false, 6><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
-    else if (variant == 2) k_trace_shadow<false, 2><<<grid, trace_threads(), 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
+    if (d_stats) k_trace_shadow<true, 2><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, d_stats, next);
+    else if (variant == 6) k_trace_shadow<false, 6><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
+    else if (variant == 2) k_trace_shadow<false, 2><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, nullptr, next);
     ctx->launches++;
     RGK_CUDA(ctx, cudaGetLastError());
     return RGK_OK;

@@ -29,7 +29,9 @@ def _p(a):
 
 
 class Context:
-    def __init__(self, device=0, stream=None, lib=None):
+    def __init__(self, device=0, stream=None, lib=None, cfg=None, **cfg_fields):
+        """cfg: an abi.DeviceCfg, or keyword fields of rgk_device_cfg changed from the library's defaults
+        (e.g. traversal="kd", chunk_paths=1 << 20).  Applied before any scene is committed."""
         self.lib = lib or abi.load_library()
         h = C.c_void_p()
         # stream: None -> the library creates its own stream; an integer cudaStream_t handle -> run on that stream
@@ -41,6 +43,25 @@ class Context:
             raise RgkError(st, self.lib.rgk_last_error(None).decode())
         self.h = h
         self._desc = None
+        if cfg is not None or cfg_fields:
+            self.configure(cfg, **cfg_fields)
+
+    def configure(self, cfg=None, **fields):
+        """rgk_context_configure: host-build / traversal fields take effect at the next commit, the others at the next call."""
+        if cfg is None:
+            cfg = self.cfg()
+        for k, v in fields.items():
+            if k == "traversal" and isinstance(v, str):
+                v = {"bvh": abi.TRAVERSAL_BVH, "kd": abi.TRAVERSAL_KD}[v]
+            if not hasattr(cfg, k) or k.startswith("_") or k == "struct_size":
+                raise AttributeError("rgk_device_cfg has no field " + k)
+            setattr(cfg, k, v)
+        self._check(self.lib.rgk_context_configure(self.h, C.byref(cfg)))
+
+    def cfg(self):
+        out = abi.DeviceCfg()
+        self._check(self.lib.rgk_context_get_cfg(self.h, C.byref(out)))
+        return out
 
     def close(self):
         if self.h:
@@ -182,11 +203,18 @@ class Context:
         self._check(self.lib.rgk_render_get_trav_stats(self.h, C.byref(a), C.byref(b)))
         return a, b
 
+    def accumulate_device(self, d_dst, d_src, n_floats, d_count=None, d_other_count=None, stream=None):
+        """EXRTexture::Accumulate on device buffers (integer addresses); stream: a cudaStream_t handle, None = the context stream."""
+        if stream is not None and int(stream) == 0:
+            stream = 1
+        self._check(self.lib.rgk_accumulate_device(self.h, _p(d_dst), _p(d_src), C.c_uint64(n_floats), _p(d_count), _p(d_other_count),
+                                                   C.c_void_p(stream) if stream is not None else None))
+
     def synchronize(self):
         self._check(self.lib.rgk_synchronize(self.h))
 
     def bvh_stats(self):
-        """Counters of the opt-in wide-BVH launches since the previous call (all 0 when RGK_WIDE_BVH was not set at commit)."""
+        """Counters of the wide-BVH launches since the previous call (all 0 on the kd-only traversal)."""
         out = (C.c_uint64 * 4)()
         self._check(self.lib.rgk_bvh_stats(self.h, C.byref(out)))
         return {"rays": out[0], "ambiguous": out[1], "nodes": out[2], "tests": out[3]}
@@ -196,10 +224,13 @@ class HostScene:
     """Host-only scene commit (rgk_host_scene_*): planes, areal lights, epsilon, bbox, kd-tree build + flatten -- what
     rgk_scene_commit computes on the CPU before uploading.  Needs no GPU."""
 
-    def __init__(self, desc, tree=None, lib=None):
+    def __init__(self, desc, tree=None, lib=None, cfg=None, **cfg_fields):
         self.lib = lib or abi.load_library()
         h = C.c_void_p()
-        st = self.lib.rgk_host_scene_create(C.byref(desc), C.byref(tree) if tree is not None else None, C.byref(h))
+        if cfg is None and cfg_fields:
+            cfg = abi.device_cfg(self.lib, **cfg_fields)
+        st = self.lib.rgk_host_scene_create(C.byref(desc), C.byref(tree) if tree is not None else None,
+                                            C.byref(cfg) if cfg is not None else None, C.byref(h))
         if st != 0:
             raise RgkError(st, self.lib.rgk_host_last_error().decode())
         self.h = h
@@ -229,8 +260,8 @@ class HostScene:
         return b
 
     def bvh(self):
-        """(nodes [n, 32] float32, order [n_triangles] uint32, depth) of the opt-in wide BVH; n == 0 unless the scene was
-        committed with RGK_WIDE_BVH=1 in the environment."""
+        """(nodes [n, 32] float32, order [n_triangles] uint32, depth) of the wide BVH; n == 0 when the scene was committed
+        with traversal="kd" (or has NaN-prone triangles, which keep it on the kd-tree)."""
         n, slots, depth = C.c_uint32(), C.c_uint32(), C.c_uint32()
         self.lib.rgk_host_scene_get_bvh_size(self.h, C.byref(n), C.byref(slots), C.byref(depth))
         nodes = np.zeros((max(1, n.value), 32), np.float32)

@@ -3,8 +3,8 @@
 // It is the C++ counterpart of what RGKrt's main() does after its config and scene are loaded (src/main.cpp:217-247);
 // argument parsing, the progress monitor and animation stay out of scope.
 //
-//   rgk_render scene.rgkpack out.exr [--rounds N | --minutes M] [--checkpoint file] [--resume] [--raw file] [--bvh]
-//   (--bvh: wide-BVH candidate pass + kd-tree arbiter, same pixels, ~1.5x faster traversal)
+//   rgk_render scene.rgkpack out.exr [--rounds N | --minutes M] [--checkpoint file] [--resume] [--raw file] [--kd]
+//   (--kd: the reference's kd-tree for every ray instead of the wide-BVH candidate pass + kd-tree arbiter; same pixels, slower)
 //              [--tiles]   (render tile by tile through PathTracer::Render, the reference's granularity)
 #include <cstdio>
 #include <cstdlib>
@@ -12,12 +12,12 @@
 #include "rgk_b200_host.hpp"
 
 int main(int argc, char** argv) {
-    if (argc < 3) { std::fprintf(stderr, "usage: rgk_render scene.rgkpack out.exr [--rounds N | --minutes M] [--checkpoint f] [--resume] [--raw f] [--tiles] [--bvh]\n"); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: rgk_render scene.rgkpack out.exr [--rounds N | --minutes M] [--checkpoint f] [--resume] [--raw f] [--tiles] [--kd]\n"); return 2; }
     try {
         rgkb::PackFile pack(argv[1]);
         const std::string out = argv[2];
         std::string checkpoint, raw;
-        bool resume = false, tiles = false, bvh = false;
+        bool resume = false, tiles = false, kd = false;
         rgkb::Config cfg = pack.config;
         for (int i = 3; i < argc; i++) {
             const std::string a = argv[i];
@@ -27,12 +27,13 @@ int main(int argc, char** argv) {
             else if (a == "--raw" && i + 1 < argc) raw = argv[++i];
             else if (a == "--resume") resume = true;
             else if (a == "--tiles") tiles = true;
-            else if (a == "--bvh") bvh = true;
+            else if (a == "--kd") kd = true;
+            else if (a == "--bvh") kd = false;            // the default since ABI 4
             else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
         }
         rgkb::Scene scene(0);
         const rgk_scene_desc desc = pack.desc();
-        scene.Commit(desc, nullptr, bvh);
+        scene.Commit(desc, nullptr, kd ? RGK_TRAVERSAL_KD : RGK_TRAVERSAL_BVH);
         const rgkb::Camera camera = pack.camera();
         rgkb::EXRTexture total(0, 0);
         rgkb::RenderDriver driver;

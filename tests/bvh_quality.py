@@ -16,8 +16,7 @@ w, hgt = (int(x) for x in args.res.split("x"))
 tot = {"nodes": 0.0, "tests": 0.0, "rays": 0}
 for scene in args.scenes.split(","):
     pack, cfg = standin.BUILDERS[scene](width=w, height=hgt, multisample=1)
-    os.environ["RGK_WIDE_BVH"] = "1"
-    hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="bvh")
     O = checkers.oracle(); h = O.scene_create(pack.desc())
     ca = cfg.camera_args()
     cam = O.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])

@@ -12,11 +12,24 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    # RGK_TEST_TRAVERSAL=bvh runs the whole GPU suite with every scene committed under RGK_WIDE_BVH=1 (the wide-BVH
-    # candidate pass + kd-tree arbiter): the gate for making that path the library default.  The tests that set or clear
-    # RGK_WIDE_BVH themselves (test_gpu_bvh.py, test_bvh_host.py) are unaffected.
-    if os.environ.get("RGK_TEST_TRAVERSAL") == "bvh":
-        os.environ["RGK_WIDE_BVH"] = "1"
+    # The library default -- what every test gets from device.Context(0) -- is the wide-BVH candidate pass + kd-tree arbiter
+    # (RGK_TRAVERSAL_BVH), the path bench.py times.  RGK_TEST_TRAVERSAL=kd (read HERE, by the test harness; the library reads
+    # no environment variable) re-runs the whole suite on the kd-only traversal: every Context / HostScene created without an
+    # explicit traversal gets traversal="kd".  Tests that name a traversal themselves (test_gpu_bvh.py, test_bvh_host.py,
+    # the kd legs of test_gpu_trace.py) are unaffected.
+    if os.environ.get("RGK_TEST_TRAVERSAL") == "kd":
+        from rgk_b200 import device
+
+        def wrap(cls):
+            init = cls.__init__
+
+            def patched(self, *a, **kw):
+                if kw.get("cfg") is None and "traversal" not in kw:
+                    kw["traversal"] = "kd"
+                init(self, *a, **kw)
+            cls.__init__ = patched
+        wrap(device.Context)
+        wrap(device.HostScene)
 
 
 @pytest.fixture(scope="session")

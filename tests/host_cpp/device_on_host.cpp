@@ -85,9 +85,9 @@ void* doh_scene_create(const uint32_t* nodes, uint32_t n_nodes, const uint32_t* 
 }
 void doh_scene_destroy(void* h) { delete (Scene*)h; }
 
-void* doh_shade_scene_create(const rgk_scene_desc* d) {
+void* doh_shade_scene_create(const rgk_scene_desc* d, const rgk_device_cfg* cfg) {
     ShadeScene* s = new ShadeScene();
-    try { host_scene_commit(d, nullptr, s->hs); } catch (...) { delete s; return nullptr; }
+    try { host_scene_commit(d, nullptr, cfg ? *cfg : default_device_cfg(), s->hs); } catch (...) { delete s; return nullptr; }
     DevScene& D = s->S;
     s->positions = pad3(d->positions, d->n_vertices); s->normals = pad3(d->normals, d->n_vertices); s->tangents = pad3(d->tangents, d->n_vertices);
     s->texcoords.resize(d->n_vertices + 1);
@@ -163,12 +163,14 @@ void doh_shade_scene_destroy(void* h) { delete (ShadeScene*)h; }
 
 // One RenderDriver round through render_round_impl -- the product's own host loop and kernels -- with caller-supplied
 // sampler tables (RGK_SAMPLER_TABLES; t1[pixel][dim][set], t2[pixel][dim][set][2]).  out_bvh: rays through the wide-BVH
-// kernels and how many of them were deferred to the kd arbiter (both 0 when the scene was committed without RGK_WIDE_BVH).
-int doh_render_round(void* h, const rgk_camera* cam, const rgk_render_params* p, const rgk_task* tasks, uint32_t n_tasks, uint32_t seedstart,
+// kernels and how many of them were deferred to the kd arbiter (both 0 when the scene was committed with RGK_TRAVERSAL_KD).
+// cfg: the rgk_device_cfg of the call (the tests switch k_bin off and refill one-lane warps after every ray).
+int doh_render_round(void* h, const rgk_device_cfg* cfg, const rgk_camera* cam, const rgk_render_params* p, const rgk_task* tasks, uint32_t n_tasks, uint32_t seedstart,
                      uint32_t seedcount_base, const float* t1, const float* t2, uint32_t n1d, uint32_t n2d, uint64_t n_pixels, float* rgb,
                      uint32_t* count, rgk_round_stats* stats, uint64_t* out_bvh) {
     ShadeScene* s = (ShadeScene*)h;
     rgk_context ctx;
+    if (cfg) ctx.cfg = *cfg;
     ctx.dev = s->S; ctx.has_scene = true;
     ctx.dev.refill_threshold = 1;
     if (s->S.n_point_lights) ctx.first_point_light = s->point_lights[0];

@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
                 cam.viewscreen_y[0], cam.viewscreen_y[1], cam.viewscreen_y[2], cam.IsSimple() ? "true" : "false");
     // --- host-only commit through the C ABI with the pack's description
     rgk_host_scene* hs = nullptr;
-    const rgk_status st = rgk_host_scene_create(&d, nullptr, &hs);
+    const rgk_status st = rgk_host_scene_create(&d, nullptr, nullptr, &hs);
     rgk_scene_info info{};
     if (st == RGK_OK) rgk_host_scene_get_info(hs, &info);
     std::printf("\"host_scene\": {\"status\": %d, \"n_nodes\": %u, \"n_refs\": %u, \"epsilon\": %.9g}, ", (int)st, info.n_nodes, info.n_refs, info.epsilon);

@@ -8,8 +8,8 @@ import checkers, test_device_on_host as T
 from rgk_b200 import standin
 lib = C.CDLL(T.SO)
 vp = C.c_void_p
-lib.doh_shade_scene_create.restype = vp; lib.doh_shade_scene_create.argtypes = [vp]; lib.doh_shade_scene_destroy.argtypes = [vp]
-lib.doh_render_round.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
+lib.doh_shade_scene_create.restype = vp; lib.doh_shade_scene_create.argtypes = [vp, vp]; lib.doh_shade_scene_destroy.argtypes = [vp]
+lib.doh_render_round.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
 O = checkers.oracle()
 for name in ("sponza", "sibenik", "conference"):
     pack, cfg = standin.BUILDERS[name](width=240, height=136, multisample=16)

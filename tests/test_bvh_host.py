@@ -1,4 +1,4 @@
-"""The opt-in wide BVH (RGK_WIDE_BVH=1; rgk_b200/csrc/host_bvh.cpp + bvh_device.cuh), checked without a GPU: structure of
+"""The wide BVH (RGK_TRAVERSAL_BVH, the default; rgk_b200/csrc/host_bvh.cpp + bvh_device.cuh), checked without a GPU: structure of
 the product-built nodes, and -- through the oracle's CPU mirror of the device traversal logic (rgko_bvh4_*) -- that every
 ray the BVH pass would commit has exactly the kd-tree's answer (Scene::FindIntersectKdOtherThan / Scene::Visibility,
 src/scene_intersect.cpp:211-327, src/scene.cpp:670-673) while only a tiny fraction is deferred to the kd pass."""
@@ -16,8 +16,7 @@ from rgk_b200 import device, standin, scenes
 @pytest.fixture(scope="module")
 def setup():
     pack, cfg = standin.sponza(width=320, height=180, multisample=1)
-    with checkers.scoped_env(RGK_WIDE_BVH=1):
-        hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="bvh")
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
     ca = cfg.camera_args()
@@ -28,10 +27,9 @@ def setup():
     hs.close()
 
 
-def test_off_by_default():
+def test_off_on_the_kd_traversal():
     pack = scenes.load_builtin("cornell-box")[0]
-    with checkers.scoped_env(RGK_WIDE_BVH=None):
-        hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="kd")
     nodes, order, depth = hs.bvh()
     assert len(nodes) == 0 and len(order) == 0 and depth == 0
     hs.close()
@@ -42,13 +40,12 @@ def test_structure(setup):
     _check_structure(pack, hs)
 
 
-@pytest.mark.parametrize("knobs", [{"RGK_BVH_REINSERT": "1"}, {"RGK_BVH_COLLAPSE": "greedy", "RGK_BVH_AXES": "1", "RGK_BVH_BINS": "16"}])
+@pytest.mark.parametrize("knobs", [{"bvh_reinsert_iters": 1}, {"bvh_greedy_collapse": 1, "bvh_all_axes": 0, "bvh_bins": 16}])
 def test_structure_under_the_builder_knobs(knobs):
     """The study knobs of host_bvh.cpp (insertion-based optimisation, the first version's greedy collapse) still produce a
     valid tree whose committed rays match the kd-tree."""
     pack, cfg = standin.sponza(width=160, height=90, multisample=1)
-    with checkers.scoped_env(RGK_WIDE_BVH=1, **knobs):
-        hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="bvh", **knobs)
     _check_structure(pack, hs)
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
@@ -167,8 +164,7 @@ def test_small_scenes_through_the_mirror(name):
     """Few, large, axis-aligned triangles (Cornell box: pixel-centre rays with zero direction components, hits on shared
     edges) and the material zoo: committed rays equal the kd-tree's answer over primary rays and three bounces."""
     pack, cfg = scenes.load_builtin("cornell-box", width=128, height=128, multisample=1) if name == "cornell-box" else scenes.material_zoo(width=128, height=96)
-    with checkers.scoped_env(RGK_WIDE_BVH=1):
-        hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="bvh")
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
     ca = cfg.camera_args()
@@ -205,8 +201,7 @@ def test_triangle_soup_stress(seed):
     tris = _triangles(rng, 3000)
     tris = np.concatenate([tris, tris[:200], tris[:100] + np.float32(1e-6)])          # exact and near-exact duplicates
     pack = _scene(tris)
-    with checkers.scoped_env(RGK_WIDE_BVH=1):
-        hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="bvh")
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
     nodes, order, depth = hs.bvh()
@@ -250,8 +245,7 @@ def test_tiny_scenes(n):
     base = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
     tris = (base + rng.normal(scale=0.5, size=(n, 3, 3))).astype(np.float32)
     pack = _scene(tris)
-    with checkers.scoped_env(RGK_WIDE_BVH=1):
-        hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="bvh")
     _check_structure(pack, hs)
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
@@ -284,8 +278,7 @@ def test_degenerate_inputs(case):
     else:
         tris = np.stack([np.stack([[i, 0, 0], [i + 0.5, 1, 0], [i + 0.5, 0, 1]]) for i in range(300)]).astype(np.float32)
     pack = _scene(tris)
-    with checkers.scoped_env(RGK_WIDE_BVH=1):
-        hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="bvh")
     _check_structure(pack, hs)
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
@@ -323,8 +316,7 @@ def test_campaign_regressions(seed):
     if seed % 3 == 0:
         tris = (tris + np.float32(rng.choice([0, 100, -5000]))).astype(np.float32)
     pack = _scene(tris)
-    with checkers.scoped_env(RGK_WIDE_BVH=1):
-        hs = device.HostScene(pack.desc())
+    hs = device.HostScene(pack.desc(), traversal="bvh")
     nodes, order, _ = hs.bvh()
     if seed in (5541, 5550):
         assert len(nodes) == 0                       # NaN-prone triangles: no wide BVH for this scene

@@ -33,17 +33,16 @@ def doh():
     lib.doh_closest.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, vp, vp, vp]
     lib.doh_shadow.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, vp, vp]
     lib.doh_shade_scene_create.restype = vp
-    lib.doh_shade_scene_create.argtypes = [vp]
+    lib.doh_shade_scene_create.argtypes = [vp, vp]
     lib.doh_shade_scene_destroy.argtypes = [vp]
     lib.doh_probe.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp]
-    lib.doh_render_round.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
+    lib.doh_render_round.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
     return lib
 
 
 class Scene:
     def __init__(self, lib, pack):
-        with checkers.scoped_env(RGK_WIDE_BVH=1):
-            hs = device.HostScene(pack.desc())
+        hs = device.HostScene(pack.desc(), traversal="bvh")
         info = hs.info()
         self.keep = [np.ascontiguousarray(a) for a in (*hs.kdtree(), *hs.records(), hs.bounds(), *hs.bvh()[:2], np.array(list(info.bbox), np.float32))]
         nodes, refs, planes, rec, bounds, bnodes, border, bbox = self.keep
@@ -176,7 +175,7 @@ class HostProber:
 
     def __init__(self, lib, desc):
         self.lib, self.desc = lib, desc
-        self.h = vp(lib.doh_shade_scene_create(C.byref(desc)))
+        self.h = vp(lib.doh_shade_scene_create(C.byref(desc), None))
         assert self.h.value
 
     def probe(self, kind, index, rows):
@@ -206,15 +205,16 @@ def test_shading_device_source_on_the_host(doh, oracle):
     ctx.close()
 
 
-def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=False, reverse=None, device_sampler=False):
+def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=False, reverse=None, device_sampler=False, **cfg_fields):
     """One round of render_round_impl compiled for the host (kernels + host loop of render.cu), fed with the oracle's
     StratifiedSampler tables, next to the oracle's own round."""
     from rgk_b200 import abi
     from test_gpu_render import _pixel_seeds
     desc = pack.desc()
     # one-lane warps: refill after every ray; no k_bin (it cooperates through shared memory)
-    with checkers.scoped_env(RGK_WIDE_BVH=1 if wide_bvh else None, RGK_BIN=0, RGK_REFILL_COHERENT=1, RGK_REFILL_INCOHERENT=1, RGK_REFILL_SHADOW=1):
-        h = vp(doh.doh_shade_scene_create(C.byref(desc)))
+    dcfg = abi.device_cfg(traversal="bvh" if wide_bvh else "kd", binning=0, refill_coherent=1, refill_incoherent=1, refill_shadow=1, **cfg_fields)
+    if True:
+        h = vp(doh.doh_shade_scene_create(C.byref(desc), C.byref(dcfg)))
         assert h.value
         ho = oracle.scene_create(desc)
         ca = cfg.camera_args()
@@ -232,7 +232,7 @@ def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=F
         t1 = np.ascontiguousarray(t1, np.float32); t2 = np.ascontiguousarray(t2, np.float32)
         rgb = np.zeros((p.yres, p.xres, 3), np.float32); cnt = np.zeros((p.yres, p.xres), np.uint32)
         st = abi.RoundStats(); bvh = np.zeros(2, np.uint64)
-        rc = doh.doh_render_round(h, C.byref(cam), C.byref(p), tasks, len(tasks), 42, seedcount_base, None if device_sampler else t1.ctypes.data,
+        rc = doh.doh_render_round(h, C.byref(dcfg), C.byref(cam), C.byref(p), tasks, len(tasks), 42, seedcount_base, None if device_sampler else t1.ctypes.data,
                                   None if device_sampler else t2.ctypes.data, n1d, n2d,
                                   len(seeds), rgb.ctypes.data, cnt.ctypes.data, C.byref(st), bvh.ctypes.data)
         assert rc == 0
@@ -310,24 +310,21 @@ def test_reference_scene_files_through_the_wavefront_on_the_host(doh, oracle):
 
 
 def test_host_loop_chunking_on_the_host(doh, oracle):
-    """render_round_impl's chunk loop (RGK_CHUNK_PATHS far below the paths of the call: many chunks, tiles split across
+    """render_round_impl's chunk loop (rgk_device_cfg::chunk_paths far below the paths of the call: many chunks, tiles split across
     them) gives the same bits as one chunk -- the host loop of render.cu itself, run on the CPU."""
     pack, cfg = _zoo()
-    with checkers.scoped_env(RGK_CHUNK_PATHS=700):
-        (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=3, wide_bvh=True)
+    (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=3, wide_bvh=True, chunk_paths=700)
     assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
     assert int(st.closest_launches) > cfg.recursion_level                          # more than one chunk was traced
 
 
 @pytest.mark.parametrize("scene", [_zoo, _cornell, _sponza])
 def test_ab_knob_kernels_on_the_host(doh, oracle, scene):
-    """The A/B candidates that are built but off by default give the same bits: RGK_SHADE_LAST=1 (the last bounce through
-    k_shade<true>, the instantiation without the BxDF sampling code, 4016 instead of 7352 SASS instructions) and
-    RGK_BVH_SHADOW_NOSORT=1 (any-hit BVH traversal entering the children in slot order) and RGK_BVH_CLOSEST_NEAREST=1
-    (closest-hit BVH traversal entering the nearest child first without sorting the others)."""
+    """The A/B candidates that are built but off by default give the same bits: rgk_device_cfg::bvh_shadow_nosort (any-hit BVH
+    traversal entering the children in slot order) and bvh_closest_nearest (closest-hit BVH traversal entering the nearest
+    child first without sorting the others)."""
     pack, cfg = scene()
-    with checkers.scoped_env(RGK_SHADE_LAST=1, RGK_BVH_SHADOW_NOSORT=1, RGK_BVH_CLOSEST_NEAREST=1):
-        (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=5, wide_bvh=True)
+    (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=5, wide_bvh=True, bvh_shadow_nosort=1, bvh_closest_nearest=1)
     assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
     assert int(st.closest_rays) == int(so.closest_rays)
 

@@ -1,4 +1,4 @@
-"""GPU parity of the opt-in wide-BVH traversal (RGK_WIDE_BVH=1 at commit; bvh_device.cuh + the kd arbiter pass) against the
+"""GPU parity of the wide-BVH traversal (RGK_TRAVERSAL_BVH, the library default; bvh_device.cuh + the kd arbiter pass) against the
 oracle, through the C ABI: hit records and visibility flags bit-exact, like the kd path (test_gpu_trace.py), with the
 BVH counters proving that the BVH kernels -- not the kd ones -- produced them."""
 import os
@@ -16,9 +16,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def setup():
     pack, cfg = standin.sponza(width=480, height=270, multisample=1)
-    with checkers.scoped_env(RGK_WIDE_BVH=1):
-        ctx = device.Context(0)
-        ctx.commit(pack.desc())
+    ctx = device.Context(0, traversal="bvh")
+    ctx.commit(pack.desc())
     O = checkers.oracle()
     h = O.scene_create(pack.desc())
     cam = ctx.camera(**cfg.camera_args())
@@ -81,10 +80,8 @@ def test_render_round_is_bit_identical_to_the_kd_path():
     the same framebuffer, bit for bit, and the same ray counts as the kd-only context."""
     pack, cfg = standin.sponza(width=256, height=144, multisample=4)
     desc = pack.desc()
-    with checkers.scoped_env(RGK_WIDE_BVH=None):
-        kd = device.Context(0); kd.commit(desc)
-    with checkers.scoped_env(RGK_WIDE_BVH=1):
-        bv = device.Context(0); bv.commit(desc)
+    kd = device.Context(0, traversal="kd"); kd.commit(desc)
+    bv = device.Context(0, traversal="bvh"); bv.commit(desc)
     out = []
     for ctx in (kd, bv):
         cam = ctx.camera(**cfg.camera_args())

@@ -87,15 +87,14 @@ def test_queue_order_never_changes_a_result(gpu_ctx, sponza, monkeypatch):
     p = cfg.params(abi.SAMPLER_MT19937)
     tasks = gpu_ctx.generate_tasks(32, 1920, 1080)
     ref_img = None
-    for env in ({"RGK_BIN": "0"}, {"RGK_BIN": "1"}, {"RGK_BIN": "1", "RGK_BIN_ITEMS": "8192", "RGK_REFILL_INCOHERENT": "4", "RGK_REFILL_SHADOW": "32"},
-                {"RGK_BIN": "1", "RGK_BIN_SHADOW0": "0", "RGK_CHUNK_PATHS": "3000000"}):
-        for k in ("RGK_BIN", "RGK_BIN_ITEMS", "RGK_REFILL_INCOHERENT", "RGK_REFILL_SHADOW", "RGK_BIN_SHADOW0", "RGK_CHUNK_PATHS"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
+    base = gpu_ctx.cfg()
+    for env in ({"binning": 0}, {"binning": 1}, {"binning": 1, "bin_items": 8192, "refill_incoherent": 4, "refill_shadow": 32},
+                {"binning": 1, "bin_shadow_first": 0, "chunk_paths": 3000000}):
+        gpu_ctx.configure(abi.DeviceCfg.from_buffer_copy(bytes(base)), **env)      # scheduling fields apply to the next call
         f, c, st = gpu_ctx.render_round(cam, p, tasks, seedcount_base=7)
         if ref_img is None:
             ref_img, ref_rays = f, (int(st.closest_rays), int(st.shadow_rays))
         else:
             assert np.array_equal(f.view(np.uint32), ref_img.view(np.uint32)), env
             assert (int(st.closest_rays), int(st.shadow_rays)) == ref_rays
+    gpu_ctx.configure(base)

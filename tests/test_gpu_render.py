@@ -180,15 +180,17 @@ def test_tile_sharding_is_independent_of_n(gpu_ctx):
 
 
 def test_chunking_does_not_change_the_image(gpu_ctx, monkeypatch):
-    """Tiny chunks (RGK_CHUNK_PATHS) split the tile list into many passes; the result must be identical."""
+    """Tiny chunks (rgk_device_cfg::chunk_paths) split the tile list into many passes; the result must be identical."""
     pack, cfg = scenes.load_builtin("cornell-box", width=96, height=64, multisample=4, recursion_max=4)
     gpu_ctx.commit(pack.desc())
     cam = gpu_ctx.camera(**cfg.camera_args())
     p = cfg.params()
     tasks = gpu_ctx.generate_tasks(32, 96, 64)
     a, ca, sa = gpu_ctx.render_round(cam, p, tasks)
-    monkeypatch.setenv("RGK_CHUNK_PATHS", "5000")
+    base = gpu_ctx.cfg()
+    gpu_ctx.configure(chunk_paths=5000)
     b, cb, sb = gpu_ctx.render_round(cam, p, tasks)
+    gpu_ctx.configure(base)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ca, cb)
     assert int(sb.kernel_launches) > int(sa.kernel_launches)
     empty = (abi.Task * 0)()

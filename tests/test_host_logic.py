@@ -90,15 +90,7 @@ def test_camera_args_fov_and_focal():
 
 def _host_tree(desc, threads):
     from rgk_b200 import device
-    old = os.environ.get("RGK_BUILD_THREADS")
-    os.environ["RGK_BUILD_THREADS"] = str(threads)
-    try:
-        hs = device.HostScene(desc)
-    finally:
-        if old is None:
-            os.environ.pop("RGK_BUILD_THREADS")
-        else:
-            os.environ["RGK_BUILD_THREADS"] = old
+    hs = device.HostScene(desc, build_threads=threads)
     info, (nodes, refs), (planes, rec) = hs.info(), hs.kdtree(), hs.records()
     hs.close()
     return info, nodes, refs, planes, rec

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the opt-in wide-BVH traversal (RGK_WIDE_BVH=1) against the kd-tree kernels on device-resident ray batches of a
+"""A/B of the wide-BVH traversal (RGK_TRAVERSAL_BVH, the default) against the kd-tree kernels on device-resident ray batches of a
 stand-in scene: Mrays/s of both (CUDA events on the launch stream), the deferred fraction, and a FULL-SIZE bit-exact
 comparison of every hit record / visibility flag between the two (the kd kernels are the ones the parity suite pins to
 the oracle).  torch-free (ctypes on libcudart) so that it starts in seconds on a fresh box.
@@ -39,7 +39,7 @@ def main():
     ap.add_argument("--render", type=int, default=2, help="also time N full render rounds of the bench workload (default scene config) on both contexts")
     ap.add_argument("--spp", type=int, default=None, help="override the samples per pixel of the render rounds")
     ap.add_argument("--render-only", action="store_true", help="skip the ray-batch A/B (for ncu runs)")
-    ap.add_argument("--sweep", action="store_true", help="render-only: time the BVH context under a list of environment knob settings")
+    ap.add_argument("--sweep", action="store_true", help="render-only: time the BVH context under a list of rgk_device_cfg settings")
     args = ap.parse_args()
     from rgk_b200 import device, standin, abi
     import raybatches
@@ -48,11 +48,8 @@ def main():
     pack, cfg = standin.BUILDERS[args.scene](width=w, height=h, multisample=1)
     desc = pack.desc()
     st = cu.stream()
-    os.environ.pop("RGK_WIDE_BVH", None)
-    kd = device.Context(0, stream=st.value); kd.commit(desc)
-    os.environ["RGK_WIDE_BVH"] = "1"
-    t0 = time.time(); bv = device.Context(0, stream=st.value); bv.commit(desc); t_commit = time.time() - t0
-    os.environ.pop("RGK_WIDE_BVH")
+    kd = device.Context(0, stream=st.value, traversal="kd"); kd.commit(desc)
+    t0 = time.time(); bv = device.Context(0, stream=st.value, traversal="bvh"); bv.commit(desc); t_commit = time.time() - t0
     if args.sweep:
         return sweep(cu, bv, args.scene, args.render, args.spp)
     if args.render_only:
@@ -108,14 +105,13 @@ def main():
         render_ab(cu, st, kd, bv, args.scene, args.render, args.spp)
 
 
-SWEEP = [{}, {"RGK_ARB_GRID": "1"}, {"RGK_ARB_GRID": "4"}, {"RGK_BVH_MINB": "8"}, {"RGK_REFILL_INCOHERENT": "16"}, {"RGK_REFILL_INCOHERENT": "28"},
-         {"RGK_REFILL_INCOHERENT": "32"}, {"RGK_REFILL_COHERENT": "24"}, {"RGK_REFILL_SHADOW": "6"}, {"RGK_REFILL_SHADOW": "20"}, {"RGK_BIN": "0"},
-         {"RGK_BIN_SHADOW0": "1"}, {"RGK_SHADE_LAST": "1"}, {"RGK_BVH_SHADOW_NOSORT": "1"}, {"RGK_BVH_CLOSEST_NEAREST": "1"},
-         {"RGK_SHADE_LAST": "1", "RGK_BVH_SHADOW_NOSORT": "1", "RGK_BVH_CLOSEST_NEAREST": "1"}, {}]
+SWEEP = [{}, {"arb_grid": 1}, {"arb_grid": 4}, {"refill_incoherent": 16}, {"refill_incoherent": 28}, {"refill_incoherent": 32},
+         {"refill_coherent": 32}, {"refill_shadow": 6}, {"refill_shadow": 20}, {"binning": 0}, {"bin_shadow_first": 0}, {"shade_path_order": 0},
+         {"bvh_shadow_nosort": 1}, {"bvh_closest_nearest": 1}, {}]
 
 
 def sweep(cu, bv, scene, rounds, spp=None):
-    """ms per round of the BVH context under each knob setting (the knobs are read per render call)."""
+    """ms per round of the BVH context under each rgk_device_cfg setting (scheduling fields apply to the next call)."""
     from rgk_b200 import standin
     pack, cfg = standin.BUILDERS[scene](**({"multisample": spp} if spp else {}))
     params = cfg.params()
@@ -124,15 +120,16 @@ def sweep(cu, bv, scene, rounds, spp=None):
     npx = params.xres * params.yres
     d_rgb, d_cnt = cu.empty(npx * 12), cu.empty(npx * 4)
     ref = None
+    from rgk_b200 import abi
+    base = bv.cfg()
     for knobs in SWEEP:
-        for k, v in knobs.items(): os.environ[k] = v
+        bv.configure(abi.DeviceCfg.from_buffer_copy(bytes(base)), **knobs)
         ms = []
         for r in range(rounds + 1):
             cu.ck(cu.rt.cudaMemset(C.c_void_p(d_rgb), 0, C.c_size_t(npx * 12))); cu.ck(cu.rt.cudaMemset(C.c_void_p(d_cnt), 0, C.c_size_t(npx * 4)))
             stats = bv.render_round_device(cam, params, tasks, d_rgb, d_cnt)
             bv.synchronize()
             ms.append((stats.gpu_ms, stats.closest_ms, stats.shadow_ms, stats.shade_ms, stats.sampler_ms))
-        for k in knobs: os.environ.pop(k)
         fb = cu.to_host(d_rgb, np.uint32, npx * 3)
         if ref is None: ref = fb
         best = min(ms[1:])

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--copies", type=int, default=2, help="jittered copies of the primary batch (>= 2^22 rays)")
     ap.add_argument("--check", type=int, default=0)
+    ap.add_argument("--traversal", default="kd", choices=["kd", "bvh"])
+    ap.add_argument("--kd-variant", dest="kd_variant", type=int, default=6, choices=[2, 6])
     ap.add_argument("--sort", type=int, default=0, help="sort secondary batches by (direction octant, origin cell on an N^3 grid)")
     args = ap.parse_args()
     import torch
@@ -33,7 +35,7 @@ def main():
     pack, cfg = standin.BUILDERS[args.scene](width=w, height=h, multisample=1)
     desc = pack.desc()
     stream = torch.cuda.current_stream().cuda_stream
-    ctx = device.Context(0, stream=stream)
+    ctx = device.Context(0, stream=stream, traversal=args.traversal, kd_variant=args.kd_variant)
     ctx.commit(desc)
     info = ctx.scene_info()
     cam = ctx.camera(**cfg.camera_args())
@@ -115,7 +117,7 @@ def main():
             O = checkers.oracle(); ho = O.scene_create(desc)
             rec["bit_exact_vs_oracle"] = bool(np.array_equal(d_v.cpu().numpy()[: args.check], O.trace_shadow(ho, a[: args.check], b[: args.check])))
         out.append(rec)
-    tag = {"scene": args.scene, "triangles": info.n_triangles, "variant": os.environ.get("RGK_TRAVERSAL", "default")}
+    tag = {"scene": args.scene, "triangles": info.n_triangles, "variant": args.kd_variant}
     for r in out:
         r.update(tag)
         print(json.dumps(r))

@@ -324,9 +324,11 @@ int rgkref_trace_closest(void* h, const rgk_ray* rays, const uint32_t* ignore, u
 int rgkref_trace_shadow(void* h, const float* a, const float* b, uint64_t n, uint8_t* visible, int nthreads) {
     const Scene& s = ((RefScene*)h)->scene;
     run_parallel(n, nthreads, [&](uint64_t lo, uint64_t hi) {
-        for (uint64_t i = lo; i < hi; i++)
-            visible[i] = s.Visibility(glm::vec3(a[3 * i], a[3 * i + 1], a[3 * i + 2]),
-                                      glm::vec3(b[3 * i], b[3 * i + 1], b[3 * i + 2])) ? 1 : 0;
+        for (uint64_t i = lo; i < hi; i++) {
+            const glm::vec3 pa(a[3 * i], a[3 * i + 1], a[3 * i + 2]), pb(b[3 * i], b[3 * i + 1], b[3 * i + 2]);
+            if (s.thinglass.size() == 0) visible[i] = s.Visibility(pa, pb) ? 1 : 0;
+            else { ThinglassIsections ti; visible[i] = s.VisibilityWithThinglass(pa, pb, ti) ? 1 : 0; }   // as src/path_tracer.cpp:431-432 selects
+        }
     });
     return 0;
 }

@@ -108,5 +108,33 @@ zoo.update(fb=fb, cnt=cnt, closest_rays=int(st.closest_rays), camera=np.frombuff
 zn, zr = R.scene_kdtree(h)
 zoo.update(nodes=zn, refs=zr)
 np.savez_compressed(os.path.join(OUT, "zoo.npz"), **zoo)
+
+# ---- 4. StratifiedSampler tables of the large set sizes (BASELINE C3 256 spp, C5 512 -> 529): the sets the device shuffles in
+# place in global memory (k_sampler_mt<false>); a few dims of two seeds keep the file small
+big = {}
+seeds2 = np.array([42 + 0x42424242, 0x9E3779B9], np.uint32)
+for ms in (256, 512):
+    t1, t2 = R.sampler_tables(seeds2, ms, 3, 4)
+    big[f"t1_{ms}"], big[f"t2_{ms}"] = t1, t2
+np.savez_compressed(os.path.join(OUT, "sampler_large.npz"), seeds=seeds2, **big)
+
+# ---- 5. a scene with a non-empty thinglass set (src/main.cpp:212): FindIntersectKdOtherThanWithThinglass / VisibilityWithThinglass
+pack, cfg = scenes.load_builtin("cornell-box", width=64, height=64, multisample=4)
+pack.thinglass = 1
+desc = pack.desc()
+h = R.scene_create(desc)
+cam = cam_of(R, cfg)
+rays = raybatches.primary(R, cam, 64, 64, jitter_seed=3)
+hits = R.trace_closest(h, rays)
+info = R.scene_info(h)
+brays, ign = raybatches.bounce(rays, hits, R.scene_planes(h)[:, :3], info.epsilon, seed=8)
+bhits = R.trace_closest(h, brays, ign)
+sa, sb = raybatches.shadow_segments(brays, bhits, (-0.005, 1.97, -0.03))
+vis = R.trace_shadow(h, sa, sb)
+p = cfg.params(); p.depth = 40
+tasks = R.generate_tasks(32, 64, 64)
+fb, cnt, st = R.render_round(h, cam, p, tasks, nthreads=4)
+np.savez_compressed(os.path.join(OUT, "cornell_thinglass.npz"), brays=brays, ign=ign, bhits=bhits, sa=sa, sb=sb, vis=vis, fb=fb, cnt=cnt,
+                    closest_rays=int(st.closest_rays))
 for f in sorted(os.listdir(OUT)):
     print(f, os.path.getsize(os.path.join(OUT, f)))

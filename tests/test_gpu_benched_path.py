@@ -113,7 +113,7 @@ def test_bidirectional_mode_on_the_default_traversal(oracle, scene, reverse):
     # light-path splats are atomic adds: their order is not defined, so kd vs BVH is compared like GPU vs oracle
     ho = oracle.scene_create(desc)
     fo, co, so = oracle.render_round(ho, cam, p, tasks, nthreads=1)
-    assert int(sb.closest_rays) == int(so.closest_rays) and int(sb.shadow_rays) == int(so.shadow_rays)
+    assert int(sb.closest_rays) == int(so.closest_rays) and int(sb.shadow_rays) + int(sb.shadow_rays_skipped) == int(so.shadow_rays)
     mean = float(fo.mean())
     for f in (fb, fk):
         assert abs(float(f.mean()) - mean) <= 2e-3 * mean

@@ -3,17 +3,24 @@
 
 Metric (BASELINE.json): Mrays/s, closest-hit + shadow rays, whole job.  Workload: BASELINE configs[1],
 scenes/sponza.json at 1920x1080, 64 spp, path tracing with next-event estimation (recursion-max 2) -- on the
-seeded ~66-71 k-triangle atrium STAND-IN, because sponza.obj is not distributed with the reference
+seeded ~71 k-triangle atrium STAND-IN, because sponza.obj is not distributed with the reference
 (rgk_b200/standin.py).  One "step" = one RenderDriver round (every pixel, 64 spp) per GPU.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sponza|cornell|sibenik|conference|dragon-sponza]
-                  [--sampler mt|fast] [--shard rounds|tiles]
+                  [--sampler mt|fast] [--shard rounds|tiles] [--traversal bvh|kd] [--cfg field=value,...] [--quick]
 
-N > 1 (torchrun): rounds are sharded (GPU g renders round step*N+g with its own seed base, weak scaling) and the
-partial framebuffers are summed with one NCCL reduce per step; --shard tiles deals the tile list round-robin
-instead (strong scaling).  `value` has inputs resident in HBM (device framebuffer); `e2e` goes through
-rgk_render_round with pinned HOST framebuffers, H2D + D2H inside the timed region.  `--impl reference` times the
-reference's own ctpl-threaded CPU renderer (oracle/_ref, else the oracle port) on a bounded crop.
+What runs is the library default: the 4-wide BVH candidate pass with the reference's kd-tree as arbiter (rgk_device_cfg,
+no environment variable).  `value`: device-resident framebuffer, CUDA events, max over ranks.  `e2e`: the same step
+through rgk_render_round with pinned HOST framebuffers, H2D + D2H inside the timed region.
+N > 1 (torchrun): rounds are sharded (GPU g renders round step*N+g with its own seed base: weak scaling); each GPU renders
+into a per-round partial buffer, ONE NCCL reduce per round runs on a second stream under the next round, and rank 0 adds
+the result to the running total (EXRTexture::Accumulate on the device).  Sample counts are analytic and not reduced.  The
+same run then times the tile-sharded (strong-scaling) variant and checks its image bit for bit against a single-GPU render
+(`strong`).  --shard tiles makes the tile-sharded variant the headline instead.
+Untimed legs of the N = 1 line: `parity` (the headline round on the kd-only traversal, framebuffers compared bit for bit),
+a counting round for the algorithmic bytes (`roofline`, `roofline_by_kernel`) and the reference's CPU renderer on a strided
+sample of the frame's own tiles (`cpu_baseline`).  `--impl reference` times that CPU renderer alone (oracle/_ref, else
+the oracle port).
 """
 import argparse
 import ctypes as C
@@ -21,7 +28,7 @@ import json
 import os
 import subprocess
 import sys
-import threading
+import tempfile
 import time
 
 import numpy as np
@@ -33,7 +40,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from rgk_b200 import abi, scenes, standin  # noqa: E402
 
 METRIC = "Mrays/s (closest-hit+shadow)"
-CROP = (960, 540)   # CPU baseline sample: centred crop of the full-resolution image, full spp (10-20 s on 16 cores)
+CPU_TILES = 128     # CPU baseline sample: this many 32x32 tiles taken at a constant stride through the frame's own task list, full spp
+KERNEL_METRICS = os.path.join(ROOT, "profiles", "r2_kernel_metrics.json")   # per-class ncu figures (tools/make_kernel_metrics.py)
 
 
 def real_asset_workload(name, spp):
@@ -91,66 +99,66 @@ def parse_cfg(text):
     return out
 
 
-def crop_camera(cam, xres, yres, cw, ch):
-    """Camera whose cw x ch image is the centred crop of cam's xres x yres image (same rays up to rounding)."""
-    x0, y0 = (xres - cw) // 2, (yres - ch) // 2
-    out = abi.Camera.from_buffer_copy(bytes(cam))
-    vs, vx, vy = (np.array(list(v), np.float64) for v in (cam.viewscreen, cam.viewscreen_x, cam.viewscreen_y))
-    nvs = vs + vx * (x0 / xres) + vy * (y0 / yres)
-    for dst, src in ((out.viewscreen, nvs), (out.viewscreen_x, vx * (cw / xres)), (out.viewscreen_y, vy * (ch / yres))):
-        for k in range(3):
-            dst[k] = float(np.float32(src[k]))
-    out.xsize, out.ysize = cw, ch
-    return out
-
-
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+class ClockSampler:
+    """The recipe's clocks line (B200_PROFILING.md): ONE nvidia-smi process looping every 200 ms while the timed region runs --
+    started before, killed after.  (Round 1 spawned a new nvidia-smi every 100 ms; each start-up takes the driver's global
+    lock for ~0.2 s, which stalled this process's kernel launches and cost ~17 % of the headline on a 16-core box.)"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
 
-    def run(self):
-        while not self.stop_flag:
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
-
-    def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+                self.proc.wait(timeout=3)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        self.out.flush()
+        self.out.seek(0)
+        rows = [[x.strip() for x in line.split(",")] for line in self.out.read().splitlines() if line.strip()]
+        self.out.close()
+        try:
+            os.unlink(self.out.name)
+        except OSError:
+            pass
+        rows = [r for r in rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        sm = sorted(int(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]) if rows[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(rows), "how": "one `nvidia-smi -lms 200` process over the warm-up and timed steps"}
 
 
-def cpu_sample(cfg, pack, desc, kind_pref, threads, crop=None):
-    """Sets up the CPU renderer on a bounded sample (centred crop of the frame, full spp)."""
+# ------------------------------------------------------------------ the CPU arm (reference renderer on the host cores)
+def strided_tasks(all_tasks, n_tiles):
+    """A constant-stride sample of the frame's own (centre-sorted) task list: tiles from the centre to the corners in the
+    proportion the frame has them -- the same camera, resolution and spp as the GPU arm, fewer tiles."""
+    n = len(all_tasks)
+    n_tiles = max(1, min(n, n_tiles))
+    idx = [int(i * n / n_tiles) for i in range(n_tiles)]
+    return (abi.Task * n_tiles)(*[all_tasks[i] for i in idx]), idx
+
+
+def cpu_setup(cfg, desc):
     import checkers
-    crop = crop or CROP
-    use_ref = kind_pref == "reference" and checkers.have_ref()
+    use_ref = checkers.have_ref()
     chk = checkers.ref() if use_ref else checkers.oracle()
     orc = checkers.oracle()
     h = chk.scene_create(desc)
     ho = orc.scene_create(desc) if use_ref else h
     ca = cfg.camera_args()
-    cam_full = orc.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
-    cw, ch = min(crop[0], cfg.xres), min(crop[1], cfg.yres)
-    cam = crop_camera(cam_full, cfg.xres, cfg.yres, cw, ch)
-    p = cfg.params()
-    p.xres, p.yres = cw, ch
-    tasks = orc.generate_tasks(32, cw, ch)
-    return chk, orc, h, ho, cam, p, tasks, use_ref, (cw, ch)
+    cam = orc.camera_init(ca["pos"], ca["lookat"], ca["up"], ca["yview"], ca["xview"], ca["xres"], ca["yres"], ca["focus_plane"], ca["lens_size"])
+    return chk, orc, h, ho, cam, use_ref
 
 
 def run_cpu(chk, h, cam, p, tasks, threads, shadow_rays=None):
@@ -162,6 +170,11 @@ def run_cpu(chk, h, cam, p, tasks, threads, shadow_rays=None):
     return dt, closest, shadow, int(st.samples)
 
 
+def cpu_sample_desc(n_tiles, n_all, cfg, samples):
+    return "%d of the frame's %d 32x32 tiles at a constant stride through the task list, %dx%d camera, %d spp (%d samples)" % (
+        n_tiles, n_all, cfg.xres, cfg.yres, cfg.multisample, samples)
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -169,13 +182,16 @@ def reference_arm(args):
     pack, cfg, label = build_workload(args.workload, args.spp)
     desc = pack.desc()
     threads = os.cpu_count() or 1
-    # size the per-step sample so that warmup + steps stay near two minutes on this box's cores: probe a small crop first
-    chk, orc, h, ho, cam, p, tasks, use_ref, _ = cpu_sample(cfg, pack, desc, "reference", threads, crop=(256, 144))
-    probe_dt, _, _, probe_samples = run_cpu(chk, h, cam, p, tasks, threads, 0)
-    budget_samples = (120.0 / max(1, args.steps + args.warmup + 1)) * probe_samples / max(probe_dt, 1e-3)
-    scale = min(1.0, (budget_samples / (CROP[0] * CROP[1] * max(1, cfg.multisample))) ** 0.5)
-    crop = (max(256, int(CROP[0] * scale) // 32 * 32), max(144, int(CROP[1] * scale) // 16 * 16))
-    chk, orc, h, ho, cam, p, tasks, use_ref, (cw, ch) = cpu_sample(cfg, pack, desc, "reference", threads, crop=crop)
+    chk, orc, h, ho, cam, use_ref = cpu_setup(cfg, desc)
+    p = cfg.params()
+    all_tasks = orc.generate_tasks(32, p.xres, p.yres)
+    # size the per-step sample so that warmup + steps stay near two minutes on this box's cores: probe a few tiles first
+    probe, _ = strided_tasks(all_tasks, max(8, threads))
+    probe_dt, _, _, probe_samples = run_cpu(chk, h, cam, p, probe, threads, 0)
+    per_tile = probe_dt / len(probe)
+    budget = 120.0 / max(1, args.steps + args.warmup + 1)
+    n_tiles = int(max(threads, min(len(all_tasks), budget / max(per_tile, 1e-4))))
+    tasks, _ = strided_tasks(all_tasks, n_tiles)
     shadow = None
     if use_ref:   # the reference does not count shadow rays (src/path_tracer.cpp:126 counts closest only): take the
         # count of the bit-identical oracle run of the same sample, untimed
@@ -188,7 +204,7 @@ def reference_arm(args):
         dt, c, s, smp = run_cpu(chk, h, cam, p, tasks, threads, shadow)
         tot_t += dt; tot_r += c + s; tot_s += smp
     value = tot_r / tot_t / 1e6
-    sample = "centred %dx%d crop of the %dx%d frame, %d spp, %d samples per step" % (cw, ch, cfg.xres, cfg.yres, cfg.multisample, tot_s // max(1, args.steps))
+    sample = cpu_sample_desc(len(tasks), len(all_tasks), cfg, tot_s // max(1, args.steps))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -199,6 +215,119 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ roofline
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def roofline_records(ctx, cam, p, tasks, ntasks, fb, cnt, stats, steps, info, clocks_mhz):
+    """An untimed counting round gives the work counters; the timed steps give the per-class kernel time (CUDA events on the
+    launch stream); profiles/r2_kernel_metrics.json gives, per kernel class, DRAM bytes and warp instructions per unit from the
+    committed `ncu --set full` capture of this command.  Per class:
+      achieved = algorithmic bytes / time (what the step's formula says must move)        -> frac      = / HBM peak
+      dram     = measured DRAM bytes / time                                                             -> frac_hbm  = / HBM peak
+      issue    = warp instructions / (SMs * 4 schedulers * clock * time)                                -> frac_issue
+    The headline `roofline` is the class with the largest share of the step."""
+    ctx.bvh_stats()
+    ctx.set_counting(True)
+    ctx.set_shard(0, 1)
+    st = ctx.render_round_device(cam, p, tasks, fb.data_ptr(), cnt.data_ptr(), 42, 100 * ntasks)
+    ctx.set_counting(False)
+    bvh = ctx.bvh_stats()
+    sh = ctx.shade_stats()
+    tc, ts = ctx.render_trav_stats()
+    bvh_on = bvh["rays"] > 0
+    n_close, n_shadow, n_samples = int(st.closest_rays), int(st.shadow_rays), int(st.samples)
+    if bvh_on:      # B_ray(bvh) = 36 + out + 128 nodes + 20 leaf slots + 32 exact tests (include/rgk_b200.h: rgk_bvh_stats)
+        def b_ray(c, out):
+            r = max(1, c["rays"])
+            return 36 + out + (128 * c["nodes"] + 20 * c["slots"] + 32 * c["tests"]) / r
+        b_closest, b_shadow = b_ray(bvh["closest"], 20), b_ray(bvh["shadow"], 1)
+        trav = {"closest": {k: bvh["closest"][k] / max(1, bvh["closest"]["rays"]) for k in ("nodes", "slots", "tests")},
+                "shadow": {k: bvh["shadow"][k] / max(1, bvh["shadow"]["rays"]) for k in ("nodes", "slots", "tests")}}
+    else:           # SURVEY 8d: 36 + out + 8 inner + 8 leaves + 4 refs + 48 tests
+        b_closest, b_shadow = tc.bytes_per_ray(20), ts.bytes_per_ray(1)
+        trav = {"closest": {k: v / max(1, tc.rays) for k, v in tc.as_dict().items() if k != "rays"},
+                "shadow": {k: v / max(1, ts.rays) for k, v in ts.as_dict().items() if k != "rays"}}
+    # k_shade, per thread (= per closest-hit ray): path state read 84 B (hit, ray origin + direction, throughput, cursor, the two
+    # sampler values, queue entry); written 33 B per light evaluation (surface point + NEE record + key), 65 B per continuation
+    # (ray, throughput, last triangle, cursor, key, two queue entries), 32 B radiance read-modify-write where no shadow ray is queued;
+    # per surface vertex 96 B of vertex attributes + 64 B material; 16 B per image texel; 208 B per LTC lobe evaluation
+    threads = sh["vertices"] + sh["sky_vertices"]
+    shade_bytes = (84 * threads + 33 * sh["light_evals"] + 65 * sh["continuations"] + 32 * (threads - sh["light_evals"])
+                   + 160 * sh["vertices"] + 16 * sh["texels"] + 208 * sh["ltc_evals"])
+    b_shade = shade_bytes / max(1, threads)
+    # sampler, per pixel: the tables it must write (the generator state it streams on top is an artefact of the implementation)
+    ms_ = int(p.multisample)
+    ss = ctx.sampler_set_size(ms_)
+    n1d, n2d = 1 + int(p.depth), 4 + int(p.depth) + (1 if cam.lens_size != 0.0 else 0)
+    npix = n_samples // ms_
+    b_sampler = (n1d * 4 + n2d * 8) * ss + 4
+
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured, sustained copy)" if peaks else "fallback 6650 GB/s (of fallback)"
+    try:
+        km = json.load(open(KERNEL_METRICS))
+    except Exception:
+        km = {}
+    sms = 148
+    clock_hz = (clocks_mhz or 1965) * 1e6
+    n = max(1, steps)
+    cls = {"closest": (sum(float(s.closest_ms) for s in stats) / n, sum(int(s.closest_rays) for s in stats) / n, b_closest, "ray"),
+           "shadow": (sum(float(s.shadow_ms) for s in stats) / n, sum(int(s.shadow_rays) for s in stats) / n, b_shadow, "ray"),
+           "shade": (sum(float(s.shade_ms) for s in stats) / n, sum(int(s.closest_rays) for s in stats) / n, b_shade, "vertex (k_shade thread)"),
+           "sampler": (sum(float(s.sampler_ms) for s in stats) / n, npix, b_sampler, "pixel")}
+    launches = {"closest": sum(int(s.closest_launches) for s in stats) / n, "shadow": sum(int(s.shadow_launches) for s in stats) / n,
+                "shade": sum(int(s.closest_launches) for s in stats) / n, "sampler": 1.0}
+    names = {"closest": "k_closest_bvh (+ k_closest_arb)" if bvh_on else "k_closest", "shadow": "k_shadow_bvh (+ k_shadow_arb)" if bvh_on else "k_shadow",
+             "shade": "k_shade (+ k_raygen, k_bin, k_finish in its event bracket)", "sampler": "k_sampler_mt (+ k_pixel_setup)"}
+    step_ms = sum(float(s.gpu_ms) for s in stats) / n
+    by = {}
+    for k, (ms, units, b_unit, unit_name) in cls.items():
+        sec = ms / 1e3
+        m = km.get(k, {})
+        rec = {"kernel": names[k], "ms_per_step": ms, "share_of_step": ms / step_ms if step_ms else None, "unit": unit_name, "units_per_step": units,
+               "launches_per_step": launches[k], "algorithmic_bytes_per_unit": b_unit,
+               "achieved_GBs": units * b_unit / sec / 1e9 if sec > 0 else 0.0}
+        rec["frac"] = rec["achieved_GBs"] / peak
+        if "dram_bytes_per_unit" in m:
+            rec["dram_bytes_per_unit"] = m["dram_bytes_per_unit"]
+            rec["frac_hbm"] = units * m["dram_bytes_per_unit"] / sec / 1e9 / peak if sec > 0 else 0.0
+        if "warp_inst_per_unit" in m:
+            rec["warp_inst_per_unit"] = m["warp_inst_per_unit"]
+            rec["active_lanes_per_instruction"] = m.get("active_lanes_per_instruction")
+            rec["frac_issue"] = units * m["warp_inst_per_unit"] / (sms * 4 * clock_hz * sec) if sec > 0 else 0.0
+        for extra in ("registers_per_thread", "achieved_occupancy_pct", "l1_hit_pct", "l2_hit_pct"):
+            if extra in m:
+                rec[extra] = m[extra]
+        rec["bound"] = "issue" if k in ("closest", "shadow") else "hbm"
+        by[k] = rec
+    top = max(by, key=lambda k: by[k]["ms_per_step"])
+    t = by[top]
+    roofline = {"bound": "hbm", "kernel": t["kernel"], "achieved": t["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": t["frac"],
+                "traffic": (t["dram_bytes_per_unit"] * t["units_per_step"] / max(1.0, t["launches_per_step"])) if "dram_bytes_per_unit" in t else None,
+                "traffic_unit": "DRAM bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum per unit (profiles/r2_kernel_metrics.json) x units per launch",
+                "algorithmic_bytes_per_launch": t["algorithmic_bytes_per_unit"] * t["units_per_step"] / max(1.0, t["launches_per_step"]),
+                "avg_launch_ms": t["ms_per_step"] / max(1.0, t["launches_per_step"]), "launches_per_step": t["launches_per_step"],
+                "share_of_step": t["share_of_step"], "frac_hbm": t.get("frac_hbm"), "frac_issue": t.get("frac_issue"),
+                "peak_source": peak_src, "class": top,
+                "note": "the kernel class with the largest share of the step; algorithmic bytes from the counting round (per-unit formulas in "
+                        "DESIGN.md 4), time from CUDA events on the launch stream over the timed steps; frac_hbm uses measured DRAM bytes and "
+                        "frac_issue measured warp instructions per unit from the committed ncu capture (%s); every class in roofline_by_kernel. "
+                        "The traversal classes are issue / divergence-bound (their structure, a few MB, lives in L1/L2): their graded fraction is "
+                        "frac_issue, and their `frac` (cache-fed algorithmic bytes over the HBM peak) may exceed 1" % (
+                            km.get("source", "profiles/r2_kernel_metrics.json missing"))}
+    extra = {"work_counters": {"traversal_per_ray": trav, "shade": sh, "prefilter": tc.device_dict() if not bvh_on else None,
+                               "counting_round": {"closest_rays": n_close, "shadow_rays": n_shadow, "samples": n_samples}},
+             "kernel_share_of_step": {k: v["share_of_step"] for k, v in by.items()},
+             "sum_of_kernel_ms_per_step": sum(v["ms_per_step"] for v in by.values())}
+    return roofline, by, extra, bvh_on
 
 
 def main():
@@ -212,6 +341,7 @@ def main():
     ap.add_argument("--sampler", default="mt", choices=["mt", "fast"])
     ap.add_argument("--shard", default="rounds", choices=["rounds", "tiles"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--quick", action="store_true", help="timed steps only: no e2e, parity, counting, strong or CPU legs (A/B runs, large workloads)")
     ap.add_argument("--traversal", default="bvh", choices=["bvh", "kd"],
                     help="bvh: the library default, the wide-BVH traversal with the kd-tree arbiter pass (results bit-identical to the kd "
                          "path); kd: the reference's kd-tree for every ray")
@@ -222,7 +352,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from rgk_b200 import device
+    from rgk_b200 import device, multigpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -235,8 +365,9 @@ def main():
 
     pack, cfg, label = build_workload(args.workload, args.spp)
     desc = pack.desc()
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = device.Context(local, stream=stream, traversal=args.traversal, **parse_cfg(args.cfg))
+    render_stream = torch.cuda.current_stream()
+    comm_stream = torch.cuda.Stream()
+    ctx = device.Context(local, stream=render_stream.cuda_stream, traversal=args.traversal, **parse_cfg(args.cfg))
     t0 = time.perf_counter()
     ctx.commit(desc)
     commit_s = time.perf_counter() - t0
@@ -246,172 +377,215 @@ def main():
     p = cfg.params(mode)
     all_tasks = ctx.generate_tasks(32, p.xres, p.yres)
     ntasks = len(all_tasks)
-    from rgk_b200 import multigpu
-    tasks = all_tasks
-    if args.shard == "tiles" and world > 1:
-        ctx.set_shard(rank, world)      # this rank renders tiles rank, rank+world, ... of every list, seeds unchanged
-    fb = torch.zeros((p.yres, p.xres, 3), dtype=torch.float32, device="cuda")
-    cnt = torch.zeros((p.yres, p.xres), dtype=torch.int32, device="cuda")
+    npx = p.yres * p.xres
+    total = torch.zeros((p.yres, p.xres, 3), dtype=torch.float32, device="cuda")     # rank 0: the running image (sum of samples)
+    cnt = torch.zeros((p.yres, p.xres), dtype=torch.int32, device="cuda")            # per-GPU sample counts (analytic globally: not reduced)
+    parts = [torch.zeros_like(total) for _ in range(2)] if world > 1 else None
+    rendered = [torch.cuda.Event() for _ in range(2)]
+    reduced = [torch.cuda.Event() for _ in range(2)]
 
-    def step(i):
-        """One round per GPU (weak) or this rank's tiles of one round (strong), then the per-round reduce."""
-        rnd = i if (args.shard == "tiles" and world > 1) else multigpu.round_for_rank(i, rank, world)
-        st = ctx.render_round_device(cam, p, tasks, fb.data_ptr(), cnt.data_ptr(), 42, multigpu.seedcount_base(rnd, ntasks))
-        multigpu.reduce_framebuffer(fb, cnt)
+    def step(i, tiles):
+        """One round per GPU (weak) or this rank's tiles of one round (strong).  world > 1: rendered into partial buffer i % 2;
+        its NCCL reduce and rank 0's accumulate run on the communication stream, under the next step's rendering."""
+        rnd = i if tiles else multigpu.round_for_rank(i, rank, world)
+        if world == 1:
+            return ctx.render_round_device(cam, p, all_tasks, total.data_ptr(), cnt.data_ptr(), 42, multigpu.seedcount_base(rnd, ntasks))
+        b = i & 1
+        render_stream.wait_event(reduced[b])                 # the reduce that last read this partial buffer (two steps ago)
+        parts[b].zero_()
+        st = ctx.render_round_device(cam, p, all_tasks, parts[b].data_ptr(), cnt.data_ptr(), 42, multigpu.seedcount_base(rnd, ntasks))
+        rendered[b].record(render_stream)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(rendered[b])
+            dist.reduce(parts[b], dst=0, op=dist.ReduceOp.SUM)     # in place on rank 0: its own partial + everybody else's
+            if rank == 0:
+                ctx.accumulate_device(total.data_ptr(), parts[b].data_ptr(), npx * 3, stream=comm_stream.cuda_stream)   # EXRTexture::Accumulate
+            reduced[b].record(comm_stream)
         return st
 
     def barrier():
+        render_stream.wait_stream(comm_stream)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
-        step(i)
+    def timed(n_steps, first, tiles):
+        """n_steps steps between barriers, CUDA events on the render stream (the communication stream is joined before the
+        closing event), max over ranks.  Returns (ms, per-step stats)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out = []
+        barrier()
+        e0.record(render_stream)
+        for i in range(n_steps):
+            out.append(step(first + i, tiles))
+        render_stream.wait_stream(comm_stream)
+        e1.record(render_stream)
+        barrier()
+        return e0.elapsed_time(e1), out
+
+    def aggregate(ms, stats):
+        rays = sum(int(s.closest_rays) + int(s.shadow_rays) for s in stats)          # rays actually traced
+        skipped = sum(int(s.shadow_rays_skipped) for s in stats)                     # reference Visibility calls proven irrelevant
+        samples = sum(int(s.samples) for s in stats)
+        launches = sum(int(s.kernel_launches) for s in stats)
+        agg = torch.tensor([ms, float(rays), float(samples), float(launches), float(skipped)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx = agg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = agg.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            return float(mx[0]), float(sm[1]), float(sm[2]), float(sm[3]), float(sm[4])
+        return tuple(float(x) for x in agg)
+
+    tiles_mode = args.shard == "tiles" and world > 1
+    if tiles_mode:
+        ctx.set_shard(rank, world)      # this rank renders tiles rank, rank+world, ... of every list, seeds unchanged
+    warm = max(3, args.warmup)
+    # started before the warm-up steps so that nvidia-smi's own start-up (~0.3 s, holds the driver lock) is over when the timed
+    # region begins; its samples cover the warm-up (same load) and the timed steps
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(warm):
+        step(i, tiles_mode)
     barrier()
-    sampler_thread = ClockSampler(local) if rank == 0 else None
-    if sampler_thread:
-        sampler_thread.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stats = []
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        stats.append(step(100 + i))
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if sampler_thread:
-        sampler_thread.stop_flag = True
-        sampler_thread.join(timeout=3)
-    rays = sum(int(s.closest_rays) + int(s.shadow_rays) for s in stats)          # rays actually traced
-    skipped = sum(int(s.shadow_rays_skipped) for s in stats)                     # reference Visibility calls proven irrelevant
-    samples = sum(int(s.samples) for s in stats)
-    launches = sum(int(s.kernel_launches) for s in stats)
-    agg = torch.tensor([ms, float(rays), float(samples), float(launches), float(skipped)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        mx = agg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = agg.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, rays, samples, launches, skipped = float(mx[0]), float(sm[1]), float(sm[2]), float(sm[3]), float(sm[4])
+    ms, stats = timed(args.steps, 100, tiles_mode)
+    clocks = sampler.stop() if sampler else None
+    ms, rays, samples, launches, skipped = aggregate(ms, stats)
     value = rays / (ms / 1e3) / 1e6
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong" if tiles_mode else "weak",
+        "vs_baseline": None, "dtype": "f32 (+f64 plane distance)", "data": "synthetic: seeded stand-in scene, procedural textures",
+        "config": {"workload": label, "sampler": "mt19937 replica (same sequence as the CPU reference)" if mode == abi.SAMPLER_MT19937 else "fast counter-based",
+                   "parallelism": ("1 GPU" if world == 1 else ("round-sharded x%d, one NCCL reduce per round overlapped with the next round" % world if not tiles_mode
+                                                               else "tile-sharded x%d, one NCCL reduce per round overlapped with the next round" % world)),
+                   "traversal": ("wide BVH candidate pass + kd-tree arbiter pass (the library default): bit-identical to the kd-tree path"
+                                 if args.traversal == "bvh" else "kd-tree (reference structure) for every ray"),
+                   "device_cfg": args.cfg or "library defaults",
+                   "l2": "no flush: per-step path state and sampler tables (GBs) exceed the 126 MB L2; the scene (a few MB) is the working set"},
+        "samples_per_s": samples / (ms / 1e3), "gpu_launches": int(launches),
+        "rays_note": "value counts rays actually traced; %d shadow queries per step whose direct term is exactly 0 are resolved without "
+                     "tracing (the reference traces them): reference-equivalent rate %.1f Mrays/s" % (
+                         int(skipped / max(1, args.steps)), (rays + skipped) / (ms / 1e3) / 1e6),
+        "clocks": clocks,
+    }
 
     # ---- e2e: the same step through rgk_render_round with pinned host framebuffers
-    h_fb = torch.zeros((p.yres, p.xres, 3), dtype=torch.float32).pin_memory()
-    h_cnt = torch.zeros((p.yres, p.xres), dtype=torch.int32).pin_memory()
-    np_fb, np_cnt = h_fb.numpy(), h_cnt.numpy().view(np.uint32)
-    def e2e_step(i):
-        rnd = i if (args.shard == "tiles" and world > 1) else multigpu.round_for_rank(i, rank, world)
-        _, _, st = ctx.render_round(cam, p, all_tasks, 42, multigpu.seedcount_base(rnd, ntasks), fb=(np_fb, np_cnt))
-        return st
-    e2e_step(0)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_rays = 0
-    for i in range(args.steps):
-        st = e2e_step(200 + i)
-        e2e_rays += int(st.closest_rays) + int(st.shadow_rays)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    agg2 = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        mx = agg2.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = agg2.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_rays = float(mx[0]), float(sm[1])
-    fb_bytes = h_fb.numel() * 4 + h_cnt.numel() * 4
-    e2e = {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": fb_bytes + C.sizeof(abi.Camera) + C.sizeof(abi.RenderParams) + 16 * ntasks,
-           "d2h_bytes_per_step": fb_bytes, "samples_per_s": (samples / max(1, args.steps)) * args.steps / e2e_s if world == 1 else None}
+    if not args.quick:
+        h_fb = torch.zeros((p.yres, p.xres, 3), dtype=torch.float32).pin_memory()
+        h_cnt = torch.zeros((p.yres, p.xres), dtype=torch.int32).pin_memory()
+        np_fb, np_cnt = h_fb.numpy(), h_cnt.numpy().view(np.uint32)
 
-    # ---- roofline of the dominant kernel (closest-hit traversal), untimed counting pass for the algorithmic bytes
-    roofline, extra = None, {}
-    if rank == 0:
-        bvh = ctx.bvh_stats()                  # every wide-BVH launch so far (warm-up, timed and e2e steps); zeros on the kd path
-        bvh_on = bvh["rays"] > 0
-        ctx.set_counting(True)
+        def e2e_step(i):
+            rnd = i if tiles_mode else multigpu.round_for_rank(i, rank, world)
+            _, _, st = ctx.render_round(cam, p, all_tasks, 42, multigpu.seedcount_base(rnd, ntasks), fb=(np_fb, np_cnt))
+            return st
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_rays = 0
+        for i in range(args.steps):
+            st = e2e_step(200 + i)
+            e2e_rays += int(st.closest_rays) + int(st.shadow_rays)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        agg2 = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx = agg2.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = agg2.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            e2e_s, e2e_rays = float(mx[0]), float(sm[1])
+        fb_bytes = h_fb.numel() * 4 + h_cnt.numel() * 4
+        line["e2e"] = {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s",
+                       "h2d_bytes_per_step": fb_bytes + C.sizeof(abi.Camera) + C.sizeof(abi.RenderParams) + 16 * ntasks,
+                       "d2h_bytes_per_step": fb_bytes, "samples_per_s": (samples / e2e_s) if world == 1 else None,
+                       "note": "per-GPU host framebuffers (no reduce in this leg)" if world > 1 else None}
+        del h_fb, h_cnt
+
+    # ---- strong scaling in the same run (world > 1, default sharding): the tile-sharded round, timed the same way, and its
+    # image compared bit for bit with a single-GPU render of the same round
+    if world > 1 and not tiles_mode and not args.quick:
+        ctx.set_shard(rank, world)
+        for i in range(2):
+            step(300 + i, True)
+        ms_s, st_s = timed(args.steps, 400, True)
+        ms_s, rays_s, samples_s, _, _ = aggregate(ms_s, st_s)
+        barrier()
+        total.zero_()
+        barrier()
+        step(500, True)                                  # one tile-sharded round into a clean total
+        barrier()
+        strong = {"ms_per_step": ms_s / max(1, args.steps), "value": rays_s / (ms_s / 1e3) / 1e6, "unit": "Mrays/s",
+                  "samples_per_s": samples_s / (ms_s / 1e3), "sharding": "32x32 tiles dealt round-robin, every pixel owned by one GPU"}
+        if rank == 0:
+            ctx.set_shard(0, 1)
+            ref = torch.zeros_like(total)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.render_round_device(cam, p, all_tasks, ref.data_ptr(), cnt.data_ptr(), 42, multigpu.seedcount_base(500, ntasks))
+            ref.zero_()
+            torch.cuda.synchronize()
+            e0.record(render_stream)
+            ctx.render_round_device(cam, p, all_tasks, ref.data_ptr(), cnt.data_ptr(), 42, multigpu.seedcount_base(500, ntasks))
+            e1.record(render_stream)
+            torch.cuda.synchronize()
+            t1 = e0.elapsed_time(e1)
+            diff = int((ref.view(torch.int32) != total.view(torch.int32)).sum().item())
+            strong.update({"n1_ms_same_round_same_run": t1, "efficiency_vs_n1": t1 / (world * strong["ms_per_step"]),
+                           "image_equal_to_n1": diff == 0, "fb_words_differing": diff,
+                           "limit": "fixed per-round cost on every GPU (sampler tables and direction binning of its own tiles, launch latency of ~12 "
+                                    "short kernels) and the full-frame reduce of a partial image that is 1/N non-zero"})
+            del ref
+        line["strong"] = strong
         ctx.set_shard(0, 1)
-        ctx.render_round_device(cam, p, all_tasks, fb.data_ptr(), cnt.data_ptr(), 42, 100 * ntasks)
-        tc, ts = ctx.render_trav_stats()
-        ctx.set_counting(False)
-        b_closest, b_shadow = tc.bytes_per_ray(20), ts.bytes_per_ray(1)
-        cl_ms = sum(float(s.closest_ms) for s in stats)
-        cl_rays = sum(int(s.closest_rays) for s in stats)
-        cl_launches = max(1, sum(int(s.closest_launches) for s in stats))
-        sh_ms = sum(float(s.shadow_ms) for s in stats)
-        sh_rays = sum(int(s.shadow_rays) for s in stats)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = cl_rays * b_closest / (cl_ms / 1e3) / 1e9 if cl_ms > 0 else 0.0
-        traffic, ncu = None, None     # DRAM bytes per launch + issue figures from the committed ncu --set full capture (profiles/r1_traffic.json)
-        try:
-            tname = "r1_traffic_bvh.json" if bvh_on else "r1_traffic.json"
-            tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
-            traffic = tj["dram_bytes_per_ray"] * cl_rays / cl_launches
-            ncu = {k: tj[k] for k in ("launches", "issue_slots_busy_pct", "active_lanes_per_instruction", "l1_hit_pct", "l2_hit_pct") if k in tj}
-            ncu["source"] = "profiles/%s (static, from the committed ncu --set full capture)" % tname
-        except Exception:
-            pass
-        kname = ("k_closest_bvh + k_closest_arb (closest hit through the wide BVH, kd-tree arbiter for the deferred rays)" if bvh_on
-                 else "k_closest (kd-tree closest-hit traversal)")
-        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write per ray x rays per launch)",
-                    "algorithmic_bytes_per_launch": cl_rays * b_closest / cl_launches, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                    "bytes_per_ray": b_closest, "avg_launch_ms": cl_ms / cl_launches, "launches_per_step": cl_launches / max(1, args.steps),
-                    "Grays_per_s_in_kernel": cl_rays / (cl_ms / 1e3) / 1e9 if cl_ms > 0 else 0.0,
-                    "note": "algorithmic bytes are those of the REFERENCE algorithm (kd-tree counters of an untimed counting pass: SURVEY 8d); "
-                            "cache-fed: the tree, planes and triangle records (a few MB) live in L1/L2, so those bytes are served ~70x from cache "
-                            "(compare `traffic`); frac > 1 against the HBM copy peak is expected, the kernel is issue/divergence-bound "
-                            "(profiles/README.md)" + ("; the wide-BVH pass does the same job in 4x fewer node visits" if bvh_on else ""),
-                    "prefilter": tc.device_dict(), "ncu": ncu,
-                    "shadow_kernel": {"bytes_per_ray": b_shadow, "achieved": sh_rays * b_shadow / (sh_ms / 1e3) / 1e9 if sh_ms > 0 else 0.0,
-                                      "Grays_per_s_in_kernel": sh_rays / (sh_ms / 1e3) / 1e9 if sh_ms > 0 else 0.0}}
-        tot_ms = sum(float(s.gpu_ms) for s in stats)
-        extra = {"kernel_share_of_step": {"closest": cl_ms / tot_ms, "shadow": sh_ms / tot_ms,
-                                          "sampler": sum(float(s.sampler_ms) for s in stats) / tot_ms,
-                                          "shade": sum(float(s.shade_ms) for s in stats) / tot_ms},
-                 "traversal": {"mode": "bvh4 + kd arbiter" if bvh_on else "kd", "bvh_rays": bvh["rays"],
-                               "deferred_to_kd_frac": bvh["ambiguous"] / max(1, bvh["rays"])},
-                 "closest_Mrays_per_s": cl_rays / (ms / 1e3) / 1e6 if world == 1 else None,
-                 "shadow_Mrays_per_s": sh_rays / (ms / 1e3) / 1e6 if world == 1 else None,
-                 "trav_counters_per_closest_ray": {k: v / max(1, tc.rays) for k, v in tc.as_dict().items() if k != "rays"},
-                 "scene": {"triangles": info.n_triangles, "kd_nodes": info.n_nodes, "kd_refs": info.n_refs, "kd_depth": info.max_depth,
-                           "commit_s": commit_s, "tag": "standin" if args.workload != "cornell" else "real"}}
+        barrier()
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        chk, orc, h, ho, ccam, cp, ctasks, use_ref, (cw, ch) = cpu_sample(cfg, pack, desc, "reference", threads)
-        shadow = None
-        if use_ref:
-            _, _, st = orc.render_round(ho, ccam, cp, ctasks, nthreads=threads)
-            shadow = int(st.shadow_rays)
-        dt, c, s, smp = run_cpu(chk, h, ccam, cp, ctasks, threads, shadow)
-        cpu = {"value": (c + s) / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "reference" if use_ref else "port",
-               "sample": "centred %dx%d crop of the %dx%d frame, %d spp (%d samples, %.1f s)" % (cw, ch, cfg.xres, cfg.yres, cfg.multisample, smp, dt),
-               "samples_per_s": smp / dt}
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak" if args.shard == "rounds" else "strong",
-            "vs_baseline": None, "dtype": "f32 (+f64 plane distance)", "data": "synthetic: seeded stand-in scene, procedural textures",
-            "config": {"workload": label, "sampler": "mt19937 replica (same sequence as the CPU reference)" if mode == abi.SAMPLER_MT19937 else "fast counter-based",
-                       "parallelism": ("1 GPU" if world == 1 else ("round-sharded x%d + NCCL reduce per round" % world if args.shard == "rounds"
-                                                                   else "tile-sharded x%d + NCCL reduce per round" % world)),
-                       "traversal": ("wide BVH candidate pass + kd-tree arbiter pass (the library default): bit-identical to the kd-tree path"
-                                     if args.traversal == "bvh" else "kd-tree (reference structure) for every ray"),
-                       "l2": "no flush: per-step path state and sampler tables (GBs) exceed the 126 MB L2; the scene (a few MB) is the working set"},
-            "samples_per_s": samples / (ms / 1e3), "gpu_launches": int(launches),
-            "rays_note": "value counts rays actually traced; %d shadow queries per step whose direct term is exactly 0 are resolved without "
-                         "tracing (the reference traces them): reference-equivalent rate %.1f Mrays/s" % (
-                             int(skipped / max(1, args.steps)), (rays + skipped) / (ms / 1e3) / 1e6),
-            "clocks": sampler_thread.summary() if sampler_thread else None,
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-        }
+    # ---- untimed legs of rank 0: parity against the kd-only traversal, counting round, CPU arm
+    if rank == 0 and not args.quick:
+        if args.traversal == "bvh" and world == 1:
+            kd = device.Context(local, stream=render_stream.cuda_stream, traversal="kd")
+            kd.commit(desc)
+            a, b = torch.zeros_like(total), torch.zeros_like(total)
+            ca, cb = torch.zeros_like(cnt), torch.zeros_like(cnt)
+            base = multigpu.seedcount_base(100, ntasks)           # the first timed round
+            ctx.bvh_stats()
+            sa = ctx.render_round_device(cam, p, all_tasks, a.data_ptr(), ca.data_ptr(), 42, base)
+            used = ctx.bvh_stats()
+            sb = kd.render_round_device(cam, p, all_tasks, b.data_ptr(), cb.data_ptr(), 42, base)
+            torch.cuda.synchronize()
+            line["parity"] = {
+                "against": "the same round (the headline workload, full frame, full spp) on the kd-only traversal, whose kernels the GPU "
+                           "suite pins to the oracle; untimed",
+                "fb_words_differing": int((a.view(torch.int32) != b.view(torch.int32)).sum().item()),
+                "counts_differing": int((ca != cb).sum().item()),
+                "rays_equal": (int(sa.closest_rays), int(sa.shadow_rays), int(sa.shadow_rays_skipped)) == (int(sb.closest_rays), int(sb.shadow_rays), int(sb.shadow_rays_skipped)),
+                "bvh_rays": used["rays"], "deferred_to_kd_frac": used["ambiguous"] / max(1, used["rays"]),
+                "kd_ms_per_round": float(sb.gpu_ms), "bvh_ms_per_round": float(sa.gpu_ms)}
+            kd.close()
+            del a, b, ca, cb
+        roofline, by, extra, bvh_on = roofline_records(ctx, cam, p, all_tasks, ntasks, total, cnt, stats, args.steps, info,
+                                                       clocks.get("sm_mhz") if clocks else None)
+        line["roofline"] = roofline
+        line["roofline_by_kernel"] = by
         line.update(extra)
+        line["host_gap_ms_per_step"] = line["ms_per_step"] - extra["sum_of_kernel_ms_per_step"] if world == 1 else None
+        line["traversal"] = {"mode": "bvh4 + kd arbiter" if bvh_on else "kd"}
+        line["closest_Mrays_per_s"] = sum(int(s.closest_rays) for s in stats) / (ms / 1e3) / 1e6 if world == 1 else None
+        line["shadow_Mrays_per_s"] = sum(int(s.shadow_rays) for s in stats) / (ms / 1e3) / 1e6 if world == 1 else None
+        line["scene"] = {"triangles": info.n_triangles, "kd_nodes": info.n_nodes, "kd_refs": info.n_refs, "kd_depth": info.max_depth,
+                         "commit_s": commit_s, "tag": "standin" if args.workload != "cornell" else "real"}
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            chk, orc, h, ho, ccam, use_ref = cpu_setup(cfg, desc)
+            cp = cfg.params()
+            ctasks, _ = strided_tasks(orc.generate_tasks(32, cp.xres, cp.yres), CPU_TILES)
+            shadow = None
+            if use_ref:
+                _, _, st = orc.render_round(ho, ccam, cp, ctasks, nthreads=threads)
+                shadow = int(st.shadow_rays)
+            dt, c, s, smp = run_cpu(chk, h, ccam, cp, ctasks, threads, shadow)
+            line["cpu_baseline"] = {"value": (c + s) / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "reference" if use_ref else "port",
+                                    "sample": cpu_sample_desc(len(ctasks), ntasks, cfg, smp) + ", %.1f s" % dt, "samples_per_s": smp / dt}
+    if rank == 0:
+        line.setdefault("e2e", None); line.setdefault("roofline", None); line.setdefault("cpu_baseline", None)
         print(json.dumps(line))
     if world > 1:
+        barrier()
         dist.destroy_process_group()
 
 

@@ -325,10 +325,11 @@ rgk_status rgk_host_scene_get_bounds(const rgk_host_scene* hs, float* bounds);
  * index, leaf = 1<<31 | (count-1)<<29 | first slot, empty = 0x7fffffff), 4 zeros; order[slot] = triangle. */
 rgk_status rgk_host_scene_get_bvh_size(const rgk_host_scene* hs, uint32_t* n_nodes, uint32_t* n_slots, uint32_t* depth);
 rgk_status rgk_host_scene_get_bvh(const rgk_host_scene* hs, float* nodes, uint32_t* order);
-/* Counters of the wide-BVH traversal launches since the previous call (synchronises the stream): out[0] rays, out[1]
- * ambiguous rays handed to the kd-tree, out[2] wide nodes visited, out[3] exact triangle tests (2-3 only while
- * rgk_render_set_counting is on).  All zero when the BVH is off. */
-rgk_status rgk_bvh_stats(rgk_context* ctx, uint64_t out[4]);
+/* Counters of the wide-BVH traversal launches since the previous call (synchronises the stream), out[0..4] for the
+ * closest-hit launches and out[5..9] for the any-hit (shadow) launches: rays, ambiguous rays handed to the kd-tree, wide
+ * nodes visited, exact triangle tests, leaf slots scanned (the last three only while rgk_render_set_counting is on: the
+ * algorithmic bytes per BVH ray are 36 in + 20 (1) out + 128 * nodes + 20 * slots + 32 * tests).  All zero when the BVH is off. */
+rgk_status rgk_bvh_stats(rgk_context* ctx, uint64_t out[10]);
 
 /* Replaces Scene::FindIntersectKdOtherThan (src/scene_intersect.cpp:211-327) over a
  * batch; ignore[i] = triangle index to skip or RGK_NO_TRIANGLE (then it is
@@ -410,6 +411,14 @@ rgk_status rgk_render_set_shard(rgk_context* ctx, uint32_t first, uint32_t strid
  * never on in a timed run) and rgk_render_get_trav_stats returns the totals of the last rendering call. */
 rgk_status rgk_render_set_counting(rgk_context* ctx, int enabled);
 rgk_status rgk_render_get_trav_stats(const rgk_context* ctx, rgk_trav_stats* closest, rgk_trav_stats* shadow);
+
+/* Work counters of the shading kernel over the last rendering call made while counting was enabled (unidirectional mode):
+ * out[0] surface vertices shaded (one GeneratePath iteration, src/path_tracer.cpp:122-302), out[1] sky vertices, out[2] image
+ * texels the vertices needed (4 per bilinear fetch, 3 per bump-slope fetch), out[3] LTC lobe evaluations (BxDF::value and the
+ * specular branch of BxDF::sample; mix materials not counted), out[4] light evaluations (NEE set-ups), out[5] continuation
+ * rays produced, out[6..7] reserved.  The algorithmic bytes of one vertex are path-state read + written + 96
+ * (vertex attributes) + 64 (material) + 16 * texels + 208 * LTC evaluations. */
+rgk_status rgk_render_get_shade_stats(const rgk_context* ctx, uint64_t out[8]);
 
 /* Parity probe (no reference counterpart): evaluates ONE device shading function on n caller-supplied inputs so
  * tests can compare it with the CPU path function by function.  Host buffers; float rows per item:

@@ -171,7 +171,7 @@ EXPORTS = [
     "rgk_host_scene_create", "rgk_host_scene_destroy", "rgk_host_last_error", "rgk_host_scene_get_info",
     "rgk_host_scene_get_kdtree", "rgk_host_scene_get_records", "rgk_host_scene_get_bounds",
     "rgk_host_scene_get_bvh_size", "rgk_host_scene_get_bvh", "rgk_bvh_stats",
-    "rgk_device_cfg_init", "rgk_context_configure", "rgk_context_get_cfg", "rgk_accumulate_device",
+    "rgk_device_cfg_init", "rgk_context_configure", "rgk_context_get_cfg", "rgk_accumulate_device", "rgk_render_get_shade_stats",
 ]
 
 
@@ -229,6 +229,7 @@ def load_library(path=None):
     lib.rgk_device_cfg_init.restype = None
     lib.rgk_context_configure.argtypes = [vp, C.POINTER(DeviceCfg)]
     lib.rgk_context_get_cfg.argtypes = [vp, C.POINTER(DeviceCfg)]
+    lib.rgk_render_get_shade_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 8)]
     lib.rgk_accumulate_device.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp]
     lib.rgk_host_scene_destroy.argtypes = [vp]
     lib.rgk_host_scene_destroy.restype = None
@@ -239,7 +240,7 @@ def load_library(path=None):
     lib.rgk_host_scene_get_bounds.argtypes = [vp, vp]
     lib.rgk_host_scene_get_bvh_size.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rgk_host_scene_get_bvh.argtypes = [vp, vp, vp]
-    lib.rgk_bvh_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
+    lib.rgk_bvh_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 10)]
     lib.rgk_render_set_counting.argtypes = [vp, C.c_int]
     lib.rgk_render_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.rgk_render_get_trav_stats.argtypes = [vp, C.POINTER(TravStats), C.POINTER(TravStats)]

@@ -209,7 +209,7 @@ rgk_status rgk_scene_commit(rgk_context* ctx, const rgk_scene_desc* d, const rgk
                 bp[j] = make_float4(q[0], q[1], q[2], q[3]);
             }
             UP(bp, &D.bvh_planes);
-            std::vector<BvhStats> z(1, BvhStats{0, 0, 0, 0});
+            std::vector<BvhStats> z(2, BvhStats{0, 0, 0, 0, 0});
             const BvhStats* dz = nullptr;
             UP(z, &dz);
             ctx->d_bvh_stats = const_cast<BvhStats*>(dz);
@@ -376,17 +376,18 @@ rgk_status rgk_host_scene_get_bvh(const rgk_host_scene* h, float* nodes, uint32_
     return RGK_OK;
 }
 
-// counters of the wide-BVH traversal launches since the previous call: rays, ambiguous (re-traced through the kd-tree),
-// wide nodes visited and exact triangle tests (the last two only while rgk_set_counting is on).  Zeros when the BVH is off.
-rgk_status rgk_bvh_stats(rgk_context* ctx, uint64_t out[4]) {
+// counters of the wide-BVH traversal launches since the previous call, closest-hit launches then any-hit launches: rays,
+// ambiguous (re-traced through the kd-tree), wide nodes visited, exact triangle tests, leaf slots scanned (the last three only
+// while rgk_render_set_counting is on).  Zeros when the BVH is off.
+rgk_status rgk_bvh_stats(rgk_context* ctx, uint64_t out[10]) {
     if (!ctx || !out) return RGK_ERR_INVALID;
-    out[0] = out[1] = out[2] = out[3] = 0;
+    for (int k = 0; k < 10; k++) out[k] = 0;
     if (!ctx->d_bvh_stats) return RGK_OK;
-    BvhStats h{};
-    RGK_CUDA(ctx, cudaMemcpyAsync(&h, ctx->d_bvh_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BvhStats h[2] = {};
+    RGK_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_bvh_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     RGK_CUDA(ctx, cudaMemsetAsync(ctx->d_bvh_stats, 0, sizeof(h), ctx->stream));
     RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    out[0] = h.rays; out[1] = h.ambiguous; out[2] = h.nodes; out[3] = h.tests;
+    for (int k = 0; k < 2; k++) { out[5 * k] = h[k].rays; out[5 * k + 1] = h[k].ambiguous; out[5 * k + 2] = h[k].nodes; out[5 * k + 3] = h[k].tests; out[5 * k + 4] = h[k].slots; }
     return RGK_OK;
 }
 
@@ -647,6 +648,12 @@ rgk_status rgk_render_set_counting(rgk_context* ctx, int enabled) {
 rgk_status rgk_render_get_trav_stats(const rgk_context* ctx, rgk_trav_stats* closest, rgk_trav_stats* shadow) {
     if (!ctx || !closest || !shadow) return RGK_ERR_INVALID;
     *closest = ctx->last_closest; *shadow = ctx->last_shadow;
+    return RGK_OK;
+}
+
+rgk_status rgk_render_get_shade_stats(const rgk_context* ctx, uint64_t out[8]) {
+    if (!ctx || !out) return RGK_ERR_INVALID;
+    for (int k = 0; k < 8; k++) out[k] = ctx->last_shade[k];
     return RGK_OK;
 }
 

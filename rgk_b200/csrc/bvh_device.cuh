@@ -20,7 +20,7 @@
 #pragma once
 #include "trace_device.cuh"
 
-struct BvhCount { uint32_t nodes, tests; };
+struct BvhCount { uint32_t nodes, tests, slots; };
 constexpr uint32_t BVH_DONE = 0x7fffffffu;      // also the code of an empty child slot
 
 // SORT: 1 = children entered by ascending entry distance (sorting network).  A/B knobs, results identical: 0 = slot order
@@ -164,6 +164,7 @@ struct BvhTraverser {
     // arithmetic of Traverser::exact_test), accepted inside [lo_t, hi_t].  Returns true when the traversal can stop
     // (ANY: a firm hit).
     __device__ __forceinline__ bool test(const DevScene& S, uint32_t p, float eps, BvhCount& cnt) {
+        if (COUNT) cnt.slots++;
         const float4 r0 = __ldg(S.bvh_planes + p);
         const float dtf = dx * r0.x + dy * r0.y + dz * r0.z;
         const float dot2f = ox * r0.x + oy * r0.y + oz * r0.z;
@@ -284,5 +285,21 @@ __device__ __forceinline__ void trace_bvh(const DevScene& S, uint32_t count, uns
             else commit(item, ANY ? stop : (T.res.tri != RGK_NO_TRIANGLE), T.res);
             active = false;
         }
+    }
+}
+
+// warp-aggregated flush of a launch's BVH counters (one atomic per counter per warp)
+template <bool COUNT>
+__device__ __forceinline__ void flush_bvh_counts(const BvhCount& c, uint32_t nrays, uint32_t deferred, BvhStats* stats) {
+    unsigned long long v[5] = {nrays, deferred, COUNT ? c.nodes : 0u, COUNT ? c.tests : 0u, COUNT ? c.slots : 0u};
+#pragma unroll
+    for (int k = 0; k < (COUNT ? 5 : 2); k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats->rays, v[0]);
+        if (v[1]) atomicAdd(&stats->ambiguous, v[1]);
+        if (COUNT) { atomicAdd(&stats->nodes, v[2]); atomicAdd(&stats->tests, v[3]); atomicAdd(&stats->slots, v[4]); }
     }
 }

@@ -45,6 +45,7 @@ struct PathBuffers {
     float *t1 = nullptr; float2 *t2 = nullptr;
     uint4 *tiles = nullptr; uint2 *tiles2 = nullptr;
     unsigned long long *counters = nullptr;   // device
+    unsigned long long *shade_counts = nullptr;   // device, 8 words: work counters of k_shade in counting rounds (rgk_render_get_shade_stats)
     unsigned long long *h_counters = nullptr; // pinned
     struct EventPool* events = nullptr;       // host only
     ReverseBuffers* reverse = nullptr;        // host only (bidirectional mode)
@@ -61,6 +62,7 @@ struct RenderConst {
     uint32_t npix;          // pixels in the chunk
     uint32_t const_light;   // 1: the scene's only light is one point light of size 0 -- every sample picks the same light record
     float4 cl_pos, cl_col;  //    (position + flags, colour + intensity), read from here instead of per-path arrays
+    uint32_t count_shade;   // 1: counting round, k_shade adds its work counters to PathBuffers::shade_counts
     uint32_t reverse;       // light path length (bidirectional mode, reverse_device.cuh); 0 = unidirectional
     uint32_t npaths;        // npix * ms
 };
@@ -515,29 +517,22 @@ struct ShadowIO {
     }
 };
 
-__device__ __forceinline__ void flush_bvh_counts(uint32_t nrays, uint32_t deferred, BvhStats* stats) {
-    unsigned long long a = nrays, b = deferred;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&stats->rays, a); if (b) atomicAdd(&stats->ambiguous, b); }
-}
-
-template <int MINB, int SORT = 1>       // MINB 6: <= 80 registers (no spills, 7 CTAs/SM at the 72 it uses); 8: <= 64 (RGK_BVH_MINB A/B knob)
+template <int MINB, int SORT = 1, bool COUNT = false>       // MINB 6: <= 80 registers (no spills, 7 CTAs/SM at the 72 it uses)
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_closest_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, BvhStats* stats,
               uint32_t* __restrict__ arb, uint32_t* arb_count) {
-    BvhCount cnt{0, 0};
+    BvhCount cnt{0, 0, 0};
     uint32_t mine = 0, deferred = 0;
     const ClosestIO io{B};
-    trace_bvh<false, false, SORT>(S, count, work, cnt, mine, deferred,
-        [&](uint32_t i, BvhTraverser<false, false, SORT>& T) {
+    trace_bvh<false, COUNT, SORT>(S, count, work, cnt, mine, deferred,
+        [&](uint32_t i, BvhTraverser<false, COUNT, SORT>& T) {
             const uint32_t slot = queue ? __ldg(queue + i) : i;
             const float4 o = B.ray_o[slot], d = B.ray_d[slot];
             return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot]);
         },
         [&](uint32_t i, bool found, const HitRec& h) { io.commit(queue ? __ldg(queue + i) : i, found, h); },
         [&](uint32_t i) { arb[atomicAdd(arb_count, 1u)] = queue ? __ldg(queue + i) : i; });
-    flush_bvh_counts(mine, deferred, stats);
+    flush_bvh_counts<COUNT>(cnt, mine, deferred, stats);
 }
 template <int MINB>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
@@ -554,18 +549,18 @@ k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const
         [&](uint32_t i, bool found, const HitRec& h) { io.commit(arb[i], found, h); });
 }
 
-template <int MINB, int SORT>
+template <int MINB, int SORT, bool COUNT = false>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
 k_shadow_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, BvhStats* stats,
              uint32_t const_light, float4 cl_pos, uint32_t* __restrict__ arb, uint32_t* arb_count) {
-    BvhCount cnt{0, 0};
+    BvhCount cnt{0, 0, 0};
     uint32_t mine = 0, deferred = 0;
     const ShadowIO io{B, clampv, const_light, cl_pos};
-    trace_bvh<true, false, SORT>(S, count, work, cnt, mine, deferred,
-        [&](uint32_t i, BvhTraverser<true, false, SORT>& T) { return io.fetch(S, __ldg(queue + i), T); },
+    trace_bvh<true, COUNT, SORT>(S, count, work, cnt, mine, deferred,
+        [&](uint32_t i, BvhTraverser<true, COUNT, SORT>& T) { return io.fetch(S, __ldg(queue + i), T); },
         [&](uint32_t i, bool blocked, const HitRec&) { io.commit(__ldg(queue + i), blocked); },
         [&](uint32_t i) { arb[atomicAdd(arb_count, 1u)] = __ldg(queue + i); });
-    flush_bvh_counts(mine, deferred, stats);
+    flush_bvh_counts<COUNT>(cnt, mine, deferred, stats);
 }
 template <int MINB>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
@@ -662,6 +657,7 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool cont = false, shadow = false, null_shadow = false;
     uint32_t slot = 0;
+    uint32_t cw = 0;       // counting rounds only (R.count_shade): bit 0 surface vertex, 1 sky vertex, 2 light evaluated, 4-5 LTC lobes, 8-11 texels
     if (i < count) {
         slot = queue ? __ldg(queue + i) : i;
         const float4 hit = B.hit[slot];
@@ -687,6 +683,7 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
             float4 t = B.tot[slot];
             t.x += sky.r * contribution.r; t.y += sky.g * contribution.g; t.z += sky.b * contribution.b;
             B.tot[slot] = t;
+            cw = 2u;
         } else {
             const uint4 tv = __ldg(S.tri_shade + tri);
             const float ia = 1.0f - hit.y - hit.z, ib = hit.y, ic = hit.z;   // Intersection a,b,c (src/scene_intersect.cpp:280-283)
@@ -716,6 +713,7 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                 }
                 const Frame fr = system_transform_z(lightN);
                 const V3 VrL = qrot(fr.g2l, Vr);
+                cw = 1u | (pre.taps << 8);
                 // ---- next-event estimation set-up (the visibility test runs in k_shadow)
                 const uint32_t lflags = __float_as_uint(lp4.w);
                 RGB emis = rgb(0.0f, 0.0f, 0.0f);
@@ -723,7 +721,10 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                 if (lflags & 1u) {
                     const V3 lpos = v3(lp4);
                     const V3 Vi = normalize(lpos - pos);
-                    const RGB f = bxdf_value(S, tv.w, mat, qrot(fr.g2l, Vi), VrL, uv, pre);
+                    const V3 ViL = qrot(fr.g2l, Vi);
+                    const RGB f = bxdf_value(S, tv.w, mat, ViL, VrL, uv, pre);
+                    cw |= 4u;
+                    if (mat.bxdf >= RGK_BXDF_LTC_BECKMANN && ViL.z > 0 && VrL.z > 0) cw += 16u;      // one LTC lobe evaluation (BxDF::value)
                     const V3 dlt = lpos - pos;
                     const float G = fabsf(dot(lightN, Vi)) / dot(dlt, dlt);
                     float df = 1.0f;
@@ -768,6 +769,14 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                 if (!LAST && n < R.depth) {
                     V3 dir; RGB tcf; bool may_leak;
                     bxdf_sample(S, mat, VrL, uv, sample, dir, tcf, may_leak, pre);
+                    if (R.count_shade) {       // did BxDF::sample evaluate an LTC lobe?  (the specular branch of the *_diffuse kinds)
+                        if (mat.bxdf == RGK_BXDF_LTC_BECKMANN || mat.bxdf == RGK_BXDF_LTC_GGX) cw += 16u;
+                        else if (mat.bxdf >= RGK_BXDF_LTC_BECKMANN_DIFFUSE) {
+                            const float dp = pre.diffuse.r + pre.diffuse.g + pre.diffuse.b, sp = pre.color.r + pre.color.g + pre.color.b;
+                            float sx = sample.x;
+                            if (!decide_and_rescale(sx, dp / (dp + sp + 0.0001f))) cw += 16u;
+                        }
+                    }
                     const bool inside = dir.z < 0;
                     dir = qrot(fr.l2g, dir);
                     if (!(dot(dir, faceN) * dot(Vr, faceN) > 0) && !may_leak) n += 10000u;
@@ -812,6 +821,15 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
     {   // Visibility queries of the reference that were provably irrelevant and therefore not traced
         const unsigned m = __ballot_sync(0xffffffffu, null_shadow);
         if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + C_SHADOW_SKIPPED, (unsigned long long)__popc(m));
+    }
+    if (R.count_shade) {       // work counters of a counting round: vertices shaded, sky vertices, image texels, LTC lobes, lights, continuations
+        uint32_t v[6] = {cw & 1u, (cw >> 1) & 1u, (cw >> 8) & 15u, (cw >> 4) & 3u, (cw >> 2) & 1u, cont ? 1u : 0u};
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(B.shade_counts + k, (unsigned long long)v[k]);
+        }
     }
 }
 
@@ -886,7 +904,7 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
     if (ok && t2_float2s > B.cap_t2) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t2, t2_float2s); B.cap_t2 = ok ? t2_float2s : 0; }
     if (ok && tiles > B.cap_tiles) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.tiles, tiles) && alloc_dev(&B.tiles2, tiles); B.cap_tiles = ok ? tiles : 0; }
     if (ok && !B.counters) {
-        ok = alloc_dev(&B.counters, (size_t)C_COUNT);
+        ok = alloc_dev(&B.counters, (size_t)C_COUNT) && alloc_dev(&B.shade_counts, (size_t)8);
         ok = ok && cudaMallocHost((void**)&B.h_counters, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
     }
     if (!ok) { cudaGetLastError(); return rgk_fail(ctx, RGK_ERR_NOMEM, "path-state allocation failed (lower rgk_device_cfg::chunk_paths)"); }
@@ -927,7 +945,7 @@ void free_path_buffers(rgk_context* ctx) {
     PathBuffers& B = *ctx->paths;
     void* ptrs[] = {B.ray_o, B.ray_d, B.hit, B.cum, B.tot, B.light_pos, B.light_col, B.light_nrm, B.sh_pos, B.sh_direct, B.sh_emis,
                     B.sh_contrib, B.last_tri, B.cur1, B.queue_a, B.queue_b, B.queue_ua, B.queue_ub, B.queue_s, B.key_next, B.key_shadow, B.pix_xy, B.pix_seed, B.pix_src, B.mt_state, B.t1, B.t2,
-                    B.tiles, B.tiles2, B.counters};
+                    B.tiles, B.tiles2, B.counters, B.shade_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (B.h_counters) cudaFreeHost(B.h_counters);
     if (B.reverse) {
@@ -1040,11 +1058,12 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     const size_t bin_items = cfg.bin_items;            // path slots per reordering group
     // the wide-BVH kernels' iterations are longer than the kd ones: refilling coherent warps at 24 idle lanes instead of 32
     // measured -1.9 ms per round (profiles/r1_bvh_sweep.json); the other thresholds are flat
-    const bool bvh_round = ctx->dev.bvh_nodes != nullptr && !ctx->counting;
+    const bool bvh_round = ctx->dev.bvh_nodes != nullptr;
     const uint32_t refill_coherent = cfg.refill_coherent ? cfg.refill_coherent : (bvh_round ? 24u : 32u), refill_incoherent = cfg.refill_incoherent;
     const uint32_t refill_shadow = cfg.refill_shadow;  // any-hit rays end at very different times: refill sooner
     rgk_trav_stats* d_st = ctx->d_stats;               // [0] closest, [1] shadow
     if (counting) RGK_CUDA(ctx, cudaMemsetAsync(d_st, 0, 2 * sizeof(rgk_trav_stats), ctx->stream));
+    bool shade_counts_cleared = false;
 
     // chunking: whole tiles, every multisample of a pixel in the same chunk
     size_t max_paths = (size_t)cfg.chunk_paths;        // default 128 Mi paths ~ 27 GB of path state: sized for 180 GB of HBM
@@ -1106,7 +1125,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         R.cam = *cam; R.xres = P->xres; R.yres = P->yres; R.ms = ms; R.depth = P->depth; R.clamp = P->clamp; R.russian = P->russian;
         R.bump_scale = P->bumpmap_scale; R.set_size = ss; R.n1d = n1d; R.n2d = n2d; R.base2 = base2; R.sampler_mode = P->sampler_mode;
         R.lens = lens; R.npix = (uint32_t)npix; R.skip_null_shadow = skip_null; R.binning = binning ? 1u : 0u;
-        R.reverse = P->reverse; R.npaths = (uint32_t)npaths;
+        R.reverse = P->reverse; R.npaths = (uint32_t)npaths; R.count_shade = counting ? 1u : 0u;
+        if (counting && !shade_counts_cleared) { RGK_CUDA(ctx, cudaMemsetAsync(B.shade_counts, 0, 8 * sizeof(unsigned long long), ctx->stream)); shade_counts_cleared = true; }
         {   // Scene::GetRandomLight with one point light and nothing else always returns it; with size 0 it is not jittered
             const DevPointLight& l0 = ctx->first_point_light;
             R.const_light = (!P->reverse && ctx->dev.n_point_lights == 1 && ctx->dev.n_areal_lights == 0 && l0.size == 0.0f && l0.intensity > 0.0f &&
@@ -1147,7 +1167,9 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         // wide BVH (RGK_TRAVERSAL_BVH at commit): BVH pass + kd arbiter pass per closest-hit / shadow launch.  The counting
         // instantiation stays on the kd kernels, and so do the bidirectional mode's shadow resolves and connection segments
         // (its closest-hit launches use the BVH)
-        const bool use_bvh = ctx->dev.bvh_nodes != nullptr && !counting;
+        // counting rounds (rgk_render_set_counting) run the counting instantiations of the BVH kernels; the arbiter and the
+        // bidirectional mode's extra segments are never counted
+        const bool use_bvh = ctx->dev.bvh_nodes != nullptr;
         // the arbiter sees ~4e-4 of the rays, all of them long (grazing) traversals: spread them over many warps
         const int arb_grid = 148 * (int)std::max<uint32_t>(1u, cfg.arb_grid);
         const bool bvh_shadow_nosort = cfg.bvh_shadow_nosort != 0;        // A/B knob: any-hit children in slot order
@@ -1253,7 +1275,8 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             // 48 registers (10 CTAs/SM) for later bounces, which gain from the extra warps
             if (use_bvh) {
                 RGK_CUDA(ctx, cudaMemsetAsync(arb_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
-                if (bvh_closest_nearest) k_closest_bvh<6, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                if (counting) k_closest_bvh<6, 1, true><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                else if (bvh_closest_nearest) k_closest_bvh<6, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                 else k_closest_bvh<6><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                 k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
                 ctx->launches++;
@@ -1293,9 +1316,11 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
                 pool.begin(ctx->stream, T_SHADOW);
                 if (use_bvh) {
-                    if (bvh_shadow_nosort) k_shadow_bvh<6, 0><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                    if (counting) k_shadow_bvh<6, 1, true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats + 1,
+                                                                                          R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
+                    else if (bvh_shadow_nosort) k_shadow_bvh<6, 0><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats + 1,
                                                                                                 R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    else k_shadow_bvh<6, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats,
+                    else k_shadow_bvh<6, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats + 1,
                                                                                 R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
                     k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 3), P->clamp, arb_ctr + 2,
                                                                                                      R.const_light, R.cl_pos);
@@ -1328,6 +1353,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     if (counting) {
         RGK_CUDA(ctx, cudaMemcpy(&ctx->last_closest, d_st, sizeof(rgk_trav_stats), cudaMemcpyDeviceToHost));
         RGK_CUDA(ctx, cudaMemcpy(&ctx->last_shadow, d_st + 1, sizeof(rgk_trav_stats), cudaMemcpyDeviceToHost));
+        if (ctx->paths && ctx->paths->shade_counts) RGK_CUDA(ctx, cudaMemcpy(ctx->last_shade, ctx->paths->shade_counts, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
     if (stats) *stats = total;
     return RGK_OK;

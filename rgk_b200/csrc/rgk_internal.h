@@ -97,8 +97,9 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rg
 rgk_device_cfg default_device_cfg();          // api.cu: what rgk_device_cfg_init writes
 
 // ------------------------------------------------------------------ context
-// counters of the wide-BVH launches since the last call (device buffer ctx->d_bvh_stats): rays, ambiguous, nodes, tests
-struct BvhStats { unsigned long long rays, ambiguous, nodes, tests; };
+// counters of the wide-BVH launches since the last call (device buffer ctx->d_bvh_stats[2]: [0] closest-hit launches, [1] any-hit):
+// rays, rays deferred to the kd arbiter, and -- counting instantiations only -- wide nodes visited, exact tests, leaf slots scanned
+struct BvhStats { unsigned long long rays, ambiguous, nodes, tests, slots; };
 struct PathBuffers;   // render.cu
 struct rgk_context {
     int device = 0;
@@ -122,6 +123,7 @@ struct rgk_context {
     bool counting = false;
     uint32_t shard_first = 0, shard_stride = 1;   // rgk_render_set_shard
     rgk_trav_stats last_closest{}, last_shadow{};
+    unsigned long long last_shade[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // k_shade work counters of the last counting round
     BvhStats* d_bvh_stats = nullptr;              // wide-BVH counters (allocated with the scene when the BVH is on)
     DevPointLight first_point_light{};            // host copy of point light 0 (single fixed light: no per-path light records)
 };

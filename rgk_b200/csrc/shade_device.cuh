@@ -257,7 +257,7 @@ __device__ __forceinline__ void fresnel_dielectric(float eta, float cosTheta, fl
 // The two colour textures of a vertex's material, fetched once per vertex: BxDF::value (NEE) and BxDF::sample
 // (continuation) of the reference each call GetPixelInterpolated with the same texture and uv, which returns the same
 // value; `have` is false for the children of a mix material (their textures differ from the top-level one's).
-struct TexPre { bool have; RGB diffuse, color; };
+struct TexPre { bool have; RGB diffuse, color; uint32_t taps; };   // taps: image texels this vertex needed (counting rounds)
 __device__ __forceinline__ RGB tex_diffuse_of(const DevScene& S, const DevMaterial& m, V2 uv, const TexPre& pre) {
     return pre.have ? pre.diffuse : tex_fetch(S, m.tex_diffuse, uv);
 }
@@ -269,7 +269,7 @@ __device__ __forceinline__ RGB tex_color_of(const DevScene& S, const DevMaterial
 // its dependent loads, not by their number.  Unused taps read texel 0 (always allocated) and are discarded; the
 // arithmetic is the very code of tex_fetch / tex_slopes.  `have` stays false for mix materials.
 __device__ __forceinline__ TexPre vertex_textures(const DevScene& S, const DevMaterial& m, V2 uv, float& right, float& bottom) {
-    TexPre pre; pre.have = m.bxdf != RGK_BXDF_MIX; pre.diffuse = rgb(0, 0, 0); pre.color = rgb(0, 0, 0);
+    TexPre pre; pre.have = m.bxdf != RGK_BXDF_MIX; pre.diffuse = rgb(0, 0, 0); pre.color = rgb(0, 0, 0); pre.taps = 0u;
     right = 0.0f; bottom = 0.0f;
     const bool uses_diffuse = m.bxdf == RGK_BXDF_DIFFUSE || m.bxdf == RGK_BXDF_LTC_BECKMANN_DIFFUSE || m.bxdf == RGK_BXDF_LTC_GGX_DIFFUSE;
     const bool uses_color = m.bxdf != RGK_BXDF_DIFFUSE && m.bxdf != RGK_BXDF_TRANSPARENT && m.bxdf != RGK_BXDF_MIX;
@@ -290,6 +290,7 @@ __device__ __forceinline__ TexPre vertex_textures(const DevScene& S, const DevMa
     if (img_c) pre.color = bilinear_mix(ac, c00, c01, c10, c11);
     else if (want_c) pre.color = rgb(tc.color[0], tc.color[1], tc.color[2]);
     if (img_b) slope_mix(bh, br, bb, right, bottom);
+    pre.taps = (img_d ? 4u : 0u) + (img_c ? 4u : 0u) + (img_b ? 3u : 0u);
     return pre;
 }
 
@@ -337,7 +338,7 @@ static __device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevM
 // explicit post-order walk (mix children always precede the mix material, so depth is bounded; cap 8).
 __device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv, const TexPre& pre) {
     if (m.bxdf != RGK_BXDF_MIX) return bxdf_value_leaf(S, m, Vi, Vr, uv, pre);
-    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0);
+    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0); none.taps = 0u;
     // stack of (material, state): state 0 = visit a, 1 = visit b, 2 = combine
     uint32_t st_m[8]; int st_s[8]; RGB val[9]; int sp = 0, vp = 0;
     st_m[0] = mi; st_s[0] = 0; sp = 1;
@@ -359,7 +360,7 @@ __device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, const 
 }
 __device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, V3 Vi, V3 Vr, V2 uv) {
     const DevMaterial m = S.materials[mi];
-    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0);
+    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0); none.taps = 0u;
     return bxdf_value(S, mi, m, Vi, Vr, uv, none);
 }
 // BxDF::sample: returns local direction, weight and may_leak
@@ -408,7 +409,7 @@ __device__ __forceinline__ void bxdf_sample(const DevScene& S, DevMaterial m, V3
 }
 
 __device__ __forceinline__ void bxdf_sample(const DevScene& S, uint32_t mi, V3 Vi, V2 uv, V2 sample, V3& dir, RGB& w, bool& may_leak) {
-    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0);
+    TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0); none.taps = 0u;
     bxdf_sample(S, S.materials[mi], Vi, uv, sample, dir, w, may_leak, none);
 }
 

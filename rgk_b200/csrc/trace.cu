@@ -81,26 +81,12 @@ k_trace_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict
 }
 
 // ---- wide BVH (RGK_TRAVERSAL_BVH, the default): BVH pass over all rays, kd pass over the deferred (ambiguous) ones ----------
-template <bool COUNT>
-__device__ __forceinline__ void flush_bvh(const BvhCount& c, uint32_t nrays, uint32_t deferred, BvhStats* stats) {
-    unsigned long long v[4] = {nrays, deferred, COUNT ? c.nodes : 0u, COUNT ? c.tests : 0u};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&stats->rays, v[0]);
-        if (v[1]) atomicAdd(&stats->ambiguous, v[1]);
-        if (COUNT) { atomicAdd(&stats->nodes, v[2]); atomicAdd(&stats->tests, v[3]); }
-    }
-}
 
 template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
 k_bvh_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __restrict__ ignore, uint64_t n,
               rgk_hit* __restrict__ hits, BvhStats* stats, unsigned long long* next, uint32_t* __restrict__ list, uint32_t* list_count) {
-    BvhCount cnt{0, 0};
+    BvhCount cnt{0, 0, 0};
     uint32_t mine = 0, deferred = 0;
     trace_bvh<false, COUNT>(S, (uint32_t)n, next, cnt, mine, deferred,
         [&](uint32_t i, BvhTraverser<false, COUNT>& T) {
@@ -116,14 +102,14 @@ k_bvh_closest(DevScene S, const rgk_ray* __restrict__ rays, const uint32_t* __re
             hits[i] = out;
         },
         [&](uint32_t i) { list[atomicAdd(list_count, 1u)] = i; });
-    flush_bvh<COUNT>(cnt, mine, deferred, stats);
+    flush_bvh_counts<COUNT>(cnt, mine, deferred, stats);
 }
 
 template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS_MAX, RGK_MIN_BLOCKS)
 k_bvh_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__ pb, uint64_t n, uint8_t* __restrict__ visible,
              BvhStats* stats, unsigned long long* next, uint32_t* __restrict__ list, uint32_t* list_count) {
-    BvhCount cnt{0, 0};
+    BvhCount cnt{0, 0, 0};
     uint32_t mine = 0, deferred = 0;
     trace_bvh<true, COUNT>(S, (uint32_t)n, next, cnt, mine, deferred,
         [&](uint32_t i, BvhTraverser<true, COUNT>& T) {
@@ -136,7 +122,7 @@ k_bvh_shadow(DevScene S, const float* __restrict__ pa, const float* __restrict__
         },
         [&](uint32_t i, bool found, const HitRec&) { visible[i] = found ? 0 : 1; },
         [&](uint32_t i) { list[atomicAdd(list_count, 1u)] = i; });
-    flush_bvh<COUNT>(cnt, mine, deferred, stats);
+    flush_bvh_counts<COUNT>(cnt, mine, deferred, stats);
 }
 
 // the kd kernels over the deferred list (count read on the device: no host round trip between the two passes)
@@ -241,8 +227,8 @@ rgk_status launch_trace_shadow(rgk_context* ctx, const float* d_a, const float* 
         uint32_t* list = (uint32_t*)rgk_scratch(ctx, 4, n * 4);
         if (!list) return rgk_fail(ctx, RGK_ERR_NOMEM, "scratch allocation failed");
         uint32_t* list_count = (uint32_t*)(next + 2);
-        if (ctx->counting) k_bvh_shadow<true><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats, next, list, list_count);
-        else k_bvh_shadow<false><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats, next, list, list_count);
+        if (ctx->counting) k_bvh_shadow<true><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats + 1, next, list, list_count);
+        else k_bvh_shadow<false><<<grid, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, n, d_visible, ctx->d_bvh_stats + 1, next, list, list_count);
         const int g2 = std::min(grid, 148);
         if (variant == 2) k_trace_shadow_list<2><<<g2, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, list, list_count, d_visible, next + 1);
         else k_trace_shadow_list<6><<<g2, threads, 0, ctx->stream>>>(ctx->dev, d_a, d_b, list, list_count, d_visible, next + 1);

@@ -210,14 +210,24 @@ class Context:
         self._check(self.lib.rgk_accumulate_device(self.h, _p(d_dst), _p(d_src), C.c_uint64(n_floats), _p(d_count), _p(d_other_count),
                                                    C.c_void_p(stream) if stream is not None else None))
 
+    def shade_stats(self):
+        """k_shade work counters of the last counting round (rgk_render_get_shade_stats)."""
+        out = (C.c_uint64 * 8)()
+        self._check(self.lib.rgk_render_get_shade_stats(self.h, C.byref(out)))
+        return dict(zip(("vertices", "sky_vertices", "texels", "ltc_evals", "light_evals", "continuations"), (int(x) for x in out)))
+
     def synchronize(self):
         self._check(self.lib.rgk_synchronize(self.h))
 
     def bvh_stats(self):
         """Counters of the wide-BVH launches since the previous call (all 0 on the kd-only traversal)."""
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 10)()
         self._check(self.lib.rgk_bvh_stats(self.h, C.byref(out)))
-        return {"rays": out[0], "ambiguous": out[1], "nodes": out[2], "tests": out[3]}
+        names = ("rays", "ambiguous", "nodes", "tests", "slots")
+        d = {n: out[k] + out[5 + k] for k, n in enumerate(names)}           # totals; per query kind below
+        d["closest"] = {n: out[k] for k, n in enumerate(names)}
+        d["shadow"] = {n: out[5 + k] for k, n in enumerate(names)}
+        return d
 
 
 class HostScene:

@@ -35,7 +35,7 @@ struct ShadeScene {
     std::vector<DevMaterial> materials; std::vector<DevTexture> textures; std::vector<DevPointLight> point_lights;
     std::vector<float> ltc_amp[2];
     std::vector<uint2> nodes; std::vector<float4> ref_planes, ref_bounds, tri_isect, bvh_nodes, bvh_planes;
-    BvhStats bvh_stats{};
+    BvhStats bvh_stats[2] = {};
     DevScene S{};
 };
 std::vector<float4> pad3(const float* src, uint32_t n) {
@@ -174,8 +174,8 @@ int doh_render_round(void* h, const rgk_device_cfg* cfg, const rgk_camera* cam, 
     ctx.dev = s->S; ctx.has_scene = true;
     ctx.dev.refill_threshold = 1;
     if (s->S.n_point_lights) ctx.first_point_light = s->point_lights[0];
-    s->bvh_stats = BvhStats{0, 0, 0, 0};
-    ctx.d_bvh_stats = s->S.bvh_nodes ? &s->bvh_stats : nullptr;
+    s->bvh_stats[0] = s->bvh_stats[1] = BvhStats{0, 0, 0, 0, 0};
+    ctx.d_bvh_stats = s->S.bvh_nodes ? s->bvh_stats : nullptr;
     if (t1 && t2) {
         ctx.d_user_t1 = const_cast<float*>(t1); ctx.d_user_t2 = const_cast<float*>(t2);
         ctx.user_n1d = n1d; ctx.user_n2d = n2d; ctx.user_ss = host_sampler_set_size(p->multisample); ctx.user_npix = n_pixels;
@@ -183,7 +183,7 @@ int doh_render_round(void* h, const rgk_device_cfg* cfg, const rgk_camera* cam, 
     rgk_round_stats local{};
     const rgk_status st = render_round_impl(&ctx, cam, p, tasks, n_tasks, seedstart, seedcount_base, rgb, count, stats ? stats : &local);
     if (st != RGK_OK) std::fprintf(stderr, "doh_render_round: %s\n", ctx.last_error.c_str());
-    if (out_bvh) { out_bvh[0] = s->bvh_stats.rays; out_bvh[1] = s->bvh_stats.ambiguous; }
+    if (out_bvh) { out_bvh[0] = s->bvh_stats[0].rays + s->bvh_stats[1].rays; out_bvh[1] = s->bvh_stats[0].ambiguous + s->bvh_stats[1].ambiguous; }
     free_path_buffers(&ctx);
     for (auto& q : ctx.scratch) if (q) std::free(q);
     return (int)st;
@@ -208,7 +208,7 @@ int doh_closest(void* h, int variant, const rgk_ray* rays, const uint32_t* ignor
     unsigned long long work = 0; uint32_t done = 0;
     if (variant == 4) {
         if (!S.bvh_nodes) return 1;
-        BvhCount cnt{0, 0}; uint32_t deferred = 0;
+        BvhCount cnt{0, 0, 0}; uint32_t deferred = 0;
         trace_bvh<false, true>(S, (uint32_t)n, &work, cnt, done, deferred,
             [&](uint32_t i, BvhTraverser<false, true>& T) {
                 const rgk_ray& r = rays[i];
@@ -244,7 +244,7 @@ int doh_shadow(void* h, int variant, const float* pa, const float* pb, uint64_t 
     };
     if (variant == 4) {
         if (!S.bvh_nodes) return 1;
-        BvhCount cnt{0, 0}; uint32_t deferred = 0;
+        BvhCount cnt{0, 0, 0}; uint32_t deferred = 0;
         trace_bvh<true, false>(S, (uint32_t)n, &work, cnt, done, deferred,
             [&](uint32_t i, BvhTraverser<true, false>& T) { return init(i, T); },
             [&](uint32_t i, bool found, const HitRec&) { visible[i] = found ? 0 : 1; status[i] = 0; },

@@ -65,12 +65,15 @@ def real_asset_workload(name, spp):
     return pack, cfg, "scenes/%s.json %dx%d %dspp on the real asset (%d tris)" % (name, w, h, spp or ms, pack.n_triangles)
 
 
-def build_workload(name, spp=None):
+def build_workload(name, spp=None, res=None):
     real = real_asset_workload(name, spp)
     if real is not None:
         return real
     if name == "sponza":
-        pack, cfg = standin.sponza(**({"multisample": spp} if spp else {}))
+        kw = {"multisample": spp} if spp else {}
+        if res:
+            kw["width"], kw["height"] = (int(x) for x in res.split("x"))
+        pack, cfg = standin.sponza(**kw)
         label = "scenes/sponza.json 1920x1080 64spp NEE recursion-max 2 (atrium stand-in, %d tris)" % pack.n_triangles
     elif name == "sibenik":
         pack, cfg = standin.sibenik(**({"multisample": spp} if spp else {}))
@@ -88,6 +91,8 @@ def build_workload(name, spp=None):
         raise SystemExit("unknown workload " + name)
     if spp:
         label += " [spp overridden to %d]" % spp
+    if res and name == "sponza":
+        label += " [resolution overridden to %s]" % res
     return pack, cfg, label
 
 
@@ -338,6 +343,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="sponza")
     ap.add_argument("--spp", type=int, default=None, help="override multisample (marks the run as non-headline)")
+    ap.add_argument("--res", default=None, help="WxH: override the resolution of a stand-in workload (profiling runs; marks the run as non-headline)")
     ap.add_argument("--sampler", default="mt", choices=["mt", "fast"])
     ap.add_argument("--shard", default="rounds", choices=["rounds", "tiles"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
@@ -363,7 +369,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    pack, cfg, label = build_workload(args.workload, args.spp)
+    pack, cfg, label = build_workload(args.workload, args.spp, args.res)
     desc = pack.desc()
     render_stream = torch.cuda.current_stream()
     comm_stream = torch.cuda.Stream()
@@ -465,6 +471,8 @@ def main():
                      "tracing (the reference traces them): reference-equivalent rate %.1f Mrays/s" % (
                          int(skipped / max(1, args.steps)), (rays + skipped) / (ms / 1e3) / 1e6),
         "clocks": clocks,
+        "closest_rays_per_step": sum(int(s_.closest_rays) for s_ in stats) / max(1, args.steps) if world == 1 else None, "spp": int(p.multisample),
+        "class_ms_per_step": {k: sum(float(getattr(s_, k + "_ms")) for s_ in stats) / max(1, args.steps) for k in ("closest", "shadow", "shade", "sampler")},
     }
 
     # ---- e2e: the same step through rgk_render_round with pinned host framebuffers

@@ -269,7 +269,9 @@ typedef struct rgk_device_cfg {
     uint32_t sampler_smem;       /* 1: sampler tables of small set sizes are shuffled in shared memory */
     uint32_t trace_threads;      /* CTA size of the batch entry points: 64, 128 (default) or 256 */
     uint32_t kd_variant;         /* control structure of the kd traversal in the batch entry points: 6 phased (default), 2 per-lane */
-    uint32_t _reserved[8];
+    uint32_t sampler_ctas_per_sm;/* persistent CTAs per SM of the sampler kernel; each owns one 312 KB generator-state block, and
+                                    SMs x this x 312 KB is its whole generator-state footprint (3: what 64 KB of shared-memory tables per CTA allows) */
+    uint32_t _reserved[7];
 } rgk_device_cfg;
 
 /* ---- entry points ------------------------------------------------------- */

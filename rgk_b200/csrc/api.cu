@@ -66,7 +66,7 @@ rgk_device_cfg default_device_cfg() {
     c.refill_batch = 16; c.refill_coherent = 0; c.refill_incoherent = 24; c.refill_shadow = 12;
     c.binning = 1; c.bin_shadow_first = 1; c.bin_items = 2048; c.bin_min_frac = 0.25f; c.shade_path_order = 1;
     c.skip_null_shadow = 1; c.const_light = 1; c.arb_grid = 8;
-    c.sampler_smem = 1; c.trace_threads = 128; c.kd_variant = 6;
+    c.sampler_smem = 1; c.trace_threads = 128; c.kd_variant = 6; c.sampler_ctas_per_sm = 3;
     return c;
 }
 
@@ -84,6 +84,7 @@ static const char* check_cfg(const rgk_device_cfg& c) {
     if (c.refill_batch < 1 || c.refill_batch > 32 || c.refill_coherent > 32 || c.refill_incoherent < 1 || c.refill_incoherent > 32 ||
         c.refill_shadow < 1 || c.refill_shadow > 32) return "rgk_device_cfg: refill thresholds are lane counts (1..32)";
     if (c.bvh_leaf_max > 4) return "rgk_device_cfg: bvh_leaf_max > 4";
+    if (c.sampler_ctas_per_sm < 1 || c.sampler_ctas_per_sm > 16) return "rgk_device_cfg: sampler_ctas_per_sm must be 1..16";
     if (c.bin_items < 64 || c.arb_grid < 1) return "rgk_device_cfg: bin_items >= 64, arb_grid >= 1";
     if (c.chunk_paths < 64 || c.table_bytes < ((uint64_t)1 << 20) || c.reverse_bytes < ((uint64_t)1 << 20)) return "rgk_device_cfg: memory sizes too small";
     return nullptr;

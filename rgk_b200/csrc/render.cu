@@ -33,7 +33,7 @@ struct ReverseBuffers {
     size_t cap_paths = 0, cap_cam = 0, cap_light = 0;
 };
 struct PathBuffers {
-    size_t cap_paths = 0, cap_pixels = 0, cap_t1 = 0, cap_t2 = 0, cap_tiles = 0;
+    size_t cap_paths = 0, cap_pixels = 0, cap_t1 = 0, cap_t2 = 0, cap_tiles = 0, cap_mt = 0;
     float4 *ray_o = nullptr, *ray_d = nullptr, *hit = nullptr, *cum = nullptr, *tot = nullptr;
     float4 *light_pos = nullptr, *light_col = nullptr, *light_nrm = nullptr;
     float4 *sh_pos = nullptr, *sh_direct = nullptr, *sh_emis = nullptr, *sh_contrib = nullptr;
@@ -79,6 +79,7 @@ template <class T> bool alloc_dev(T** p, size_t n) {
 // / std::shuffle (pairwise) -- SURVEY Appendix C.  One thread per pixel; the 624-word generator state lives in
 // global memory, interleaved across threads (state[k * stride + thread]) so every access is coalesced.
 constexpr int MT_LANES = 128;   // threads per CTA of the sampler kernels = width of a state block
+
 struct MT {
     uint32_t* st;      // this thread's column of its CTA's state block: word k at st[k * MT_LANES] (32-bit offsets, coalesced)
     int k0, cur;
@@ -194,17 +195,25 @@ __device__ void dev_shuffle(T* base, I stride, uint32_t n, MT& g, bool store) {
 // (entry k of thread t at [k * blockDim + t]: every swap of the shuffle is bank-conflict free whatever its random
 // position), and are copied out coalesced once shuffled.  SMEM = false (set sizes too large for shared memory):
 // built in place in the global table, one scratch dimension appended for dims nobody reads.
+// Persistent CTAs: the grid is a few CTAs per SM and every CTA walks the pixel groups blockIdx.x, blockIdx.x + gridDim.x, ...
+// with ONE generator-state block (624 x MT_LANES words, 312 KB) that it reuses for every group.  The live state of the whole
+// launch is then grid x 312 KB (~90 MB at two CTAs per SM) instead of 2.5 KB for every pixel of the chunk (5 GB at 1080p): it
+// stays in the 126 MB L2, and the state words -- each read twice and written once per 624 draws -- stop travelling to HBM.
+// The finished tables are written with streaming stores so that they do not push the state out of L2.
 template <bool SMEM>
 __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
                              float* __restrict__ t1, float2* __restrict__ t2, uint32_t* __restrict__ state) {
     extern __shared__ float sm[];
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    MT g; g.st = state + (size_t)blockIdx.x * (624 * MT_LANES) + threadIdx.x;
-    if (p < npix) g.seed(seeds[p]);
     const float len1 = 1.0f / (float)ss, len2 = 1.0f / (float)sq;
     const uint32_t last_dim = max(n1d, n2d);   // dims >= last_dim are never read: stop there (the stream is not reused)
-    if (p >= npix) return;
     typedef typename std::conditional<SMEM, uint32_t, size_t>::type I;
+    const uint32_t ngroups = (npix + MT_LANES - 1) / MT_LANES;
+  for (uint32_t group = blockIdx.x; group < ngroups; group += gridDim.x) {
+    const uint32_t p = group * MT_LANES + threadIdx.x;
+    if (SMEM) __syncwarp();                    // the previous group's last copy-out has left the warp's shared tables
+    if (p >= npix) continue;
+    MT g; g.st = state + (size_t)blockIdx.x * (624 * MT_LANES) + threadIdx.x;
+    g.seed(seeds[p]);
     // Shared-memory tables are private to a warp (entry k of lane l at [k * 32 + l] of the warp's region: every swap of
     // the shuffle is bank-conflict free whatever its random position).  The 2-D table reuses the storage of the 1-D one:
     // a dimension's 1-D table is built, shuffled and copied out before its 2-D table is started, so only one of them is
@@ -225,7 +234,7 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
             if (keep1) a[(I)k * as] = v;
         }
         dev_shuffle(a, as, ss, g, keep1);
-        if (SMEM && keep1) { float* o = out1; for (uint32_t k = 0; k < ss; k++, o += npix) *o = s1[k * (uint32_t)bd]; }
+        if (SMEM && keep1) { float* o = out1; for (uint32_t k = 0; k < ss; k++, o += npix) __stcs(o, s1[k * (uint32_t)bd]); }
         if (SMEM) __syncwarp();
         float2* out2 = t2 + ((size_t)(keep2 ? dim : n2d) * ss) * npix + p;
         float2* b = SMEM ? s2 : out2;
@@ -237,9 +246,10 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
                 if (keep2) b[(I)(sy * sq + sx) * as] = make_float2(x, y);
             }
         dev_shuffle(b, as, ss, g, keep2);
-        if (SMEM && keep2) { float2* o = out2; for (uint32_t k = 0; k < ss; k++, o += npix) *o = s2[k * (uint32_t)bd]; }
+        if (SMEM && keep2) { float2* o = out2; for (uint32_t k = 0; k < ss; k++, o += npix) __stcs(o, s2[k * (uint32_t)bd]); }
         if (SMEM) __syncwarp();
     }
+  }
 }
 
 // RGK_SAMPLER_TABLES: caller tables [pixel in call order][dim][set] -> chunk layout [dim][set][pixel position]
@@ -259,7 +269,14 @@ __global__ void k_tables_from_user(const float* __restrict__ u1, const float* __
 }
 
 // launches the table generation with the best block size the set size allows
-static void launch_sampler_mt(cudaStream_t stream, bool use_smem, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
+// CTAs of a sampler launch (= generator-state blocks it needs): ctas_per_sm per SM, never more than there are pixel groups
+static uint32_t sampler_grid(int device, uint32_t npix, uint32_t ctas_per_sm) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const uint32_t groups = (npix + MT_LANES - 1) / MT_LANES;
+    return std::max(1u, std::min(groups, (uint32_t)sms * std::max(1u, ctas_per_sm)));
+}
+static void launch_sampler_mt(cudaStream_t stream, bool use_smem, uint32_t grid, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
                               float* t1, float2* t2, uint32_t* state) {
     // per device (function attributes are), so set on every launch rather than once per process: contexts on several
     // GPUs may live in one process
@@ -270,11 +287,11 @@ static void launch_sampler_mt(cudaStream_t stream, bool use_smem, const uint32_t
     if (use_smem) {
         const size_t bytes = (size_t)MT_LANES * ss * 8;
         if (bytes <= 100 * 1024) {
-            k_sampler_mt<true><<<(npix + MT_LANES - 1) / MT_LANES, MT_LANES, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
+            k_sampler_mt<true><<<grid, MT_LANES, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
             return;
         }
     }
-    k_sampler_mt<false><<<(npix + MT_LANES - 1) / MT_LANES, MT_LANES, 0, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
+    k_sampler_mt<false><<<grid, MT_LANES, 0, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
 }
 
 // Counter-based sampler with the same structure (jittered strata visited in a per-(pixel,dim) random order),
@@ -880,7 +897,7 @@ int machine_blocks(rgk_context* ctx, const void* kernel, int threads) {
     return sms * std::max(per, 1);
 }
 
-rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t t1_floats, size_t t2_float2s, size_t tiles, bool need_mt) {
+rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t t1_floats, size_t t2_float2s, size_t tiles, size_t mt_blocks) {
     if (!ctx->paths) ctx->paths = new PathBuffers();
     PathBuffers& B = *ctx->paths;
     bool ok = true;
@@ -896,10 +913,9 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
     if (ok && pixels > B.cap_pixels) {
         RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ok = alloc_dev(&B.pix_xy, pixels) && alloc_dev(&B.pix_seed, pixels) && alloc_dev(&B.pix_src, pixels);
-        if (ok && B.mt_state) { cudaFree(B.mt_state); B.mt_state = nullptr; }
         B.cap_pixels = ok ? pixels : 0;
     }
-    if (ok && need_mt && !B.mt_state) ok = alloc_dev(&B.mt_state, (B.cap_pixels + MT_LANES - 1) / MT_LANES * MT_LANES * 624);
+    if (ok && mt_blocks > B.cap_mt) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.mt_state, mt_blocks * MT_LANES * 624); B.cap_mt = ok ? mt_blocks : 0; }
     if (ok && t1_floats > B.cap_t1) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t1, t1_floats); B.cap_t1 = ok ? t1_floats : 0; }
     if (ok && t2_float2s > B.cap_t2) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t2, t2_float2s); B.cap_t2 = ok ? t2_float2s : 0; }
     if (ok && tiles > B.cap_tiles) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.tiles, tiles) && alloc_dev(&B.tiles2, tiles); B.cap_tiles = ok ? tiles : 0; }
@@ -994,11 +1010,11 @@ rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint
     float* t1 = nullptr; float2* t2 = nullptr; uint32_t* st = nullptr;
     const size_t e1 = (size_t)(n1d + 1) * ss * n_seeds, e2 = (size_t)(n2d + 1) * ss * n_seeds;
     if (cudaMalloc((void**)&t1, e1 * 4) != cudaSuccess || cudaMalloc((void**)&t2, e2 * 8) != cudaSuccess ||
-        cudaMalloc((void**)&st, ((size_t)n_seeds + MT_LANES - 1) / MT_LANES * MT_LANES * 624 * 4) != cudaSuccess) {
+        cudaMalloc((void**)&st, (size_t)sampler_grid(ctx->device, n_seeds, ctx->cfg.sampler_ctas_per_sm) * MT_LANES * 624 * 4) != cudaSuccess) {
         cudaGetLastError(); if (t1) cudaFree(t1); if (t2) cudaFree(t2); if (st) cudaFree(st);
         return rgk_fail(ctx, RGK_ERR_NOMEM, "sampler table allocation failed");
     }
-    launch_sampler_mt(ctx->stream, ctx->cfg.sampler_smem != 0, d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
+    launch_sampler_mt(ctx->stream, ctx->cfg.sampler_smem != 0, sampler_grid(ctx->device, n_seeds, ctx->cfg.sampler_ctas_per_sm), d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && n1d) e = cudaMemcpyAsync(d_out1, t1, (size_t)n1d * ss * n_seeds * 4, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1080,12 +1096,12 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         const size_t per_path = 112 * (size_t)P->depth + 80 * (size_t)P->reverse + 64;
         max_paths = std::max<size_t>(std::min(max_paths, (size_t)cfg.reverse_bytes / per_path), 4096);
     }
-    const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss + 624 * 4 : 0;
+    const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss : 0;
     size_t max_table_bytes = (size_t)cfg.table_bytes;
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t have = ctx->paths ? (ctx->paths->cap_t1 * 4 + ctx->paths->cap_t2 * 8 + ctx->paths->cap_pixels * 624 * 4) : 0;
+            const size_t have = ctx->paths ? (ctx->paths->cap_t1 * 4 + ctx->paths->cap_t2 * 8) : 0;
             max_table_bytes = std::min(max_table_bytes, std::max<size_t>(have + (size_t)(0.25 * (double)free_b), (size_t)64 << 20));
         }
     }
@@ -1116,7 +1132,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         const size_t npaths = npix * ms;
         if (npaths > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "a single chunk exceeds 2^32 paths");
         rgk_status s = ensure_buffers(ctx, npaths, npix, tables ? (size_t)(n1d + 1) * ss * npix : 0, tables ? (size_t)(n2d + 1) * ss * npix : 0,
-                                      h_tiles.size(), mt);
+                                      h_tiles.size(), mt ? sampler_grid(ctx->device, (uint32_t)npix, cfg.sampler_ctas_per_sm) : 0);
         if (s != RGK_OK) return s;
         PathBuffers& B = *ctx->paths;
         RGK_CUDA(ctx, cudaMemcpyAsync(B.tiles, h_tiles.data(), h_tiles.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
@@ -1145,7 +1161,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed, B.pix_src, (uint32_t)call_pixels);
         ctx->launches++;
         if (mt) {
-            launch_sampler_mt(ctx->stream, cfg.sampler_smem != 0, B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
+            launch_sampler_mt(ctx->stream, cfg.sampler_smem != 0, sampler_grid(ctx->device, (uint32_t)npix, cfg.sampler_ctas_per_sm), B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
             ctx->launches++;
         } else if (user_tables) {
             k_tables_from_user<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_user_t1, ctx->d_user_t2, ctx->user_n1d, ctx->user_n2d,

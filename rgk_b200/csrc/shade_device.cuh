@@ -129,6 +129,21 @@ __device__ __forceinline__ bool decide_and_rescale(float& sample, float probabil
     return false;
 }
 
+// What the BxDF functions read of the scene, as a value: the functions below are templates over the scene type so that an
+// out-of-line callee (the mix-material walk) can be handed these seven pointers in registers.  Passing `const DevScene&` to a
+// __noinline__ function makes the compiler copy the whole kernel-parameter struct (~300 B) into the caller's local memory --
+// round 1's k_shade paid a 592-byte stack frame and a call sequence per vertex for that.
+struct ShadeTables {
+    const DevMaterial* materials; const DevTexture* textures; const float4* texels;
+    const float4* ltc_M[2]; const float* ltc_amp[2];
+};
+__device__ __forceinline__ ShadeTables shade_tables(const DevScene& S) {
+    ShadeTables t; t.materials = S.materials; t.textures = S.textures; t.texels = S.texels;
+    t.ltc_M[0] = S.ltc_M[0]; t.ltc_M[1] = S.ltc_M[1]; t.ltc_amp[0] = S.ltc_amp[0]; t.ltc_amp[1] = S.ltc_amp[1];
+    return t;
+}
+__device__ __forceinline__ ShadeTables shade_tables(const ShadeTables& S) { return S; }
+
 // ---- textures (src/texture.cpp:35-102; manual fp32 bilinear)
 __device__ __forceinline__ float frepeat(float x) { return x - floorf(x); }
 // Address part and arithmetic part of FileTexture::GetPixelInterpolated (src/texture.cpp:35-76), split so that several
@@ -156,7 +171,8 @@ __device__ __forceinline__ RGB bilinear_mix(const BilinearTaps& a, float4 c00, f
     const RGB c1s = rgb(fx * c10.x + gx * c11.x, fx * c10.y + gx * c11.y, fx * c10.z + gx * c11.z);
     return rgb(fy * c0s.r + gy * c1s.r, fy * c0s.g + gy * c1s.g, fy * c0s.b + gy * c1s.b);
 }
-__device__ __forceinline__ RGB tex_fetch(const DevScene& S, int32_t id, V2 uv) {
+template <class SC>
+__device__ __forceinline__ RGB tex_fetch(const SC& S, int32_t id, V2 uv) {
     if (id < 0) return rgb(0.0f, 0.0f, 0.0f);
     const DevTexture t = S.textures[id];
     if (t.kind == 0) return rgb(t.color[0], t.color[1], t.color[2]);
@@ -180,7 +196,8 @@ __device__ __forceinline__ void slope_mix(float4 h, float4 r, float4 b, float& r
     right = here - (r.x + r.y + r.z) / 3;
     bottom = here - (b.x + b.y + b.z) / 3;
 }
-__device__ __forceinline__ void tex_slopes(const DevScene& S, int32_t id, V2 uv, float& right, float& bottom) {
+template <class SC>
+__device__ __forceinline__ void tex_slopes(const SC& S, int32_t id, V2 uv, float& right, float& bottom) {
     right = 0.0f; bottom = 0.0f;
     if (id < 0) return;
     const DevTexture t = S.textures[id];
@@ -190,7 +207,8 @@ __device__ __forceinline__ void tex_slopes(const DevScene& S, int32_t id, V2 uv,
 }
 
 // ---- LTC (src/LTC/ltc.cpp:20-143); N is always +Z (BxDFUpVector)
-__device__ __forceinline__ void ltc_bilinear(const DevScene& S, int which, float theta, float alpha, M3& M, float& amp) {
+template <class SC>
+__device__ __forceinline__ void ltc_bilinear(const SC& S, int which, float theta, float alpha, M3& M, float& amp) {
     float t = gmax(0.0f, gmin(1.0f, theta / (0.5f * 3.14159f)));
     float a = gmax(0.0f, gmin(1.0f, sqrtf(alpha)));
     if (t >= 1.0f) t = 0.999f;
@@ -215,7 +233,8 @@ __device__ __forceinline__ void ltc_bilinear(const DevScene& S, int which, float
     amp = __ldg(At + i11) * dt2 * da2 + __ldg(At + i12) * dt2 * da1 + __ldg(At + i21) * dt1 * da2 + __ldg(At + i22) * dt1 * da1;
 }
 // LTC::GetPDF(ltc, N, Vr, Vi, alpha) -- parameter names as in src/LTC/ltc.cpp:59
-__device__ __forceinline__ float ltc_pdf(const DevScene& S, int which, V3 Vr, V3 Vi, float alpha) {
+template <class SC>
+__device__ __forceinline__ float ltc_pdf(const SC& S, int which, V3 Vr, V3 Vi, float alpha) {
     const V3 N = v3(0.0f, 0.0f, 1.0f);
     const V3 tangent = cross(N, Vi), Vi_cast = cross(tangent, N);
     M3 rot; rot.c0 = Vi_cast; rot.c1 = tangent; rot.c2 = N;
@@ -232,7 +251,8 @@ __device__ __forceinline__ float ltc_pdf(const DevScene& S, int which, V3 Vr, V3
     const float D = 1.0f / 3.14159f * gmax(0.0f, p.z);
     return amp * D / J;
 }
-__device__ __forceinline__ V3 ltc_random(const DevScene& S, int which, V3 Vi, float roughness, V3 rnd) {
+template <class SC>
+__device__ __forceinline__ V3 ltc_random(const SC& S, int which, V3 Vi, float roughness, V3 rnd) {
     const V3 N = v3(0.0f, 0.0f, 1.0f);
     const V3 tangent = cross(N, Vi), Vi_cast = cross(tangent, N);
     M3 rot; rot.c0 = Vi_cast; rot.c1 = tangent; rot.c2 = N;
@@ -258,17 +278,20 @@ __device__ __forceinline__ void fresnel_dielectric(float eta, float cosTheta, fl
 // (continuation) of the reference each call GetPixelInterpolated with the same texture and uv, which returns the same
 // value; `have` is false for the children of a mix material (their textures differ from the top-level one's).
 struct TexPre { bool have; RGB diffuse, color; uint32_t taps; };   // taps: image texels this vertex needed (counting rounds)
-__device__ __forceinline__ RGB tex_diffuse_of(const DevScene& S, const DevMaterial& m, V2 uv, const TexPre& pre) {
+template <class SC>
+__device__ __forceinline__ RGB tex_diffuse_of(const SC& S, const DevMaterial& m, V2 uv, const TexPre& pre) {
     return pre.have ? pre.diffuse : tex_fetch(S, m.tex_diffuse, uv);
 }
-__device__ __forceinline__ RGB tex_color_of(const DevScene& S, const DevMaterial& m, V2 uv, const TexPre& pre) {
+template <class SC>
+__device__ __forceinline__ RGB tex_color_of(const SC& S, const DevMaterial& m, V2 uv, const TexPre& pre) {
     return pre.have ? pre.color : tex_fetch(S, m.tex_color, uv);
 }
 // Everything a vertex reads from textures, in one batch: the three descriptors first, then all eleven texels (four
 // diffuse, four colour, three bump) are requested before any is used -- the shading kernel is bound by the latency of
 // its dependent loads, not by their number.  Unused taps read texel 0 (always allocated) and are discarded; the
 // arithmetic is the very code of tex_fetch / tex_slopes.  `have` stays false for mix materials.
-__device__ __forceinline__ TexPre vertex_textures(const DevScene& S, const DevMaterial& m, V2 uv, float& right, float& bottom) {
+template <class SC>
+__device__ __forceinline__ TexPre vertex_textures(const SC& S, const DevMaterial& m, V2 uv, float& right, float& bottom) {
     TexPre pre; pre.have = m.bxdf != RGK_BXDF_MIX; pre.diffuse = rgb(0, 0, 0); pre.color = rgb(0, 0, 0); pre.taps = 0u;
     right = 0.0f; bottom = 0.0f;
     const bool uses_diffuse = m.bxdf == RGK_BXDF_DIFFUSE || m.bxdf == RGK_BXDF_LTC_BECKMANN_DIFFUSE || m.bxdf == RGK_BXDF_LTC_GGX_DIFFUSE;
@@ -295,7 +318,8 @@ __device__ __forceinline__ TexPre vertex_textures(const DevScene& S, const DevMa
 }
 
 // value of a non-mix material
-static __device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv, TexPre pre) {
+template <class SC>
+static __device__ __forceinline__ RGB bxdf_value_leaf(const SC& S, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv, TexPre pre) {
     switch (m.bxdf) {
     case RGK_BXDF_DIFFUSE: {
         if (Vi.z <= 0 || Vr.z <= 0) return rgb(0, 0, 0);
@@ -336,8 +360,10 @@ static __device__ __noinline__ RGB bxdf_value_leaf(const DevScene& S, const DevM
 }
 // BxDFMix::value (src/bxdf/bxdf.cpp:235-239) is a binary tree of lerps; evaluated without recursion by an
 // explicit post-order walk (mix children always precede the mix material, so depth is bounded; cap 8).
-__device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv, const TexPre& pre) {
-    if (m.bxdf != RGK_BXDF_MIX) return bxdf_value_leaf(S, m, Vi, Vr, uv, pre);
+// Kept out of line: mix materials are rare, and their walk needs indexable stacks (local memory) and a second copy of the
+// nine-way leaf -- inlined into k_shade they cost every vertex registers, instruction-cache footprint and a call
+// sequence around the common leaf.
+static __device__ __noinline__ RGB bxdf_value_mix(const ShadeTables S, uint32_t mi, V3 Vi, V3 Vr, V2 uv) {
     TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0); none.taps = 0u;
     // stack of (material, state): state 0 = visit a, 1 = visit b, 2 = combine
     uint32_t st_m[8]; int st_s[8]; RGB val[9]; int sp = 0, vp = 0;
@@ -358,13 +384,20 @@ __device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, const 
     }
     return val[0];
 }
-__device__ __forceinline__ RGB bxdf_value(const DevScene& S, uint32_t mi, V3 Vi, V3 Vr, V2 uv) {
+template <class SC>
+__device__ __forceinline__ RGB bxdf_value(const SC& S, uint32_t mi, const DevMaterial& m, V3 Vi, V3 Vr, V2 uv, const TexPre& pre) {
+    if (m.bxdf != RGK_BXDF_MIX) return bxdf_value_leaf(S, m, Vi, Vr, uv, pre);
+    return bxdf_value_mix(shade_tables(S), mi, Vi, Vr, uv);
+}
+template <class SC>
+__device__ __forceinline__ RGB bxdf_value(const SC& S, uint32_t mi, V3 Vi, V3 Vr, V2 uv) {
     const DevMaterial m = S.materials[mi];
     TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0); none.taps = 0u;
     return bxdf_value(S, mi, m, Vi, Vr, uv, none);
 }
 // BxDF::sample: returns local direction, weight and may_leak
-__device__ __forceinline__ void bxdf_sample(const DevScene& S, DevMaterial m, V3 Vi, V2 uv, V2 sample, V3& dir, RGB& w, bool& may_leak, TexPre pre) {
+template <class SC>
+__device__ __forceinline__ void bxdf_sample(const SC& S, DevMaterial m, V3 Vi, V2 uv, V2 sample, V3& dir, RGB& w, bool& may_leak, TexPre pre) {
     for (int guard = 0; m.bxdf == RGK_BXDF_MIX && guard < 16; guard++) {        // BxDFMix::sample, src/bxdf/bxdf.cpp:241-249
         m = S.materials[decide_and_rescale(sample.x, m.amount) ? m.mix_a : m.mix_b];
         pre.have = false;
@@ -408,7 +441,8 @@ __device__ __forceinline__ void bxdf_sample(const DevScene& S, DevMaterial m, V3
     dir = v3(0, 1, 0); w = rgb(0, 0, 0);
 }
 
-__device__ __forceinline__ void bxdf_sample(const DevScene& S, uint32_t mi, V3 Vi, V2 uv, V2 sample, V3& dir, RGB& w, bool& may_leak) {
+template <class SC>
+__device__ __forceinline__ void bxdf_sample(const SC& S, uint32_t mi, V3 Vi, V2 uv, V2 sample, V3& dir, RGB& w, bool& may_leak) {
     TexPre none; none.have = false; none.diffuse = rgb(0, 0, 0); none.color = rgb(0, 0, 0); none.taps = 0u;
     bxdf_sample(S, S.materials[mi], Vi, uv, sample, dir, w, may_leak, none);
 }

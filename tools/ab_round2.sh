@@ -1,0 +1,14 @@
+#!/bin/bash
+# A/B runs of a round-2 session: library variants (tools/build_variant.sh) x rgk_device_cfg settings, headline workload, per-class ms
+run() { echo "== $1 | $2"; RGK_B200_LIB=$1 python bench.py --quick --steps 3 --warmup 3 --cfg "$2" 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('  ', round(d['ms_per_step'],2), 'ms', round(d['value']), 'Mrays/s', {k: round(v,2) for k,v in d['class_ms_per_step'].items()})
+    elif 'rror' in l: print(l.strip()[:300])"; }
+L=rgk_b200/librgk_b200.so
+run $L ""
+run rgk_b200/librgk_b200_nopre.so ""
+run rgk_b200/librgk_b200_nostcs.so ""
+run $L "sampler_ctas_per_sm=2"
+run $L ""

@@ -16,7 +16,15 @@
 //
 // Boxes are exact triangle bounds; conservativeness against the exact test's rounding (the accepted hit point can lie
 // ~2^-22 (|o| + |t|) outside the true triangle) comes from a per-ray margin m = 2^-17 (|ox| + |oy| + |oz| + |t1|) added
-// to every box (folded into two shifted copies of the origin), and from widening the interval bounds by 2^-20 relative.
+// to every box, and from widening the interval bounds by 2^-20 relative.
+//
+// Slab test (round 2).  Per ray and axis the sign of 1/d says which of a child's two planes is entered first, so the ray
+// carries (a) the position of its near / far plane rows inside a node (a 16-byte offset: the node stores lo and hi as
+// separate rows, so "near" is a choice of ADDRESS, not a min/max per child) and (b) two constants c = -(o -+ m) / d, the
+// margin shifting the near plane towards the ray and the far plane away from it.  A child's entry and exit distances are
+// then 3 + 3 fused multiply-adds and 2 + 2 (three-input) max / min: 10 instructions instead of the 24 of
+// (plane - o) * (1/d), min, max per axis.  The FMA rounds plane/d + c once; c itself carries one rounding of (o -+ m)/d,
+// i.e. a position error of 2^-24 |o| -- 1/128 of the margin, which was sized 32x above what the exact test needs.
 #pragma once
 #include "trace_device.cuh"
 
@@ -31,7 +39,8 @@ constexpr uint32_t BVH_DONE = 0x7fffffffu;      // also the code of an empty chi
 template <bool ANY, bool COUNT, int SORT = 1>
 struct BvhTraverser {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz;
-    float opx, opy, opz, omx, omy, omz;          // o + m, o - m
+    float cnx, cny, cnz, cfx, cfy, cfz;          // near / far slab constants: t = plane * (1/d) + c
+    uint32_t rows;                               // byte offsets of the near rows inside a node: x | y << 8 | z << 16 (the far row is the other of the pair)
     float lo_t, hi_t;                            // accept interval of the exact test: root interval -+ eps
     float firm_lo, firm_hi;                      // hits inside are beyond the reach of the kd rule's end effects
     float low_w;                                 // lo_t widened (box test)
@@ -57,7 +66,9 @@ struct BvhTraverser {
         second_t = __int_as_float(0x7f800000); border = false; best_edge = false; sp = 0;
         ix = 1.f / dx; iy = 1.f / dy; iz = 1.f / dz;
         const float inf = __int_as_float(0x7f800000);
-        degenerate = !(fabsf(ix) < inf) || !(fabsf(iy) < inf) || !(fabsf(iz) < inf);
+        // (1e30 rather than infinity: plane * (1/d) of the slab test must not overflow for coordinates below 3e8)
+        degenerate = !(fabsf(ix) < 1e30f) || !(fabsf(iy) < 1e30f) || !(fabsf(iz) < 1e30f);
+        (void)inf;
         if (degenerate) return true;
         float t0 = tnear, t1 = tfar;
         {
@@ -84,8 +95,13 @@ struct BvhTraverser {
         firm_lo = t0 + eps; firm_hi = t1 - eps;
         const float m = (((fabsf(ox) + fabsf(oy)) + fabsf(oz)) + fabsf(t1)) * 7.62939453125e-6f;
         marg = m;
-        opx = ox + m; opy = oy + m; opz = oz + m;
-        omx = ox - m; omy = oy - m; omz = oz - m;
+        {   // d > 0: the near plane is lo, met at (lo - (o + m)) / d; d < 0: the near plane is hi, met at (hi - (o - m)) / d
+            const bool sx = ix < 0.0f, sy = iy < 0.0f, sz = iz < 0.0f;
+            cnx = -(((sx ? ox - m : ox + m)) * ix); cfx = -(((sx ? ox + m : ox - m)) * ix);
+            cny = -(((sy ? oy - m : oy + m)) * iy); cfy = -(((sy ? oy + m : oy - m)) * iy);
+            cnz = -(((sz ? oz - m : oz + m)) * iz); cfz = -(((sz ? oz + m : oz - m)) * iz);
+            rows = (sx ? 16u : 0u) | ((sy ? 48u : 32u) << 8) | ((sz ? 80u : 64u) << 16);
+        }
         low_w = (lo_t - fabsf(lo_t) * 9.5367431640625e-7f) - 1e-30f;
         set_limit(eps);
         return true;
@@ -96,13 +112,10 @@ struct BvhTraverser {
         limit = (l + fabsf(l) * 9.5367431640625e-7f) + 1e-30f;
     }
 
-    // entry distance of child c of the node (lo/hi rows already loaded), +inf on a miss
-    __device__ __forceinline__ float child_entry(float lx, float hx, float ly, float hy, float lz, float hz) const {
-        const float ax = (lx - opx) * ix, bx = (hx - omx) * ix;
-        const float ay = (ly - opy) * iy, by = (hy - omy) * iy;
-        const float az = (lz - opz) * iz, bz = (hz - omz) * iz;
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), low_w));
-        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), limit));
+    // entry distance of a child from its near / far planes (rows picked by the ray's direction signs), +inf on a miss
+    __device__ __forceinline__ float child_entry(float nx, float fx, float ny, float fy, float nz, float fz) const {
+        const float tn = max3f(__fmaf_rn(nx, ix, cnx), __fmaf_rn(ny, iy, cny), fmaxf(__fmaf_rn(nz, iz, cnz), low_w));
+        const float tf = min3f(__fmaf_rn(fx, ix, cfx), __fmaf_rn(fy, iy, cfy), fminf(__fmaf_rn(fz, iz, cfz), limit));
         return tn <= tf ? tn : __int_as_float(0x7f800000);
     }
 
@@ -119,13 +132,19 @@ struct BvhTraverser {
     // One inner node: returns the next thing to visit (nearest entered child, else the next stack entry, else BVH_DONE).
     __device__ __forceinline__ uint32_t step(const DevScene& S, uint32_t node, TravStack& K, BvhCount& cnt) {
         if (COUNT) cnt.nodes++;
-        const float4* n = S.bvh_nodes + 8 * (size_t)node;
-        const float4 lx = __ldg(n), hx = __ldg(n + 1), ly = __ldg(n + 2), hy = __ldg(n + 3), lz = __ldg(n + 4), hz = __ldg(n + 5);
-        const float4 cf = __ldg(n + 6);
-        float t0 = child_entry(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x);
-        float t1 = child_entry(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y);
-        float t2 = child_entry(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z);
-        float t3 = child_entry(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w);
+        // rows of the node: lo.x hi.x lo.y hi.y lo.z hi.z codes (16 bytes each); the near row of an axis is at `rows`, the far one
+        // at the other position of the pair (offset ^ 16); 32-bit offsets from the array base (nodes < 2^25)
+        const char* base = reinterpret_cast<const char*>(S.bvh_nodes);
+        const uint32_t at = node << 7;
+        const uint32_t rx = rows & 0xffu, ry = (rows >> 8) & 0xffu, rz = rows >> 16;
+        const float4 nx = __ldg(reinterpret_cast<const float4*>(base + (at + rx))), fx = __ldg(reinterpret_cast<const float4*>(base + (at + (rx ^ 16u))));
+        const float4 ny = __ldg(reinterpret_cast<const float4*>(base + (at + ry))), fy = __ldg(reinterpret_cast<const float4*>(base + (at + (ry ^ 16u))));
+        const float4 nz = __ldg(reinterpret_cast<const float4*>(base + (at + rz))), fz = __ldg(reinterpret_cast<const float4*>(base + (at + (rz ^ 16u))));
+        const float4 cf = __ldg(reinterpret_cast<const float4*>(base + (at + 96u)));
+        float t0 = child_entry(nx.x, fx.x, ny.x, fy.x, nz.x, fz.x);
+        float t1 = child_entry(nx.y, fx.y, ny.y, fy.y, nz.y, fz.y);
+        float t2 = child_entry(nx.z, fx.z, ny.z, fy.z, nz.z, fz.z);
+        float t3 = child_entry(nx.w, fx.w, ny.w, fy.w, nz.w, fz.w);
         uint32_t c0 = __float_as_uint(cf.x), c1 = __float_as_uint(cf.y), c2 = __float_as_uint(cf.z), c3 = __float_as_uint(cf.w);
         const float inf = __int_as_float(0x7f800000);
         if (SORT == 2) {

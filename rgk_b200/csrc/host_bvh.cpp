@@ -291,5 +291,6 @@ void host_bvh_build(const std::vector<float> ev[3], uint32_t nt, const rgk_devic
     hs.bvh_order.swap(b.order);
     hs.bvh_depth = b.deepest;
     // a node pushes at most 3 entries and continues into the 4th child
-    if (3 * (size_t)hs.bvh_depth + 1 > RGK_STACK_CAP) { hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0; }
+    // ... and the traversal addresses a node by a 32-bit byte offset (node << 7): at most 2^25 nodes
+    if (3 * (size_t)hs.bvh_depth + 1 > RGK_STACK_CAP || hs.bvh_nodes.size() / 32 >= ((size_t)1 << 25)) { hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0; }
 }

@@ -48,6 +48,26 @@ __device__ __forceinline__ float rcp_approx(float x) {
 #endif
 }
 
+// three-input max / min (FMNMX3 on sm_100a); NaN operands are ignored like fmaxf / fminf ignore them
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+#else
+    return fminf(fminf(a, b), c);
+#endif
+}
+
 template <bool ANY, bool COUNT>
 struct Traverser {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz, tfar, troot;

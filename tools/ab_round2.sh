@@ -8,7 +8,11 @@ for l in sys.stdin:
     elif 'rror' in l: print(l.strip()[:300])"; }
 L=rgk_b200/librgk_b200.so
 run $L ""
-run rgk_b200/librgk_b200_nopre.so ""
-run rgk_b200/librgk_b200_nostcs.so ""
-run $L "sampler_ctas_per_sm=2"
-run $L ""
+run $L "refill_incoherent=16"
+run $L "refill_incoherent=12"
+run $L "refill_incoherent=8"
+run $L "refill_incoherent=4"
+run $L "refill_shadow=4"
+run $L "refill_shadow=20"
+run $L "refill_coherent=16"
+run $L "refill_coherent=8"

@@ -1112,6 +1112,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     if (!ctx->paths) ctx->paths = new PathBuffers();
     if (!ctx->paths->events) ctx->paths->events = new EventPool();
     EventPool& pool = *ctx->paths->events;
+    pool.used = 0; pool.tag.clear();            // an earlier call that returned on an error between begin and end leaves nothing behind
     float kind_ms[T_KINDS] = {0, 0, 0, 0};
     const uint32_t stride = ctx->shard_stride ? ctx->shard_stride : 1u;
     uint32_t ti = ctx->shard_first;

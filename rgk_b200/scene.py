@@ -520,6 +520,16 @@ def load_config(root, cfgdir=".", overrides=None, mesh_loader=None, texture_load
     cfg.russian = float(root.get("russian", 0.74))
     cfg.reverse = int(root.get("reverse", 0))
     cfg.force_fresnell = bool(root.get("force-fresnell", False))
+    if "output-scale" in root:                       # src/config.cpp:303-312: a number, or the string "auto" (-1: normalise by 1 / max)
+        v = root["output-scale"]
+        if isinstance(v, str):
+            if v != "auto":
+                raise ConfigFileException('The value of "output-scale" must either be a number, or "auto".')
+            cfg.output_scale = -1.0
+        elif isinstance(v, (int, float)) and not isinstance(v, bool):
+            cfg.output_scale = float(np.float32(v))
+        else:
+            raise ConfigFileException('The value of "output-scale" must either be a number, or "auto".')
     if "camera" not in root:
         raise ConfigFileException('Value "camera" is missing.')
     cfg.camera = root["camera"]

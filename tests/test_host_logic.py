@@ -41,6 +41,23 @@ def test_config_errors_mirror_reference_exceptions():
         scene.load_config(bad)
 
 
+def test_output_scale_key(tmp_path):
+    """"output-scale": a number, or "auto" (src/config.cpp:303-312); it travels through the RGKPACK1 file to the C++ drivers."""
+    d = scenes.cornell_box(width=32, height=16, multisample=1)
+    assert scene.load_config(d)[1].output_scale == -1.0                     # absent: auto
+    for given, want in ((0.5, 0.5), (2, 2.0), ("auto", -1.0)):
+        dd = dict(d); dd["output-scale"] = given
+        pack, cfg = scene.load_config(dd)
+        assert cfg.output_scale == want
+        path = str(tmp_path / "s.rgkpack")
+        pack.save(path, cfg)
+        assert scene.load_pack(path)[1].output_scale == want
+    for bad_value in ("manual", [1.0], True, None):
+        dd = dict(d); dd["output-scale"] = bad_value
+        with pytest.raises(scene.ConfigFileException, match="output-scale"):
+            scene.load_config(dd)
+
+
 def test_color255_and_broadcast_vectors():
     d = scenes.cornell_box()
     d["materials"][0] = {"name": "LeftWall", "diffuse255": [255, 0, 127.5], "brdf": "diffuse"}

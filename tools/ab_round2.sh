@@ -7,12 +7,5 @@ for l in sys.stdin:
         d=json.loads(l); print('  ', round(d['ms_per_step'],2), 'ms', round(d['value']), 'Mrays/s', {k: round(v,2) for k,v in d['class_ms_per_step'].items()})
     elif 'rror' in l: print(l.strip()[:300])"; }
 L=rgk_b200/librgk_b200.so
+for v in "$@"; do run rgk_b200/librgk_b200_$v.so ""; done
 run $L ""
-run $L "refill_incoherent=16"
-run $L "refill_incoherent=12"
-run $L "refill_incoherent=8"
-run $L "refill_incoherent=4"
-run $L "refill_shadow=4"
-run $L "refill_shadow=20"
-run $L "refill_coherent=16"
-run $L "refill_coherent=8"

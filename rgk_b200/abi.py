@@ -139,7 +139,8 @@ class DeviceCfg(C.Structure):
                 ("bin_min_frac", C.c_float), ("shade_path_order", C.c_uint32), ("skip_null_shadow", C.c_uint32),
                 ("const_light", C.c_uint32), ("arb_grid", C.c_uint32), ("bvh_shadow_nosort", C.c_uint32),
                 ("bvh_closest_nearest", C.c_uint32), ("sampler_smem", C.c_uint32), ("trace_threads", C.c_uint32),
-                ("kd_variant", C.c_uint32), ("sampler_ctas_per_sm", C.c_uint32), ("_reserved", C.c_uint32 * 7)]
+                ("kd_variant", C.c_uint32), ("sampler_ctas_per_sm", C.c_uint32), ("sampler_kernel", C.c_uint32),
+                ("sampler_slots", C.c_uint32), ("_reserved", C.c_uint32 * 5)]
 
 
 def device_cfg(lib=None, **fields):

@@ -85,6 +85,7 @@ static const char* check_cfg(const rgk_device_cfg& c) {
         c.refill_shadow < 1 || c.refill_shadow > 32) return "rgk_device_cfg: refill thresholds are lane counts (1..32)";
     if (c.bvh_leaf_max > 4) return "rgk_device_cfg: bvh_leaf_max > 4";
     if (c.sampler_ctas_per_sm < 1 || c.sampler_ctas_per_sm > 16) return "rgk_device_cfg: sampler_ctas_per_sm must be 1..16";
+    if (c.sampler_kernel > 2 || c.sampler_slots > 32) return "rgk_device_cfg: sampler_kernel is 0..2, sampler_slots at most 32";
     if (c.bin_items < 64 || c.arb_grid < 1) return "rgk_device_cfg: bin_items >= 64, arb_grid >= 1";
     if (c.chunk_paths < 64 || c.table_bytes < ((uint64_t)1 << 20) || c.reverse_bytes < ((uint64_t)1 << 20)) return "rgk_device_cfg: memory sizes too small";
     return nullptr;

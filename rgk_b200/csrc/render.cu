@@ -268,16 +268,270 @@ __global__ void k_tables_from_user(const float* __restrict__ u1, const float* __
         }
 }
 
-// launches the table generation with the best block size the set size allows
-// CTAs of a sampler launch (= generator-state blocks it needs): ctas_per_sm per SM, never more than there are pixel groups
-static uint32_t sampler_grid(int device, uint32_t npix, uint32_t ctas_per_sm) {
+// ---- warp-cooperative builder (the default where the set fits): one warp per pixel, the generator state in shared memory.
+// The thread-per-pixel kernel above streams its 2.5 KB of state per pixel through L2 / HBM for every generation (12 B per
+// draw: 54 GB per 1080p x 64 spp round, half of the DRAM peak for 16 ms); here the 624 state words of the pixel a warp is
+// working on live in the warp's shared memory, the twist runs 32 words per step across the lanes (word k needs old k, old
+// k + 1 and word k + 397 mod 624, which is old for k < 227 and renewed at least 227 words earlier otherwise: ascending
+// 32-word steps in place give the standard generator's words), and a phase of the table construction takes its draws 32
+// at a time:
+//   * seeding is a 624-step dependent chain (no parallel form), so it is done for 32 pixels at once, one per lane; the
+//     seeded states go through a 32 x 33 transposing tile to a per-warp scratch block in global memory (80 KB, written
+//     and read back once, coalesced), and the warp then builds the 32 pixels one after the other;
+//   * tables nobody reads (the caller's keep masks) are not built: their strata draws are skipped without being looked at
+//     (only the twists happen), their shuffle draws are only checked for a Lemire rejection (which would shift the stream);
+//   * strata: lane j computes entry k0 + j from draw j; shuffle draws: lane j turns draw j into the swap partners of the
+//     pair of positions it stands for (std::shuffle's two-swaps-per-draw loop); a rejected draw ends the batch after the
+//     lanes before it, and the next batch starts at that pair with the following draw;
+//   * the swaps themselves are sequential (position i is exchanged with an earlier, random one): they are applied from
+//     the stored partner lists when the warp's table slots are full, one table per lane, then the finished tables are
+//     written out.  A slot is a table of one (pixel, dimension): several pixels share the slots so that more lanes have a
+//     table to shuffle.
+// Every decision above is warp-uniform.  WL = 1 in the host build of tests/host_cpp (one-lane warps): same code, batches of one.
+#ifndef RGK_WARP_LANES
+#define RGK_WARP_LANES 32
+#endif
+constexpr uint32_t WL = RGK_WARP_LANES;
+constexpr uint32_t SW_WARPS = 8;           // warps per CTA of k_sampler_warp
+constexpr uint32_t SW_TILE = WL * (WL + 1u);   // words of the transposing tile of the seeding phase (aliases state + slots)
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+    return y;
+}
+
+struct WarpMT {
+    uint32_t* st;        // the pixel's 624 state words (shared memory, private to the warp)
+    uint32_t pos;        // draws taken from the current generation, warp-uniform; 624 = exhausted (the state of a fresh mt19937)
+    uint32_t lane;
+    __device__ __forceinline__ void twist() {
+#pragma unroll
+        for (uint32_t base = 0; base < 624u; base += WL) {
+            const uint32_t k = base + lane;
+            uint32_t a = 0, b = 0, c = 0;
+            if (k < 624u) { a = st[k]; b = st[k + 1u < 624u ? k + 1u : 0u]; c = st[k < 227u ? k + 397u : k - 227u]; }
+            __syncwarp();
+            if (k < 624u) {
+                const uint32_t y0 = (a & 0x80000000u) | (b & 0x7fffffffu);
+                st[k] = c ^ (y0 >> 1) ^ ((y0 & 1u) ? 0x9908b0dfu : 0u);
+            }
+            __syncwarp();
+        }
+    }
+    // the next m <= WL draws: lane j < m gets the j-th
+    __device__ __forceinline__ uint32_t take(uint32_t m) {
+        uint32_t w = 0;
+        const uint32_t first = min(m, 624u - pos);          // of them in the current generation
+        if (lane < first) w = st[pos + lane];
+        if (first < m) {
+            twist();
+            if (lane >= first && lane < m) w = st[lane - first];
+            pos = m - first;
+        } else pos += m;
+        return mt_temper(w);
+    }
+    __device__ __forceinline__ void skip(uint32_t n) {
+        pos += n;
+        while (pos > 624u) { twist(); pos -= 624u; }
+    }
+    // The draws of std::shuffle over n elements (n / 2 accepted ones: one swap for the second element of an even n, then two
+    // swaps per draw) turned into partner[i] = the position element i is exchanged with, i = 1 .. n - 1 in that order.
+    // KEEP false: only the stream position is kept right (rejections).
+    template <bool KEEP>
+    __device__ __forceinline__ void shuffle_draws(uint32_t n, uint16_t* partner) {
+        const uint32_t odd = n & 1u, nd = n / 2u;
+        uint32_t t = 0;
+        while (t < nd) {
+            if (pos == 624u) { twist(); pos = 0u; }
+            const uint32_t m = min(min(WL, nd - t), 624u - pos);
+            const uint32_t tt = t + lane, i = 2u * tt + odd;
+            uint32_t hi = 0;
+            bool rej = false;
+            if (lane < m) {
+                const uint32_t w = mt_temper(st[pos + lane]);
+                const uint32_t range = (odd || tt) ? (i + 1u) * (i + 2u) : 2u;
+                const unsigned long long product = (unsigned long long)w * (unsigned long long)range;     // Lemire, as MT::lemire
+                const uint32_t low = (uint32_t)product;
+                hi = (uint32_t)(product >> 32);
+                rej = low < range && low < (0u - range) % range;
+            }
+            const unsigned rm = __ballot_sync(0xffffffffu, rej);
+            const uint32_t acc = rm ? (uint32_t)(__ffs((int)rm) - 1) : m;
+            if (KEEP && lane < acc) {
+                if (!odd && tt == 0u) partner[1] = (uint16_t)hi;
+                else { partner[i] = (uint16_t)(hi / (i + 2u)); partner[i + 1u] = (uint16_t)(hi % (i + 2u)); }
+            }
+            pos += rm ? acc + 1u : m;       // the rejected draw is used up too; the pair it stood for draws again
+            t += acc;
+        }
+    }
+};
+
+// uniform_real_distribution<float>(0, len) of an already drawn word: generate_canonical, then * (len - 0) + 0
+__device__ __forceinline__ float mt_real_of(uint32_t word, float len) {
+    float r = __uint2float_rn(word) / 4294967296.0f;
+    if (r >= 1.0f) r = 0.99999994f;
+    return r * (len - 0.0f) + 0.0f;
+}
+
+// slot g of a warp: float2 data[ss] (a 1-D table uses .x), then uint16 partner[ss]; slot_words apart (even; = 2 mod 32 so that
+// the lanes of the swap phase, one slot each, start in different banks)
+__device__ __forceinline__ void sampler_flush(uint32_t* slots, const uint32_t* meta, uint32_t filled, uint32_t slot_words, uint32_t ss, uint32_t npix,
+                                              uint32_t pix0, uint32_t w, uint32_t lane, float* __restrict__ t1, float2* __restrict__ t2) {
+    __syncwarp();
+    if (lane < filled) {
+        float2* d = reinterpret_cast<float2*>(slots + lane * slot_words);
+        const uint16_t* pr = reinterpret_cast<const uint16_t*>(slots + lane * slot_words + 2u * ss);
+        for (uint32_t i = 1; i < ss; i++) {
+            const uint32_t j = pr[i];
+            const float2 a = d[i], b = d[j];
+            d[i] = b; d[j] = a;
+        }
+    }
+    __syncwarp();
+    for (uint32_t g = 0; g < filled; g++) {
+        const uint32_t m = meta[g];
+        const uint32_t pix = pix0 + (m & 0xffu) * SW_WARPS + w, dim = (m >> 8) & 0xffu;
+        const float2* d = reinterpret_cast<const float2*>(slots + g * slot_words);
+        if (m >> 16) { float2* o = t2 + ((size_t)dim * ss) * npix + pix; for (uint32_t k = lane; k < ss; k += WL) __stcs(o + (size_t)k * npix, d[k]); }
+        else { float* o = t1 + ((size_t)dim * ss) * npix + pix; for (uint32_t k = lane; k < ss; k += WL) __stcs(o + (size_t)k * npix, d[k].x); }
+    }
+    __syncwarp();
+}
+
+#ifndef RGK_SAMPLER_WARP_MINB
+#define RGK_SAMPLER_WARP_MINB 5
+#endif
+__global__ void __launch_bounds__(SW_WARPS * WL, RGK_SAMPLER_WARP_MINB)
+k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t ndims, uint64_t keep1m, uint64_t keep2m,
+               float* __restrict__ t1, float2* __restrict__ t2, uint32_t* __restrict__ scratch, uint32_t nslots, uint32_t slot_words, uint32_t warp_words) {
+    extern __shared__ uint32_t swm[];
+    const uint32_t lane = threadIdx.x % WL, w = threadIdx.x / WL;
+    uint32_t* wsm = swm + w * warp_words;
+    uint32_t* slots = wsm + 624u;
+    uint32_t* meta = slots + nslots * slot_words;
+    uint32_t* my_scratch = scratch + ((size_t)blockIdx.x * SW_WARPS + w) * (WL * 624u);
+    WarpMT g; g.st = wsm; g.lane = lane; g.pos = 624u;
+    const float len1 = 1.0f / (float)ss, len2 = 1.0f / (float)sq;
+    const uint32_t per_block = SW_WARPS * WL, nblocks = (npix + per_block - 1u) / per_block;
+    for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        // a CTA owns per_block consecutive pixels; its warps walk them side by side (warp w: pixels pix0 + q * SW_WARPS + w), so the
+        // sectors of a table row are completed by the CTA's warps at about the same time
+        const uint32_t pix0 = blk * per_block;
+        {   // ---- mt19937::seed for WL pixels, lane q its q-th: word_i = 1812433253 * (word_{i-1} ^ (word_{i-1} >> 30)) + i
+            const uint32_t pix = pix0 + lane * SW_WARPS + w;
+            uint32_t x = pix < npix ? seeds[pix] : 0u;
+            for (uint32_t c0 = 0; c0 < 624u; c0 += WL) {
+                const uint32_t nw = min(WL, 624u - c0);
+#pragma unroll 8
+                for (uint32_t j = 0; j < nw; j++) {
+                    if (c0 + j) x = MT::lcg(x, c0 + j);
+                    wsm[j * (WL + 1u) + lane] = x;
+                }
+                __syncwarp();
+                if (lane < nw) {
+#pragma unroll 8
+                    for (uint32_t q = 0; q < WL; q++) __stcg(my_scratch + q * 624u + c0 + lane, wsm[lane * (WL + 1u) + q]);
+                }
+                __syncwarp();
+            }
+        }
+        uint32_t filled = 0;
+        for (uint32_t q = 0; q < WL; q++) {
+            if (pix0 + q * SW_WARPS + w >= npix) break;
+            for (uint32_t k = lane; k < 624u; k += WL) wsm[k] = __ldcg(my_scratch + q * 624u + k);
+            __syncwarp();
+            g.pos = 624u;
+            for (uint32_t dim = 0; dim < ndims; dim++) {
+                const bool keep1 = (keep1m >> dim) & 1u, keep2 = (keep2m >> dim) & 1u;
+                if (keep1) {
+                    if (filled == nslots) { sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2); filled = 0; }
+                    float2* d = reinterpret_cast<float2*>(slots + filled * slot_words);
+                    for (uint32_t k0 = 0; k0 < ss; k0 += WL) {
+                        const uint32_t m = min(WL, ss - k0);
+                        const uint32_t word = g.take(m);
+                        const uint32_t k = k0 + lane;
+                        if (lane < m) d[k].x = (float)k / (float)ss + mt_real_of(word, len1);
+                    }
+                    g.shuffle_draws<true>(ss, reinterpret_cast<uint16_t*>(slots + filled * slot_words + 2u * ss));
+                    if (lane == 0) meta[filled] = q | (dim << 8);
+                    filled++;
+                } else { g.skip(ss); g.shuffle_draws<false>(ss, nullptr); }
+                if (dim + 1u == ndims && !keep2) break;        // nothing after the last table anybody reads
+                if (keep2) {
+                    if (filled == nslots) { sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2); filled = 0; }
+                    float* d = reinterpret_cast<float*>(slots + filled * slot_words);
+                    for (uint32_t j0 = 0; j0 < 2u * ss; j0 += WL) {           // cell c = sy * sq + sx takes draws 2 c (x) and 2 c + 1 (y)
+                        const uint32_t m = min(WL, 2u * ss - j0);
+                        const uint32_t word = g.take(m);
+                        const uint32_t j = j0 + lane, c = j >> 1;
+                        const uint32_t s = (j & 1u) ? c / sq : c % sq;
+                        if (lane < m) d[j] = (float)s / (float)sq + mt_real_of(word, len2);
+                    }
+                    g.shuffle_draws<true>(ss, reinterpret_cast<uint16_t*>(slots + filled * slot_words + 2u * ss));
+                    if (lane == 0) meta[filled] = q | (dim << 8) | (1u << 16);
+                    filled++;
+                } else { g.skip(2u * ss); g.shuffle_draws<false>(ss, nullptr); }
+            }
+        }
+        sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2);     // the seeding tile reuses the slots
+    }
+}
+
+// launch geometry of the table generation.  kind 0: thread per pixel (k_sampler_mt), 1: warp per pixel (k_sampler_warp)
+struct SamplerPlan { uint32_t kind, grid, nslots, slot_words, warp_words; size_t smem, scratch_words; };
+static SamplerPlan sampler_plan(int device, const rgk_device_cfg& cfg, uint32_t npix, uint32_t ss, uint32_t kept_per_pixel) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    SamplerPlan p{};
+    if (cfg.sampler_kernel != 1u) {
+        uint32_t sw = 2u * ss + (ss + 1u) / 2u;
+        sw += sw & 1u;
+        while (sw % 32u != 2u) sw += 2u;
+        // slots: the tables of about two pixels, so that more lanes have one to shuffle (all of them are flushed at the end of a
+        // 32-pixel block anyway), while five CTAs still fit an SM
+        uint32_t want = cfg.sampler_slots ? cfg.sampler_slots : std::max(1u, std::min(2u * std::max(1u, kept_per_pixel), 8u));
+        want = std::min(want, WL);
+        int per = 0;
+        for (uint32_t ns = want; ns >= 1u; ns--) {
+            uint32_t ww = std::max(SW_TILE, 624u + ns * sw + ns);
+            ww += ww & 1u;
+            const size_t smem = (size_t)ww * 4u * SW_WARPS;
+            if (smem > 200u * 1024u) continue;
+            cudaFuncSetAttribute(k_sampler_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            per = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sampler_warp, (int)(SW_WARPS * WL), smem);
+            // at least 32 warps per SM; with one slot left, 16 (below that the thread-per-pixel kernel, unless this one is forced)
+            const int need = cfg.sampler_slots ? 1 : (ns > 1u ? 4 : (cfg.sampler_kernel == 2u ? 1 : 2));
+            if (per >= need) { p.nslots = ns; p.slot_words = sw; p.warp_words = ww; p.smem = smem; break; }
+        }
+        if (p.nslots) {
+            const uint32_t blocks = (npix + SW_WARPS * WL - 1u) / (SW_WARPS * WL);
+            p.kind = 1u;
+            p.grid = std::max(1u, std::min(blocks, (uint32_t)(sms * per)));
+            p.scratch_words = (size_t)p.grid * SW_WARPS * WL * 624u;
+            return p;
+        }
+    }
     const uint32_t groups = (npix + MT_LANES - 1) / MT_LANES;
-    return std::max(1u, std::min(groups, (uint32_t)sms * std::max(1u, ctas_per_sm)));
+    p.kind = 0u;
+    p.grid = std::max(1u, std::min(groups, (uint32_t)sms * std::max(1u, cfg.sampler_ctas_per_sm)));
+    p.scratch_words = (size_t)p.grid * MT_LANES * 624u;
+    return p;
 }
-static void launch_sampler_mt(cudaStream_t stream, bool use_smem, uint32_t grid, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
-                              float* t1, float2* t2, uint32_t* state) {
+// keep masks: bit d = the 1-D / 2-D table of dimension d is read by somebody (the thread-per-pixel kernel builds them all)
+static void launch_sampler_mt(cudaStream_t stream, const SamplerPlan& plan, bool use_smem, const uint32_t* seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t n1d, uint32_t n2d,
+                              float* t1, float2* t2, uint32_t* state, uint64_t keep1m = ~0ull, uint64_t keep2m = ~0ull) {
+    if (plan.kind == 1u) {
+        keep1m &= n1d >= 64u ? ~0ull : ((1ull << n1d) - 1ull);
+        keep2m &= n2d >= 64u ? ~0ull : ((1ull << n2d) - 1ull);
+        uint32_t ndims = 0;
+        for (uint32_t d = 0; d < 64u; d++) if (((keep1m | keep2m) >> d) & 1ull) ndims = d + 1u;
+        if (!ndims) return;
+        cudaFuncSetAttribute(k_sampler_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+        k_sampler_warp<<<plan.grid, SW_WARPS * WL, plan.smem, stream>>>(seeds, npix, ss, sq, ndims, keep1m, keep2m, t1, t2, state, plan.nslots, plan.slot_words, plan.warp_words);
+        return;
+    }
     // per device (function attributes are), so set on every launch rather than once per process: contexts on several
     // GPUs may live in one process
     cudaFuncSetAttribute(k_sampler_mt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -287,11 +541,11 @@ static void launch_sampler_mt(cudaStream_t stream, bool use_smem, uint32_t grid,
     if (use_smem) {
         const size_t bytes = (size_t)MT_LANES * ss * 8;
         if (bytes <= 100 * 1024) {
-            k_sampler_mt<true><<<grid, MT_LANES, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
+            k_sampler_mt<true><<<plan.grid, MT_LANES, bytes, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
             return;
         }
     }
-    k_sampler_mt<false><<<grid, MT_LANES, 0, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
+    k_sampler_mt<false><<<plan.grid, MT_LANES, 0, stream>>>(seeds, npix, ss, sq, n1d, n2d, t1, t2, state);
 }
 
 // Counter-based sampler with the same structure (jittered strata visited in a per-(pixel,dim) random order),
@@ -897,7 +1151,7 @@ int machine_blocks(rgk_context* ctx, const void* kernel, int threads) {
     return sms * std::max(per, 1);
 }
 
-rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t t1_floats, size_t t2_float2s, size_t tiles, size_t mt_blocks) {
+rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t t1_floats, size_t t2_float2s, size_t tiles, size_t mt_words) {
     if (!ctx->paths) ctx->paths = new PathBuffers();
     PathBuffers& B = *ctx->paths;
     bool ok = true;
@@ -915,7 +1169,7 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
         ok = alloc_dev(&B.pix_xy, pixels) && alloc_dev(&B.pix_seed, pixels) && alloc_dev(&B.pix_src, pixels);
         B.cap_pixels = ok ? pixels : 0;
     }
-    if (ok && mt_blocks > B.cap_mt) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.mt_state, mt_blocks * MT_LANES * 624); B.cap_mt = ok ? mt_blocks : 0; }
+    if (ok && mt_words > B.cap_mt) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.mt_state, mt_words); B.cap_mt = ok ? mt_words : 0; }
     if (ok && t1_floats > B.cap_t1) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t1, t1_floats); B.cap_t1 = ok ? t1_floats : 0; }
     if (ok && t2_float2s > B.cap_t2) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t2, t2_float2s); B.cap_t2 = ok ? t2_float2s : 0; }
     if (ok && tiles > B.cap_tiles) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.tiles, tiles) && alloc_dev(&B.tiles2, tiles); B.cap_tiles = ok ? tiles : 0; }
@@ -1008,13 +1262,14 @@ rgk_status launch_sampler_tables(rgk_context* ctx, const uint32_t* d_seeds, uint
     const uint32_t sq = (uint32_t)(std::sqrt((double)ss) + 0.5f);
     // tables need one scratch dim each; the caller's buffers have exactly n1d / n2d dims, so run into private buffers
     float* t1 = nullptr; float2* t2 = nullptr; uint32_t* st = nullptr;
+    const SamplerPlan plan = sampler_plan(ctx->device, ctx->cfg, n_seeds, ss, n1d + n2d);
     const size_t e1 = (size_t)(n1d + 1) * ss * n_seeds, e2 = (size_t)(n2d + 1) * ss * n_seeds;
     if (cudaMalloc((void**)&t1, e1 * 4) != cudaSuccess || cudaMalloc((void**)&t2, e2 * 8) != cudaSuccess ||
-        cudaMalloc((void**)&st, (size_t)sampler_grid(ctx->device, n_seeds, ctx->cfg.sampler_ctas_per_sm) * MT_LANES * 624 * 4) != cudaSuccess) {
+        cudaMalloc((void**)&st, plan.scratch_words * 4) != cudaSuccess) {
         cudaGetLastError(); if (t1) cudaFree(t1); if (t2) cudaFree(t2); if (st) cudaFree(st);
         return rgk_fail(ctx, RGK_ERR_NOMEM, "sampler table allocation failed");
     }
-    launch_sampler_mt(ctx->stream, ctx->cfg.sampler_smem != 0, sampler_grid(ctx->device, n_seeds, ctx->cfg.sampler_ctas_per_sm), d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
+    launch_sampler_mt(ctx->stream, plan, ctx->cfg.sampler_smem != 0, d_seeds, n_seeds, ss, sq, n1d, n2d, t1, t2, st);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && n1d) e = cudaMemcpyAsync(d_out1, t1, (size_t)n1d * ss * n_seeds * 4, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1114,6 +1369,26 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     EventPool& pool = *ctx->paths->events;
     pool.used = 0; pool.tag.clear();            // an earlier call that returned on an error between begin and end leaves nothing behind
     float kind_ms[T_KINDS] = {0, 0, 0, 0};
+    // Scene::GetRandomLight with one point light and nothing else always returns it; with size 0 it is not jittered
+    const bool const_light = !P->reverse && ctx->dev.n_point_lights == 1 && ctx->dev.n_areal_lights == 0 && ctx->first_point_light.size == 0.0f &&
+                             ctx->first_point_light.intensity > 0.0f && cfg.const_light;
+    // Which sampler tables does the round read?  (The generator walks through all of them either way; the warp-cooperative
+    // builder does not build the others.)  2-D: the pixel jitter, the lens sample, the light's surface sample and choice
+    // unless the light is the one fixed point light, and one direction per path vertex except the last, which never
+    // continues.  1-D: the light's triangle sample (same condition) and the Russian-roulette cursor, which is at most
+    // depth - 1 when it is last looked at.  The bidirectional mode keeps everything (its light paths continue the camera
+    // path's dimensions).
+    uint64_t keep1 = ~0ull, keep2 = ~0ull;
+    if (!P->reverse && mt) {
+        keep2 = 1ull | (lens ? 2ull : 0ull);
+        keep1 = 0ull;
+        if (!const_light) { keep2 |= (1ull << (base2 - 3u)) | (1ull << (base2 - 1u)); keep1 |= 1ull; }
+        for (uint32_t j = 0; j + 1u < P->depth; j++) keep2 |= 1ull << (base2 + j);
+        for (uint32_t c = 1; c < P->depth; c++) keep1 |= 1ull << c;
+    }
+    keep1 &= n1d >= 64u ? ~0ull : ((1ull << n1d) - 1ull);
+    keep2 &= n2d >= 64u ? ~0ull : ((1ull << n2d) - 1ull);
+    SamplerPlan splan{};
     const uint32_t stride = ctx->shard_stride ? ctx->shard_stride : 1u;
     uint32_t ti = ctx->shard_first;
     while (ti < n_tasks) {
@@ -1133,7 +1408,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         const size_t npaths = npix * ms;
         if (npaths > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "a single chunk exceeds 2^32 paths");
         rgk_status s = ensure_buffers(ctx, npaths, npix, tables ? (size_t)(n1d + 1) * ss * npix : 0, tables ? (size_t)(n2d + 1) * ss * npix : 0,
-                                      h_tiles.size(), mt ? sampler_grid(ctx->device, (uint32_t)npix, cfg.sampler_ctas_per_sm) : 0);
+                                      h_tiles.size(), mt ? (splan = sampler_plan(ctx->device, cfg, (uint32_t)npix, ss, (uint32_t)(__builtin_popcountll(keep1) + __builtin_popcountll(keep2)))).scratch_words : 0);
         if (s != RGK_OK) return s;
         PathBuffers& B = *ctx->paths;
         RGK_CUDA(ctx, cudaMemcpyAsync(B.tiles, h_tiles.data(), h_tiles.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
@@ -1144,10 +1419,9 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         R.lens = lens; R.npix = (uint32_t)npix; R.skip_null_shadow = skip_null; R.binning = binning ? 1u : 0u;
         R.reverse = P->reverse; R.npaths = (uint32_t)npaths; R.count_shade = counting ? 1u : 0u;
         if (counting && !shade_counts_cleared) { RGK_CUDA(ctx, cudaMemsetAsync(B.shade_counts, 0, 8 * sizeof(unsigned long long), ctx->stream)); shade_counts_cleared = true; }
-        {   // Scene::GetRandomLight with one point light and nothing else always returns it; with size 0 it is not jittered
+        {
             const DevPointLight& l0 = ctx->first_point_light;
-            R.const_light = (!P->reverse && ctx->dev.n_point_lights == 1 && ctx->dev.n_areal_lights == 0 && l0.size == 0.0f && l0.intensity > 0.0f &&
-                             cfg.const_light) ? 1u : 0u;
+            R.const_light = const_light ? 1u : 0u;
             const uint32_t flags = 1u; float fbits; std::memcpy(&fbits, &flags, 4);       // valid, FULL_SPHERE
             R.cl_pos = make_float4(l0.pos[0], l0.pos[1], l0.pos[2], fbits);
             R.cl_col = make_float4(l0.color[0], l0.color[1], l0.color[2], l0.intensity);
@@ -1162,7 +1436,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         k_pixel_setup<<<(unsigned)h_tiles.size(), 256, 0, ctx->stream>>>(B.tiles, B.tiles2, B.pix_xy, B.pix_seed, B.pix_src, (uint32_t)call_pixels);
         ctx->launches++;
         if (mt) {
-            launch_sampler_mt(ctx->stream, cfg.sampler_smem != 0, sampler_grid(ctx->device, (uint32_t)npix, cfg.sampler_ctas_per_sm), B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state);
+            launch_sampler_mt(ctx->stream, splan, cfg.sampler_smem != 0, B.pix_seed, (uint32_t)npix, ss, sq, n1d, n2d, B.t1, B.t2, B.mt_state, keep1, keep2);
             ctx->launches++;
         } else if (user_tables) {
             k_tables_from_user<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_user_t1, ctx->d_user_t2, ctx->user_n1d, ctx->user_n2d,

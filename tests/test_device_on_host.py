@@ -212,6 +212,8 @@ def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=F
     from test_gpu_render import _pixel_seeds
     desc = pack.desc()
     # one-lane warps: refill after every ray; no k_bin (it cooperates through shared memory)
+    if device_sampler:
+        cfg_fields.setdefault("sampler_kernel", 2)       # the warp-per-pixel builder (the GPU default) unless a test asks otherwise
     dcfg = abi.device_cfg(traversal="bvh" if wide_bvh else "kd", binning=0, refill_coherent=1, refill_incoherent=1, refill_shadow=1, **cfg_fields)
     if True:
         h = vp(doh.doh_shade_scene_create(C.byref(desc), C.byref(dcfg)))
@@ -329,13 +331,16 @@ def test_ab_knob_kernels_on_the_host(doh, oracle, scene):
     assert int(st.closest_rays) == int(so.closest_rays)
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("multisample", [4, 9, 121])
-def test_device_sampler_in_the_wavefront_on_the_host(doh, oracle, multisample):
+def test_device_sampler_in_the_wavefront_on_the_host(doh, oracle, multisample, kernel):
     """RGK_SAMPLER_MT19937: k_sampler_mt (the device replica of StratifiedSampler over libstdc++'s mt19937 / shuffle) inside
     the host-compiled wavefront instead of caller-supplied tables -- still the oracle's framebuffer bit for bit.  Set size
-    121 exceeds the shared-memory budget and takes the in-place global-memory instantiation."""
+    121 exceeds the shared-memory budget of the thread-per-pixel kernel (1) and takes its in-place global-memory instantiation;
+    kernel 2 is the warp-per-pixel builder k_sampler_warp (one-lane warps here: batches of one draw, one table slot), which
+    only builds the tables the round reads."""
     pack, cfg = scenes.material_zoo(width=16, height=12, multisample=multisample, recursion_max=3, lens=0.04)
-    (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=2, wide_bvh=True, device_sampler=True)
+    (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=2, wide_bvh=True, device_sampler=True, sampler_kernel=kernel)
     assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
 
 

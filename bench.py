@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--traversal", default="bvh", choices=["bvh", "kd"],
                     help="bvh: the library default, the wide-BVH traversal with the kd-tree arbiter pass (results bit-identical to the kd "
                          "path); kd: the reference's kd-tree for every ray")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: no nvidia-smi process beside the run (the line then has no clocks record)")
     ap.add_argument("--cfg", default="", help="rgk_device_cfg fields changed from the library defaults, e.g. binning=0,refill_shadow=20 (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -447,7 +448,7 @@ def main():
     warm = max(3, args.warmup)
     # started before the warm-up steps so that nvidia-smi's own start-up (~0.3 s, holds the driver lock) is over when the timed
     # region begins; its samples cover the warm-up (same load) and the timed steps
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not args.no_clocks else None
     for i in range(warm):
         step(i, tiles_mode)
     barrier()

@@ -300,14 +300,66 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     return y;
 }
 
+// One wide step of the twist: words [128 S, 128 S + 128) of the generation, four consecutive words per lane (one 128-bit load for
+// old k .. k + 3, old k + 4 for the pair of the fourth word, the four k + 397-mod-624 words one by one -- 397 and 227 are odd, they
+// never line up for a wide load -- and one 128-bit store): 38 instructions per 128 words instead of 54 in 32-word steps.  Word k
+// needs old k, old k + 1 (new 0 for k = 623) and word k + 397 mod 624, which is old for k < 227 and was renewed by an earlier
+// step otherwise; reads and writes of a step are separated by a warp barrier.
+template <int S>
+__device__ __forceinline__ void mt_twist_wide(uint32_t* __restrict__ st, uint32_t lane) {
+    constexpr uint32_t base = 128u * S;
+    const uint32_t k = base + 4u * lane;
+    const bool on = k < 624u;                 // the last step covers 112 words: lanes 0 .. 27
+    uint4 a = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t a4 = 0u, c[4] = {0u, 0u, 0u, 0u};
+    if (on) {
+        a = *reinterpret_cast<const uint4*>(st + k);
+        a4 = st[k + 4u < 624u ? k + 4u : 0u];
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; j++) {
+            const uint32_t kj = k + j;
+            c[j] = st[(base + 127u < 227u || (base < 227u && kj < 227u)) ? kj + 397u : kj - 227u];
+        }
+    }
+    __syncwarp();
+    if (on) {
+        const uint32_t own[5] = {a.x, a.y, a.z, a.w, a4};
+        uint32_t out[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t y0 = (own[j] & 0x80000000u) | (own[j + 1] & 0x7fffffffu);
+            out[j] = c[j] ^ (y0 >> 1) ^ ((y0 & 1u) ? 0x9908b0dfu : 0u);
+        }
+        *reinterpret_cast<uint4*>(st + k) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    __syncwarp();
+}
+// step s of the current generation (one copy in the kernel: the callers only pay a call)
+static __device__ __noinline__ void mt_twist_step(uint32_t* st, uint32_t lane, uint32_t s) {
+    switch (s) {
+    case 0: mt_twist_wide<0>(st, lane); break;
+    case 1: mt_twist_wide<1>(st, lane); break;
+    case 2: mt_twist_wide<2>(st, lane); break;
+    case 3: mt_twist_wide<3>(st, lane); break;
+    default: mt_twist_wide<4>(st, lane); break;
+    }
+}
+
 struct WarpMT {
     uint32_t* st;        // the pixel's 624 state words (shared memory, private to the warp)
     uint32_t pos;        // draws taken from the current generation, warp-uniform; 624 = exhausted (the state of a fresh mt19937)
+    uint32_t ren;        // words of the current generation already renewed: st[0, ren) new, st[ren, 624) still the previous generation
     uint32_t lane;
-    __device__ __forceinline__ void twist() {
-#pragma unroll
-        for (uint32_t base = 0; base < 624u; base += WL) {
-            const uint32_t k = base + lane;
+    // The twist is lazy: a generation is renewed in ascending steps only as far as draws are asked for, so the unused tail of a
+    // pixel's last generation is never computed.  32-lane warps: wide steps of 128 words; the one-lane warps of the host build
+    // (tests/host_cpp): word by word, the textbook loop.
+    __device__ __forceinline__ void renew(uint32_t upto) {
+        if (WL == 32u) {
+            while (ren < upto) { mt_twist_step(st, lane, ren >> 7); ren = min(ren + 128u, 624u); }
+            return;
+        }
+        while (ren < upto) {
+            const uint32_t k = ren + lane;
             uint32_t a = 0, b = 0, c = 0;
             if (k < 624u) { a = st[k]; b = st[k + 1u < 624u ? k + 1u : 0u]; c = st[k < 227u ? k + 397u : k - 227u]; }
             __syncwarp();
@@ -316,15 +368,19 @@ struct WarpMT {
                 st[k] = c ^ (y0 >> 1) ^ ((y0 & 1u) ? 0x9908b0dfu : 0u);
             }
             __syncwarp();
+            ren = min(ren + WL, 624u);
         }
     }
+    __device__ __forceinline__ void next_generation() { renew(624u); pos = 0u; ren = 0u; }
     // the next m <= WL draws: lane j < m gets the j-th
     __device__ __forceinline__ uint32_t take(uint32_t m) {
         uint32_t w = 0;
         const uint32_t first = min(m, 624u - pos);          // of them in the current generation
+        renew(pos + first);
         if (lane < first) w = st[pos + lane];
         if (first < m) {
-            twist();
+            next_generation();
+            renew(m - first);
             if (lane >= first && lane < m) w = st[lane - first];
             pos = m - first;
         } else pos += m;
@@ -332,18 +388,18 @@ struct WarpMT {
     }
     __device__ __forceinline__ void skip(uint32_t n) {
         pos += n;
-        while (pos > 624u) { twist(); pos -= 624u; }
+        while (pos > 624u) { const uint32_t over = pos - 624u; next_generation(); pos = over; }
     }
     // The draws of std::shuffle over n elements (n / 2 accepted ones: one swap for the second element of an even n, then two
     // swaps per draw) turned into partner[i] = the position element i is exchanged with, i = 1 .. n - 1 in that order.
-    // KEEP false: only the stream position is kept right (rejections).
-    template <bool KEEP>
-    __device__ __forceinline__ void shuffle_draws(uint32_t n, uint16_t* partner) {
+    // keep false: only the stream position is kept right (rejections).
+    __device__ __forceinline__ void shuffle_draws(uint32_t n, uint16_t* partner, bool keep) {
         const uint32_t odd = n & 1u, nd = n / 2u;
         uint32_t t = 0;
         while (t < nd) {
-            if (pos == 624u) { twist(); pos = 0u; }
+            if (pos == 624u) next_generation();
             const uint32_t m = min(min(WL, nd - t), 624u - pos);
+            renew(pos + m);
             const uint32_t tt = t + lane, i = 2u * tt + odd;
             uint32_t hi = 0;
             bool rej = false;
@@ -357,9 +413,9 @@ struct WarpMT {
             }
             const unsigned rm = __ballot_sync(0xffffffffu, rej);
             const uint32_t acc = rm ? (uint32_t)(__ffs((int)rm) - 1) : m;
-            if (KEEP && lane < acc) {
+            if (keep && lane < acc) {
                 if (!odd && tt == 0u) partner[1] = (uint16_t)hi;
-                else { partner[i] = (uint16_t)(hi / (i + 2u)); partner[i + 1u] = (uint16_t)(hi % (i + 2u)); }
+                else { const uint32_t p1 = hi / (i + 2u); partner[i] = (uint16_t)p1; partner[i + 1u] = (uint16_t)(hi - p1 * (i + 2u)); }
             }
             pos += rm ? acc + 1u : m;       // the rejected draw is used up too; the pair it stood for draws again
             t += acc;
@@ -376,8 +432,8 @@ __device__ __forceinline__ float mt_real_of(uint32_t word, float len) {
 
 // slot g of a warp: float2 data[ss] (a 1-D table uses .x), then uint16 partner[ss]; slot_words apart (even; = 2 mod 32 so that
 // the lanes of the swap phase, one slot each, start in different banks)
-__device__ __forceinline__ void sampler_flush(uint32_t* slots, const uint32_t* meta, uint32_t filled, uint32_t slot_words, uint32_t ss, uint32_t npix,
-                                              uint32_t pix0, uint32_t w, uint32_t lane, float* __restrict__ t1, float2* __restrict__ t2) {
+__device__ __noinline__ void sampler_flush(uint32_t* slots, const uint32_t* meta, uint32_t filled, uint32_t slot_words, uint32_t ss, uint32_t npix,
+                                           uint32_t pix0, uint32_t w, uint32_t lane, float* __restrict__ t1, float2* __restrict__ t2) {
     __syncwarp();
     if (lane < filled) {
         float2* d = reinterpret_cast<float2*>(slots + lane * slot_words);
@@ -400,18 +456,28 @@ __device__ __forceinline__ void sampler_flush(uint32_t* slots, const uint32_t* m
 }
 
 #ifndef RGK_SAMPLER_WARP_MINB
-#define RGK_SAMPLER_WARP_MINB 5
+#define RGK_SAMPLER_WARP_MINB 4
 #endif
+// Shared memory: [ss + sq floats: the stratum origins k / ss and s / sq, computed once per CTA with the reference's division]
+// [per warp: 624 state words | nslots slots | nslots meta words].  sq_magic = ceil(2^32 / sq): c / sq = umulhi(c, sq_magic)
+// exactly for c < ss (c * sq < 2^32 is checked by the launcher).
 __global__ void __launch_bounds__(SW_WARPS * WL, RGK_SAMPLER_WARP_MINB)
-k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t ndims, uint64_t keep1m, uint64_t keep2m,
+k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t sq_magic, uint32_t ndims, uint64_t keep1m, uint64_t keep2m,
                float* __restrict__ t1, float2* __restrict__ t2, uint32_t* __restrict__ scratch, uint32_t nslots, uint32_t slot_words, uint32_t warp_words) {
     extern __shared__ uint32_t swm[];
     const uint32_t lane = threadIdx.x % WL, w = threadIdx.x / WL;
-    uint32_t* wsm = swm + w * warp_words;
+    float* begin1 = reinterpret_cast<float*>(swm);
+    float* begin2 = begin1 + ss;
+    // (every warp writes the whole table -- the same values -- so that a warp depends on no other: the host build of the tests
+    // runs the "warps" of a CTA one after the other)
+    for (uint32_t k = lane; k < ss; k += WL) begin1[k] = (float)k / (float)ss;
+    for (uint32_t k = lane; k < sq; k += WL) begin2[k] = (float)k / (float)sq;
+    __syncthreads();
+    uint32_t* wsm = swm + ((ss + sq + 3u) & ~3u) + w * warp_words;          // 16-byte aligned: the wide twist loads 128 bits
     uint32_t* slots = wsm + 624u;
     uint32_t* meta = slots + nslots * slot_words;
     uint32_t* my_scratch = scratch + ((size_t)blockIdx.x * SW_WARPS + w) * (WL * 624u);
-    WarpMT g; g.st = wsm; g.lane = lane; g.pos = 624u;
+    WarpMT g; g.st = wsm; g.lane = lane; g.pos = 624u; g.ren = 624u;
     const float len1 = 1.0f / (float)ss, len2 = 1.0f / (float)sq;
     const uint32_t per_block = SW_WARPS * WL, nblocks = (npix + per_block - 1u) / per_block;
     for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
@@ -441,37 +507,30 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
             if (pix0 + q * SW_WARPS + w >= npix) break;
             for (uint32_t k = lane; k < 624u; k += WL) wsm[k] = __ldcg(my_scratch + q * 624u + k);
             __syncwarp();
-            g.pos = 624u;
-            for (uint32_t dim = 0; dim < ndims; dim++) {
-                const bool keep1 = (keep1m >> dim) & 1u, keep2 = (keep2m >> dim) & 1u;
-                if (keep1) {
-                    if (filled == nslots) { sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2); filled = 0; }
-                    float2* d = reinterpret_cast<float2*>(slots + filled * slot_words);
-                    for (uint32_t k0 = 0; k0 < ss; k0 += WL) {
-                        const uint32_t m = min(WL, ss - k0);
-                        const uint32_t word = g.take(m);
-                        const uint32_t k = k0 + lane;
-                        if (lane < m) d[k].x = (float)k / (float)ss + mt_real_of(word, len1);
+            g.pos = 624u; g.ren = 624u;
+            // table tb: the 1-D (even) / 2-D (odd) table of dimension tb / 2; nothing after the last table anybody reads
+            const uint32_t ntab = 2u * ndims - (((keep2m >> (ndims - 1u)) & 1ull) ? 0u : 1u);
+            for (uint32_t tb = 0; tb < ntab; tb++) {
+                const uint32_t dim = tb >> 1, two = tb & 1u;
+                const bool keep = ((two ? keep2m : keep1m) >> dim) & 1ull;
+                const uint32_t ndraws = ss << two;
+                if (!keep) { g.skip(ndraws); g.shuffle_draws(ss, nullptr, false); continue; }
+                if (filled == nslots) { sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2); filled = 0; }
+                float* d = reinterpret_cast<float*>(slots + filled * slot_words);
+                for (uint32_t j0 = 0; j0 < ndraws; j0 += WL) {
+                    const uint32_t m = min(WL, ndraws - j0);
+                    const uint32_t word = g.take(m);
+                    const uint32_t j = j0 + lane;
+                    if (lane < m) {
+                        if (two) {                  // cell c = sy * sq + sx takes draws 2 c (x) and 2 c + 1 (y)
+                            const uint32_t c = j >> 1, sy = __umulhi(c, sq_magic), sx = c - sy * sq;
+                            d[j] = begin2[(j & 1u) ? sy : sx] + mt_real_of(word, len2);
+                        } else d[2u * j] = begin1[j] + mt_real_of(word, len1);
                     }
-                    g.shuffle_draws<true>(ss, reinterpret_cast<uint16_t*>(slots + filled * slot_words + 2u * ss));
-                    if (lane == 0) meta[filled] = q | (dim << 8);
-                    filled++;
-                } else { g.skip(ss); g.shuffle_draws<false>(ss, nullptr); }
-                if (dim + 1u == ndims && !keep2) break;        // nothing after the last table anybody reads
-                if (keep2) {
-                    if (filled == nslots) { sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2); filled = 0; }
-                    float* d = reinterpret_cast<float*>(slots + filled * slot_words);
-                    for (uint32_t j0 = 0; j0 < 2u * ss; j0 += WL) {           // cell c = sy * sq + sx takes draws 2 c (x) and 2 c + 1 (y)
-                        const uint32_t m = min(WL, 2u * ss - j0);
-                        const uint32_t word = g.take(m);
-                        const uint32_t j = j0 + lane, c = j >> 1;
-                        const uint32_t s = (j & 1u) ? c / sq : c % sq;
-                        if (lane < m) d[j] = (float)s / (float)sq + mt_real_of(word, len2);
-                    }
-                    g.shuffle_draws<true>(ss, reinterpret_cast<uint16_t*>(slots + filled * slot_words + 2u * ss));
-                    if (lane == 0) meta[filled] = q | (dim << 8) | (1u << 16);
-                    filled++;
-                } else { g.skip(2u * ss); g.shuffle_draws<false>(ss, nullptr); }
+                }
+                g.shuffle_draws(ss, reinterpret_cast<uint16_t*>(slots + filled * slot_words + 2u * ss), true);
+                if (lane == 0) meta[filled] = q | (dim << 8) | (two << 16);
+                filled++;
             }
         }
         sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2);     // the seeding tile reuses the slots
@@ -495,8 +554,8 @@ static SamplerPlan sampler_plan(int device, const rgk_device_cfg& cfg, uint32_t 
         int per = 0;
         for (uint32_t ns = want; ns >= 1u; ns--) {
             uint32_t ww = std::max(SW_TILE, 624u + ns * sw + ns);
-            ww += ww & 1u;
-            const size_t smem = (size_t)ww * 4u * SW_WARPS;
+            ww = (ww + 3u) & ~3u;
+            const size_t smem = ((size_t)ww * SW_WARPS + ((ss + (uint32_t)std::lround(std::sqrt((double)ss)) + 3u) & ~3u)) * 4u;
             if (smem > 200u * 1024u) continue;
             cudaFuncSetAttribute(k_sampler_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             per = 0;
@@ -529,7 +588,8 @@ static void launch_sampler_mt(cudaStream_t stream, const SamplerPlan& plan, bool
         for (uint32_t d = 0; d < 64u; d++) if (((keep1m | keep2m) >> d) & 1ull) ndims = d + 1u;
         if (!ndims) return;
         cudaFuncSetAttribute(k_sampler_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-        k_sampler_warp<<<plan.grid, SW_WARPS * WL, plan.smem, stream>>>(seeds, npix, ss, sq, ndims, keep1m, keep2m, t1, t2, state, plan.nslots, plan.slot_words, plan.warp_words);
+        const uint32_t sq_magic = sq > 1u ? (uint32_t)((0x100000000ull + sq - 1u) / sq) : 0u;      // sq == 1: c is always 0
+        k_sampler_warp<<<plan.grid, SW_WARPS * WL, plan.smem, stream>>>(seeds, npix, ss, sq, sq_magic, ndims, keep1m, keep2m, t1, t2, state, plan.nslots, plan.slot_words, plan.warp_words);
         return;
     }
     // per device (function attributes are), so set on every launch rather than once per process: contexts on several

@@ -33,6 +33,7 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }      // streaming store: cache hint only
 template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((unsigned long long)a * b) >> 32); }
 #define RGK_WARP_LANES 1                                                  // k_sampler_warp: batches of one draw
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }

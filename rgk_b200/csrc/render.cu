@@ -33,7 +33,7 @@ struct ReverseBuffers {
     size_t cap_paths = 0, cap_cam = 0, cap_light = 0;
 };
 struct PathBuffers {
-    size_t cap_paths = 0, cap_pixels = 0, cap_t1 = 0, cap_t2 = 0, cap_tiles = 0, cap_mt = 0;
+    size_t cap_paths = 0, cap_pixels = 0, cap_t1 = 0, cap_t2 = 0, cap_tiles = 0, cap_mt = 0, cap_bounces = 0;
     float4 *ray_o = nullptr, *ray_d = nullptr, *hit = nullptr, *cum = nullptr, *tot = nullptr;
     float4 *light_pos = nullptr, *light_col = nullptr, *light_nrm = nullptr;
     float4 *sh_pos = nullptr, *sh_direct = nullptr, *sh_emis = nullptr, *sh_contrib = nullptr;
@@ -46,19 +46,32 @@ struct PathBuffers {
     uint4 *tiles = nullptr; uint2 *tiles2 = nullptr;
     unsigned long long *counters = nullptr;   // device
     unsigned long long *shade_counts = nullptr;   // device, 8 words: work counters of k_shade in counting rounds (rgk_render_get_shade_stats)
-    unsigned long long *h_counters = nullptr; // pinned
+    unsigned long long *h_counters = nullptr; // pinned: H_CHUNKS chunks x cap_bounces bounces x C_COUNT words, then cap_bounces words of early read-backs
+    std::vector<cudaEvent_t>* term_events = nullptr;   // host only: completion of bounce b's early read-back
     struct EventPool* events = nullptr;       // host only
     ReverseBuffers* reverse = nullptr;        // host only (bidirectional mode)
 };
 
-enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_SHADOW_SKIPPED = 4, C_NEXT_U = 5, C_COUNT = 8 };
+// One block of counters per bounce (C_COUNT words, zeroed once per chunk): the queue lengths a bounce produces are read by the
+// next kernels ON THE DEVICE (its own shadow launch, the next bounce), so the host never waits for them inside a chunk.
+enum { C_NEXT = 0, C_SHADOW = 1, C_WORK_A = 2, C_WORK_B = 3, C_SHADOW_SKIPPED = 4, C_NEXT_U = 5,
+       C_ARB_WORK = 8, C_ARB_COUNT = 9, C_ARB_SWORK = 10, C_ARB_SCOUNT = 11, C_COUNT = 16 };
+// What a kernel of bounce b needs to know about a queue length: a device word (written by the previous kernels) or, where the
+// host knows it (camera rays, the bidirectional mode), a value.  Binning decisions that depend on a length are taken on the
+// device from the same words: a bounce is binned when its live paths number at least bin_thresh.
+struct QueueLen {
+    const unsigned long long* ptr; uint32_t val;
+    __device__ __forceinline__ uint32_t get() const { return ptr ? (uint32_t)*ptr : val; }
+};
 
 struct RenderConst {
     rgk_camera cam;
     uint32_t xres, yres, ms, depth;
     float clamp, russian, bump_scale;
     uint32_t set_size, n1d, n2d, base2, sampler_mode, lens, skip_null_shadow;
-    uint32_t binning;       // 1: k_shade writes direction-bin keys and k_bin builds the queues (coherence reordering)
+    uint32_t binning;       // what MAY be binned this bounce (bit 0 continuation rays, bit 1 shadow rays): k_shade writes direction-bin keys and
+                            // k_bin builds the queues (coherence reordering) if the bounce has at least bin_thresh live paths
+    uint32_t bin_thresh;
     uint32_t npix;          // pixels in the chunk
     uint32_t const_light;   // 1: the scene's only light is one point light of size 0 -- every sample picks the same light record
     float4 cl_pos, cl_col;  //    (position + flags, colour + intensity), read from here instead of per-path arrays
@@ -750,7 +763,8 @@ __device__ __forceinline__ void flush_counts(const TravCount& c, uint32_t nrays,
 // closest-hit over the live queue (queue == nullptr: identity), persistent warps
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
-k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, rgk_trav_stats* stats) {
+k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, QueueLen len, unsigned long long* work, rgk_trav_stats* stats) {
+    const uint32_t count = len.get();
     TravCount cnt{0, 0, 0, 0, 0, 0, 0};
     uint32_t mine = 0;
     trace_rays<RGK_RENDER_VARIANT, false, COUNT>(S, count, work, cnt, mine,
@@ -769,8 +783,9 @@ k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_
 // shadow traversal fused with the NEE resolve (src/path_tracer.cpp:431-460,485-496)
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
-k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, rgk_trav_stats* stats,
+k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, QueueLen len, float clampv, unsigned long long* work, rgk_trav_stats* stats,
          uint32_t const_light, float4 cl_pos) {
+    const uint32_t count = len.get();
     TravCount cnt{0, 0, 0, 0, 0, 0, 0};
     uint32_t mine = 0;
     trace_rays<RGK_RENDER_VARIANT, true, COUNT>(S, count, work, cnt, mine,
@@ -850,8 +865,9 @@ struct ShadowIO {
 
 template <int MINB, int SORT = 1, bool COUNT = false>       // MINB 6: <= 80 registers (no spills, 7 CTAs/SM at the 72 it uses)
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
-k_closest_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, unsigned long long* work, BvhStats* stats,
+k_closest_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, QueueLen len, unsigned long long* work, BvhStats* stats,
               uint32_t* __restrict__ arb, uint32_t* arb_count) {
+    const uint32_t count = len.get();
     BvhCount cnt{0, 0, 0};
     uint32_t mine = 0, deferred = 0;
     const ClosestIO io{B};
@@ -882,8 +898,9 @@ k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const
 
 template <int MINB, int SORT, bool COUNT = false>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
-k_shadow_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count, float clampv, unsigned long long* work, BvhStats* stats,
+k_shadow_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, QueueLen len, float clampv, unsigned long long* work, BvhStats* stats,
              uint32_t const_light, float4 cl_pos, uint32_t* __restrict__ arb, uint32_t* arb_count) {
+    const uint32_t count = len.get();
     BvhCount cnt{0, 0, 0};
     uint32_t mine = 0, deferred = 0;
     const ShadowIO io{B, clampv, const_light, cl_pos};
@@ -929,7 +946,8 @@ __device__ __forceinline__ uint8_t dir_bin(float x, float y, float z) {
 constexpr int BIN_THREADS = 256;
 __global__ void __launch_bounds__(BIN_THREADS)
 k_bin(const uint8_t* __restrict__ keys, uint32_t npix, uint32_t ms, uint32_t PG, uint32_t SG, uint32_t n_pgroups,
-      uint32_t* __restrict__ out, unsigned long long* counter) {
+      uint32_t* __restrict__ out, unsigned long long* counter, QueueLen live, uint32_t bin_thresh) {
+    if (live.get() < bin_thresh) return;          // too few live paths: k_shade compacted this bounce with its atomics instead
     __shared__ uint32_t hist[256];
     __shared__ uint32_t warp_tot[BIN_THREADS / 32];
     __shared__ unsigned long long base_s;
@@ -983,8 +1001,16 @@ __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* 
 // results from a kernel without the BxDF sampling code (4016 instead of 7352 SASS instructions; measured -3 ms per headline round)
 template <bool LAST>
 __global__ void __launch_bounds__(128, RGK_SHADE_MINB)
-k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue, uint32_t count,
-        uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ next_unsorted, unsigned long long* counters) {
+k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue_sorted, const uint32_t* __restrict__ queue_path_order,
+        QueueLen len, QueueLen prev_len, uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ next_unsorted,
+        unsigned long long* counters) {
+    // The grid covers an upper bound of the queue's length (the host launches without knowing it): CTAs past the end leave.  The
+    // queue is read through its path-ordered twin when the previous bounce was binned (it was if it had at least bin_thresh live
+    // paths: the same test k_bin made); this bounce is binned under the same rule.
+    const uint32_t count = len.get();
+    if (blockIdx.x * blockDim.x >= count) return;
+    const uint32_t* __restrict__ queue = (queue_path_order && prev_len.get() >= R.bin_thresh) ? queue_path_order : queue_sorted;
+    const uint32_t binmask = count >= R.bin_thresh ? R.binning : 0u;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool cont = false, shadow = false, null_shadow = false;
     uint32_t slot = 0;
@@ -1137,13 +1163,13 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
     // queues: either built by k_bin from direction-bin keys (rays of one pixel block are reordered by direction so that
     // the lanes of a traversal warp follow similar paths through the tree), or by warp-aggregated atomic compaction in
     // path order.  R.binning bit 0: continuation rays, bit 1: shadow rays.  The order of a queue never changes a result.
-    if (R.binning & 1u) {
+    if (binmask & 1u) {
         if (cont) { const float4 d = B.ray_d[slot]; B.key_next[slot] = dir_bin(d.x, d.y, d.z); }
         // the same paths once more in path order: the next k_shade gathers its per-path state through this list
         // (coalesced), the traversal goes through the direction-sorted one
         push_queue(next_unsorted, counters + C_NEXT_U, cont, slot);
     } else push_queue(next_queue, counters + C_NEXT, cont, slot);
-    if (R.binning & 2u) {
+    if (binmask & 2u) {
         if (shadow) {
             const float4 a = R.const_light ? R.cl_pos : B.light_pos[slot], b = B.sh_pos[slot];
             B.key_shadow[slot] = dir_bin(b.x - a.x, b.y - a.y, b.z - a.z);
@@ -1211,7 +1237,8 @@ int machine_blocks(rgk_context* ctx, const void* kernel, int threads) {
     return sms * std::max(per, 1);
 }
 
-rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t t1_floats, size_t t2_float2s, size_t tiles, size_t mt_words) {
+constexpr size_t H_CHUNKS = 16;    // chunks whose counter blocks can wait in pinned memory for the end of the round
+rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t t1_floats, size_t t2_float2s, size_t tiles, size_t mt_words, size_t bounces) {
     if (!ctx->paths) ctx->paths = new PathBuffers();
     PathBuffers& B = *ctx->paths;
     bool ok = true;
@@ -1233,9 +1260,13 @@ rgk_status ensure_buffers(rgk_context* ctx, size_t paths, size_t pixels, size_t 
     if (ok && t1_floats > B.cap_t1) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t1, t1_floats); B.cap_t1 = ok ? t1_floats : 0; }
     if (ok && t2_float2s > B.cap_t2) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.t2, t2_float2s); B.cap_t2 = ok ? t2_float2s : 0; }
     if (ok && tiles > B.cap_tiles) { RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); ok = alloc_dev(&B.tiles, tiles) && alloc_dev(&B.tiles2, tiles); B.cap_tiles = ok ? tiles : 0; }
-    if (ok && !B.counters) {
-        ok = alloc_dev(&B.counters, (size_t)C_COUNT) && alloc_dev(&B.shade_counts, (size_t)8);
-        ok = ok && cudaMallocHost((void**)&B.h_counters, C_COUNT * sizeof(unsigned long long)) == cudaSuccess;
+    bounces = std::max<size_t>(bounces, 1);
+    if (ok && bounces > B.cap_bounces) {
+        RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (B.h_counters) { cudaFreeHost(B.h_counters); B.h_counters = nullptr; }
+        ok = alloc_dev(&B.counters, bounces * C_COUNT) && (B.shade_counts || alloc_dev(&B.shade_counts, (size_t)8));
+        ok = ok && cudaMallocHost((void**)&B.h_counters, (H_CHUNKS * bounces * C_COUNT + bounces) * sizeof(unsigned long long)) == cudaSuccess;
+        B.cap_bounces = ok ? bounces : 0;
     }
     if (!ok) { cudaGetLastError(); return rgk_fail(ctx, RGK_ERR_NOMEM, "path-state allocation failed (lower rgk_device_cfg::chunk_paths)"); }
     return RGK_OK;
@@ -1286,6 +1317,7 @@ void free_path_buffers(rgk_context* ctx) {
         delete B.reverse;
     }
     free_event_pool(B.events);
+    if (B.term_events) { for (cudaEvent_t e : *B.term_events) cudaEventDestroy(e); delete B.term_events; }
     delete ctx->paths;
     ctx->paths = nullptr;
 }
@@ -1398,27 +1430,28 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
 
     // chunking: whole tiles, every multisample of a pixel in the same chunk
     size_t max_paths = (size_t)cfg.chunk_paths;        // default 128 Mi paths ~ 27 GB of path state: sized for 180 GB of HBM
-    {   // never plan a chunk whose path state (~210 B per path, on top of what is already allocated) would not fit in 60 %
-        // of the memory that is free right now (other contexts, smaller parts)
+    const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss : 0;
+    size_t max_table_bytes = (size_t)cfg.table_bytes;
+    {   // Never plan a chunk whose path state (~210 B per path, on top of what is already allocated) would not fit in 60 % of the
+        // memory that is free right now (other contexts, smaller parts), nor tables beyond a quarter of it.  cudaMemGetInfo is
+        // only asked when this call could need more than the context already holds: in the steady state of a frame (round
+        // after round of the same size) it is skipped -- on a shared node the query was seen to take 1 - 90 ms, with the GPU idle.
+        size_t call_pixels_total = 0;
+        for (uint32_t i = ctx->shard_first; i < n_tasks; i += (ctx->shard_stride ? ctx->shard_stride : 1u))
+            call_pixels_total += (size_t)(tasks[i].x2 - tasks[i].x1) * (tasks[i].y2 - tasks[i].y1);
+        const size_t have_paths = ctx->paths ? ctx->paths->cap_paths : 0;
+        const size_t have_tables = ctx->paths ? (ctx->paths->cap_t1 * 4 + ctx->paths->cap_t2 * 8) : 0;
+        const bool paths_fit = have_paths >= std::min(max_paths, call_pixels_total * ms);
+        const bool tables_fit = have_tables >= std::min(max_table_bytes, call_pixels_total * per_pixel_table);
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t have = ctx->paths ? ctx->paths->cap_paths : 0;
-            const size_t fit = have + (size_t)(0.6 * (double)free_b / 210.0);
-            max_paths = std::min(max_paths, std::max<size_t>(fit, (size_t)1 << 20));
+        if ((!paths_fit || !tables_fit) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            if (!paths_fit) max_paths = std::min(max_paths, std::max<size_t>(have_paths + (size_t)(0.6 * (double)free_b / 210.0), (size_t)1 << 20));
+            if (!tables_fit) max_table_bytes = std::min(max_table_bytes, std::max<size_t>(have_tables + (size_t)(0.25 * (double)free_b), (size_t)64 << 20));
         }
     }
     if (P->reverse) {      // bidirectional mode keeps every vertex of the camera and light paths: 112 B and 80 B per vertex
         const size_t per_path = 112 * (size_t)P->depth + 80 * (size_t)P->reverse + 64;
         max_paths = std::max<size_t>(std::min(max_paths, (size_t)cfg.reverse_bytes / per_path), 4096);
-    }
-    const size_t per_pixel_table = tables ? ((size_t)(n1d + 1) * 4 + (size_t)(n2d + 1) * 8) * ss : 0;
-    size_t max_table_bytes = (size_t)cfg.table_bytes;
-    {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t have = ctx->paths ? (ctx->paths->cap_t1 * 4 + ctx->paths->cap_t2 * 8) : 0;
-            max_table_bytes = std::min(max_table_bytes, std::max<size_t>(have + (size_t)(0.25 * (double)free_b), (size_t)64 << 20));
-        }
     }
     std::vector<uint4> h_tiles; std::vector<uint2> h_tiles2;
     rgk_round_stats total{};
@@ -1449,6 +1482,23 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     keep1 &= n1d >= 64u ? ~0ull : ((1ull << n1d) - 1ull);
     keep2 &= n2d >= 64u ? ~0ull : ((1ull << n2d) - 1ull);
     SamplerPlan splan{};
+    // chunks whose counter blocks are on their way to pinned memory: (paths, bounces enqueued)
+    std::vector<std::pair<uint32_t, uint32_t>> pending;
+    std::vector<bool> term_recorded(P->depth + 1u, false);
+    auto drain = [&]() -> rgk_status {
+        RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const PathBuffers& Bd = *ctx->paths;
+        for (size_t c = 0; c < pending.size(); c++) {
+            const unsigned long long* h = Bd.h_counters + c * Bd.cap_bounces * C_COUNT;
+            for (uint32_t b = 0; b < pending[c].second; b++) {
+                total.closest_rays += b ? h[(size_t)(b - 1) * C_COUNT + C_NEXT] : pending[c].first;
+                total.shadow_rays += h[(size_t)b * C_COUNT + C_SHADOW];
+                total.shadow_rays_skipped += h[(size_t)b * C_COUNT + C_SHADOW_SKIPPED];
+            }
+        }
+        pending.clear();
+        return RGK_OK;
+    };
     const uint32_t stride = ctx->shard_stride ? ctx->shard_stride : 1u;
     uint32_t ti = ctx->shard_first;
     while (ti < n_tasks) {
@@ -1468,7 +1518,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
         const size_t npaths = npix * ms;
         if (npaths > 0xFFFFFFF0ull) return rgk_fail(ctx, RGK_ERR_UNSUPPORTED, "a single chunk exceeds 2^32 paths");
         rgk_status s = ensure_buffers(ctx, npaths, npix, tables ? (size_t)(n1d + 1) * ss * npix : 0, tables ? (size_t)(n2d + 1) * ss * npix : 0,
-                                      h_tiles.size(), mt ? (splan = sampler_plan(ctx->device, cfg, (uint32_t)npix, ss, (uint32_t)(__builtin_popcountll(keep1) + __builtin_popcountll(keep2)))).scratch_words : 0);
+                                      h_tiles.size(), mt ? (splan = sampler_plan(ctx->device, cfg, (uint32_t)npix, ss, (uint32_t)(__builtin_popcountll(keep1) + __builtin_popcountll(keep2)))).scratch_words : 0, P->depth);
         if (s != RGK_OK) return s;
         PathBuffers& B = *ctx->paths;
         RGK_CUDA(ctx, cudaMemcpyAsync(B.tiles, h_tiles.data(), h_tiles.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
@@ -1551,12 +1601,12 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 pool.begin(ctx->stream, T_CLOSEST);
                 if (use_bvh) {
                     cudaMemsetAsync(arb_ctr, 0, 2 * sizeof(unsigned long long), ctx->stream);
-                    k_closest_bvh<6><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                    k_closest_bvh<6><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, QueueLen{nullptr, n}, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                     k_closest_arb<RGK_INCOH_MINB><<<std::min(g, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
                     ctx->launches++;
                 }
-                else if (coherent) k_closest<false, RGK_COH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, nullptr);
-                else k_closest<false, RGK_INCOH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, n, B.counters + C_WORK_A, nullptr);
+                else if (coherent) k_closest<false, RGK_COH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, QueueLen{nullptr, n}, B.counters + C_WORK_A, nullptr);
+                else k_closest<false, RGK_INCOH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, QueueLen{nullptr, n}, B.counters + C_WORK_A, nullptr);
                 pool.end(ctx->stream);
                 ctx->launches++; total.closest_launches++; total.closest_rays += n;
             };
@@ -1612,80 +1662,112 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
             total.shadow_rays += lcount;                       // connection rays (Visibility calls of phases 2 and 3)
             count = 0;
         }
-        const uint32_t* shade_q = nullptr;          // the live queue in path order, when the traversal queue is direction-sorted
-        uint32_t* unext = B.queue_ua;
-        for (uint32_t bounce = 0; bounce < P->depth && count > 0; bounce++) {
-            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, 6 * sizeof(unsigned long long), ctx->stream));
-            const int g1 = (int)std::min<uint64_t>(tgrid, ((uint64_t)count + TRACE_THREADS - 1) / TRACE_THREADS);
-            // camera rays (and the shadow rays of their hit points) are coherent: keep warps in lockstep (refill only
-            // when the whole warp is done); later bounces are incoherent: refill as soon as a quarter of the warp idles
-            DevScene dev = ctx->dev;
-            dev.refill_threshold = bounce == 0 ? refill_coherent : refill_incoherent;
-            pool.begin(ctx->stream, T_CLOSEST);
-            // two register budgets of the same kernel: 56 registers (9 CTAs/SM) for the issue-bound coherent camera rays,
-            // 48 registers (10 CTAs/SM) for later bounces, which gain from the extra warps
-            if (use_bvh) {
-                RGK_CUDA(ctx, cudaMemsetAsync(arb_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
-                if (counting) k_closest_bvh<6, 1, true><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
-                else if (bvh_closest_nearest) k_closest_bvh<6, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
-                else k_closest_bvh<6><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
-                k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
-                ctx->launches++;
-            }
-            else if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, d_st);
-            else if (bounce == 0) k_closest<false, RGK_COH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
-            else k_closest<false, RGK_INCOH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, count, B.counters + C_WORK_A, nullptr);
-            pool.end(ctx->stream);
-            pool.begin(ctx->stream, T_SHADE);
-            const bool last_bounce = bounce + 1 >= P->depth;       // no continuation rays: k_shade ends every path (n == depth)
-            // camera-ray hit points are already in image order: their shadow rays are binned only on request
-            // k_bin reads every slot of the chunk, the traversal only gains on the live ones: deep bounces with few
-            // survivors go back to the atomic compaction
-            const bool worth = binning && (double)count >= bin_min_frac * (double)npaths;
-            const bool bin_next = worth && !last_bounce, bin_shadow = worth && (bounce > 0 || bin_shadow0);
-            R.binning = (bin_next ? 1u : 0u) | (bin_shadow ? 2u : 0u);
-            if (bin_next) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
-            if (bin_shadow) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
-            if (last_bounce) k_shade<true><<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
-            else k_shade<false><<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, shade_q ? shade_q : queue, count, qnext, B.queue_s, unext, B.counters);
-            if (bin_next) {
-                k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, B.counters + C_NEXT);
-                ctx->launches++;
-            }
-            if (bin_shadow) {
-                k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_shadow, (uint32_t)npix, ms, PG, SG, n_pgroups, B.queue_s, B.counters + C_SHADOW);
-                ctx->launches++;
-            }
-            pool.end(ctx->stream);
-            ctx->launches += 2; total.closest_launches++;
-            RGK_CUDA(ctx, cudaMemcpyAsync(B.h_counters, B.counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-            RGK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            const uint32_t next_count = (uint32_t)B.h_counters[C_NEXT], shadow_count = (uint32_t)B.h_counters[C_SHADOW];
-            total.closest_rays += count; total.shadow_rays += shadow_count; total.shadow_rays_skipped += B.h_counters[C_SHADOW_SKIPPED];
-            if (shadow_count) {
-                dev.refill_threshold = bounce == 0 ? refill_coherent : refill_shadow;
-                const int g2 = (int)std::min<uint64_t>(tgrid, ((uint64_t)shadow_count + TRACE_THREADS - 1) / TRACE_THREADS);
-                pool.begin(ctx->stream, T_SHADOW);
+        // ---- unidirectional bounce loop.  Nothing in it waits for the device: queue lengths stay in the per-bounce counter
+        // blocks and every kernel reads the ones it needs there (persistent grids sized for the machine, not for the queue), so the
+        // whole chunk is enqueued back to back and host jitter cannot open gaps between its kernels.  The lengths travel to the
+        // host once, at the end of the chunk, for the statistics.  Deep paths (recursion-max > 2): bounce b's surviving-path count
+        // is also copied back right after the bounce; counts never grow, so one that has ARRIVED (no wait) bounds every later
+        // bounce: it sizes their grids, and once it is zero the host stops enqueueing (the bounces enqueued in between find empty
+        // queues and exit).
+        if (!P->reverse) {
+            const uint32_t nb = P->depth;
+            RGK_CUDA(ctx, cudaMemsetAsync(B.counters, 0, (size_t)nb * C_COUNT * sizeof(unsigned long long), ctx->stream));
+            if (pending.size() == H_CHUNKS) { rgk_status ds = drain(); if (ds != RGK_OK) return ds; }
+            unsigned long long* h_term = B.h_counters + H_CHUNKS * B.cap_bounces * C_COUNT;
+            if (!B.term_events) B.term_events = new std::vector<cudaEvent_t>();
+            const uint32_t thresh = binning ? (uint32_t)std::min<double>(4294967295.0, std::ceil(bin_min_frac * (double)npaths)) : 0xFFFFFFFFu;
+            uint64_t live_ub = npaths;                  // upper bound of the live paths of the bounce being enqueued
+            const uint32_t* unsorted_prev = nullptr;    // the previous bounce's continuation queue in path order (if it may have been binned)
+            uint32_t* unext = B.queue_ua;
+            uint32_t launched = 0;
+            std::fill(term_recorded.begin(), term_recorded.end(), false);
+            for (uint32_t bounce = 0; bounce < nb; bounce++) {
+                for (uint32_t back = 1; back <= 2 && back <= bounce; back++)       // a count that has arrived (never waits)
+                    if (term_recorded[bounce - back] && cudaEventQuery((*B.term_events)[bounce - back]) == cudaSuccess)
+                        live_ub = std::min<uint64_t>(live_ub, h_term[bounce - back]);
+                if (live_ub == 0) break;
+                unsigned long long* blk = B.counters + (size_t)bounce * C_COUNT;
+                const QueueLen in{bounce ? blk - C_COUNT + C_NEXT : nullptr, (uint32_t)npaths};
+                const QueueLen prev_in{bounce > 1 ? blk - 2 * C_COUNT + C_NEXT : nullptr, (uint32_t)npaths};
+                const QueueLen shadow_len{blk + C_SHADOW, 0u};
+                // camera rays (and the shadow rays of their hit points) are coherent: keep warps in lockstep (refill only
+                // when the whole warp is done); later bounces are incoherent: refill as soon as a quarter of the warp idles
+                DevScene dev = ctx->dev;
+                dev.refill_threshold = bounce == 0 ? refill_coherent : refill_incoherent;
+                const int g1 = (int)std::min<uint64_t>(tgrid, (live_ub + TRACE_THREADS - 1) / TRACE_THREADS);
+                pool.begin(ctx->stream, T_CLOSEST);
+                // two register budgets of the kd kernel: 56 registers (9 CTAs/SM) for the issue-bound coherent camera rays,
+                // 48 registers (10 CTAs/SM) for later bounces, which gain from the extra warps
                 if (use_bvh) {
-                    if (counting) k_shadow_bvh<6, 1, true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats + 1,
-                                                                                          R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    else if (bvh_shadow_nosort) k_shadow_bvh<6, 0><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats + 1,
-                                                                                                R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    else k_shadow_bvh<6, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, ctx->d_bvh_stats + 1,
-                                                                                R.const_light, R.cl_pos, arb_list, (uint32_t*)(arb_ctr + 3));
-                    k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 3), P->clamp, arb_ctr + 2,
-                                                                                                     R.const_light, R.cl_pos);
+                    uint32_t* arb_n = (uint32_t*)(blk + C_ARB_COUNT);
+                    if (counting) k_closest_bvh<6, 1, true><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
+                    else if (bvh_closest_nearest) k_closest_bvh<6, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
+                    else k_closest_bvh<6><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
+                    k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, arb_n, blk + C_ARB_WORK);
                     ctx->launches++;
                 }
-                else if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, d_st + 1, R.const_light, R.cl_pos);
-                else k_shadow<false, RGK_INCOH_MINB><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_count, P->clamp, B.counters + C_WORK_B, nullptr, R.const_light, R.cl_pos);
+                else if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, d_st);
+                else if (bounce == 0) k_closest<false, RGK_COH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, nullptr);
+                else k_closest<false, RGK_INCOH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, nullptr);
                 pool.end(ctx->stream);
-                ctx->launches++; total.shadow_launches++;
+                pool.begin(ctx->stream, T_SHADE);
+                const bool last_bounce = bounce + 1 >= nb;       // no continuation rays: k_shade ends every path (n == depth)
+                // camera-ray hit points are already in image order: their shadow rays are binned only on request.  k_bin reads
+                // every slot of the chunk, the traversal only gains on the live ones: bounces with few survivors (fewer than
+                // bin_thresh, decided on the device) go back to the atomic compaction
+                R.binning = (binning && !last_bounce ? 1u : 0u) | (binning && (bounce > 0 || bin_shadow0) ? 2u : 0u);
+                R.bin_thresh = thresh;
+                if (R.binning & 1u) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
+                if (R.binning & 2u) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
+                const unsigned sg = (unsigned)((live_ub + 127) / 128);
+                if (last_bounce) k_shade<true><<<sg, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, unsorted_prev, in, prev_in, qnext, B.queue_s, unext, blk);
+                else k_shade<false><<<sg, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, unsorted_prev, in, prev_in, qnext, B.queue_s, unext, blk);
+                if (R.binning & 1u) {
+                    k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, blk + C_NEXT, in, thresh);
+                    ctx->launches++;
+                }
+                if (R.binning & 2u) {
+                    k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_shadow, (uint32_t)npix, ms, PG, SG, n_pgroups, B.queue_s, blk + C_SHADOW, in, thresh);
+                    ctx->launches++;
+                }
+                pool.end(ctx->stream);
+                ctx->launches += 2; total.closest_launches++;
+                if (nb > 2 && !last_bounce) {         // early read-back of the survivors' count (see above)
+                    while (B.term_events->size() <= bounce) { cudaEvent_t e; RGK_CUDA(ctx, cudaEventCreate(&e)); B.term_events->push_back(e); }
+                    RGK_CUDA(ctx, cudaMemcpyAsync(h_term + bounce, blk + C_NEXT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+                    RGK_CUDA(ctx, cudaEventRecord((*B.term_events)[bounce], ctx->stream));
+                    term_recorded[bounce] = true;
+                }
+                {
+                    dev.refill_threshold = bounce == 0 ? refill_coherent : refill_shadow;
+                    const int g2 = (int)std::min<uint64_t>(tgrid, (live_ub + TRACE_THREADS - 1) / TRACE_THREADS);
+                    pool.begin(ctx->stream, T_SHADOW);
+                    if (use_bvh) {
+                        uint32_t* arb_n = (uint32_t*)(blk + C_ARB_SCOUNT);
+                        if (counting) k_shadow_bvh<6, 1, true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, ctx->d_bvh_stats + 1,
+                                                                                              R.const_light, R.cl_pos, arb_list, arb_n);
+                        else if (bvh_shadow_nosort) k_shadow_bvh<6, 0><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, ctx->d_bvh_stats + 1,
+                                                                                                    R.const_light, R.cl_pos, arb_list, arb_n);
+                        else k_shadow_bvh<6, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, ctx->d_bvh_stats + 1,
+                                                                                    R.const_light, R.cl_pos, arb_list, arb_n);
+                        k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, arb_n, P->clamp, blk + C_ARB_SWORK,
+                                                                                                         R.const_light, R.cl_pos);
+                        ctx->launches++;
+                    }
+                    else if (counting) k_shadow<true, 9><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, d_st + 1, R.const_light, R.cl_pos);
+                    else k_shadow<false, RGK_INCOH_MINB><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, nullptr, R.const_light, R.cl_pos);
+                    pool.end(ctx->stream);
+                    ctx->launches++; total.shadow_launches++;
+                }
+                queue = qnext; qnext = (qnext == B.queue_a) ? B.queue_b : B.queue_a;
+                unsorted_prev = ((R.binning & 1u) && path_order_shade) ? unext : nullptr;
+                unext = (unext == B.queue_ua) ? B.queue_ub : B.queue_ua;
+                launched++;
             }
-            queue = qnext; qnext = (qnext == B.queue_a) ? B.queue_b : B.queue_a;
-            shade_q = (bin_next && path_order_shade) ? unext : nullptr;
-            unext = (unext == B.queue_ua) ? B.queue_ub : B.queue_ua;
-            count = next_count;
+            // the chunk's counter blocks: to pinned memory now, into the statistics when the round is over
+            RGK_CUDA(ctx, cudaMemcpyAsync(B.h_counters + pending.size() * B.cap_bounces * C_COUNT, B.counters, (size_t)nb * C_COUNT * sizeof(unsigned long long),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            pending.push_back(std::make_pair((uint32_t)npaths, launched));
         }
         pool.begin(ctx->stream, T_SHADE);
         k_finish<<<(unsigned)((npix + 127) / 128), 128, 0, ctx->stream>>>(R, B, d_rgb, d_count);
@@ -1696,6 +1778,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
     }
     RGK_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
     RGK_CUDA(ctx, cudaEventSynchronize(ev1));
+    { rgk_status ds = drain(); if (ds != RGK_OK) return ds; }
     float ms_total = 0.0f; cudaEventElapsedTime(&ms_total, ev0, ev1);
     pool.collect(kind_ms);
     total.gpu_ms = ms_total; total.closest_ms = kind_ms[T_CLOSEST]; total.shadow_ms = kind_ms[T_SHADOW];

@@ -96,6 +96,7 @@ template <class F> static inline cudaError_t doh_cudaFuncSetAttribute(F, cudaFun
 #define cudaEventRecord doh_cudaEventOp
 #define cudaEventSynchronize doh_cudaEventOp
 #define cudaEventDestroy doh_cudaEventOp
+#define cudaEventQuery(e) doh_ok()
 #define cudaEventElapsedTime doh_cudaEventElapsedTime
 #define cudaMemGetInfo doh_cudaMemGetInfo
 #define cudaDeviceGetAttribute doh_cudaDeviceGetAttribute

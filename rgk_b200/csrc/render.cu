@@ -306,6 +306,9 @@ __global__ void k_tables_from_user(const float* __restrict__ u1, const float* __
 #endif
 constexpr uint32_t WL = RGK_WARP_LANES;
 constexpr uint32_t SW_WARPS = 8;           // warps per CTA of k_sampler_warp
+#ifndef RGK_SAMPLER_X
+#define RGK_SAMPLER_X 0     // timing experiments only (results wrong): 1 no seeding, 2 no swaps, 4 no table write-out, 8 no twist, 16 no shuffle draws, 32 no state load
+#endif
 constexpr uint32_t SW_TILE = WL * (WL + 1u);   // words of the transposing tile of the seeding phase (aliases state + slots)
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
@@ -367,6 +370,7 @@ struct WarpMT {
     // pixel's last generation is never computed.  32-lane warps: wide steps of 128 words; the one-lane warps of the host build
     // (tests/host_cpp): word by word, the textbook loop.
     __device__ __forceinline__ void renew(uint32_t upto) {
+        if (RGK_SAMPLER_X & 8) { ren = upto; return; }
         if (WL == 32u) {
             while (ren < upto) { mt_twist_step(st, lane, ren >> 7); ren = min(ren + 128u, 624u); }
             return;
@@ -408,6 +412,7 @@ struct WarpMT {
     // keep false: only the stream position is kept right (rejections).
     __device__ __forceinline__ void shuffle_draws(uint32_t n, uint16_t* partner, bool keep) {
         const uint32_t odd = n & 1u, nd = n / 2u;
+        if (RGK_SAMPLER_X & 16) { skip(nd); return; }
         uint32_t t = 0;
         while (t < nd) {
             if (pos == 624u) next_generation();
@@ -444,28 +449,55 @@ __device__ __forceinline__ float mt_real_of(uint32_t word, float len) {
 }
 
 // slot g of a warp: float2 data[ss] (a 1-D table uses .x), then uint16 partner[ss]; slot_words apart (even; = 2 mod 32 so that
-// the lanes of the swap phase, one slot each, start in different banks)
-__device__ __noinline__ void sampler_flush(uint32_t* slots, const uint32_t* meta, uint32_t filled, uint32_t slot_words, uint32_t ss, uint32_t npix,
-                                           uint32_t pix0, uint32_t w, uint32_t lane, float* __restrict__ t1, float2* __restrict__ t2) {
+// the lanes of the swap phase, one slot each, start in different banks).  meta[g] = q | dim << 8 | 2-D << 16 | not built << 31
+// (a warp whose pixel lies past the end of the chunk keeps the slot count of its CTA but builds nothing).
+// The copy-out is done by the whole CTA: its warps hold the same table (q, dim) of SW_WARPS consecutive pixels, so entry k of
+// all of them is one run of 32 / 64 bytes in the global table -- whole sectors.  (A warp writing its own pixel alone puts 4 or 8
+// bytes into each of 32 sectors per store: 660 M partial-sector writes per 1080p x 64 spp round, which L2 takes at about one per
+// slice and clock -- that, not the generator, bounded the kernel: 11.1 ms with, 7.3 ms without the copy-out.)
+__device__ __noinline__ void sampler_flush(uint32_t* warp0, uint32_t warp_words, uint32_t nslots_unused, uint32_t filled, uint32_t slot_words, uint32_t ss,
+                                           uint32_t npix, uint32_t pix0, uint32_t w, uint32_t lane, float* __restrict__ t1, float2* __restrict__ t2) {
+    (void)nslots_unused;
+    uint32_t* slots = warp0 + w * warp_words + 624u;
+    const uint32_t* meta = slots + nslots_unused * slot_words;
     __syncwarp();
-    if (lane < filled) {
+    if (!(RGK_SAMPLER_X & 2) && lane < filled && !(meta[lane] >> 31)) {
         float2* d = reinterpret_cast<float2*>(slots + lane * slot_words);
         const uint16_t* pr = reinterpret_cast<const uint16_t*>(slots + lane * slot_words + 2u * ss);
+        uint32_t jn = ss > 1u ? pr[1] : 0u;          // the next partner is requested before the current exchange (the list is not touched by it)
         for (uint32_t i = 1; i < ss; i++) {
-            const uint32_t j = pr[i];
+            const uint32_t j = jn;
+            jn = pr[i + 1u < ss ? i + 1u : i];
             const float2 a = d[i], b = d[j];
             d[i] = b; d[j] = a;
         }
     }
-    __syncwarp();
-    for (uint32_t g = 0; g < filled; g++) {
-        const uint32_t m = meta[g];
-        const uint32_t pix = pix0 + (m & 0xffu) * SW_WARPS + w, dim = (m >> 8) & 0xffu;
-        const float2* d = reinterpret_cast<const float2*>(slots + g * slot_words);
-        if (m >> 16) { float2* o = t2 + ((size_t)dim * ss) * npix + pix; for (uint32_t k = lane; k < ss; k += WL) __stcs(o + (size_t)k * npix, d[k]); }
-        else { float* o = t1 + ((size_t)dim * ss) * npix + pix; for (uint32_t k = lane; k < ss; k += WL) __stcs(o + (size_t)k * npix, d[k].x); }
+    if (WL == 1u) {          // host build of the tests: the "warps" of a CTA run one after the other, each writes its own pixel
+        for (uint32_t g = 0; g < filled; g++) {
+            const uint32_t m = meta[g];
+            if (m >> 31) continue;
+            const uint32_t pix = pix0 + (m & 0xffu) * SW_WARPS + w, dim = (m >> 8) & 0xffu;
+            const float2* d = reinterpret_cast<const float2*>(slots + g * slot_words);
+            if ((m >> 16) & 1u) { float2* o = t2 + ((size_t)dim * ss) * npix + pix; for (uint32_t k = lane; k < ss; k += WL) __stcs(o + (size_t)k * npix, d[k]); }
+            else { float* o = t1 + ((size_t)dim * ss) * npix + pix; for (uint32_t k = lane; k < ss; k += WL) __stcs(o + (size_t)k * npix, d[k].x); }
+        }
+        return;
     }
-    __syncwarp();
+    __syncthreads();         // every warp's slots are final
+    for (uint32_t g = 0; g < ((RGK_SAMPLER_X & 4) ? 0u : filled); g++) {
+        const uint32_t m = meta[g];
+        const uint32_t pixbase = pix0 + (m & 0xffu) * SW_WARPS, dim = (m >> 8) & 0xffu;
+        const bool two = (m >> 16) & 1u;
+        const uint32_t* src0 = warp0 + 624u + g * slot_words;
+        for (uint32_t e = threadIdx.x; e < ss * SW_WARPS; e += SW_WARPS * WL) {
+            const uint32_t k = e / SW_WARPS, wp = e % SW_WARPS;
+            if (pixbase + wp >= npix) continue;
+            const float2 v = *reinterpret_cast<const float2*>(src0 + wp * warp_words + 2u * k);
+            const size_t at = ((size_t)dim * ss + k) * npix + pixbase + wp;
+            if (two) __stcs(t2 + at, v); else __stcs(t1 + at, v.x);
+        }
+    }
+    __syncthreads();         // before the slots are filled again
 }
 
 #ifndef RGK_SAMPLER_WARP_MINB
@@ -486,7 +518,8 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
     for (uint32_t k = lane; k < ss; k += WL) begin1[k] = (float)k / (float)ss;
     for (uint32_t k = lane; k < sq; k += WL) begin2[k] = (float)k / (float)sq;
     __syncthreads();
-    uint32_t* wsm = swm + ((ss + sq + 3u) & ~3u) + w * warp_words;          // 16-byte aligned: the wide twist loads 128 bits
+    uint32_t* warp0 = swm + ((ss + sq + 3u) & ~3u);                          // 16-byte aligned: the wide twist loads 128 bits
+    uint32_t* wsm = warp0 + w * warp_words;
     uint32_t* slots = wsm + 624u;
     uint32_t* meta = slots + nslots * slot_words;
     uint32_t* my_scratch = scratch + ((size_t)blockIdx.x * SW_WARPS + w) * (WL * 624u);
@@ -497,6 +530,7 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
         // a CTA owns per_block consecutive pixels; its warps walk them side by side (warp w: pixels pix0 + q * SW_WARPS + w), so the
         // sectors of a table row are completed by the CTA's warps at about the same time
         const uint32_t pix0 = blk * per_block;
+        if (!(RGK_SAMPLER_X & 1))
         {   // ---- mt19937::seed for WL pixels, lane q its q-th: word_i = 1812433253 * (word_{i-1} ^ (word_{i-1} >> 30)) + i
             const uint32_t pix = pix0 + lane * SW_WARPS + w;
             uint32_t x = pix < npix ? seeds[pix] : 0u;
@@ -517,9 +551,15 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
         }
         uint32_t filled = 0;
         for (uint32_t q = 0; q < WL; q++) {
-            if (pix0 + q * SW_WARPS + w >= npix) break;
-            for (uint32_t k = lane; k < 624u; k += WL) wsm[k] = __ldcg(my_scratch + q * 624u + k);
-            __syncwarp();
+            if (pix0 + q * SW_WARPS >= npix) break;                      // no warp of the CTA has a pixel in this row
+            const bool valid = pix0 + q * SW_WARPS + w < npix;          // (the other warps still need this one at their flushes)
+            if (valid) {
+                if (!(RGK_SAMPLER_X & 32)) for (uint32_t k = lane; k < 624u; k += WL) wsm[k] = __ldcg(my_scratch + q * 624u + k);
+#ifdef __CUDA_ARCH__
+                if (q + 1u < WL && lane < 20u) asm volatile("prefetch.global.L2 [%0];" :: "l"(my_scratch + (q + 1u) * 624u + lane * 32u));
+#endif
+                __syncwarp();
+            }
             g.pos = 624u; g.ren = 624u;
             // table tb: the 1-D (even) / 2-D (odd) table of dimension tb / 2; nothing after the last table anybody reads
             const uint32_t ntab = 2u * ndims - (((keep2m >> (ndims - 1u)) & 1ull) ? 0u : 1u);
@@ -527,26 +567,28 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
                 const uint32_t dim = tb >> 1, two = tb & 1u;
                 const bool keep = ((two ? keep2m : keep1m) >> dim) & 1ull;
                 const uint32_t ndraws = ss << two;
-                if (!keep) { g.skip(ndraws); g.shuffle_draws(ss, nullptr, false); continue; }
-                if (filled == nslots) { sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2); filled = 0; }
-                float* d = reinterpret_cast<float*>(slots + filled * slot_words);
-                for (uint32_t j0 = 0; j0 < ndraws; j0 += WL) {
-                    const uint32_t m = min(WL, ndraws - j0);
-                    const uint32_t word = g.take(m);
-                    const uint32_t j = j0 + lane;
-                    if (lane < m) {
-                        if (two) {                  // cell c = sy * sq + sx takes draws 2 c (x) and 2 c + 1 (y)
-                            const uint32_t c = j >> 1, sy = __umulhi(c, sq_magic), sx = c - sy * sq;
-                            d[j] = begin2[(j & 1u) ? sy : sx] + mt_real_of(word, len2);
-                        } else d[2u * j] = begin1[j] + mt_real_of(word, len1);
+                if (!keep) { if (valid) { g.skip(ndraws); g.shuffle_draws(ss, nullptr, false); } continue; }
+                if (filled == nslots) { sampler_flush(warp0, warp_words, nslots, filled, slot_words, ss, npix, pix0, w, lane, t1, t2); filled = 0; }
+                if (valid) {
+                    float* d = reinterpret_cast<float*>(slots + filled * slot_words);
+                    for (uint32_t j0 = 0; j0 < ndraws; j0 += WL) {
+                        const uint32_t m = min(WL, ndraws - j0);
+                        const uint32_t word = g.take(m);
+                        const uint32_t j = j0 + lane;
+                        if (lane < m) {
+                            if (two) {                  // cell c = sy * sq + sx takes draws 2 c (x) and 2 c + 1 (y)
+                                const uint32_t c = j >> 1, sy = __umulhi(c, sq_magic), sx = c - sy * sq;
+                                d[j] = begin2[(j & 1u) ? sy : sx] + mt_real_of(word, len2);
+                            } else d[2u * j] = begin1[j] + mt_real_of(word, len1);
+                        }
                     }
+                    g.shuffle_draws(ss, reinterpret_cast<uint16_t*>(slots + filled * slot_words + 2u * ss), true);
                 }
-                g.shuffle_draws(ss, reinterpret_cast<uint16_t*>(slots + filled * slot_words + 2u * ss), true);
-                if (lane == 0) meta[filled] = q | (dim << 8) | (two << 16);
+                if (lane == 0) meta[filled] = q | (dim << 8) | (two << 16) | (valid ? 0u : 0x80000000u);
                 filled++;
             }
         }
-        sampler_flush(slots, meta, filled, slot_words, ss, npix, pix0, w, lane, t1, t2);     // the seeding tile reuses the slots
+        sampler_flush(warp0, warp_words, nslots, filled, slot_words, ss, npix, pix0, w, lane, t1, t2);     // the seeding tile reuses the slots
     }
 }
 

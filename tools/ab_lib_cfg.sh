@@ -1,4 +1,4 @@
-run() { echo "== $1 | $2"; RGK_B200_LIB=$1 python bench.py --quick --steps 3 --warmup 3 --cfg "$2" 2>&1 | python -c "
+run() { echo "== $1 | $2"; RGK_B200_LIB=$1 timeout 120 python bench.py --quick --steps 3 --warmup 3 --cfg "$2" 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):

@@ -271,8 +271,8 @@ typedef struct rgk_device_cfg {
     uint32_t kd_variant;         /* control structure of the kd traversal in the batch entry points: 6 phased (default), 2 per-lane */
     uint32_t sampler_ctas_per_sm;/* persistent CTAs per SM of the sampler kernel; each owns one 312 KB generator-state block, and
                                     SMs x this x 312 KB is its whole generator-state footprint (3: what 64 KB of shared-memory tables per CTA allows) */
-    uint32_t sampler_kernel;     /* 0: the warp-per-pixel table builder (generator state in shared memory) where the set size leaves it
-                                    16 warps per SM, else the thread-per-pixel one; 1: always thread per pixel; 2: always warp per pixel */
+    uint32_t sampler_kernel;     /* 0: the warp-per-pixel table builder (generator state in shared memory) for set sizes above 16 that leave
+                                    it 16 warps per SM, else the thread-per-pixel one; 1: always thread per pixel; 2: always warp per pixel */
     uint32_t sampler_slots;      /* table slots per warp of the warp-per-pixel builder (0 = built-in: about two pixels' worth) */
     uint32_t _reserved[5];
 } rgk_device_cfg;

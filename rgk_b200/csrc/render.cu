@@ -461,17 +461,59 @@ __device__ __noinline__ void sampler_flush(uint32_t* warp0, uint32_t warp_words,
     uint32_t* slots = warp0 + w * warp_words + 624u;
     const uint32_t* meta = slots + nslots_unused * slot_words;
     __syncwarp();
+    // The exchanges of std::shuffle are sequential by definition (element i goes to an earlier, random place p_i); the first
+    // `serial` of them are applied that way, one table per lane.  Beyond that the partners of 32 consecutive exchanges seldom
+    // meet -- two exchanges of a batch touch a common element only if they have the same partner or one's partner is the other's
+    // own position (expected 500 / i pairs per batch at position i) -- so the warp applies a batch in a few WAVES: an exchange
+    // waits for the earlier batch-mates it shares an element with (its wave = 1 + theirs), exchanges of one wave touch disjoint
+    // elements and go together.  Same result as the sequential order; a 256-entry table takes ~25 steps instead of 255.
+    const uint32_t serial = (WL == 32u) ? min(ss, 64u) : ss;
     if (!(RGK_SAMPLER_X & 2) && lane < filled && !(meta[lane] >> 31)) {
         float2* d = reinterpret_cast<float2*>(slots + lane * slot_words);
         const uint16_t* pr = reinterpret_cast<const uint16_t*>(slots + lane * slot_words + 2u * ss);
         uint32_t jn = ss > 1u ? pr[1] : 0u;          // the next partner is requested before the current exchange (the list is not touched by it)
-        for (uint32_t i = 1; i < ss; i++) {
+        for (uint32_t i = 1; i < serial; i++) {
             const uint32_t j = jn;
             jn = pr[i + 1u < ss ? i + 1u : i];
             const float2 a = d[i], b = d[j];
             d[i] = b; d[j] = a;
         }
     }
+#ifdef __CUDA_ARCH__
+    if (serial < ss && !(RGK_SAMPLER_X & 2)) {
+        __syncwarp();
+        for (uint32_t g = 0; g < filled; g++) {
+            if (meta[g] >> 31) continue;
+            float2* d = reinterpret_cast<float2*>(slots + g * slot_words);
+            const uint16_t* pr = reinterpret_cast<const uint16_t*>(slots + g * slot_words + 2u * ss);
+            for (uint32_t i0 = serial; i0 < ss; i0 += 32u) {
+                const uint32_t i = i0 + lane;
+                const bool on = i < ss;
+                const uint32_t pt = on ? pr[i] : 0xffff0000u + lane;              // lanes past the end: a partner nobody shares
+                const unsigned same = __match_any_sync(0xffffffffu, pt);
+                const unsigned before = same & ((1u << lane) - 1u);               // earlier batch-mates with my partner
+                const int prev_same = before ? 31 - __clz((int)before) : -1;
+                const int dep_own = (on && pt >= i0 && pt < i) ? (int)(pt - i0) : -1;   // my partner is an earlier batch-mate's own position
+                uint32_t wave = 0;
+                for (;;) {
+                    const uint32_t wa = __shfl_sync(0xffffffffu, wave, prev_same < 0 ? 0 : prev_same);
+                    const uint32_t wb = __shfl_sync(0xffffffffu, wave, dep_own < 0 ? 0 : dep_own);
+                    uint32_t nw = wave;
+                    if (prev_same >= 0) nw = max(nw, wa + 1u);
+                    if (dep_own >= 0) nw = max(nw, wb + 1u);
+                    const bool changed = nw != wave;
+                    wave = nw;
+                    if (!__any_sync(0xffffffffu, changed)) break;
+                }
+                const uint32_t waves = __reduce_max_sync(0xffffffffu, wave) + 1u;
+                for (uint32_t wv = 0; wv < waves; wv++) {
+                    if (on && wave == wv && pt != i) { const float2 a = d[i], b = d[pt]; d[i] = b; d[pt] = a; }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+#endif
     if (WL == 1u) {          // host build of the tests: the "warps" of a CTA run one after the other, each writes its own pixel
         for (uint32_t g = 0; g < filled; g++) {
             const uint32_t m = meta[g];
@@ -508,7 +550,10 @@ __device__ __noinline__ void sampler_flush(uint32_t* warp0, uint32_t warp_words,
 // exactly for c < ss (c * sq < 2^32 is checked by the launcher).
 __global__ void __launch_bounds__(SW_WARPS * WL, RGK_SAMPLER_WARP_MINB)
 k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, uint32_t sq, uint32_t sq_magic, uint32_t ndims, uint64_t keep1m, uint64_t keep2m,
-               float* __restrict__ t1, float2* __restrict__ t2, uint32_t* __restrict__ scratch, uint32_t nslots, uint32_t slot_words, uint32_t warp_words) {
+               float* __restrict__ t1, float2* __restrict__ t2, uint32_t* __restrict__ scratch, uint32_t nslots, uint32_t slot_words, uint32_t warp_words,
+               uint32_t ppw) {
+    // ppw: pixels a warp seeds at once and then builds one after the other: WL where the chunk has enough pixels to keep every
+    // resident warp busy that way, fewer (idle lanes in the seeding phase only) for small images
     extern __shared__ uint32_t swm[];
     const uint32_t lane = threadIdx.x % WL, w = threadIdx.x / WL;
     float* begin1 = reinterpret_cast<float*>(swm);
@@ -525,7 +570,7 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
     uint32_t* my_scratch = scratch + ((size_t)blockIdx.x * SW_WARPS + w) * (WL * 624u);
     WarpMT g; g.st = wsm; g.lane = lane; g.pos = 624u; g.ren = 624u;
     const float len1 = 1.0f / (float)ss, len2 = 1.0f / (float)sq;
-    const uint32_t per_block = SW_WARPS * WL, nblocks = (npix + per_block - 1u) / per_block;
+    const uint32_t per_block = SW_WARPS * ppw, nblocks = (npix + per_block - 1u) / per_block;
     for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         // a CTA owns per_block consecutive pixels; its warps walk them side by side (warp w: pixels pix0 + q * SW_WARPS + w), so the
         // sectors of a table row are completed by the CTA's warps at about the same time
@@ -533,7 +578,7 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
         if (!(RGK_SAMPLER_X & 1))
         {   // ---- mt19937::seed for WL pixels, lane q its q-th: word_i = 1812433253 * (word_{i-1} ^ (word_{i-1} >> 30)) + i
             const uint32_t pix = pix0 + lane * SW_WARPS + w;
-            uint32_t x = pix < npix ? seeds[pix] : 0u;
+            uint32_t x = (lane < ppw && pix < npix) ? seeds[pix] : 0u;
             for (uint32_t c0 = 0; c0 < 624u; c0 += WL) {
                 const uint32_t nw = min(WL, 624u - c0);
 #pragma unroll 8
@@ -544,19 +589,19 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
                 __syncwarp();
                 if (lane < nw) {
 #pragma unroll 8
-                    for (uint32_t q = 0; q < WL; q++) __stcg(my_scratch + q * 624u + c0 + lane, wsm[lane * (WL + 1u) + q]);
+                    for (uint32_t q = 0; q < ppw; q++) __stcg(my_scratch + q * 624u + c0 + lane, wsm[lane * (WL + 1u) + q]);
                 }
                 __syncwarp();
             }
         }
         uint32_t filled = 0;
-        for (uint32_t q = 0; q < WL; q++) {
+        for (uint32_t q = 0; q < ppw; q++) {
             if (pix0 + q * SW_WARPS >= npix) break;                      // no warp of the CTA has a pixel in this row
             const bool valid = pix0 + q * SW_WARPS + w < npix;          // (the other warps still need this one at their flushes)
             if (valid) {
                 if (!(RGK_SAMPLER_X & 32)) for (uint32_t k = lane; k < 624u; k += WL) wsm[k] = __ldcg(my_scratch + q * 624u + k);
 #ifdef __CUDA_ARCH__
-                if (q + 1u < WL && lane < 20u) asm volatile("prefetch.global.L2 [%0];" :: "l"(my_scratch + (q + 1u) * 624u + lane * 32u));
+                if (q + 1u < ppw && lane < 20u) asm volatile("prefetch.global.L2 [%0];" :: "l"(my_scratch + (q + 1u) * 624u + lane * 32u));
 #endif
                 __syncwarp();
             }
@@ -593,18 +638,22 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
 }
 
 // launch geometry of the table generation.  kind 0: thread per pixel (k_sampler_mt), 1: warp per pixel (k_sampler_warp)
-struct SamplerPlan { uint32_t kind, grid, nslots, slot_words, warp_words; size_t smem, scratch_words; };
+struct SamplerPlan { uint32_t kind, grid, nslots, slot_words, warp_words, ppw; size_t smem, scratch_words; };
 static SamplerPlan sampler_plan(int device, const rgk_device_cfg& cfg, uint32_t npix, uint32_t ss, uint32_t kept_per_pixel) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     SamplerPlan p{};
-    if (cfg.sampler_kernel != 1u) {
+    // Small sets (<= 16: a handful of draws per dimension, less than one generation per pixel) stay with the thread-per-pixel
+    // kernel, which never materialises the seeded state and whose lanes are all busy; measured at 1080p, thread vs warp kernel:
+    // 1 spp 0.5 / 3.1 ms, 4 spp 1.1 / 4.7, 16 spp 3.8 / 5.3, 36 spp 10.4 / 7.1, 64 spp 16.3 / 8.7, 256 spp (540p) 37.4 / 9.0.
+    if (cfg.sampler_kernel == 2u || (cfg.sampler_kernel == 0u && ss > 16u)) {
         uint32_t sw = 2u * ss + (ss + 1u) / 2u;
         sw += sw & 1u;
         while (sw % 32u != 2u) sw += 2u;
         // slots: the tables of about two pixels, so that more lanes have one to shuffle (all of them are flushed at the end of a
         // 32-pixel block anyway), while five CTAs still fit an SM
-        uint32_t want = cfg.sampler_slots ? cfg.sampler_slots : std::max(1u, std::min(2u * std::max(1u, kept_per_pixel), 8u));
+        // (sets above 64 apply most of a shuffle warp-wide, wave by wave: one slot keeps the lanes busy and leaves room for more warps)
+        uint32_t want = cfg.sampler_slots ? cfg.sampler_slots : (ss > 64u ? 1u : std::max(1u, std::min(2u * std::max(1u, kept_per_pixel), 8u)));
         want = std::min(want, WL);
         int per = 0;
         for (uint32_t ns = want; ns >= 1u; ns--) {
@@ -620,7 +669,9 @@ static SamplerPlan sampler_plan(int device, const rgk_device_cfg& cfg, uint32_t 
             if (per >= need) { p.nslots = ns; p.slot_words = sw; p.warp_words = ww; p.smem = smem; break; }
         }
         if (p.nslots) {
-            const uint32_t blocks = (npix + SW_WARPS * WL - 1u) / (SW_WARPS * WL);
+            const uint32_t resident_warps = (uint32_t)(sms * per) * SW_WARPS;
+            p.ppw = std::max(1u, std::min(WL, (npix + resident_warps - 1u) / resident_warps));
+            const uint32_t blocks = (npix + SW_WARPS * p.ppw - 1u) / (SW_WARPS * p.ppw);
             p.kind = 1u;
             p.grid = std::max(1u, std::min(blocks, (uint32_t)(sms * per)));
             p.scratch_words = (size_t)p.grid * SW_WARPS * WL * 624u;
@@ -644,7 +695,7 @@ static void launch_sampler_mt(cudaStream_t stream, const SamplerPlan& plan, bool
         if (!ndims) return;
         cudaFuncSetAttribute(k_sampler_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
         const uint32_t sq_magic = sq > 1u ? (uint32_t)((0x100000000ull + sq - 1u) / sq) : 0u;      // sq == 1: c is always 0
-        k_sampler_warp<<<plan.grid, SW_WARPS * WL, plan.smem, stream>>>(seeds, npix, ss, sq, sq_magic, ndims, keep1m, keep2m, t1, t2, state, plan.nslots, plan.slot_words, plan.warp_words);
+        k_sampler_warp<<<plan.grid, SW_WARPS * WL, plan.smem, stream>>>(seeds, npix, ss, sq, sq_magic, ndims, keep1m, keep2m, t1, t2, state, plan.nslots, plan.slot_words, plan.warp_words, plan.ppw);
         return;
     }
     // per device (function attributes are), so set on every launch rather than once per process: contexts on several

@@ -72,6 +72,9 @@ struct RenderConst {
     uint32_t binning;       // what MAY be binned this bounce (bit 0 continuation rays, bit 1 shadow rays): k_shade writes direction-bin keys and
                             // k_bin builds the queues (coherence reordering) if the bounce has at least bin_thresh live paths
     uint32_t bin_thresh;
+    uint32_t first_bounce;  // 1: k_shade of the camera rays' hit points in the unidirectional loop -- throughput (1, 1, 1), no bounce done,
+                            // Russian-roulette cursor 1, no radiance yet: the initial path state is known, k_raygen does not store it and
+                            // this launch does not load it (48 B per path less through HBM)
     uint32_t npix;          // pixels in the chunk
     uint32_t const_light;   // 1: the scene's only light is one point light of size 0 -- every sample picks the same light record
     float4 cl_pos, cl_col;  //    (position + flags, colour + intensity), read from here instead of per-path arrays
@@ -813,10 +816,12 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
     B.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
     if (cam_o) cam_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);             // camerapos of the sample (bidirectional mode)
     B.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
-    B.cum[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));      // .w = n (bounces done)
-    B.tot[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    B.last_tri[slot] = RGK_NO_TRIANGLE;
-    B.cur1[slot] = 1u;
+    if (R.reverse) {         // (the unidirectional loop knows this initial state: RenderConst::first_bounce; camera rays ignore no triangle)
+        B.cum[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));      // .w = n (bounces done)
+        B.tot[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        B.last_tri[slot] = RGK_NO_TRIANGLE;
+        B.cur1[slot] = 1u;
+    }
     if (R.const_light) return;      // GetRandomLight can only return that one light, unjittered (size 0): kept in RenderConst
     LightRec L = random_light(S, choice, ls, areal);
     if (L.valid && L.type == 0) { const V3 dir = sphere_uniform(areal); L.pos = L.pos + L.size * dir; }
@@ -864,7 +869,7 @@ k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, QueueLe
         [&](uint32_t i, Traverser<false, COUNT>& T) {
             const uint32_t slot = queue ? __ldg(queue + i) : i;
             const float4 o = B.ray_o[slot], d = B.ray_d[slot];
-            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot]);
+            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, queue ? B.last_tri[slot] : RGK_NO_TRIANGLE);
         },
         [&](uint32_t i, bool found, const HitRec& h) {
             const uint32_t slot = queue ? __ldg(queue + i) : i;
@@ -968,7 +973,7 @@ k_closest_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, Que
         [&](uint32_t i, BvhTraverser<false, COUNT, SORT>& T) {
             const uint32_t slot = queue ? __ldg(queue + i) : i;
             const float4 o = B.ray_o[slot], d = B.ray_d[slot];
-            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot]);
+            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, queue ? B.last_tri[slot] : RGK_NO_TRIANGLE);
         },
         [&](uint32_t i, bool found, const HitRec& h) { io.commit(queue ? __ldg(queue + i) : i, found, h); },
         [&](uint32_t i) { arb[atomicAdd(arb_count, 1u)] = queue ? __ldg(queue + i) : i; });
@@ -976,7 +981,7 @@ k_closest_bvh(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, Que
 }
 template <int MINB>
 __global__ void __launch_bounds__(TRACE_THREADS, MINB)
-k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const uint32_t* __restrict__ arb_count, unsigned long long* work) {
+k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const uint32_t* __restrict__ arb_count, unsigned long long* work, uint32_t camera_rays) {
     TravCount cnt{0, 0, 0, 0, 0, 0, 0};
     uint32_t mine = 0;
     const ClosestIO io{B};
@@ -984,7 +989,7 @@ k_closest_arb(DevScene S, PathBuffers B, const uint32_t* __restrict__ arb, const
         [&](uint32_t i, Traverser<false, false>& T) {
             const uint32_t slot = arb[i];
             const float4 o = B.ray_o[slot], d = B.ray_d[slot];
-            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, B.last_tri[slot]);
+            return T.init(S, o.x, o.y, o.z, d.x, d.y, d.z, 0.0f, 10000.0f, camera_rays ? RGK_NO_TRIANGLE : B.last_tri[slot]);
         },
         [&](uint32_t i, bool found, const HitRec& h) { io.commit(arb[i], found, h); });
 }
@@ -1105,7 +1110,8 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
     const uint32_t* __restrict__ queue = (queue_path_order && prev_len.get() >= R.bin_thresh) ? queue_path_order : queue_sorted;
     const uint32_t binmask = count >= R.bin_thresh ? R.binning : 0u;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool cont = false, shadow = false, null_shadow = false;
+    bool cont = false, shadow = false, null_shadow = false, tot_written = false;
+    const bool first = R.first_bounce != 0u;
     uint32_t slot = 0;
     uint32_t cw = 0;       // counting rounds only (R.count_shade): bit 0 surface vertex, 1 sky vertex, 2 light evaluated, 4-5 LTC lobes, 8-11 texels
     if (i < count) {
@@ -1114,14 +1120,14 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
         const uint32_t tri = __float_as_uint(hit.w);
         const float4 ro4 = B.ray_o[slot], rd4 = B.ray_d[slot];
         const V3 ro = v3(ro4), rd = v3(rd4);
-        float4 cum4 = B.cum[slot];
+        float4 cum4 = first ? make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u)) : B.cum[slot];
         uint32_t n = __float_as_uint(cum4.w) + 1u;
         // everything else that is addressed by the slot alone is requested here, ahead of the dependent chain
         // triangle -> vertices / material -> textures -> LTC taps (the kernel is latency-bound): the sample's light and
         // the two sampler values this vertex may consume (continuation direction, Russian roulette)
         const float4 lp4 = R.const_light ? R.cl_pos : B.light_pos[slot];
         const float4 lc = R.const_light ? R.cl_col : B.light_col[slot];
-        const uint32_t c1 = B.cur1[slot];
+        const uint32_t c1 = first ? 1u : B.cur1[slot];
         const uint32_t pixel = slot % R.npix, set = slot / R.npix;
         const uint32_t seed = B.pix_seed[pixel];
         const V2 sample = smp.get2d(pixel, seed, set, R.base2 + (n - 1u));
@@ -1130,9 +1136,9 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
         const V3 Vr = -rd;
         if (tri == RGK_NO_TRIANGLE) {
             const RGB sky = sky_radiance(S, Vr);
-            float4 t = B.tot[slot];
+            float4 t = first ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : B.tot[slot];
             t.x += sky.r * contribution.r; t.y += sky.g * contribution.g; t.z += sky.b * contribution.b;
-            B.tot[slot] = t;
+            B.tot[slot] = t; tot_written = true;
             cw = 2u;
         } else {
             const uint4 tv = __ldg(S.tri_shade + tri);
@@ -1209,9 +1215,9 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                     if (here.r > R.clamp) here.r = R.clamp;
                     if (here.g > R.clamp) here.g = R.clamp;
                     if (here.b > R.clamp) here.b = R.clamp;
-                    float4 t = B.tot[slot];
+                    float4 t = first ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : B.tot[slot];
                     t.x += here.r * contribution.r; t.y += here.g * contribution.g; t.z += here.b * contribution.b;
-                    B.tot[slot] = t;
+                    B.tot[slot] = t; tot_written = true;
                 }
                 // ---- continuation
                 // A path whose next vertex would exceed recursion-max ends here whatever BxDF::sample returns (the loop
@@ -1235,8 +1241,9 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                     cum = rgb(tcf.r * cum.r, tcf.g * cum.g, tcf.b * cum.b);
                     cont = true;
                     if (gmax(gmax(cum.r, cum.g), cum.b) < 0.001f) cont = false;
+                    uint32_t c1_next = c1;
                     if (cont && !mat.no_russian && R.russian >= 0.0f) {
-                        B.cur1[slot] = c1 + 1u;
+                        c1_next = c1 + 1u;
                         if (roulette > R.russian) cont = false;
                     }
                     if (cont && n > R.depth) cont = false;
@@ -1248,10 +1255,13 @@ k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_
                         B.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, 0.0f);
                         B.cum[slot] = make_float4(cum.r, cum.g, cum.b, __uint_as_float(n));
                         B.last_tri[slot] = tri;
+                        if (first || c1_next != c1) B.cur1[slot] = c1_next;      // (only a path that goes on looks at its cursor again)
                     }
                 }
             }
         }
+        // first bounce: the radiance sum starts here (k_shadow adds to it, k_finish reads it)
+        if (first && !tot_written) B.tot[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     // queues: either built by k_bin from direction-bin keys (rays of one pixel block are reordered by direction so that
     // the lanes of a traversal warp follow similar paths through the tree), or by warp-aggregated atomic compaction in
@@ -1695,7 +1705,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 if (use_bvh) {
                     cudaMemsetAsync(arb_ctr, 0, 2 * sizeof(unsigned long long), ctx->stream);
                     k_closest_bvh<6><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, QueueLen{nullptr, n}, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
-                    k_closest_arb<RGK_INCOH_MINB><<<std::min(g, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr);
+                    k_closest_arb<RGK_INCOH_MINB><<<std::min(g, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr, 0u);
                     ctx->launches++;
                 }
                 else if (coherent) k_closest<false, RGK_COH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, QueueLen{nullptr, n}, B.counters + C_WORK_A, nullptr);
@@ -1796,7 +1806,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                     if (counting) k_closest_bvh<6, 1, true><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
                     else if (bvh_closest_nearest) k_closest_bvh<6, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
                     else k_closest_bvh<6><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
-                    k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, arb_n, blk + C_ARB_WORK);
+                    k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, arb_n, blk + C_ARB_WORK, bounce == 0 ? 1u : 0u);
                     ctx->launches++;
                 }
                 else if (counting) k_closest<true, 9><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, d_st);
@@ -1810,6 +1820,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 // bin_thresh, decided on the device) go back to the atomic compaction
                 R.binning = (binning && !last_bounce ? 1u : 0u) | (binning && (bounce > 0 || bin_shadow0) ? 2u : 0u);
                 R.bin_thresh = thresh;
+                R.first_bounce = bounce == 0 ? 1u : 0u;
                 if (R.binning & 1u) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
                 if (R.binning & 2u) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
                 const unsigned sg = (unsigned)((live_ub + 127) / 128);

@@ -553,8 +553,10 @@ def main():
             diff = int((ref.view(torch.int32) != total.view(torch.int32)).sum().item())
             strong.update({"n1_ms_same_round_same_run": t1, "efficiency_vs_n1": t1 / (world * strong["ms_per_step"]),
                            "image_equal_to_n1": diff == 0, "fb_words_differing": diff,
-                           "limit": "fixed per-round cost on every GPU (sampler tables and direction binning of its own tiles, launch latency of ~12 "
-                                    "short kernels) and the full-frame reduce of a partial image that is 1/N non-zero"})
+                           "limit": "per-round cost that does not shrink with a GPU's share: the four kd-arbiter launches (a few hundred long rays each, "
+                                    "0.2 - 0.35 ms of single-ray latency whatever their number: ~1.1 ms per round), the tail of the sampler's and the "
+                                    "traversal's persistent grids on 1/N of the tiles, ~17 kernel launches; the full-frame reduce of a partial image "
+                                    "that is 1/N non-zero is overlapped with the next round"})
             del ref
         line["strong"] = strong
         ctx.set_shard(0, 1)

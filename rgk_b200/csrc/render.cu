@@ -482,7 +482,7 @@ __device__ __noinline__ void sampler_flush(uint32_t* warp0, uint32_t warp_words,
             d[i] = b; d[j] = a;
         }
     }
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(__CUDA_ARCH_EMULATED_LANES__)      // (the latter: the 32-lane host build of tests/host_cpp/device_shim_mt.h)
     if (serial < ss && !(RGK_SAMPLER_X & 2)) {
         __syncwarp();
         for (uint32_t g = 0; g < filled; g++) {
@@ -561,10 +561,12 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
     const uint32_t lane = threadIdx.x % WL, w = threadIdx.x / WL;
     float* begin1 = reinterpret_cast<float*>(swm);
     float* begin2 = begin1 + ss;
-    // (every warp writes the whole table -- the same values -- so that a warp depends on no other: the host build of the tests
-    // runs the "warps" of a CTA one after the other)
-    for (uint32_t k = lane; k < ss; k += WL) begin1[k] = (float)k / (float)ss;
-    for (uint32_t k = lane; k < sq; k += WL) begin2[k] = (float)k / (float)sq;
+    // (written by the CTA's first warp alone: the one-lane host build of the tests runs the "warps" of a CTA one after the other,
+    // the first one first)
+    if (w == 0u) {
+        for (uint32_t k = lane; k < ss; k += WL) begin1[k] = (float)k / (float)ss;
+        for (uint32_t k = lane; k < sq; k += WL) begin2[k] = (float)k / (float)sq;
+    }
     __syncthreads();
     uint32_t* warp0 = swm + ((ss + sq + 3u) & ~3u);                          // 16-byte aligned: the wide twist loads 128 bits
     uint32_t* wsm = warp0 + w * warp_words;
@@ -602,6 +604,7 @@ k_sampler_warp(const uint32_t* __restrict__ seeds, uint32_t npix, uint32_t ss, u
             if (pix0 + q * SW_WARPS >= npix) break;                      // no warp of the CTA has a pixel in this row
             const bool valid = pix0 + q * SW_WARPS + w < npix;          // (the other warps still need this one at their flushes)
             if (valid) {
+                __syncwarp();          // the previous pixel's last draws have been read by every lane (set size 1: no ballot follows them)
                 if (!(RGK_SAMPLER_X & 32)) for (uint32_t k = lane; k < 624u; k += WL) wsm[k] = __ldcg(my_scratch + q * 624u + k);
 #ifdef __CUDA_ARCH__
                 if (q + 1u < ppw && lane < 20u) asm volatile("prefetch.global.L2 [%0];" :: "l"(my_scratch + (q + 1u) * 624u + lane * 32u));

@@ -2,7 +2,9 @@
 // function: the sampler-table entry point (launch_sampler_tables -> k_sampler_warp / k_sampler_mt).  tests/
 // test_sampler_lanes_on_host.py compares the tables with the oracle's bit for bit; tools/tsan_sampler_on_host.sh runs the same
 // under ThreadSanitizer and AddressSanitizer.  Test infrastructure only.
-//   g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -pthread -I/usr/local/cuda/include -Ibuild/host/gen32 -Iinclude -Itests/host_cpp \
+// (-fvisibility=hidden -fno-gnu-unique: the one-lane build libdevice_on_host.so compiles the same sources into the same symbol
+// names; loaded into one process, the two must not share inline variables)
+//   g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -pthread -fvisibility=hidden -fno-gnu-unique -I/usr/local/cuda/include -Ibuild/host/gen32 -Iinclude -Itests/host_cpp \
 //       tests/host_cpp/sampler_mt.cpp -o build/host/libsampler_mt.so
 #include "device_shim_mt.h"
 #include <cstdio>
@@ -22,6 +24,7 @@ void* rgk_scratch(rgk_context* ctx, int slot, size_t bytes) {
 extern "C" {
 // tables of n seeds: out1[n1d][set size][n], out2[n2d][set size][n][2] (the layout of rgk_sampler_tables' device buffers);
 // kernel: rgk_device_cfg::sampler_kernel (2 = the warp-per-pixel builder), slots: ::sampler_slots.  Returns the status.
+__attribute__((visibility("default")))
 int doh32_sampler_tables(const uint32_t* seeds, uint32_t n, uint32_t multisample, uint32_t n1d, uint32_t n2d, float* out1, float* out2,
                          uint32_t kernel, uint32_t slots, const char** error) {
     static rgk_context ctx;

@@ -6,7 +6,16 @@
 // build (__graft_entry__.build): python tests/host_cpp/gen_host_sources.py rgk_b200/csrc build/host/gen, then
 //        g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -I/usr/local/cuda/include -Ibuild/host/gen -Iinclude
 //        tests/host_cpp/device_on_host.cpp -o build/host/libdevice_on_host.so      (-ffp-contract=off = nvcc -fmad=false)
+// -DRGK_DOH_MT: the same harness over device_shim_mt.h (a CUDA thread is a host thread, warps have 32 lanes, barriers are pthread
+// barriers): libdevice_on_host_mt.so, whose doh_render_round runs whole rounds of the wavefront with real warps -- k_bin's
+// shared-memory counting sort, the ballots of the queue compaction, the refill logic of the persistent traversal at its shipped
+// thresholds (tests/test_wavefront_lanes_on_host.py).  Only the scene / round entry points are exported from that build.
+#ifdef RGK_DOH_MT
+#include "device_shim_mt.h"
+#else
 #include "device_shim.h"
+#endif
+#define DOH_API __attribute__((visibility("default")))
 #include <algorithm>
 #include <cstdio>
 #include <string>
@@ -85,7 +94,7 @@ void* doh_scene_create(const uint32_t* nodes, uint32_t n_nodes, const uint32_t* 
 }
 void doh_scene_destroy(void* h) { delete (Scene*)h; }
 
-void* doh_shade_scene_create(const rgk_scene_desc* d, const rgk_device_cfg* cfg) {
+DOH_API void* doh_shade_scene_create(const rgk_scene_desc* d, const rgk_device_cfg* cfg) {
     ShadeScene* s = new ShadeScene();
     try { host_scene_commit(d, nullptr, cfg ? *cfg : default_device_cfg(), s->hs); } catch (...) { delete s; return nullptr; }
     DevScene& D = s->S;
@@ -159,13 +168,13 @@ void* doh_shade_scene_create(const rgk_scene_desc* d, const rgk_device_cfg* cfg)
     D.total_point_power = in.total_point_power; D.total_areal_power = in.total_areal_power; D.epsilon = in.epsilon;
     return s;
 }
-void doh_shade_scene_destroy(void* h) { delete (ShadeScene*)h; }
+DOH_API void doh_shade_scene_destroy(void* h) { delete (ShadeScene*)h; }
 
 // One RenderDriver round through render_round_impl -- the product's own host loop and kernels -- with caller-supplied
 // sampler tables (RGK_SAMPLER_TABLES; t1[pixel][dim][set], t2[pixel][dim][set][2]).  out_bvh: rays through the wide-BVH
 // kernels and how many of them were deferred to the kd arbiter (both 0 when the scene was committed with RGK_TRAVERSAL_KD).
 // cfg: the rgk_device_cfg of the call (the tests switch k_bin off and refill one-lane warps after every ray).
-int doh_render_round(void* h, const rgk_device_cfg* cfg, const rgk_camera* cam, const rgk_render_params* p, const rgk_task* tasks, uint32_t n_tasks, uint32_t seedstart,
+DOH_API int doh_render_round(void* h, const rgk_device_cfg* cfg, const rgk_camera* cam, const rgk_render_params* p, const rgk_task* tasks, uint32_t n_tasks, uint32_t seedstart,
                      uint32_t seedcount_base, const float* t1, const float* t2, uint32_t n1d, uint32_t n2d, uint64_t n_pixels, float* rgb,
                      uint32_t* count, rgk_round_stats* stats, uint64_t* out_bvh) {
     ShadeScene* s = (ShadeScene*)h;

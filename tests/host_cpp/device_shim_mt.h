@@ -5,7 +5,7 @@
 // lanes, Lemire rejections ending a batch at a lane, shuffles applied in waves of independent exchanges, the CTA-wide
 // copy-out -- which the one-lane emulation of device_shim.h cannot exercise.  Because every barrier is a pthread barrier, the
 // build also runs under ThreadSanitizer: a missing __syncwarp between a shared-memory store and another lane's load is a
-// data race it reports (tools/tsan_sampler_on_host.sh), and under AddressSanitizer for out-of-bounds shared / global accesses.
+// data race it reports (tools/tsan_lanes_on_host.sh), and under AddressSanitizer for out-of-bounds shared / global accesses.
 // Test infrastructure only (tests/host_cpp/sampler_mt.cpp, tests/test_sampler_lanes_on_host.py).
 #pragma once
 #include <cuda_runtime.h>
@@ -13,8 +13,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -37,8 +42,22 @@
 #define __CUDA_ARCH_EMULATED_LANES__ 32
 
 struct doh_idx { unsigned x, y, z; };
-struct DohWarp { pthread_barrier_t bar; unsigned long long slot[32]; };
-struct DohBlock { pthread_barrier_t bar; std::vector<DohWarp> warps; };
+// a warp: the full-mask barrier is a pthread barrier; a collective over a partial mask (the lanes that took a branch: e.g. the
+// shuffle of push_queue among the lanes that queue a ray) meets at a per-mask counter under the warp's mutex
+struct DohGroup { unsigned arrived = 0, generation = 0; };
+struct DohWarp {
+    pthread_barrier_t bar; unsigned long long slot[32];
+    std::mutex mu; std::condition_variable cv; std::map<unsigned, DohGroup> groups;
+    void meet(unsigned mask) {
+        if (mask == 0xffffffffu) { pthread_barrier_wait(&bar); return; }
+        std::unique_lock<std::mutex> lock(mu);
+        DohGroup& g = groups[mask];
+        const unsigned mine = g.generation;
+        if (++g.arrived == (unsigned)__builtin_popcount(mask)) { g.arrived = 0; g.generation++; cv.notify_all(); }
+        else cv.wait(lock, [&] { return g.generation != mine; });
+    }
+};
+struct DohBlock { pthread_barrier_t bar; std::unique_ptr<DohWarp[]> warps; };
 inline thread_local doh_idx doh_threadIdx{0, 0, 0}, doh_blockIdx{0, 0, 0};
 inline doh_idx doh_blockDim{1, 1, 1}, doh_gridDim{1, 1, 1};
 inline thread_local DohWarp* doh_warp = nullptr;
@@ -49,32 +68,32 @@ inline thread_local unsigned doh_lane = 0;
 #define blockDim doh_blockDim
 #define gridDim doh_gridDim
 
-static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&doh_warp->bar); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { doh_warp->meet(mask); }
 static inline void __syncthreads() { pthread_barrier_wait(&doh_block->bar); }
 // every collective: publish, barrier, read, barrier (the second barrier keeps a fast lane's next publish from overtaking a slow reader)
-template <class F> static inline auto doh_exchange(unsigned long long mine, F read) {
+template <class F> static inline auto doh_exchange(unsigned mask, unsigned long long mine, F read) {
     doh_warp->slot[doh_lane] = mine;
-    pthread_barrier_wait(&doh_warp->bar);
+    doh_warp->meet(mask);
     auto r = read(doh_warp->slot);
-    pthread_barrier_wait(&doh_warp->bar);
+    doh_warp->meet(mask);
     return r;
 }
-static inline unsigned __ballot_sync(unsigned, int pred) {
-    return doh_exchange(pred ? 1ull : 0ull, [](const unsigned long long* s) { unsigned m = 0; for (int l = 0; l < 32; l++) if (s[l]) m |= 1u << l; return m; });
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+    return doh_exchange(mask, pred ? 1ull : 0ull, [mask](const unsigned long long* s) { unsigned m = 0; for (int l = 0; l < 32; l++) if (((mask >> l) & 1u) && s[l]) m |= 1u << l; return m; });
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
-template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) {
     unsigned long long bits = 0; std::memcpy(&bits, &v, sizeof(T));
-    const unsigned long long r = doh_exchange(bits, [src](const unsigned long long* s) { return s[src & 31]; });
+    const unsigned long long r = doh_exchange(mask, bits, [src](const unsigned long long* s) { return s[src & 31]; });
     T out; std::memcpy(&out, &r, sizeof(T)); return out;
 }
 template <class T> static inline T __shfl_xor_sync(unsigned m, T v, int mask) { return __shfl_sync(m, v, (int)(doh_lane ^ (unsigned)mask)); }
 template <class T> static inline T __shfl_up_sync(unsigned m, T v, unsigned d) { return __shfl_sync(m, v, doh_lane >= d ? (int)(doh_lane - d) : (int)doh_lane); }
-static inline unsigned __match_any_sync(unsigned, unsigned v) {
-    return doh_exchange((unsigned long long)v, [v](const unsigned long long* s) { unsigned m = 0; for (int l = 0; l < 32; l++) if ((unsigned)s[l] == v) m |= 1u << l; return m; });
+static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+    return doh_exchange(mask, (unsigned long long)v, [mask, v](const unsigned long long* s) { unsigned m = 0; for (int l = 0; l < 32; l++) if (((mask >> l) & 1u) && (unsigned)s[l] == v) m |= 1u << l; return m; });
 }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
-    return doh_exchange((unsigned long long)v, [](const unsigned long long* s) { unsigned m = 0; for (int l = 0; l < 32; l++) m = std::max(m, (unsigned)s[l]); return m; });
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    return doh_exchange(mask, (unsigned long long)v, [mask](const unsigned long long* s) { unsigned m = 0; for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) m = std::max(m, (unsigned)s[l]); return m; });
 }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
@@ -102,10 +121,12 @@ static inline float __uint2float_rn(uint32_t x) { return (float)x; }
 template <class... KArgs, class... Args>
 inline void doh_launch(void (*kernel)(KArgs...), size_t grid, size_t block, size_t, cudaStream_t, Args&&... args) {
     doh_gridDim = {(unsigned)grid, 1, 1}; doh_blockDim = {(unsigned)block, 1, 1};
+    static const bool trace = std::getenv("DOH_TRACE") != nullptr;      // one line per launch on stderr (finding a launch that never ends)
+    if (trace) std::fprintf(stderr, "doh_launch %p grid %zu block %zu\n", (void*)kernel, grid, block);
     for (unsigned b = 0; b < (unsigned)grid; b++) {
         DohBlock blk;
         const unsigned nwarps = ((unsigned)block + 31u) / 32u;
-        blk.warps = std::vector<DohWarp>(nwarps);
+        blk.warps.reset(new DohWarp[nwarps]);
         pthread_barrier_init(&blk.bar, nullptr, (unsigned)block);
         for (unsigned w = 0; w < nwarps; w++) pthread_barrier_init(&blk.warps[w].bar, nullptr, std::min(32u, (unsigned)block - 32u * w));
         std::vector<std::thread> th;

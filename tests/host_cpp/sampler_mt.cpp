@@ -1,6 +1,6 @@
 // sampler_mt.cpp -- render.cu compiled for the host with 32-lane warps made of real threads (device_shim_mt.h), behind one C
 // function: the sampler-table entry point (launch_sampler_tables -> k_sampler_warp / k_sampler_mt).  tests/
-// test_sampler_lanes_on_host.py compares the tables with the oracle's bit for bit; tools/tsan_sampler_on_host.sh runs the same
+// test_sampler_lanes_on_host.py compares the tables with the oracle's bit for bit; tools/tsan_lanes_on_host.sh runs the same
 // under ThreadSanitizer and AddressSanitizer.  Test infrastructure only.
 // (-fvisibility=hidden -fno-gnu-unique: the one-lane build libdevice_on_host.so compiles the same sources into the same symbol
 // names; loaded into one process, the two must not share inline variables)

@@ -1,7 +1,7 @@
 // sampler_mt_main.cpp -- the 32-lane host build of the sampler kernels (sampler_mt.cpp) as a plain program, for the sanitizers:
 // ThreadSanitizer sees every __syncwarp / __syncthreads as a pthread barrier, so a shared-memory access of one lane that is not
 // ordered against another lane's by a barrier is reported as a data race; AddressSanitizer checks the bounds of the shared and
-// global arrays.  tools/tsan_sampler_on_host.sh builds and runs it twice.  Prints one checksum per configuration.  (The thread-per-pixel
+// global arrays.  tools/tsan_lanes_on_host.sh builds and runs it twice.  Prints one checksum per configuration.  (The thread-per-pixel
 // kernel gets whole warps of pixels here: its lanes past the end of the chunk leave the kernel, which a pthread barrier -- unlike
 // bar.warp.sync -- keeps waiting for.)
 #include <cstdint>

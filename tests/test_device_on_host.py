@@ -214,7 +214,9 @@ def _host_round(doh, oracle, pack, cfg, depth=None, seedcount_base=0, wide_bvh=F
     # one-lane warps: refill after every ray; no k_bin (it cooperates through shared memory)
     if device_sampler:
         cfg_fields.setdefault("sampler_kernel", 2)       # the warp-per-pixel builder (the GPU default) unless a test asks otherwise
-    dcfg = abi.device_cfg(traversal="bvh" if wide_bvh else "kd", binning=0, refill_coherent=1, refill_incoherent=1, refill_shadow=1, **cfg_fields)
+    fields = dict(binning=0, refill_coherent=1, refill_incoherent=1, refill_shadow=1)
+    fields.update(cfg_fields)       # (the 32-lane build of test_wavefront_lanes_on_host.py passes the library's own scheduling defaults)
+    dcfg = abi.device_cfg(traversal="bvh" if wide_bvh else "kd", **fields)
     if True:
         h = vp(doh.doh_shade_scene_create(C.byref(desc), C.byref(dcfg)))
         assert h.value

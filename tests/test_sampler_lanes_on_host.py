@@ -4,7 +4,7 @@ pthread barriers and the warp collectives (ballot, shuffle, match, reduce) throu
 one-lane emulation of test_device_on_host.py cannot reach are compared with the oracle here, without a GPU: 128-word twist
 steps across the lanes, batches of 32 draws, a Lemire rejection ending a batch at a lane, shuffles above 64 entries applied
 in waves of independent exchanges, table slots shared by several pixels, the CTA-wide copy-out, CTAs whose last pixel row is
-partly empty.  tools/tsan_sampler_on_host.sh runs the same build under ThreadSanitizer (a missing barrier between two lanes'
+partly empty.  tools/tsan_lanes_on_host.sh runs the same build under ThreadSanitizer (a missing barrier between two lanes'
 shared-memory accesses is a reported race; checked with a barrier removed) and AddressSanitizer + UBSan."""
 import ctypes as C
 import os

@@ -225,9 +225,12 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
     typedef typename std::conditional<SMEM, uint32_t, size_t>::type I;
     const uint32_t ngroups = (npix + MT_LANES - 1) / MT_LANES;
   for (uint32_t group = blockIdx.x; group < ngroups; group += gridDim.x) {
-    const uint32_t p = group * MT_LANES + threadIdx.x;
+    uint32_t p = group * MT_LANES + threadIdx.x;
+    const bool live = p < npix;
     if (SMEM) __syncwarp();                    // the previous group's last copy-out has left the warp's shared tables
-    if (p >= npix) continue;
+    // SMEM: every lane of a warp goes through the same warp barriers -- a lane past the end of the chunk builds the last
+    // pixel once more and keeps nothing (__syncwarp needs every non-exited lane of its mask)
+    if (!live) { if (!SMEM) continue; p = npix - 1u; }
     MT g; g.st = state + (size_t)blockIdx.x * (624 * MT_LANES) + threadIdx.x;
     g.seed(seeds[p]);
     // Shared-memory tables are private to a warp (entry k of lane l at [k * 32 + l] of the warp's region: every swap of
@@ -240,7 +243,7 @@ __global__ void k_sampler_mt(const uint32_t* __restrict__ seeds, uint32_t npix, 
     float* s1 = wbase + (threadIdx.x & 31);                        // ss floats
     float2* s2 = reinterpret_cast<float2*>(wbase) + (threadIdx.x & 31);   // ss float2 (8-byte lanes: 2-way, still cheap)
     for (uint32_t dim = 0; dim < last_dim; dim++) {
-        const bool keep1 = dim < n1d, keep2 = dim < n2d;
+        const bool keep1 = live && dim < n1d, keep2 = live && dim < n2d;
         float* out1 = t1 + ((size_t)(keep1 ? dim : n1d) * ss) * npix + p;
         float* a = SMEM ? s1 : out1;
         const I as = SMEM ? bd : (I)npix;

@@ -68,9 +68,9 @@ def test_lemire_rejection_inside_a_batch(lanes32, oracle):
 
 
 def test_thread_builder_with_32_lane_warps(lanes32, oracle):
-    """k_sampler_mt (thread per pixel) under the same emulation: whole warps of pixels (its lanes past the end of a chunk leave
-    the kernel, which a pthread barrier -- unlike bar.warp.sync -- would keep waiting for)."""
-    seeds = _seeds(128, 9)
+    """k_sampler_mt (thread per pixel, the builder of set sizes <= 16) under the same emulation, with a partly filled last warp:
+    its lanes past the end of the chunk go through the warp barriers of the shared-memory tables with a pixel they drop."""
+    seeds = _seeds(150, 9)
     t1, t2 = _tables(lanes32, oracle, seeds, 16, 3, 4, kernel=1)
     a1, a2 = oracle.sampler_tables(seeds, 16, 3, 4)
     assert np.array_equal(t1.view(np.uint32), a1.view(np.uint32)) and np.array_equal(t2.view(np.uint32), a2.view(np.uint32))

@@ -56,3 +56,13 @@ def test_binned_and_compacted_bounces_with_32_lane_warps(doh32, oracle):
     (rgb, cnt, st, bvh), (fo, co, so) = _host_round(doh32, oracle, pack, cfg, seedcount_base=1, wide_bvh=True, device_sampler=True, **fields)
     assert np.array_equal(cnt, co) and int(st.closest_rays) == int(so.closest_rays) and int(st.shadow_rays) + int(st.shadow_rays_skipped) == int(so.shadow_rays)
     assert np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
+
+
+def test_bidirectional_round_with_32_lane_warps(doh32, oracle):
+    """reverse = 2 on the Cornell box: the light paths, the camera connections (atomic splats: another order of summation than
+    the oracle's, hence the tolerance of test_device_on_host's bidirectional test) and the vertex connections with real warps."""
+    pack, cfg = scenes.load_builtin("cornell-box", width=24, height=24, multisample=4, recursion_max=3)
+    (rgb, cnt, st, bvh), (fo, co, so) = _host_round(doh32, oracle, pack, cfg, seedcount_base=2, wide_bvh=True, reverse=2, **DEFAULTS)
+    assert int(st.closest_rays) == int(so.closest_rays) and int(st.shadow_rays) + int(st.shadow_rays_skipped) == int(so.shadow_rays)
+    assert np.array_equal(cnt, co)
+    assert np.allclose(rgb, fo, rtol=2e-5, atol=2e-5 * float(np.abs(fo).max()))

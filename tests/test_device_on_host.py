@@ -322,6 +322,16 @@ def test_host_loop_chunking_on_the_host(doh, oracle):
     assert int(st.closest_launches) > cfg.recursion_level                          # more than one chunk was traced
 
 
+def test_more_chunks_than_pending_counter_blocks_on_the_host(doh, oracle):
+    """A call of 21 chunks: the per-chunk counter blocks wait in pinned memory for the end of the round, 16 of them at most
+    (H_CHUNKS) -- the 17th chunk makes the host drain them first.  Ray counts (summed from those blocks) and image as the oracle's."""
+    pack, cfg = scenes.material_zoo(width=224, height=96, multisample=1, recursion_max=3, lens=0.0)
+    (rgb, cnt, st, _), (fo, co, so) = _host_round(doh, oracle, pack, cfg, seedcount_base=1, wide_bvh=True, chunk_paths=64)
+    assert np.array_equal(cnt, co) and np.array_equal(rgb.view(np.uint32), fo.view(np.uint32))
+    assert int(st.closest_rays) == int(so.closest_rays) and int(st.shadow_rays) + int(st.shadow_rays_skipped) == int(so.shadow_rays)
+    assert int(st.closest_launches) >= 21 * 1
+
+
 @pytest.mark.parametrize("scene", [_zoo, _cornell, _sponza])
 def test_ab_knob_kernels_on_the_host(doh, oracle, scene):
     """The A/B candidates that are built but off by default give the same bits: rgk_device_cfg::bvh_shadow_nosort (any-hit BVH

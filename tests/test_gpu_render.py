@@ -193,6 +193,17 @@ def test_chunking_does_not_change_the_image(gpu_ctx, monkeypatch):
     gpu_ctx.configure(base)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ca, cb)
     assert int(sb.kernel_launches) > int(sa.kernel_launches)
+    # more chunks than the 16 counter blocks that can wait in pinned memory for the end of the round: the host drains in between
+    pack2, cfg2 = scenes.load_builtin("cornell-box", width=224, height=96, multisample=1, recursion_max=4)
+    cam2 = gpu_ctx.camera(**cfg2.camera_args())
+    tasks2 = gpu_ctx.generate_tasks(32, 224, 96)
+    c, cc, sc = gpu_ctx.render_round(cam2, cfg2.params(), tasks2)
+    gpu_ctx.configure(chunk_paths=64)
+    d, cd, sd = gpu_ctx.render_round(cam2, cfg2.params(), tasks2)
+    gpu_ctx.configure(base)
+    assert np.array_equal(c.view(np.uint32), d.view(np.uint32)) and np.array_equal(cc, cd)
+    assert (int(sc.closest_rays), int(sc.shadow_rays), int(sc.shadow_rays_skipped)) == (int(sd.closest_rays), int(sd.shadow_rays), int(sd.shadow_rays_skipped))
+    assert int(sd.closest_launches) >= 21
     empty = (abi.Task * 0)()
     z, cz, sz = gpu_ctx.render_round(cam, p, empty)
     assert not z.any() and int(sz.samples) == 0

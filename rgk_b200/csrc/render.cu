@@ -1104,7 +1104,10 @@ __device__ __forceinline__ void push_queue(uint32_t* queue, unsigned long long* 
 // LAST: the launch of the last bounce (every vertex of the queue has n == depth, so no continuation is ever sampled): the same
 // results from a kernel without the BxDF sampling code (4016 instead of 7352 SASS instructions; measured -3 ms per headline round)
 template <bool LAST>
-__global__ void __launch_bounds__(128, RGK_SHADE_MINB)
+#ifndef RGK_SHADE_THREADS
+#define RGK_SHADE_THREADS 128
+#endif
+__global__ void __launch_bounds__(RGK_SHADE_THREADS, RGK_SHADE_MINB * 128 / RGK_SHADE_THREADS)
 k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue_sorted, const uint32_t* __restrict__ queue_path_order,
         QueueLen len, QueueLen prev_len, uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ next_unsorted,
         unsigned long long* counters) {
@@ -1829,9 +1832,9 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 R.first_bounce = bounce == 0 ? 1u : 0u;
                 if (R.binning & 1u) RGK_CUDA(ctx, cudaMemsetAsync(B.key_next, 0xFF, npaths, ctx->stream));
                 if (R.binning & 2u) RGK_CUDA(ctx, cudaMemsetAsync(B.key_shadow, 0xFF, npaths, ctx->stream));
-                const unsigned sg = (unsigned)((live_ub + 127) / 128);
-                if (last_bounce) k_shade<true><<<sg, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, unsorted_prev, in, prev_in, qnext, B.queue_s, unext, blk);
-                else k_shade<false><<<sg, 128, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, unsorted_prev, in, prev_in, qnext, B.queue_s, unext, blk);
+                const unsigned sg = (unsigned)((live_ub + RGK_SHADE_THREADS - 1) / RGK_SHADE_THREADS);
+                if (last_bounce) k_shade<true><<<sg, RGK_SHADE_THREADS, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, unsorted_prev, in, prev_in, qnext, B.queue_s, unext, blk);
+                else k_shade<false><<<sg, RGK_SHADE_THREADS, 0, ctx->stream>>>(ctx->dev, R, smp, B, queue, unsorted_prev, in, prev_in, qnext, B.queue_s, unext, blk);
                 if (R.binning & 1u) {
                     k_bin<<<n_pgroups * n_sgroups, BIN_THREADS, 0, ctx->stream>>>(B.key_next, (uint32_t)npix, ms, PG, SG, n_pgroups, qnext, blk + C_NEXT, in, thresh);
                     ctx->launches++;

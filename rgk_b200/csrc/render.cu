@@ -843,6 +843,16 @@ constexpr int TRACE_THREADS = 128;
 #ifndef RGK_COH_MINB
 #define RGK_COH_MINB 9      // camera rays: 56 registers
 #endif
+#ifndef RGK_CLOSEST_BVH_MINB
+#define RGK_CLOSEST_BVH_MINB 8   // CTAs/SM the wide-BVH closest-hit kernel is compiled for: 64 registers, 8 B spilled (per headline round: 6 CTAs / 78
+                                 // registers 31.75 ms, 7 / 72: 30.8, 8 / 64: 29.8, 9 / 56: 30.8, 10 / 48: 33.7)
+#endif
+#ifndef RGK_CLOSEST_BVH_MINB_CAMERA
+#define RGK_CLOSEST_BVH_MINB_CAMERA RGK_CLOSEST_BVH_MINB
+#endif
+#ifndef RGK_SHADOW_BVH_MINB
+#define RGK_SHADOW_BVH_MINB 8    // likewise the any-hit kernel (6 CTAs / 72 registers 14.1 ms, 8 / 64: 13.5, 9: 13.6, 10: 14.3)
+#endif
 #ifndef RGK_RENDER_VARIANT
 #define RGK_RENDER_VARIANT 6   // phase-synchronised traversal (trace_device.cuh)
 #endif
@@ -1713,7 +1723,7 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 pool.begin(ctx->stream, T_CLOSEST);
                 if (use_bvh) {
                     cudaMemsetAsync(arb_ctr, 0, 2 * sizeof(unsigned long long), ctx->stream);
-                    k_closest_bvh<6><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, QueueLen{nullptr, n}, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
+                    k_closest_bvh<RGK_CLOSEST_BVH_MINB><<<g, TRACE_THREADS, 0, ctx->stream>>>(dev, B, q, QueueLen{nullptr, n}, B.counters + C_WORK_A, ctx->d_bvh_stats, arb_list, (uint32_t*)(arb_ctr + 1));
                     k_closest_arb<RGK_INCOH_MINB><<<std::min(g, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, (const uint32_t*)(arb_ctr + 1), arb_ctr, 0u);
                     ctx->launches++;
                 }
@@ -1813,8 +1823,9 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                 if (use_bvh) {
                     uint32_t* arb_n = (uint32_t*)(blk + C_ARB_COUNT);
                     if (counting) k_closest_bvh<6, 1, true><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
-                    else if (bvh_closest_nearest) k_closest_bvh<6, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
-                    else k_closest_bvh<6><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
+                    else if (bvh_closest_nearest) k_closest_bvh<RGK_CLOSEST_BVH_MINB, 2><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
+                    else if (bounce == 0) k_closest_bvh<RGK_CLOSEST_BVH_MINB_CAMERA><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
+                    else k_closest_bvh<RGK_CLOSEST_BVH_MINB><<<g1, TRACE_THREADS, 0, ctx->stream>>>(dev, B, queue, in, blk + C_WORK_A, ctx->d_bvh_stats, arb_list, arb_n);
                     k_closest_arb<RGK_INCOH_MINB><<<std::min(g1, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, arb_n, blk + C_ARB_WORK, bounce == 0 ? 1u : 0u);
                     ctx->launches++;
                 }
@@ -1859,9 +1870,9 @@ rgk_status render_round_impl(rgk_context* ctx, const rgk_camera* cam, const rgk_
                         uint32_t* arb_n = (uint32_t*)(blk + C_ARB_SCOUNT);
                         if (counting) k_shadow_bvh<6, 1, true><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, ctx->d_bvh_stats + 1,
                                                                                               R.const_light, R.cl_pos, arb_list, arb_n);
-                        else if (bvh_shadow_nosort) k_shadow_bvh<6, 0><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, ctx->d_bvh_stats + 1,
+                        else if (bvh_shadow_nosort) k_shadow_bvh<RGK_SHADOW_BVH_MINB, 0><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, ctx->d_bvh_stats + 1,
                                                                                                     R.const_light, R.cl_pos, arb_list, arb_n);
-                        else k_shadow_bvh<6, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, ctx->d_bvh_stats + 1,
+                        else k_shadow_bvh<RGK_SHADOW_BVH_MINB, 1><<<g2, TRACE_THREADS, 0, ctx->stream>>>(dev, B, B.queue_s, shadow_len, P->clamp, blk + C_WORK_B, ctx->d_bvh_stats + 1,
                                                                                     R.const_light, R.cl_pos, arb_list, arb_n);
                         k_shadow_arb<RGK_INCOH_MINB><<<std::min(g2, arb_grid), TRACE_THREADS, 0, ctx->stream>>>(dev, B, arb_list, arb_n, P->clamp, blk + C_ARB_SWORK,
                                                                                                          R.const_light, R.cl_pos);

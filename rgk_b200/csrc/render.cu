@@ -1117,7 +1117,10 @@ template <bool LAST>
 #ifndef RGK_SHADE_THREADS
 #define RGK_SHADE_THREADS 128
 #endif
-__global__ void __launch_bounds__(RGK_SHADE_THREADS, RGK_SHADE_MINB * 128 / RGK_SHADE_THREADS)
+#ifndef RGK_SHADE_LAST_MINB
+#define RGK_SHADE_LAST_MINB RGK_SHADE_MINB
+#endif
+__global__ void __launch_bounds__(RGK_SHADE_THREADS, (LAST ? RGK_SHADE_LAST_MINB : RGK_SHADE_MINB) * 128 / RGK_SHADE_THREADS)
 k_shade(DevScene S, RenderConst R, SamplerView smp, PathBuffers B, const uint32_t* __restrict__ queue_sorted, const uint32_t* __restrict__ queue_path_order,
         QueueLen len, QueueLen prev_len, uint32_t* __restrict__ next_queue, uint32_t* __restrict__ shadow_queue, uint32_t* __restrict__ next_unsorted,
         unsigned long long* counters) {

@@ -1069,9 +1069,31 @@ k_bin(const uint8_t* __restrict__ keys, uint32_t npix, uint32_t ms, uint32_t PG,
     const uint32_t np = min(PG, npix - p0), ns = min(SG, ms - s0), n = np * ns;
     hist[threadIdx.x] = 0u;
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k < n; k += BIN_THREADS) {
-        const uint32_t key = keys[(size_t)(s0 + k / np) * npix + p0 + k % np];
-        if (key != 0xFFu) atomicAdd(&hist[key], 1u);
+    // Where the rows of the group are whole aligned words (the usual case: 32 pixel positions per row) a thread reads four keys
+    // at a time and keeps its words in registers for the second pass: a quarter of the loads and of the row / column divisions,
+    // no second read of the keys.
+    constexpr int KEEP = 4;                           // words per thread: groups of up to 4096 slots
+    const uint32_t wpr = np >> 2, nwords = wpr * ns;
+    const bool words = (((np | p0 | npix) & 3u) == 0u) && nwords <= (uint32_t)(KEEP * BIN_THREADS);
+    uint32_t kw[KEEP], at[KEEP];
+    if (words) {
+#pragma unroll
+        for (int i = 0; i < KEEP; i++) {
+            const uint32_t w = threadIdx.x + (uint32_t)i * BIN_THREADS;
+            kw[i] = 0xFFFFFFFFu; at[i] = 0u;
+            if (w < nwords) {
+                const uint32_t row = w / wpr, col = w - row * wpr;
+                at[i] = (s0 + row) * npix + p0 + 4u * col;
+                kw[i] = *reinterpret_cast<const uint32_t*>(keys + at[i]);
+#pragma unroll
+                for (int b = 0; b < 4; b++) { const uint32_t key = (kw[i] >> (8 * b)) & 0xFFu; if (key != 0xFFu) atomicAdd(&hist[key], 1u); }
+            }
+        }
+    } else {
+        for (uint32_t k = threadIdx.x; k < n; k += BIN_THREADS) {
+            const uint32_t key = keys[(size_t)(s0 + k / np) * npix + p0 + k % np];
+            if (key != 0xFFu) atomicAdd(&hist[key], 1u);
+        }
     }
     __syncthreads();
     // exclusive scan of the 256 bins (one per thread)
@@ -1089,6 +1111,17 @@ k_bin(const uint8_t* __restrict__ keys, uint32_t npix, uint32_t ms, uint32_t PG,
     hist[threadIdx.x] = before + incl - mine;
     __syncthreads();
     const unsigned long long base = base_s;
+    if (words) {
+#pragma unroll
+        for (int i = 0; i < KEEP; i++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t key = (kw[i] >> (8 * b)) & 0xFFu;
+                if (key != 0xFFu) out[base + atomicAdd(&hist[key], 1u)] = at[i] + (uint32_t)b;
+            }
+        }
+        return;
+    }
     for (uint32_t k = threadIdx.x; k < n; k += BIN_THREADS) {
         const uint32_t slot = (s0 + k / np) * npix + p0 + k % np;
         const uint32_t key = keys[slot];

@@ -815,10 +815,6 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
     if (R.lens) lens = smp.get2d(pixel, seed, set, d2++);
     V3 o, d;
     camera_ray(R.cam, (int)(xy & 0xffffu), (int)(xy >> 16), R.xres, R.yres, coords, lens, o, d);
-    const V2 areal = smp.get2d(pixel, seed, set, d2++);
-    d2++;                                                       // lightdir_sample: drawn, unused when reverse == 0
-    const V2 choice = smp.get2d(pixel, seed, set, d2++);
-    const float ls = smp.get1d(pixel, seed, set, 0);
     B.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
     if (cam_o) cam_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);             // camerapos of the sample (bidirectional mode)
     B.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
@@ -829,6 +825,10 @@ __global__ void k_raygen(DevScene S, RenderConst R, SamplerView smp, PathBuffers
         B.cur1[slot] = 1u;
     }
     if (R.const_light) return;      // GetRandomLight can only return that one light, unjittered (size 0): kept in RenderConst
+    const V2 areal = smp.get2d(pixel, seed, set, d2++);         // (read here, not above: with the fixed light these tables are not even built)
+    d2++;                                                       // lightdir_sample: drawn, unused when reverse == 0
+    const V2 choice = smp.get2d(pixel, seed, set, d2++);
+    const float ls = smp.get1d(pixel, seed, set, 0);
     LightRec L = random_light(S, choice, ls, areal);
     if (L.valid && L.type == 0) { const V3 dir = sphere_uniform(areal); L.pos = L.pos + L.size * dir; }
     B.light_pos[slot] = make_float4(L.pos.x, L.pos.y, L.pos.z, __uint_as_float((L.valid ? 1u : 0u) | ((uint32_t)L.type << 1)));

@@ -477,12 +477,24 @@ __device__ __noinline__ void sampler_flush(uint32_t* warp0, uint32_t warp_words,
     if (!(RGK_SAMPLER_X & 2) && lane < filled && !(meta[lane] >> 31)) {
         float2* d = reinterpret_cast<float2*>(slots + lane * slot_words);
         const uint16_t* pr = reinterpret_cast<const uint16_t*>(slots + lane * slot_words + 2u * ss);
-        uint32_t jn = ss > 1u ? pr[1] : 0u;          // the next partner is requested before the current exchange (the list is not touched by it)
-        for (uint32_t i = 1; i < serial; i++) {
-            const uint32_t j = jn;
-            jn = pr[i + 1u < ss ? i + 1u : i];
-            const float2 a = d[i], b = d[j];
-            d[i] = b; d[j] = a;
+        // partners two at a time (positions 2 k and 2 k + 1 share a word of the list), the next pair requested before the current
+        // exchanges (the list is not touched by them)
+        if (serial > 1u) { const uint32_t j = pr[1]; const float2 a = d[1], b = d[j]; d[1] = b; d[j] = a; }
+        const uint32_t* pr2 = reinterpret_cast<const uint32_t*>(pr);
+        uint32_t pn = serial > 2u ? pr2[1] : 0u;
+        for (uint32_t i = 2; i < serial; i += 2u) {
+            const uint32_t pp = pn;
+            pn = pr2[(i + 2u < serial) ? (i >> 1) + 1u : (i >> 1)];
+            {
+                const uint32_t j = pp & 0xffffu;
+                const float2 a = d[i], b = d[j];
+                d[i] = b; d[j] = a;
+            }
+            if (i + 1u < serial) {
+                const uint32_t j = pp >> 16;
+                const float2 a = d[i + 1u], b = d[j];
+                d[i + 1u] = b; d[j] = a;
+            }
         }
     }
 #if defined(__CUDA_ARCH__) || defined(__CUDA_ARCH_EMULATED_LANES__)      // (the latter: the 32-lane host build of tests/host_cpp/device_shim_mt.h)

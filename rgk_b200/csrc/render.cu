@@ -461,11 +461,10 @@ __device__ __forceinline__ float mt_real_of(uint32_t word, float len) {
 // all of them is one run of 32 / 64 bytes in the global table -- whole sectors.  (A warp writing its own pixel alone puts 4 or 8
 // bytes into each of 32 sectors per store: 660 M partial-sector writes per 1080p x 64 spp round, which L2 takes at about one per
 // slice and clock -- that, not the generator, bounded the kernel: 11.1 ms with, 7.3 ms without the copy-out.)
-__device__ __noinline__ void sampler_flush(uint32_t* warp0, uint32_t warp_words, uint32_t nslots_unused, uint32_t filled, uint32_t slot_words, uint32_t ss,
+__device__ __noinline__ void sampler_flush(uint32_t* warp0, uint32_t warp_words, uint32_t nslots, uint32_t filled, uint32_t slot_words, uint32_t ss,
                                            uint32_t npix, uint32_t pix0, uint32_t w, uint32_t lane, float* __restrict__ t1, float2* __restrict__ t2) {
-    (void)nslots_unused;
     uint32_t* slots = warp0 + w * warp_words + 624u;
-    const uint32_t* meta = slots + nslots_unused * slot_words;
+    const uint32_t* meta = slots + nslots * slot_words;
     __syncwarp();
     // The exchanges of std::shuffle are sequential by definition (element i goes to an earlier, random place p_i); the first
     // `serial` of them are applied that way, one table per lane.  Beyond that the partners of 32 consecutive exchanges seldom

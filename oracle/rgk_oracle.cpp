@@ -1434,7 +1434,8 @@ Bvh4Out bvh4_trace(const Scene& s, const float* nodes, const uint32_t* order, co
                 const float q1x = v1[i1] - v0[i1], q1y = v1[i2] - v0[i2], q2x = v2[i1] - v0[i1], q2y = v2[i2] - v0[i2];
                 const float den = q2y * q1x - q2x * q1y;
                 const float longest = std::fmax(std::fmax(std::fabs(q1x), std::fabs(q1y)), std::fmax(std::fabs(q2x), std::fabs(q2y)));
-                const float delta = std::fmax(3.0517578125e-5f, 0.125f * m * longest / std::fabs(den));
+                float delta = std::fmax(3.0517578125e-5f, 0.125f * m * longest / std::fabs(den));
+                if (q1x > -eps && q1x < eps && q1x != 0.0f) delta += 2.0f * (std::fabs(q1x / q2x) * (1.0f + std::fabs(q2y / q1y)));    // sheared accept region (src/primitives.cpp:141-147)
                 edge = !(a >= delta) || !(b >= delta) || !((a + b) <= 1.0f - delta);
             }
             if (any) { if (!edge && t >= firm_lo && t <= firm_hi) stop = true; else border = true; continue; }

@@ -223,7 +223,12 @@ struct BvhTraverser {
         // "on the boundary" in units of this ray's position uncertainty: an eighth of the margin m (8x the rounding of o + d t) over the
         // triangle's smallest projected height |denom| / longest projected edge, and never less than 2^-15
         const float longest = fmaxf(fmaxf(fabsf(r1.z), fabsf(r1.w)), fmaxf(fabsf(r2.x), fabsf(r2.y)));
-        const float delta = fmaxf(3.0517578125e-5f, 0.125f * marg * longest / fabsf(r2.z));
+        float delta = fmaxf(3.0517578125e-5f, 0.125f * marg * longest / fabsf(r2.z));
+        // A triangle of the |q1.x| < eps branch with q1.x != 0 is tested as its sheared twin (q1.x dropped: host_scene.cpp
+        // adds that region to the boxes): alpha and beta are up to s = |q1.x / q2.x| (1 + |q2.y / q1.y|) (times |alpha'| <
+        // 4/3 while s < 1/4) away from the true barycentrics, and the kd-tree holds the TRUE triangle -- a hit less than
+        // that inside the sheared boundary may lie in a cell that does not reference it.  Wider boundary (everything at s >= 1/4).
+        if ((flags & 4u) && r1.z != 0.0f) delta += 2.0f * (fabsf(r1.z / r2.x) * (1.0f + fabsf(r2.y / r1.w)));
         const bool edge = !(alpha >= delta) || !(beta >= delta) || !((alpha + beta) <= 1.0f - delta);
         if (ANY) {
             if (!edge && t >= firm_lo && t <= firm_hi) return true;

@@ -312,6 +312,7 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rg
     // intersection records: the ray-independent part of Triangle::TestIntersection (src/primitives.cpp:83,104-133,141,149)
     hs.tri_isect.resize(12 * (size_t)nt);
     hs.tri_bounds.resize(4 * (size_t)nt);
+    std::vector<float> ev_bvh[3];            // ev with the sheared triangles' accept regions added (copied on the first such triangle)
     for (uint32_t i = 0; i < nt; i++) {
         const float* p = &hs.planes[4 * (size_t)i];
         const float px = std::fabs(p[0]), py = std::fabs(p[1]), pz = std::fabs(p[2]);
@@ -330,6 +331,24 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rg
         r[4] = comp(v0, i1); r[5] = comp(v0, i2); r[6] = q1x; r[7] = q1y;
         r[8] = q2x; r[9] = q2y; r[10] = denom; std::memcpy(&r[11], &code, 4);
         tri_prefilter_bounds(r, code, &hs.tri_bounds[4 * (size_t)i]);
+        // The |q1.x| < eps branch of TestIntersection (src/primitives.cpp:141-147) drops q1.x: what it accepts is the triangle
+        // v0, v1', v2 with v1' = v1 moved to v0's first projected coordinate (a shear of up to eps), on the stored plane.  The
+        // wide BVH's boxes must hold that region too (the kd-tree keeps the true extents: ev feeds the reference's build).
+        if ((code & 4u) && q1x != 0.0f && p[3 - i1 - i2] != 0.0f && std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]) && std::isfinite(p[3])) {
+            const int k = 3 - i1 - i2;
+            double w[3];
+            w[i1] = comp(v0, i1); w[i2] = comp(v1, i2);
+            w[k] = -((double)p[3] + (double)p[i1] * w[i1] + (double)p[i2] * w[i2]) / (double)p[k];
+            if (std::isfinite(w[k])) {
+                if (ev_bvh[0].empty()) for (int ax = 0; ax < 3; ax++) ev_bvh[ax] = ev[ax];
+                for (int ax = 0; ax < 3; ax++) {
+                    float lo = (float)w[ax], hi = lo;
+                    for (int n = 0; n < 2; n++) { lo = std::nextafterf(lo, -std::numeric_limits<float>::infinity()); hi = std::nextafterf(hi, std::numeric_limits<float>::infinity()); }
+                    ev_bvh[ax][2 * (size_t)i] = std::min(ev_bvh[ax][2 * (size_t)i], lo);
+                    ev_bvh[ax][2 * (size_t)i + 1] = std::max(ev_bvh[ax][2 * (size_t)i + 1], hi);
+                }
+            }
+        }
     }
 
     // Triangles whose record can produce NaN barycentrics (projected edges exactly collinear: denom == 0, or q2.x == 0 /
@@ -353,7 +372,7 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rg
     hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0;
     std::thread bvh_thread; std::exception_ptr bvh_error;
     if (cfg.traversal == RGK_TRAVERSAL_BVH && nan_prone == 0)
-        bvh_thread = std::thread([&] { try { host_bvh_build(ev, nt, cfg, hs); } catch (...) { bvh_error = std::current_exception(); } });
+        bvh_thread = std::thread([&] { try { host_bvh_build(ev_bvh[0].empty() ? ev : ev_bvh, nt, cfg, hs); } catch (...) { bvh_error = std::current_exception(); } });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{bvh_thread};     // also on the throwing paths below
 
     // kd-tree

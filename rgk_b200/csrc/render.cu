@@ -20,6 +20,10 @@
 #include "trace_device.cuh"
 #include "bvh_device.cuh"
 #include "shade_device.cuh"
+#ifdef RGK_DOH_DEBUG
+#include <cstdio>
+static long long doh_debug_slot = std::getenv("DOH_SLOT") ? std::atoll(std::getenv("DOH_SLOT")) : -1;
+#endif
 
 // ------------------------------------------------------------------ buffers
 // vertex storage of the bidirectional mode (reverse_device.cuh)
@@ -900,6 +904,13 @@ k_closest(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, QueueLe
         },
         [&](uint32_t i, bool found, const HitRec& h) {
             const uint32_t slot = queue ? __ldg(queue + i) : i;
+#ifdef RGK_DOH_DEBUG
+            if ((long long)slot == doh_debug_slot) {
+                const float4 o = B.ray_o[slot], d = B.ray_d[slot];
+                std::fprintf(stderr, "CLOSEST slot %u o %.9g %.9g %.9g d %.9g %.9g %.9g -> %s tri %u t %.9g a %.9g b %.9g\n", slot, o.x, o.y, o.z, d.x, d.y, d.z,
+                             found ? "hit" : "miss", h.tri, h.t, h.alpha, h.beta);
+            }
+#endif
             B.hit[slot] = make_float4(h.t, h.alpha, h.beta, __uint_as_float(found ? h.tri : RGK_NO_TRIANGLE));
         });
     flush_counts<COUNT>(cnt, mine, stats);
@@ -925,6 +936,12 @@ k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, QueueLen
         },
         [&](uint32_t i, bool blocked, const HitRec&) {
             const uint32_t slot = __ldg(queue + i);
+#ifdef RGK_DOH_DEBUG
+            if ((long long)slot == doh_debug_slot) {
+                const float4 a = const_light ? cl_pos : B.light_pos[slot], b = B.sh_pos[slot];
+                std::fprintf(stderr, "SHADOW slot %u from %.9g %.9g %.9g to %.9g %.9g %.9g -> %s\n", slot, a.x, a.y, a.z, b.x, b.y, b.z, blocked ? "blocked" : "visible");
+            }
+#endif
             const float4 dr = B.sh_direct[slot];
             if (__float_as_uint(dr.w) == 0u) {                 // vertex without emission: dr = min(direct, clamp) * contribution
                 if (blocked) return;
@@ -953,6 +970,13 @@ k_shadow(DevScene S, PathBuffers B, const uint32_t* __restrict__ queue, QueueLen
 struct ClosestIO {
     PathBuffers B;
     __device__ __forceinline__ void commit(uint32_t slot, bool found, const HitRec& h) const {
+#ifdef RGK_DOH_DEBUG      // host build of the tests only: follow one path slot through its bounces
+        if ((long long)slot == doh_debug_slot) {
+            const float4 o = B.ray_o[slot], d = B.ray_d[slot];
+            std::fprintf(stderr, "CLOSEST slot %u o %.9g %.9g %.9g d %.9g %.9g %.9g -> %s tri %u t %.9g a %.9g b %.9g\n", slot, o.x, o.y, o.z, d.x, d.y, d.z,
+                         found ? "hit" : "miss", h.tri, h.t, h.alpha, h.beta);
+        }
+#endif
         B.hit[slot] = make_float4(h.t, h.alpha, h.beta, __uint_as_float(found ? h.tri : RGK_NO_TRIANGLE));
     }
 };
@@ -968,6 +992,12 @@ struct ShadowIO {
         return tr.init(S, a.x, a.y, a.z, ex * inv, ey * inv, ez * inv, 0.0f + e20, len - e20, RGK_NO_TRIANGLE);
     }
     __device__ __forceinline__ void commit(uint32_t slot, bool blocked) const {       // the NEE resolve of k_shadow
+#ifdef RGK_DOH_DEBUG
+        if ((long long)slot == doh_debug_slot) {
+            const float4 a = const_light ? cl_pos : B.light_pos[slot], b = B.sh_pos[slot];
+            std::fprintf(stderr, "SHADOW slot %u from %.9g %.9g %.9g to %.9g %.9g %.9g -> %s\n", slot, a.x, a.y, a.z, b.x, b.y, b.z, blocked ? "blocked" : "visible");
+        }
+#endif
         const float4 dr = B.sh_direct[slot];
         if (__float_as_uint(dr.w) == 0u) {
             if (blocked) return;

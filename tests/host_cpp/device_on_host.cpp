@@ -192,6 +192,24 @@ DOH_API int doh_render_round(void* h, const rgk_device_cfg* cfg, const rgk_camer
     rgk_round_stats local{};
     const rgk_status st = render_round_impl(&ctx, cam, p, tasks, n_tasks, seedstart, seedcount_base, rgb, count, stats ? stats : &local);
     if (st != RGK_OK) std::fprintf(stderr, "doh_render_round: %s\n", ctx.last_error.c_str());
+    if (const char* px = std::getenv("DOH_DUMP_PIXEL")) {      // "x,y": the per-sample radiance sums of that pixel (last chunk of the call), for diffing two runs
+        unsigned x = 0, y = 0;
+        if (std::sscanf(px, "%u,%u", &x, &y) == 2 && ctx.paths) {
+            const PathBuffers& B = *ctx.paths;
+            const uint32_t want = x | (y << 16);
+            const size_t npix = B.cap_pixels;
+            for (size_t pos = 0; pos < npix; pos++)
+                if (B.pix_xy[pos] == want) {
+                    // (the chunk's pixel count is the stride of the sample index; single-tile calls: the tile's pixel count)
+                    const size_t stride = (size_t)(tasks[0].x2 - tasks[0].x1) * (tasks[0].y2 - tasks[0].y1);
+                    for (uint32_t smp = 0; smp < p->multisample; smp++) {
+                        const float4 t = B.tot[(size_t)smp * stride + pos];
+                        std::fprintf(stderr, "DUMP pos %zu sample %u slot %zu tot %.9g %.9g %.9g\n", pos, smp, (size_t)smp * stride + pos, t.x, t.y, t.z);
+                    }
+                    break;
+                }
+        }
+    }
     if (out_bvh) { out_bvh[0] = s->bvh_stats[0].rays + s->bvh_stats[1].rays; out_bvh[1] = s->bvh_stats[0].ambiguous + s->bvh_stats[1].ambiguous; }
     free_path_buffers(&ctx);
     for (auto& q : ctx.scratch) if (q) std::free(q);

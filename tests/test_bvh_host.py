@@ -70,6 +70,22 @@ def _check_structure(pack, hs):
     pos = np.asarray(arr["positions"], np.float32).reshape(-1, 3)
     tri = np.asarray(arr["indices"], np.uint32).reshape(-1, 3)
     tlo, thi = pos[tri].min(1), pos[tri].max(1)
+    # triangles of the |q1.x| < eps branch with q1.x != 0 are accepted as their sheared twin (src/primitives.cpp:141-147): v1
+    # moved to v0's first projected coordinate, on the stored plane; their boxes hold that point too (2 ulps outwards)
+    planes, rec = hs.records()
+    planes = np.asarray(planes, np.float32).reshape(-1, 4); rec = np.asarray(rec, np.float32).reshape(-1, 12)
+    flags = rec[:, 11].view(np.uint32)
+    for t in np.nonzero(((flags & 4) != 0) & (rec[:, 6] != 0))[0]:
+        code = int(flags[t] & 3)
+        i1, i2 = ((1, 2), (0, 2), (0, 1))[code]
+        k = 3 - i1 - i2
+        w = np.zeros(3)
+        w[i1] = pos[tri[t, 0], i1]; w[i2] = pos[tri[t, 1], i2]
+        w[k] = -(float(planes[t, 3]) + float(planes[t, i1]) * w[i1] + float(planes[t, i2]) * w[i2]) / float(planes[t, k])
+        lo = hi = w.astype(np.float32)
+        for _ in range(2):
+            lo = np.nextafter(lo, np.float32(-np.inf)); hi = np.nextafter(hi, np.float32(np.inf))
+        tlo[t] = np.minimum(tlo[t], lo); thi[t] = np.maximum(thi[t], hi)
     seen_inner, covered = set(), np.zeros(nt, bool)
     # subtree bounds bottom-up: children always have larger indices than their parent (preorder emission)
     sub_lo, sub_hi = np.zeros((len(nodes), 3), np.float32), np.zeros((len(nodes), 3), np.float32)
@@ -86,7 +102,7 @@ def _check_structure(pack, hs):
                 t = order[first:first + cnt]
                 assert not covered[t].any()
                 covered[t] = True
-                assert (tlo[t].min(0) == lo).all() and (thi[t].max(0) == hi).all()     # exact bounds of its triangles
+                assert (tlo[t].min(0) == lo).all() and (thi[t].max(0) == hi).all()     # exact bounds of its triangles' accept regions
             else:
                 assert i < code < len(nodes) and code not in seen_inner
                 seen_inner.add(code)
@@ -344,4 +360,66 @@ def test_campaign_regressions(seed):
     ign = np.where(rng.random(len(rays)) < 0.3, pick[keep], 0xFFFFFFFF).astype(np.uint32)
     got, deferred, _ = closest(rays, ign)
     assert _same(got[~deferred], O.trace_closest(h, rays, ign)[~deferred])
+    hs.close()
+
+
+def sheared_fan(seed=7, n=40000):
+    """A fan of triangles facing +z whose v1 is q1x (|q1x| < eps, != 0) off v0 in the first projected coordinate, inside a
+    20 x 200 x 20 frame (eps = 1e-5 * diameter ~ 2e-3, the rays' box margin ~ 1e-4).  v1 is the lowest vertex of a plane sloped
+    in x, so for q1x > 0 the sheared corner lies ~1e-3 below the triangle's extents; the neighbour across v0-v1 is attached for
+    q1x < 0 and moved 1 below otherwise (a free sheared corner).  Rays aimed across the true and the sheared edge, and segments
+    through the same points.  -> pack, triangles, rays, (a, b)"""
+    from test_prefilter_bounds import _scene
+    rng = np.random.default_rng(seed)
+    box = np.array([[[-10, -100, -10], [10, -100, -10], [-10, 100, -10]], [[10, 100, 10], [-10, 100, 10], [10, -100, 10]]], np.float32)
+    tris = [box[0], box[1]]
+    q1xs = [1.8e-3, -1.8e-3, 6e-4, -1.2e-3, 2e-3, 1e-4]
+    for j, q1x in enumerate(q1xs):
+        v0 = np.array([j - 3.0, -0.5, 0.1 * j], np.float32)
+        tris.append(np.stack([v0, v0 + np.array([q1x, 0.02, -1e-4], np.float32), v0 + np.array([0.03, 0.0, 0.015], np.float32)]))
+        nb = np.stack([v0, v0 + np.array([-0.03, 0.02, -0.014], np.float32), v0 + np.array([q1x, 0.02, -1e-4], np.float32)])
+        tris.append(nb if j % 2 == 1 else nb + np.array([0, 0, -1], np.float32))       # every other neighbour 1 below: a free sheared corner
+    tris = np.stack(tris).astype(np.float32)
+    pick = 2 + 2 * rng.integers(0, len(q1xs), n)
+    v0, v1 = tris[pick, 0], tris[pick, 1]
+    s = rng.random((n, 1)).astype(np.float32)
+    target = v0 + s * (v1 - v0)
+    target[:, 0] += rng.uniform(-4e-3, 4e-3, n).astype(np.float32)
+    origin = target + np.stack([rng.normal(scale=0.3, size=n), rng.normal(scale=0.3, size=n), rng.uniform(0.5, 3.0, n)], 1).astype(np.float32)
+    d = (target - origin).astype(np.float32)
+    rays = np.zeros(n, checkers.RAY_DT)
+    rays["origin"] = origin
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tfar"] = 10000.0
+    return _scene(tris), tris, rays, (origin, (target + 0.5 * d).astype(np.float32))
+
+
+def test_sheared_accept_region():
+    """Triangle::TestIntersection's |q1.x| < eps branch (src/primitives.cpp:141-147) drops q1.x: a triangle whose second vertex
+    is within eps of the first in the first projected coordinate is accepted as a sheared twin, up to eps outside its true
+    extents.  Found by the 4K x 1024 spp conference frame (one pixel of 8.3 M: a chair-leg triangle hit 4e-5 inside the sheared
+    edge and 1e-4 outside its box; tools/find_bvh_mismatch.py, tools/repro_tile_on_host.py).  The boxes hold the sheared region,
+    and hits near its boundary defer."""
+    pack, tris, rays, (a, b) = sheared_fan()
+    hs = device.HostScene(pack.desc(), traversal="bvh")
+    _check_structure(pack, hs)
+    rec = np.asarray(hs.records()[1], np.float32).reshape(-1, 12)
+    sheared = ((rec[:, 11].view(np.uint32) & 4) != 0) & (rec[:, 6] != 0)
+    assert sheared[2::2].all()
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    nodes, order, _ = hs.bvh()
+    closest, shadow = _mirror(O, h, nodes, order)
+    want = O.trace_closest(h, rays)
+    got, deferred, _ = closest(rays)
+    hit = want["triangle"] != 0xFFFFFFFF
+    on_sheared = np.isin(want["triangle"], np.nonzero(sheared)[0])
+    # some of the reference's hits lie outside the hit triangle's true extents: the case the exact boxes missed
+    p = rays["origin"] + rays["direction"] * want["t"][:, None]
+    tw = tris[np.where(hit, want["triangle"], 0)]
+    outside = hit & ((p < tw.min(1) - 3e-4) | (p > tw.max(1) + 3e-4)).any(1)
+    assert on_sheared.mean() > 0.2 and outside.sum() > 100 and 0.0 < deferred.mean() < 0.9
+    assert _same(got[~deferred], want[~deferred])
+    vis, dfs, _ = shadow(a, b)
+    assert (vis[~dfs] == O.trace_shadow(h, a, b)[~dfs]).all()
     hs.close()

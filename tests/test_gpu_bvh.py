@@ -97,3 +97,22 @@ def test_render_round_is_bit_identical_to_the_kd_path():
     assert st0.closest_rays == st1.closest_rays and st0.shadow_rays == st1.shadow_rays
     assert (fb0[0].view(np.uint32) == fb1[0].view(np.uint32)).all() and (fb0[1] == fb1[1]).all()
     kd.close(); bv.close()
+
+
+def test_sheared_accept_region():
+    """Triangles of TestIntersection's |q1.x| < eps branch (src/primitives.cpp:141-147) are accepted up to eps outside their true
+    extents (tests/test_bvh_host.py::test_sheared_accept_region): BVH pass + kd arbiter against the oracle on rays across the
+    true and the sheared edges."""
+    from test_bvh_host import sheared_fan
+    pack, tris, rays, (a, b) = sheared_fan()
+    ctx = device.Context(0, traversal="bvh")
+    ctx.commit(pack.desc())
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    ctx.bvh_stats()
+    got = ctx.trace_closest(rays)
+    s = ctx.bvh_stats()
+    assert s["rays"] == len(rays) and 0 < s["ambiguous"] < len(rays)
+    assert _same(got, O.trace_closest(h, rays))
+    assert (ctx.trace_shadow(a, b) == O.trace_shadow(h, a, b)).all()
+    ctx.close()

@@ -1437,6 +1437,15 @@ Bvh4Out bvh4_trace(const Scene& s, const float* nodes, const uint32_t* order, co
                 float delta = std::fmax(3.0517578125e-5f, 0.125f * m * longest / std::fabs(den));
                 if (q1x > -eps && q1x < eps && q1x != 0.0f) delta += 2.0f * (std::fabs(q1x / q2x) * (1.0f + std::fabs(q2y / q1y)));    // sheared accept region (src/primitives.cpp:141-147)
                 edge = !(a >= delta) || !(b >= delta) || !((a + b) <= 1.0f - delta);
+                // flag 8 of the product's record: the stored plane misses one of the triangle's own vertices by more than eps / 4 along the dominant axis
+                const int k = 3 - i1 - i2;
+                if (tr.p[k] != 0.0f && std::isfinite(tr.p[0]) && std::isfinite(tr.p[1]) && std::isfinite(tr.p[2]) && std::isfinite(tr.p[3])) {
+                    const V3 vs[3] = {v0, v1, v2};
+                    for (int c = 0; c < 3; c++) {
+                        const double lifted = -((double)tr.p[3] + (double)tr.p[i1] * (double)vs[c][i1] + (double)tr.p[i2] * (double)vs[c][i2]) / (double)tr.p[k];
+                        if (!(std::fabs(lifted - (double)vs[c][k]) <= 0.25 * (double)eps)) edge = true;
+                    }
+                }
             }
             if (any) { if (!edge && t >= firm_lo && t <= firm_hi) stop = true; else border = true; continue; }
             if (t < best_t) { second_t = best_t; best_t = t; best_edge = edge; out.hit.tri = ti; out.hit.t = t; out.hit.a = 1.0f - a - b; out.hit.b = a; out.hit.c = b; set_limit(); }

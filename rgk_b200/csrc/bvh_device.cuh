@@ -14,9 +14,10 @@
 // origins, tiny triangles) is therefore treated the same way.  Such rays (~3e-4 of them) are NOT committed: they are appended
 // to a list that the kd kernels re-trace.  The kd-tree stays the authority.
 //
-// Boxes are exact triangle bounds; conservativeness against the exact test's rounding (the accepted hit point can lie
-// ~2^-22 (|o| + |t|) outside the true triangle) comes from a per-ray margin m = 2^-17 (|ox| + |oy| + |oz| + |t1|) added
-// to every box, and from widening the interval bounds by 2^-20 relative.
+// Boxes bound the region the exact test accepts (the triangle's extents plus the corners of the projected -- for the
+// |q1.x| < eps branch: sheared -- triangle lifted onto the stored plane, host_scene.cpp); conservativeness against the
+// exact test's rounding (the accepted hit point can lie ~2^-22 (|o| + |t|) outside that region) comes from a per-ray
+// margin m = 2^-17 (|ox| + |oy| + |oz| + |t1|) added to every box, and from widening the interval bounds by 2^-20 relative.
 //
 // Slab test (round 2).  Per ray and axis the sign of 1/d says which of a child's two planes is entered first, so the ray
 // carries (a) the position of its near / far plane rows inside a node (a 16-byte offset: the node stores lo and hi as
@@ -229,7 +230,7 @@ struct BvhTraverser {
         // 4/3 while s < 1/4) away from the true barycentrics, and the kd-tree holds the TRUE triangle -- a hit less than
         // that inside the sheared boundary may lie in a cell that does not reference it.  Wider boundary (everything at s >= 1/4).
         if ((flags & 4u) && r1.z != 0.0f) delta += 2.0f * (fabsf(r1.z / r2.x) * (1.0f + fabsf(r2.y / r1.w)));
-        const bool edge = !(alpha >= delta) || !(beta >= delta) || !((alpha + beta) <= 1.0f - delta);
+        const bool edge = !(alpha >= delta) || !(beta >= delta) || !((alpha + beta) <= 1.0f - delta) || (flags & 8u);     // 8: plane off its own vertices (host_scene.cpp)
         if (ANY) {
             if (!edge && t >= firm_lo && t <= firm_hi) return true;
             border = true;

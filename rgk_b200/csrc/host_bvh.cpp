@@ -19,7 +19,8 @@
 //   [24..27] child codes (uint32 bits): inner = node index (< 2^31 - 1); leaf = 1<<31 | (count-1)<<29 | first slot
 //   [28..31] zero.  Empty child: lo = hi = +inf (a box at infinity: the slab test gives an empty interval for every
 //   direction -- an inverted box would NOT, min/max of the two plane distances un-inverts it), code 0x7fffffff.
-// Boxes are the exact fp32 bounds of the triangles (no padding: the traversal pads per ray).
+// Boxes are the fp32 bounds host_scene.cpp hands in: the triangles' extents and the corners of the region TestIntersection
+// accepts (no padding beyond that: the traversal pads per ray).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>

@@ -312,7 +312,9 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rg
     // intersection records: the ray-independent part of Triangle::TestIntersection (src/primitives.cpp:83,104-133,141,149)
     hs.tri_isect.resize(12 * (size_t)nt);
     hs.tri_bounds.resize(4 * (size_t)nt);
-    std::vector<float> ev_bvh[3];            // ev with the sheared triangles' accept regions added (copied on the first such triangle)
+    const bool want_bvh = cfg.traversal == RGK_TRAVERSAL_BVH;
+    std::vector<float> ev_bvh[3];                              // ev with the corners of the accept regions added (wide BVH only)
+    if (want_bvh) for (int ax = 0; ax < 3; ax++) ev_bvh[ax] = ev[ax];
     for (uint32_t i = 0; i < nt; i++) {
         const float* p = &hs.planes[4 * (size_t)i];
         const float px = std::fabs(p[0]), py = std::fabs(p[1]), pz = std::fabs(p[2]);
@@ -331,16 +333,23 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rg
         r[4] = comp(v0, i1); r[5] = comp(v0, i2); r[6] = q1x; r[7] = q1y;
         r[8] = q2x; r[9] = q2y; r[10] = denom; std::memcpy(&r[11], &code, 4);
         tri_prefilter_bounds(r, code, &hs.tri_bounds[4 * (size_t)i]);
-        // The |q1.x| < eps branch of TestIntersection (src/primitives.cpp:141-147) drops q1.x: what it accepts is the triangle
-        // v0, v1', v2 with v1' = v1 moved to v0's first projected coordinate (a shear of up to eps), on the stored plane.  The
-        // wide BVH's boxes must hold that region too (the kd-tree keeps the true extents: ev feeds the reference's build).
-        if ((code & 4u) && q1x != 0.0f && p[3 - i1 - i2] != 0.0f && std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]) && std::isfinite(p[3])) {
-            const int k = 3 - i1 - i2;
-            double w[3];
-            w[i1] = comp(v0, i1); w[i2] = comp(v1, i2);
-            w[k] = -((double)p[3] + (double)p[i1] * w[i1] + (double)p[i2] * w[i2]) / (double)p[k];
-            if (std::isfinite(w[k])) {
-                if (ev_bvh[0].empty()) for (int ax = 0; ax < 3; ax++) ev_bvh[ax] = ev[ax];
+        // What TestIntersection accepts is a planar region, not the triangle: the PROJECTED triangle -- with v1 moved to v0's
+        // first projected coordinate in the |q1.x| < eps branch (src/primitives.cpp:141-147 drops q1.x: a shear of up to eps)
+        // -- lifted onto the STORED fp32 plane, whose normal is off by ~2^-24 / sin(angle) for a sliver (:24-36).  The wide
+        // BVH's boxes hold the three corners of that region as well (the kd-tree keeps the true extents: ev feeds the
+        // reference's build).  A triangle whose plane misses one of its own vertices by more than eps / 4 along the dominant
+        // axis is marked (flag 8): the kd-tree references it by its true extents, so its hits always go to the kd pass.
+        const int k = 3 - i1 - i2;
+        if (p[k] != 0.0f && std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]) && std::isfinite(p[3])) {
+            auto lift = [&](double a, double b) { return -((double)p[3] + (double)p[i1] * a + (double)p[i2] * b) / (double)p[k]; };
+            const F3 vs[3] = {v0, v1, v2};
+            bool off_plane = false;
+            for (int c = 0; c < 3; c++) {
+                if (!(std::fabs(lift(comp(vs[c], i1), comp(vs[c], i2)) - (double)comp(vs[c], k)) <= 0.25 * (double)eps)) off_plane = true;
+                double w[3];
+                w[i1] = (c == 1 && (code & 4u)) ? comp(v0, i1) : comp(vs[c], i1); w[i2] = comp(vs[c], i2);
+                w[k] = lift(w[i1], w[i2]);
+                if (!want_bvh || !std::isfinite(w[k])) continue;
                 for (int ax = 0; ax < 3; ax++) {
                     float lo = (float)w[ax], hi = lo;
                     for (int n = 0; n < 2; n++) { lo = std::nextafterf(lo, -std::numeric_limits<float>::infinity()); hi = std::nextafterf(hi, std::numeric_limits<float>::infinity()); }
@@ -348,6 +357,7 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rg
                     ev_bvh[ax][2 * (size_t)i + 1] = std::max(ev_bvh[ax][2 * (size_t)i + 1], hi);
                 }
             }
+            if (off_plane) { code |= 8u; std::memcpy(&r[11], &code, 4); }
         }
     }
 
@@ -371,8 +381,8 @@ void host_scene_commit(const rgk_scene_desc* d, const rgk_kdtree* tree, const rg
     // own thread meanwhile
     hs.bvh_nodes.clear(); hs.bvh_order.clear(); hs.bvh_depth = 0;
     std::thread bvh_thread; std::exception_ptr bvh_error;
-    if (cfg.traversal == RGK_TRAVERSAL_BVH && nan_prone == 0)
-        bvh_thread = std::thread([&] { try { host_bvh_build(ev_bvh[0].empty() ? ev : ev_bvh, nt, cfg, hs); } catch (...) { bvh_error = std::current_exception(); } });
+    if (want_bvh && nan_prone == 0)
+        bvh_thread = std::thread([&] { try { host_bvh_build(ev_bvh, nt, cfg, hs); } catch (...) { bvh_error = std::current_exception(); } });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } bvh_joiner{bvh_thread};     // also on the throwing paths below
 
     // kd-tree

@@ -1,7 +1,7 @@
 """Randomized differential campaign: the host-compiled device source (kd traversal, variant 6, and the wide-BVH pass, variant 4)
 against the oracle on random triangle soups (tiny / huge / sliver / far / axis-aligned / duplicated triangles, scenes moved far
 from the origin, rays aimed at vertices and edges from inside and from ~2000 units away).  Found the two rules added at the end
-of round 1 (scaled boundary width, NaN-prone triangles).   python tests/bvh_campaign.py <seconds> [first seed]"""
+of round 1 (scaled boundary width, NaN-prone triangles); every fourth soup has sheared twins (round 2).   python tests/bvh_campaign.py <seconds> [first seed]"""
 import os, sys, time, numpy as np, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -24,6 +24,12 @@ while time.time() < t_end:
     tris = _triangles(rng, n_t)
     if seed % 2: tris = np.concatenate([tris, tris[: n_t // 10]])
     if seed % 3 == 0: tris = (tris + np.float32(rng.choice([0, 100, -5000]))).astype(np.float32)     # far from the origin
+    if seed % 4 == 0:                                                   # sheared twins: v1 within ~eps of v0 in one coordinate (|q1.x| < eps branch)
+        diam = np.linalg.norm(tris.reshape(-1, 3).max(0) - tris.reshape(-1, 3).min(0))
+        sel = rng.random(len(tris)) < 0.4
+        ax = rng.integers(0, 3, len(tris))
+        snap = tris[np.arange(len(tris)), 0, ax] + (rng.uniform(-2, 2, len(tris)) * 1e-5 * diam).astype(np.float32)
+        tris[np.arange(len(tris))[sel], 1, ax[sel]] = snap[sel]
     pack = _scene(tris)
     h = O.scene_create(pack.desc()); S = T.Scene(lib, pack)
     has_bvh = len(S.keep[5]) > 0

@@ -70,22 +70,25 @@ def _check_structure(pack, hs):
     pos = np.asarray(arr["positions"], np.float32).reshape(-1, 3)
     tri = np.asarray(arr["indices"], np.uint32).reshape(-1, 3)
     tlo, thi = pos[tri].min(1), pos[tri].max(1)
-    # triangles of the |q1.x| < eps branch with q1.x != 0 are accepted as their sheared twin (src/primitives.cpp:141-147): v1
-    # moved to v0's first projected coordinate, on the stored plane; their boxes hold that point too (2 ulps outwards)
+    # what TestIntersection accepts is the projected triangle (v1 moved to v0's first projected coordinate in the |q1.x| < eps
+    # branch, src/primitives.cpp:141-147) lifted onto the stored fp32 plane: the boxes hold those three corners too (2 ulps outwards)
     planes, rec = hs.records()
-    planes = np.asarray(planes, np.float32).reshape(-1, 4); rec = np.asarray(rec, np.float32).reshape(-1, 12)
+    planes = np.asarray(planes, np.float32).reshape(-1, 4).astype(np.float64); rec = np.asarray(rec, np.float32).reshape(-1, 12)
     flags = rec[:, 11].view(np.uint32)
-    for t in np.nonzero(((flags & 4) != 0) & (rec[:, 6] != 0))[0]:
-        code = int(flags[t] & 3)
-        i1, i2 = ((1, 2), (0, 2), (0, 1))[code]
-        k = 3 - i1 - i2
-        w = np.zeros(3)
-        w[i1] = pos[tri[t, 0], i1]; w[i2] = pos[tri[t, 1], i2]
-        w[k] = -(float(planes[t, 3]) + float(planes[t, i1]) * w[i1] + float(planes[t, i2]) * w[i2]) / float(planes[t, k])
+    i1 = np.where((flags & 3) == 0, 1, 0); i2 = np.where((flags & 3) == 2, 1, 2); k = 3 - i1 - i2
+    rows = np.arange(nt)
+    ok = (planes[rows, k] != 0) & np.isfinite(planes).all(1)
+    v = pos[tri].astype(np.float64)                                         # [nt, 3 corners, 3]
+    for c in range(3):
+        a = np.where((c == 1) & ((flags & 4) != 0), v[rows, 0, i1], v[rows, c, i1]); b = v[rows, c, i2]
+        with np.errstate(all="ignore"):
+            lifted = -(planes[:, 3] + planes[rows, i1] * a + planes[rows, i2] * b) / planes[rows, k]
+        w = np.zeros((nt, 3)); w[rows, i1] = a; w[rows, i2] = b; w[rows, k] = lifted
+        use = ok & np.isfinite(lifted)
         lo = hi = w.astype(np.float32)
         for _ in range(2):
             lo = np.nextafter(lo, np.float32(-np.inf)); hi = np.nextafter(hi, np.float32(np.inf))
-        tlo[t] = np.minimum(tlo[t], lo); thi[t] = np.maximum(thi[t], hi)
+        tlo[use] = np.minimum(tlo[use], lo[use]); thi[use] = np.maximum(thi[use], hi[use])
     seen_inner, covered = set(), np.zeros(nt, bool)
     # subtree bounds bottom-up: children always have larger indices than their parent (preorder emission)
     sub_lo, sub_hi = np.zeros((len(nodes), 3), np.float32), np.zeros((len(nodes), 3), np.float32)
@@ -422,4 +425,55 @@ def test_sheared_accept_region():
     assert _same(got[~deferred], want[~deferred])
     vis, dfs, _ = shadow(a, b)
     assert (vis[~dfs] == O.trace_shadow(h, a, b)[~dfs]).all()
+    hs.close()
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_slivers_off_their_plane(seed):
+    """Long slivers (5 units by 1e-4 .. 1e-2): the cross product behind Triangle::CalculatePlane (src/primitives.cpp:24-36) loses
+    its direction, so the stored plane misses the triangle's own far vertices and the accepted region (projected triangle
+    lifted onto that plane) leaves the true extents.  The boxes hold the lifted corners; triangles whose plane is off by more
+    than eps / 4 carry flag 8 and always defer.  Committed rays must be the kd-tree's answer."""
+    from test_prefilter_bounds import _scene
+    rng = np.random.default_rng(seed)
+    n_t = 400
+    a = rng.uniform(-6, 6, (n_t, 3))
+    u = rng.normal(size=(n_t, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    w = np.cross(u, rng.normal(size=(n_t, 3))); w /= np.linalg.norm(w, axis=1, keepdims=True)
+    height = 10.0 ** rng.uniform(-4, -2, (n_t, 1))
+    tris = np.stack([a, a + 5.0 * u, a + 2.5 * u + height * w], 1).astype(np.float32)
+    walls = rng.uniform(-8, 8, (40, 1, 3)) + rng.normal(scale=2.0, size=(40, 3, 3))
+    tris = np.concatenate([tris, walls.astype(np.float32)])
+    pack = _scene(tris)
+    hs = device.HostScene(pack.desc(), traversal="bvh")
+    nodes, order, _ = hs.bvh()
+    if len(nodes) == 0:
+        pytest.skip("a sliver collapsed onto collinear fp32 vertices: the scene keeps the kd-tree")
+    _check_structure(pack, hs)
+    rec = np.asarray(hs.records()[1], np.float32).reshape(-1, 12)
+    off_plane = (rec[:, 11].view(np.uint32) & 8) != 0
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    closest, shadow = _mirror(O, h, nodes, order)
+    n = 40000
+    pick = rng.integers(0, n_t, n)
+    s = rng.random((n, 1)); t = rng.random((n, 1)) * 1.2 - 0.1
+    target = (tris[pick, 0] * (1 - s) + tris[pick, 1] * s) * (1 - t) + tris[pick, 2] * t
+    origin = target + rng.normal(scale=2.0, size=(n, 3))
+    d = (target - origin).astype(np.float32)
+    rays = np.zeros(n, checkers.RAY_DT)
+    rays["origin"] = origin.astype(np.float32)
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tfar"] = 10000.0
+    want = O.trace_closest(h, rays)
+    got, deferred, _ = closest(rays)
+    hit = want["triangle"] != 0xFFFFFFFF
+    print("off-plane triangles", int(off_plane.sum()), "hits", hit.mean(), "hits on slivers", (want["triangle"][hit] < n_t).mean(), "deferred", deferred.mean())
+    assert (want["triangle"][hit] < n_t).mean() > 0.05
+    assert _same(got[~deferred], want[~deferred])
+    assert off_plane[:n_t].sum() > 20 and not off_plane[n_t:].any()
+    assert deferred[hit & off_plane[np.where(hit, want["triangle"], 0)]].all()         # every ray whose answer is such a triangle went to the kd pass
+    b = (target + 0.3 * d).astype(np.float32)
+    vis, dfs, _ = shadow(rays["origin"], b)
+    assert (vis[~dfs] == O.trace_shadow(h, rays["origin"], b)[~dfs]).all()
     hs.close()

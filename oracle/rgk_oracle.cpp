@@ -1437,8 +1437,10 @@ Bvh4Out bvh4_trace(const Scene& s, const float* nodes, const uint32_t* order, co
                 float delta = std::fmax(3.0517578125e-5f, 0.125f * m * longest / std::fabs(den));
                 if (q1x > -eps && q1x < eps && q1x != 0.0f) delta += 2.0f * (std::fabs(q1x / q2x) * (1.0f + std::fabs(q2y / q1y)));    // sheared accept region (src/primitives.cpp:141-147)
                 edge = !(a >= delta) || !(b >= delta) || !((a + b) <= 1.0f - delta);
-                const float p1 = (std::fabs(r.o.x + r.d.x * t) + std::fabs(r.o.y + r.d.y * t)) + std::fabs(r.o.z + r.d.z * t);
-                if (std::fabs(dot(r.d, pn)) * eps < p1 * 2.384185791015625e-7f) edge = true;      // grazing: the plane's miss of the extents is more than eps of ray parameter
+                if (std::fabs(dot(r.d, pn)) * eps < m * 0.0546875f) {      // grazing: the plane's miss of the extents is more than eps of ray parameter (cheap bound, then |P|_1)
+                    const float p1 = (std::fabs(r.o.x + r.d.x * t) + std::fabs(r.o.y + r.d.y * t)) + std::fabs(r.o.z + r.d.z * t);
+                    if (std::fabs(dot(r.d, pn)) * eps < p1 * 2.384185791015625e-7f) edge = true;
+                }
                 // flag 8 of the product's record: the stored plane misses one of the triangle's own vertices by more than eps / 4 along the dominant axis
                 const int k = 3 - i1 - i2;
                 if (tr.p[k] != 0.0f && std::isfinite(tr.p[0]) && std::isfinite(tr.p[1]) && std::isfinite(tr.p[2]) && std::isfinite(tr.p[3])) {

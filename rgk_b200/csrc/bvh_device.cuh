@@ -201,6 +201,18 @@ struct BvhTraverser {
         const float t = (float)(-((double)r0.w + (double)dot2f) / (double)dtf);
         if (t < lo_t || t > hi_t) return false;
         if (!ANY && t > res.t + 2.0f * eps) return false;                // beyond the window of the best so far
+        // Grazing hits: the plane misses the triangle's own extents by up to ~an ulp of the coordinates (fp32 plane, fp32 vertices), and
+        // along a ray at cosine |dtf| to it that is ulp / |dtf| of ray parameter -- more than eps for |dtf| below ~1e-2: the hit then
+        // lies in a kd cell beyond the triangle's extents, which does not reference it (Cornell box, a ray 0.04 degrees off the
+        // ceiling: the leaf holding the ceiling ends 1.9e-4 before the hit).  Bound of the miss: 2^-22 |P|_1 (normalised fp32 normal,
+        // fp32 offset -n.v0: ~3 roundings of magnitude |v|_1 2^-24, 4x what the Cornell case shows).
+        // The kernel is issue-bound (14 more instructions per accepted hit cost 3 % of the closest-hit launches): a two-instruction
+        // bound first, |P|_1 <= |o|_1 + sqrt(3) t <= sqrt(3) 2^17 m (0.0546875 = 1.75 / 32), the exact |P|_1 for the ~1 % that pass it.
+        bool grazing = fabsf(dtf) * eps < marg * 0.0546875f;
+        if (grazing) {
+            const float p1 = (fabsf(ox + dx * t) + fabsf(oy + dy * t)) + fabsf(oz + dz * t);
+            grazing = fabsf(dtf) * eps < p1 * 2.384185791015625e-7f;
+        }
         const float4* rec = S.tri_isect + 3 * (size_t)ti;
         const float4 r1 = __ldg(rec + 1);
         const float4 r2 = __ldg(rec + 2);
@@ -230,13 +242,6 @@ struct BvhTraverser {
         // 4/3 while s < 1/4) away from the true barycentrics, and the kd-tree holds the TRUE triangle -- a hit less than
         // that inside the sheared boundary may lie in a cell that does not reference it.  Wider boundary (everything at s >= 1/4).
         if ((flags & 4u) && r1.z != 0.0f) delta += 2.0f * (fabsf(r1.z / r2.x) * (1.0f + fabsf(r2.y / r1.w)));
-        // Grazing hits: the plane misses the triangle's own extents by up to ~an ulp of the coordinates (fp32 plane, fp32 vertices), and
-        // along a ray at cosine |dtf| to it that is ulp / |dtf| of ray parameter -- more than eps for |dtf| below ~1e-2: the hit then
-        // lies in a kd cell beyond the triangle's extents, which does not reference it (Cornell box, a ray 0.04 degrees off the
-        // ceiling: the leaf holding the ceiling ends 1.9e-4 before the hit).  Bound of the miss: 2^-22 |P|_1 (normalised fp32 normal,
-        // fp32 offset -n.v0: ~3 roundings of magnitude |v|_1 2^-24, 4x what the Cornell case shows).
-        const float p1 = (fabsf(ox + dx * t) + fabsf(oy + dy * t)) + fabsf(oz + dz * t);
-        const bool grazing = fabsf(dtf) * eps < p1 * 2.384185791015625e-7f;
         const bool edge = !(alpha >= delta) || !(beta >= delta) || !((alpha + beta) <= 1.0f - delta) || (flags & 8u) || grazing;     // 8: plane off its own vertices (host_scene.cpp)
         if (ANY) {
             if (!edge && t >= firm_lo && t <= firm_hi) return true;

@@ -479,6 +479,26 @@ def test_slivers_off_their_plane(seed):
     hs.close()
 
 
+def grazing_rays(n=200000, seed=3):
+    """The Cornell-box ray of test_grazing_hits (first entry; its ignore triangle is 1) and n rays skimming the box's walls:
+    origins 1e-5 .. 1e-2 off a wall, drifting towards it at 1e-5 .. 3e-2 of the direction.  -> rays, ignore"""
+    rng = np.random.default_rng(seed)
+    lo, hi = np.array([-1, 0, -1], np.float32), np.array([1, 2, 1], np.float32)
+    origin = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    ax = rng.integers(0, 3, n); side = rng.integers(0, 2, n)
+    wall = np.where(side == 1, hi[ax], lo[ax]); inward = np.where(side == 1, -1.0, 1.0)
+    origin[np.arange(n), ax] = wall + inward * 10.0 ** rng.uniform(-5, -2, n)
+    d = rng.normal(size=(n, 3))
+    d[np.arange(n), ax] = -inward * 10.0 ** rng.uniform(-5, -1.5, n)
+    rays = np.zeros(n + 1, checkers.RAY_DT)
+    rays["origin"][1:] = origin
+    rays["direction"][1:] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["origin"][0] = (0.403505802, 1.99871016, -0.999653339); rays["direction"][0] = (-0.23824501, 0.000627510715, 0.971204877)
+    rays["tfar"] = 10000.0
+    ign = np.full(n + 1, 0xFFFFFFFF, np.uint32); ign[0] = 1
+    return rays, ign
+
+
 def test_grazing_hits():
     """A ray 0.04 degrees off the Cornell box's ceiling (whose fp32 plane passes a quarter ulp above the triangle's highest
     vertex): the hit is interior to the triangle but lies beyond its extents, in a kd cell that does not reference it, 1.9e-4 of
@@ -490,27 +510,10 @@ def test_grazing_hits():
     h = O.scene_create(pack.desc())
     nodes, order, _ = hs.bvh()
     closest, shadow = _mirror(O, h, nodes, order)
-    rays = np.zeros(1, checkers.RAY_DT)
-    rays["origin"][0] = (0.403505802, 1.99871016, -0.999653339); rays["direction"][0] = (-0.23824501, 0.000627510715, 0.971204877); rays["tfar"] = 10000.0
-    ign = np.array([1], np.uint32)
+    rays, ign = grazing_rays()
     want = O.trace_closest(h, rays, ign)
     got, deferred, _ = closest(rays, ign)
     assert want["triangle"][0] == 0xFFFFFFFF and deferred[0]
-    rng = np.random.default_rng(3)
-    n = 200000
-    lo, hi = np.array([-1, 0, -1], np.float32), np.array([1, 2, 1], np.float32)
-    origin = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
-    ax = rng.integers(0, 3, n); side = rng.integers(0, 2, n)
-    wall = np.where(side == 1, hi[ax], lo[ax]); inward = np.where(side == 1, -1.0, 1.0)
-    origin[np.arange(n), ax] = wall + inward * 10.0 ** rng.uniform(-5, -2, n)          # 1e-5 .. 1e-2 off a wall
-    d = rng.normal(size=(n, 3))
-    d[np.arange(n), ax] = -inward * 10.0 ** rng.uniform(-5, -1.5, n)                    # drifting towards it
-    rays = np.zeros(n, checkers.RAY_DT)
-    rays["origin"] = origin
-    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
-    rays["tfar"] = 10000.0
-    want = O.trace_closest(h, rays)
-    got, deferred, _ = closest(rays)
     assert deferred.mean() < 0.8 and (want["triangle"] != 0xFFFFFFFF).mean() > 0.5
     assert _same(got[~deferred], want[~deferred])
     hs.close()

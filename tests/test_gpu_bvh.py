@@ -116,3 +116,23 @@ def test_sheared_accept_region():
     assert _same(got, O.trace_closest(h, rays))
     assert (ctx.trace_shadow(a, b) == O.trace_shadow(h, a, b)).all()
     ctx.close()
+
+
+def test_grazing_hits():
+    """Rays skimming the Cornell box's walls (tests/test_bvh_host.py::test_grazing_hits; the first one is the ray of the soak that the
+    kd-tree misses and the BVH alone would hit): BVH pass + kd arbiter against the oracle."""
+    from test_bvh_host import grazing_rays
+    from rgk_b200 import scenes
+    pack = scenes.load_builtin("cornell-box")[0]
+    ctx = device.Context(0, traversal="bvh")
+    ctx.commit(pack.desc())
+    O = checkers.oracle()
+    h = O.scene_create(pack.desc())
+    rays, ign = grazing_rays()
+    ctx.bvh_stats()
+    got = ctx.trace_closest(rays, ign)
+    s = ctx.bvh_stats()
+    want = O.trace_closest(h, rays, ign)
+    assert s["rays"] == len(rays) and 0 < s["ambiguous"] < len(rays)
+    assert want["triangle"][0] == 0xFFFFFFFF and _same(got, want)
+    ctx.close()
